@@ -1,0 +1,128 @@
+// api.cu -- the extern "C" boundary of libbgarena.so (include/bgarena.h).  No torch / C++ types cross it.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "eval.cuh"
+#include "movegen.cuh"
+#include "select.cuh"
+
+namespace bg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int32_t check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return BG_OK;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return BG_ERR_CUDA;
+}
+
+static int32_t require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available (libbgarena has no CPU fallback)");
+    return BG_ERR_CUDA;
+  }
+  return BG_OK;
+}
+
+}  // namespace bg
+
+using namespace bg;
+
+#define BG_REQUIRE(cond, msg)   \
+  do {                          \
+    if (!(cond)) {              \
+      set_error("%s", msg);     \
+      return BG_ERR_ARG;        \
+    }                           \
+  } while (0)
+
+extern "C" {
+
+int32_t bg_abi_version(void) { return BG_ABI_VERSION; }
+
+const char* bg_last_error(void) { return g_err; }
+
+int32_t bg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int64_t bg_movegen_workspace_bytes(int64_t B) { return movegen_workspace_bytes(B < 0 ? 0 : B); }
+
+int32_t bg_movegen(const int8_t* boards, const uint8_t* players, const uint8_t* rolls, int64_t B, int32_t item_cap,
+                   int64_t pool_cap, int8_t* out_boards, uint8_t* out_submoves, int32_t* out_owner, int64_t* out_offsets,
+                   int32_t* out_count, int64_t* out_total, int32_t* out_status, void* workspace, int64_t workspace_bytes,
+                   void* stream) {
+  BG_REQUIRE(B >= 0, "bg_movegen: B < 0");
+  BG_REQUIRE(B == 0 || (boards && players && rolls && out_offsets && out_count), "bg_movegen: null input/output pointer");
+  BG_REQUIRE(pool_cap == 0 || out_boards, "bg_movegen: out_boards is null");
+  BG_REQUIRE(workspace, "bg_movegen: workspace is null");
+  int32_t rc = require_device();
+  if (rc != BG_OK) return rc;
+  MovegenArgs a{boards,      players,   rolls,     B,          item_cap,  pool_cap,  out_boards,     out_submoves,
+                out_owner,   out_offsets, out_count, out_total, out_status, workspace, workspace_bytes};
+  return movegen_launch(a, (cudaStream_t)stream);
+}
+
+int32_t bg_encode(const int8_t* boards, const uint8_t* flag_player, int64_t N, float* out, void* stream) {
+  BG_REQUIRE(N >= 0, "bg_encode: N < 0");
+  BG_REQUIRE(N == 0 || (boards && flag_player && out), "bg_encode: null pointer");
+  int32_t rc = require_device();
+  if (rc != BG_OK) return rc;
+  return encode_launch(boards, flag_player, N, out, (cudaStream_t)stream);
+}
+
+int64_t bg_prepared_weights_bytes(int32_t H) { return prepared_weights_bytes(H); }
+
+int32_t bg_prepare_weights(const float* packed, int32_t H, float* prepared, void* stream) {
+  BG_REQUIRE(packed && prepared, "bg_prepare_weights: null pointer");
+  int32_t rc = require_device();
+  if (rc != BG_OK) return rc;
+  return prepare_weights_launch(packed, H, prepared, (cudaStream_t)stream);
+}
+
+int32_t bg_eval(const int8_t* boards, const uint8_t* flags, const int32_t* owner, const uint8_t* owner_players, int64_t N,
+                const float* prepared, int32_t H, float* out_v, void* stream) {
+  BG_REQUIRE(N >= 0, "bg_eval: N < 0");
+  BG_REQUIRE(N == 0 || (boards && prepared && out_v), "bg_eval: null pointer");
+  int32_t rc = require_device();
+  if (rc != BG_OK) return rc;
+  EvalArgs a{boards, flags, owner, owner_players, N, nullptr, N, prepared, H, out_v};
+  return eval_launch(a, (cudaStream_t)stream);
+}
+
+int32_t bg_eval_indirect(const int8_t* boards, const uint8_t* flags, const int32_t* owner, const uint8_t* owner_players,
+                         const int64_t* N_dev, int64_t max_N, const float* prepared, int32_t H, float* out_v, void* stream) {
+  BG_REQUIRE(max_N >= 0 && N_dev, "bg_eval_indirect: bad N");
+  BG_REQUIRE(max_N == 0 || (boards && prepared && out_v), "bg_eval_indirect: null pointer");
+  int32_t rc = require_device();
+  if (rc != BG_OK) return rc;
+  EvalArgs a{boards, flags, owner, owner_players, 0, N_dev, max_N, prepared, H, out_v};
+  return eval_launch(a, (cudaStream_t)stream);
+}
+
+int32_t bg_select(const float* v, const int64_t* offsets, const int32_t* counts, int32_t item_cap, int64_t B, float temperature,
+                  uint64_t seed, uint64_t ctr, int64_t item_id_base, int32_t* out_action, void* stream) {
+  BG_REQUIRE(B >= 0, "bg_select: B < 0");
+  BG_REQUIRE(B == 0 || (v && offsets && counts && out_action), "bg_select: null pointer");
+  int32_t rc = require_device();
+  if (rc != BG_OK) return rc;
+  SelectArgs a{v, offsets, counts, item_cap, B, temperature, seed, ctr, item_id_base, out_action};
+  return select_launch(a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// bg_common.cuh -- shared device helpers for libbgarena (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bgarena.h"
+
+#define BG_WARP 32
+#define BG_FULL 0xffffffffu
+
+namespace bg {
+
+// thread-local error string (host side)
+void set_error(const char* fmt, ...);
+int32_t check_cuda(cudaError_t e, const char* what);
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// expand 4 nibbles (low 16 bits) to 4 bytes
+__device__ __forceinline__ uint32_t nib4_to_bytes(uint32_t x) {
+  return (x & 0xfu) | ((x & 0xf0u) << 4) | ((x & 0xf00u) << 8) | ((x & 0xf000u) << 12);
+}
+// pack 4 bytes (each < 16) to 4 nibbles
+__device__ __forceinline__ uint32_t bytes_to_nib4(uint32_t x) {
+  return (x & 0xfu) | ((x >> 4) & 0xf0u) | ((x >> 8) & 0xf00u) | ((x >> 12) & 0xf000u);
+}
+// spread 4 bits to the LSB of 4 bytes
+__device__ __forceinline__ uint32_t bits4_to_bytes(uint32_t h) {
+  return (h & 1u) | ((h & 2u) << 7) | ((h & 4u) << 14) | ((h & 8u) << 21);
+}
+
+__device__ __forceinline__ uint32_t mix32(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  uint32_t h = a * 0x9E3779B1u;
+  h = (h ^ (h >> 15)) + b * 0x85EBCA77u;
+  h = (h ^ (h >> 13)) + c * 0xC2B2AE3Du;
+  h = (h ^ (h >> 16)) + d * 0x27D4EB2Fu;
+  h ^= h >> 15;
+  h *= 0x2C1B3C6Du;
+  h ^= h >> 12;
+  return h;
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter-based
+struct Philox {
+  static __device__ __forceinline__ void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+    uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0;
+    c[1] = n1;
+    c[2] = n2;
+    c[3] = n3;
+  }
+  static __device__ __forceinline__ void gen(uint64_t key, uint64_t ctr_lo, uint64_t ctr_hi, uint32_t (&out)[4]) {
+    uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+    out[0] = (uint32_t)ctr_lo;
+    out[1] = (uint32_t)(ctr_lo >> 32);
+    out[2] = (uint32_t)ctr_hi;
+    out[3] = (uint32_t)(ctr_hi >> 32);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      round(out, k0, k1);
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+  }
+};
+
+}  // namespace bg

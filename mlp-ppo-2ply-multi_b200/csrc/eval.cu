@@ -1,0 +1,321 @@
+// eval.cu -- fused 198-feature encode + sigmoid-MLP value, and the stand-alone encoder (sm_100a).
+//
+// Replaces ImmutableBoard.get_board_features (reference src/backgammon/board/immutable_board.py:86-128),
+// generate_all_board_features (src/environments/env_helper.py:7-24) and BackgammonPolicyNetwork.forward
+// (src/agents/policy_network.py:53-70).
+//
+// The 198-vector of a board has <= ~31 non-zeros and the four per-point features are a thermometer code of the
+// checker count, so layer 1 is evaluated as a gather-sum of pre-accumulated weight rows held in shared memory:
+//   z = b1 + sum_{occupied (player, point)} Tcum[player][point][min(c,3)] + (c-3) * Thalf[player][point] + bar/off/flag rows
+// i.e. one 512-byte (H=128) conflict-free row read per occupied point instead of a dense 198xH contraction; features
+// never exist in memory.  One warp per board, lane owns H/32 hidden units; fp32 FFMA (meets the 1e-5 contract; a bf16
+// tensor-core path would not).  Persistent CTAs keep the 100 KB table resident in shared memory.
+#include "eval.cuh"
+
+namespace bg {
+
+namespace {
+
+__constant__ float c_off15[16];  // (float)(n / 15.0), reference immutable_board.py:117,120
+
+constexpr int NUM_SMS = 148;
+constexpr int EVAL_THREADS = 256;
+
+// prepared layout: rows [0,192): (pl*24+pt)*4 + k  (k=0: r0, 1: r0+r1, 2: r0+r1+r2, 3: 0.5*r3)
+//                  rows 192..197: 0.5*W[192], W[193], 0.5*W[194], W[195], W[196], W[197]; then b1[H], w2[H], b2
+__global__ void k_prepare(const float* __restrict__ packed, int H, float* __restrict__ prep) {
+  const int total = 198 * H;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total + 2 * H + 1; i += gridDim.x * blockDim.x) {
+    if (i >= total) {
+      prep[i] = packed[i];
+      continue;
+    }
+    const int row = i / H, h = i - row * H;
+    float v;
+    if (row < 192) {
+      const int k = row & 3, f0 = row - k;
+      const float r0 = packed[(f0 + 0) * H + h], r1 = packed[(f0 + 1) * H + h], r2 = packed[(f0 + 2) * H + h];
+      v = k == 0 ? r0 : k == 1 ? r0 + r1 : k == 2 ? (r0 + r1) + r2 : 0.5f * packed[(f0 + 3) * H + h];
+    } else {
+      v = packed[i];
+      if (row == 192 || row == 194) v *= 0.5f;
+    }
+    prep[i] = v;
+  }
+}
+
+template <int HPL>
+struct Acc {
+  float a[HPL];
+};
+
+template <int HPL>
+__device__ __forceinline__ void add_row(Acc<HPL>& z, const float* row, int lane) {
+  if constexpr (HPL == 4) {
+    const float4 r = *reinterpret_cast<const float4*>(row + lane * 4);
+    z.a[0] += r.x;
+    z.a[1] += r.y;
+    z.a[2] += r.z;
+    z.a[3] += r.w;
+  } else if constexpr (HPL == 8) {
+    const float4 r = *reinterpret_cast<const float4*>(row + lane * 4);
+    const float4 s = *reinterpret_cast<const float4*>(row + 128 + lane * 4);
+    z.a[0] += r.x;
+    z.a[1] += r.y;
+    z.a[2] += r.z;
+    z.a[3] += r.w;
+    z.a[4] += s.x;
+    z.a[5] += s.y;
+    z.a[6] += s.z;
+    z.a[7] += s.w;
+  } else {
+#pragma unroll
+    for (int q = 0; q < HPL; ++q) z.a[q] += row[q * 32 + lane];
+  }
+}
+
+template <int HPL>
+__device__ __forceinline__ void fma_row(Acc<HPL>& z, float s, const float* row, int lane) {
+  if constexpr (HPL == 4) {
+    const float4 r = *reinterpret_cast<const float4*>(row + lane * 4);
+    z.a[0] = fmaf(s, r.x, z.a[0]);
+    z.a[1] = fmaf(s, r.y, z.a[1]);
+    z.a[2] = fmaf(s, r.z, z.a[2]);
+    z.a[3] = fmaf(s, r.w, z.a[3]);
+  } else if constexpr (HPL == 8) {
+    const float4 r = *reinterpret_cast<const float4*>(row + lane * 4);
+    const float4 t = *reinterpret_cast<const float4*>(row + 128 + lane * 4);
+    z.a[0] = fmaf(s, r.x, z.a[0]);
+    z.a[1] = fmaf(s, r.y, z.a[1]);
+    z.a[2] = fmaf(s, r.z, z.a[2]);
+    z.a[3] = fmaf(s, r.w, z.a[3]);
+    z.a[4] = fmaf(s, t.x, z.a[4]);
+    z.a[5] = fmaf(s, t.y, z.a[5]);
+    z.a[6] = fmaf(s, t.z, z.a[6]);
+    z.a[7] = fmaf(s, t.w, z.a[7]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < HPL; ++q) z.a[q] = fmaf(s, row[q * 32 + lane], z.a[q]);
+  }
+}
+
+// hidden-unit ownership of a lane must match add_row's addressing:
+//   HPL==4: units lane*4..+3 ; HPL==8: lane*4..+3 and 128+lane*4..+3 ; else q*32+lane
+template <int HPL>
+__device__ __forceinline__ int unit_index(int lane, int q) {
+  if constexpr (HPL == 4)
+    return lane * 4 + q;
+  else if constexpr (HPL == 8)
+    return (q >> 2) * 128 + lane * 4 + (q & 3);
+  else
+    return q * 32 + lane;
+}
+
+template <int HPL>
+__device__ __forceinline__ void accumulate_side(Acc<HPL>& z, const float* T, int H, uint32_t cnt, int lane) {
+  // cnt: this lane's checker count at point `lane` (lanes >= 24 hold 0)
+  const uint32_t ge1 = __ballot_sync(BG_FULL, cnt >= 1), ge2 = __ballot_sync(BG_FULL, cnt >= 2),
+                 ge3 = __ballot_sync(BG_FULL, cnt >= 3), gt3 = __ballot_sync(BG_FULL, cnt > 3);
+  uint32_t m = ge1;
+  while (m) {
+    const int p = __ffs(m) - 1;
+    m &= m - 1;
+    const int k = ((ge2 >> p) & 1) + ((ge3 >> p) & 1);
+    add_row<HPL>(z, T + (p * 4 + k) * H, lane);
+  }
+  m = gt3;
+  while (m) {
+    const int p = __ffs(m) - 1;
+    m &= m - 1;
+    const int c = __shfl_sync(BG_FULL, (int)cnt, p);
+    fma_row<HPL>(z, (float)(c - 3), T + (p * 4 + 3) * H, lane);
+  }
+}
+
+template <int HPL>
+__global__ void __launch_bounds__(EVAL_THREADS) k_eval(const int8_t* __restrict__ boards, const uint8_t* __restrict__ flags,
+                                                      const int32_t* __restrict__ owner, const uint8_t* __restrict__ owner_players,
+                                                      int64_t N_host, const int64_t* __restrict__ N_dev, int64_t max_N,
+                                                      const float* __restrict__ prep, float* __restrict__ out_v) {
+  constexpr int H = HPL * 32;
+  extern __shared__ __align__(16) float sT[];
+  const int n_floats = 200 * H + 1;
+  for (int i = threadIdx.x; i < n_floats; i += blockDim.x) sT[i] = prep[i];
+  __syncthreads();
+  const float* sb1 = sT + 198 * H;
+  const float* sw2 = sb1 + H;
+  const float b2 = sw2[H];
+  int64_t N = N_dev ? *N_dev : N_host;
+  if (N > max_N) N = max_N;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (EVAL_THREADS / 32) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (EVAL_THREADS / 32);
+  const uint32_t* b32 = reinterpret_cast<const uint32_t*>(boards);
+  float w2r[HPL], b1r[HPL];
+#pragma unroll
+  for (int q = 0; q < HPL; ++q) {
+    w2r[q] = sw2[unit_index<HPL>(lane, q)];
+    b1r[q] = sb1[unit_index<HPL>(lane, q)];
+  }
+  for (int64_t i = warp; i < N; i += nwarps) {
+    const uint32_t myw = lane < 13 ? __ldg(b32 + i * 13 + lane) : 0u;
+    int flag;
+    if (flags)
+      flag = flags[i];
+    else
+      flag = owner_players[owner[i]];
+    const uint32_t wa = __shfl_sync(BG_FULL, myw, lane >> 2);
+    const uint32_t wb = __shfl_sync(BG_FULL, myw, 6 + (lane >> 2));
+    const uint32_t w12 = __shfl_sync(BG_FULL, myw, 12);
+    const uint32_t c0 = lane < 24 ? (wa >> ((lane & 3) * 8)) & 0xffu : 0u;
+    const uint32_t c1 = lane < 24 ? (wb >> ((lane & 3) * 8)) & 0xffu : 0u;
+    Acc<HPL> z;
+#pragma unroll
+    for (int q = 0; q < HPL; ++q) z.a[q] = b1r[q];
+    accumulate_side<HPL>(z, sT, H, c0, lane);
+    accumulate_side<HPL>(z, sT + 96 * H, H, c1, lane);
+    const uint32_t bar0 = w12 & 0xffu, bar1 = (w12 >> 8) & 0xffu, off0 = (w12 >> 16) & 0xffu, off1 = w12 >> 24;
+    if (bar0) fma_row<HPL>(z, (float)bar0, sT + 192 * H, lane);
+    if (off0) fma_row<HPL>(z, c_off15[off0 & 15u], sT + 193 * H, lane);
+    if (bar1) fma_row<HPL>(z, (float)bar1, sT + 194 * H, lane);
+    if (off1) fma_row<HPL>(z, c_off15[off1 & 15u], sT + 195 * H, lane);
+    add_row<HPL>(z, sT + (196 + (flag & 1)) * H, lane);
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < HPL; ++q) {
+      const float s = __fdividef(1.0f, 1.0f + __expf(-z.a[q]));
+      v = fmaf(w2r[q], s, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(BG_FULL, v, o);
+    if (lane == 0) out_v[i] = v + b2;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_encode(const int8_t* __restrict__ boards, const uint8_t* __restrict__ flags, int64_t N,
+                                                float* __restrict__ out) {
+  __shared__ uint32_t sb[8][16];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + wib, nwarps = (int64_t)gridDim.x * 8;
+  const uint32_t* b32 = reinterpret_cast<const uint32_t*>(boards);
+  for (int64_t i = warp; i < N; i += nwarps) {
+    __syncwarp();
+    if (lane < 13) sb[wib][lane] = __ldg(b32 + i * 13 + lane);
+    __syncwarp();
+    const uint8_t* bb = reinterpret_cast<const uint8_t*>(sb[wib]);
+    const int flag = flags[i] & 1;
+    float* o = out + i * 198;
+    for (int f = lane; f < 198; f += 32) {
+      float x;
+      if (f < 192) {
+        const int c = (int8_t)bb[f >> 2], k = f & 3;
+        x = k == 0 ? (c >= 1 ? 1.f : 0.f) : k == 1 ? (c >= 2 ? 1.f : 0.f) : k == 2 ? (c >= 3 ? 1.f : 0.f) : (c > 3 ? (float)(c - 3) * 0.5f : 0.f);
+      } else if (f == 192) {
+        x = (float)(int8_t)bb[48] * 0.5f;
+      } else if (f == 193) {
+        x = c_off15[bb[50] & 15u];
+      } else if (f == 194) {
+        x = (float)(int8_t)bb[49] * 0.5f;
+      } else if (f == 195) {
+        x = c_off15[bb[51] & 15u];
+      } else {
+        x = (f - 196) == flag ? 1.f : 0.f;
+      }
+      o[f] = x;
+    }
+  }
+}
+
+int32_t init_constants() {
+  static bool done = false;
+  if (done) return BG_OK;
+  float h[16];
+  for (int n = 0; n < 16; ++n) h[n] = (float)((double)n / 15.0);
+  cudaError_t e = cudaMemcpyToSymbol(c_off15, h, sizeof(h));
+  if (e != cudaSuccess) return check_cuda(e, "cudaMemcpyToSymbol(c_off15)");
+  done = true;
+  return BG_OK;
+}
+
+template <int HPL>
+int32_t launch_eval_t(const EvalArgs& a, cudaStream_t stream) {
+  constexpr int H = HPL * 32;
+  const size_t smem = ((size_t)(200 * H + 1) * 4 + 15) / 16 * 16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k_eval<HPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_eval)");
+    attr_done = true;
+  }
+  const int ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;
+  const int64_t bound = a.N_dev ? a.max_N : a.N;
+  int64_t want = (bound + (EVAL_THREADS / 32) - 1) / (EVAL_THREADS / 32);
+  if (want < 1) want = 1;
+  const int grid = (int)(want < (int64_t)NUM_SMS * ctas_per_sm ? want : (int64_t)NUM_SMS * ctas_per_sm);
+  k_eval<HPL><<<grid, EVAL_THREADS, smem, stream>>>(a.boards, a.flags, a.owner, a.owner_players, a.N, a.N_dev, a.max_N, a.prepared,
+                                                    a.out_v);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return check_cuda(e, "k_eval launch");
+  return BG_OK;
+}
+
+}  // namespace
+
+int64_t prepared_weights_bytes(int32_t H) { return ((int64_t)(200 * H + 1) * 4 + 255) / 256 * 256; }
+
+int32_t prepare_weights_launch(const float* packed, int32_t H, float* prepared, cudaStream_t stream) {
+  if (H < 32 || H > 256 || H % 32) {
+    set_error("H must be a multiple of 32 in [32,256], got %d", H);
+    return BG_ERR_ARG;
+  }
+  k_prepare<<<64, 256, 0, stream>>>(packed, H, prepared);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return check_cuda(e, "k_prepare launch");
+  return BG_OK;
+}
+
+int32_t eval_launch(const EvalArgs& a, cudaStream_t stream) {
+  if (a.H < 32 || a.H > 256 || a.H % 32) {
+    set_error("bg_eval: H must be a multiple of 32 in [32,256] (got %d)", a.H);
+    return BG_ERR_ARG;
+  }
+  if (!a.flags && !(a.owner && a.owner_players)) {
+    set_error("bg_eval: need flags or (owner, owner_players)");
+    return BG_ERR_ARG;
+  }
+  if ((a.N_dev ? a.max_N : a.N) <= 0) return BG_OK;
+  int32_t rc = init_constants();
+  if (rc != BG_OK) return rc;
+  switch (a.H / 32) {
+    case 1:
+      return launch_eval_t<1>(a, stream);
+    case 2:
+      return launch_eval_t<2>(a, stream);
+    case 3:
+      return launch_eval_t<3>(a, stream);
+    case 4:
+      return launch_eval_t<4>(a, stream);
+    case 5:
+      return launch_eval_t<5>(a, stream);
+    case 6:
+      return launch_eval_t<6>(a, stream);
+    case 7:
+      return launch_eval_t<7>(a, stream);
+    default:
+      return launch_eval_t<8>(a, stream);
+  }
+}
+
+int32_t encode_launch(const int8_t* boards, const uint8_t* flags, int64_t N, float* out, cudaStream_t stream) {
+  if (N <= 0) return BG_OK;
+  int32_t rc = init_constants();
+  if (rc != BG_OK) return rc;
+  int64_t want = (N + 7) / 8;
+  const int grid = (int)(want < (int64_t)NUM_SMS * 8 ? want : (int64_t)NUM_SMS * 8);
+  k_encode<<<grid, 256, 0, stream>>>(boards, flags, N, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return check_cuda(e, "k_encode launch");
+  return BG_OK;
+}
+
+}  // namespace bg

@@ -1,0 +1,25 @@
+// eval.cuh -- host-side launch interface of the fused evaluator / encoder (see eval.cu)
+#pragma once
+#include "bg_common.cuh"
+
+namespace bg {
+
+struct EvalArgs {
+  const int8_t* boards;
+  const uint8_t* flags;
+  const int32_t* owner;
+  const uint8_t* owner_players;
+  int64_t N;
+  const int64_t* N_dev;
+  int64_t max_N;
+  const float* prepared;
+  int32_t H;
+  float* out_v;
+};
+
+int64_t prepared_weights_bytes(int32_t H);
+int32_t prepare_weights_launch(const float* packed, int32_t H, float* prepared, cudaStream_t stream);
+int32_t eval_launch(const EvalArgs& a, cudaStream_t stream);
+int32_t encode_launch(const int8_t* boards, const uint8_t* flags, int64_t N, float* out, cudaStream_t stream);
+
+}  // namespace bg

@@ -1,0 +1,559 @@
+// movegen.cu -- legal-move generation for batches of (board, player, roll) items on sm_100a.
+//
+// Replaces get_all_possible_moves (reference src/backgammon/moves/generate_all_moves.py:7-90,
+// handle_move_types.py:7-221, get_moves_one_die.py:13-251, conditions.py) + execute_full_move_on_board_copy
+// (src/environments/env_helper.py:27-91).  Output order == the reference's (first-occurrence DFS order).
+//
+// Design (one warp per item, nothing but the result leaves the SM):
+//   * a node is a 128-bit exact key: mover's 24 point counts as nibbles (3 words) + {hit-mask of opponent
+//     blots (24b), mover bar (4b), mover off (4b)}; plus 2 words of sub-move history.  The opponent side is
+//     root-constant except for hit blots, so the key identifies the resulting board exactly (no hash-only dedup).
+//   * breadth-first by ply: the frontier of unique nodes after k sub-moves is kept ordered by the
+//     lexicographically smallest sub-move index sequence that reaches it.  Expanding frontier nodes in order,
+//     children in the reference's one-die order (lane == move slot: 0..23 point moves ascending, 24 bar entry,
+//     25 bear-off of the farthest checker, 26 exact bear-off), with first-occurrence dedup through a
+//     shared-memory hash set, reproduces the reference's DFS first-occurrence order while visiting each
+//     distinct intermediate board once (the reference re-expands ~5x-8x duplicates).
+//   * non-doubles keep the reference's literal control flow (both die orders, singles only when an order has
+//     no two-move play, quirk Q1 skip, shared seen-set, max-length filter).
+//   * three capacity tiers (128 / 1024 nodes per ply in shared memory, 4096 in L2-resident global scratch);
+//     an item overflowing a tier is queued for the next one.  Overflowing the last tier is BG_ERR_CAPACITY.
+#include "movegen.cuh"
+
+#include <stdio.h>
+
+namespace bg {
+
+namespace {
+
+constexpr int NF = 6;  // words per node: k0..k3 key, m0 m1 sub-move history
+
+template <int CAP, bool GLOBAL>
+struct Frontier {
+  uint32_t* base;  // [2][NF][CAP]
+  __device__ __forceinline__ uint32_t ld(int lvl, int f, int pos) const {
+    if constexpr (GLOBAL)
+      return __ldcg(base + (lvl * NF + f) * CAP + pos);
+    else
+      return base[(lvl * NF + f) * CAP + pos];
+  }
+  __device__ __forceinline__ void st(int lvl, int f, int pos, uint32_t v) const {
+    if constexpr (GLOBAL)
+      __stcg(base + (lvl * NF + f) * CAP + pos, v);
+    else
+      base[(lvl * NF + f) * CAP + pos] = v;
+  }
+};
+
+struct Root {
+  int player;
+  int dirsign;        // +1 / -1
+  uint32_t blocked;   // opponent >= 2 (24 bits)
+  uint32_t blot;      // opponent == 1 (24 bits)
+  uint32_t home;      // mover's home mask
+  bool valid15;       // mover has exactly 15 checkers (conditions.py:191-194)
+};
+
+struct Node {
+  uint32_t k0, k1, k2, k3, m0, m1;
+};
+
+// One-die expansion of `p` for this lane's move slot (reference get_moves_with_one_die order == slot order).
+__device__ __forceinline__ bool expand(const Node& p, const Root& r, int die, int depth, int lane, Node& c) {
+  const uint32_t pk[3] = {p.k0, p.k1, p.k2};
+  uint32_t cnt = 0;
+  if (lane < 24) cnt = (pk[lane >> 3] >> ((lane & 7) * 4)) & 15u;
+  const uint32_t occ = __ballot_sync(BG_FULL, cnt > 0) & 0xffffffu;
+  const uint32_t bar = (p.k3 >> 24) & 15u, off = p.k3 >> 28;
+  const uint32_t blot = r.blot & ~p.k3;
+  bool valid = false;
+  int s = lane, e = 0;
+  if (off == 15u) {
+    // GAME_OVER: no moves (conditions.py:16-17)
+  } else if (bar > 0) {  // ON_BAR (get_moves_one_die.py:86-130)
+    if (lane == 24) {
+      e = r.player == 0 ? die - 1 : 24 - die;
+      valid = !((r.blocked >> e) & 1u);
+    }
+  } else {
+    if (lane < 24) {  // NORMAL (:40-83) and in-home moves of BEAR_OFF (:164-189)
+      e = lane + r.dirsign * die;
+      valid = cnt > 0 && e >= 0 && e < 24 && !((r.blocked >> (e & 31)) & 1u);
+    } else if (r.valid15 && (occ & ~r.home) == 0) {  // BEAR_OFF (:192-249)
+      const int last = r.player == 0 ? (occ ? __ffs(occ) - 1 : 18) : (occ ? 31 - __clz(occ) : 5);
+      if (lane == 25) {
+        s = last;
+        e = 25;
+        valid = r.player == 0 ? (last + die >= 24) : (last - die < 0);
+      } else if (lane == 26) {
+        const int ps = r.player == 0 ? 24 - die : die - 1;
+        s = ps;
+        e = 25;
+        valid = ps != last && ((occ >> ps) & 1u);
+      }
+    }
+  }
+  if (!valid) return false;
+  uint32_t k[3] = {p.k0, p.k1, p.k2};
+  uint32_t k3 = p.k3;
+  uint32_t hit = 0;
+  if (s == 24) {
+    k3 -= 1u << 24;
+  } else {
+    const uint32_t ds = 1u << ((s & 7) * 4);
+    const int ws = s >> 3;
+    k[0] -= ws == 0 ? ds : 0u;
+    k[1] -= ws == 1 ? ds : 0u;
+    k[2] -= ws == 2 ? ds : 0u;
+  }
+  if (e == 25) {
+    k3 += 1u << 28;
+  } else {
+    const uint32_t de = 1u << ((e & 7) * 4);
+    const int we = e >> 3;
+    k[0] += we == 0 ? de : 0u;
+    k[1] += we == 1 ? de : 0u;
+    k[2] += we == 2 ? de : 0u;
+    hit = (blot >> e) & 1u;
+    k3 |= hit << e;
+  }
+  const uint32_t sm = (uint32_t)s | ((uint32_t)e << 5) | (hit << 10) | (1u << 11);
+  c.k0 = k[0];
+  c.k1 = k[1];
+  c.k2 = k[2];
+  c.k3 = k3;
+  c.m0 = depth < 2 ? (p.m0 | (sm << (16 * depth))) : p.m0;
+  c.m1 = depth < 2 ? p.m1 : (p.m1 | (sm << (16 * (depth - 2))));
+  return true;
+}
+
+// First-occurrence dedup + ordered append of this chunk's valid nodes into level `lvl`.
+// Within one chunk all valid keys are distinct (children of one parent via distinct moves, or distinct
+// frontier nodes), so only earlier chunks can hold a duplicate.  Returns false on capacity overflow.
+template <int CAP, bool GLOBAL>
+__device__ __forceinline__ bool append(const Frontier<CAP, GLOBAL>& F, uint32_t* tab, int lvl, int& n, bool valid,
+                                       const Node& c, int lane, uint32_t& appended_mask) {
+  constexpr uint32_t TMASK = 2 * CAP - 1;
+  const uint32_t h = mix32(c.k0, c.k1, c.k2, c.k3);
+  const uint32_t fp = h >> 16;
+  uint32_t idx = h & TMASK;
+  bool found = false;
+  if (valid) {
+    while (true) {
+      const uint32_t s = tab[idx];
+      if (!s) break;
+      if ((s >> 16) == fp) {
+        const int pp = (int)(s & 0xffffu) - 1;
+        if (F.ld(lvl, 0, pp) == c.k0 && F.ld(lvl, 1, pp) == c.k1 && F.ld(lvl, 2, pp) == c.k2 &&
+            F.ld(lvl, 3, pp) == c.k3) {
+          found = true;
+          break;
+        }
+      }
+      idx = (idx + 1) & TMASK;
+    }
+  }
+  const bool isnew = valid && !found;
+  const uint32_t bal = __ballot_sync(BG_FULL, isnew);
+  appended_mask = bal;
+  const int cnt = __popc(bal);
+  if (n + cnt > CAP) return false;
+  if (isnew) {
+    const int pos = n + __popc(bal & ((1u << lane) - 1u));
+    F.st(lvl, 0, pos, c.k0);
+    F.st(lvl, 1, pos, c.k1);
+    F.st(lvl, 2, pos, c.k2);
+    F.st(lvl, 3, pos, c.k3);
+    F.st(lvl, 4, pos, c.m0);
+    F.st(lvl, 5, pos, c.m1);
+    const uint32_t word = (fp << 16) | (uint32_t)(pos + 1);
+    while (atomicCAS(&tab[idx], 0u, word) != 0u) idx = (idx + 1) & TMASK;
+  }
+  n += cnt;
+  __syncwarp();
+  return true;
+}
+
+template <int CAP, bool GLOBAL>
+__device__ __forceinline__ Node load_node(const Frontier<CAP, GLOBAL>& F, int lvl, int pos) {
+  Node p;
+  p.k0 = F.ld(lvl, 0, pos);
+  p.k1 = F.ld(lvl, 1, pos);
+  p.k2 = F.ld(lvl, 2, pos);
+  p.k3 = F.ld(lvl, 3, pos);
+  p.m0 = F.ld(lvl, 4, pos);
+  p.m1 = F.ld(lvl, 5, pos);
+  return p;
+}
+
+template <int CAP>
+__device__ __forceinline__ void clear_table(uint32_t* tab, int lane) {
+#pragma unroll 4
+  for (int i = lane; i < 2 * CAP; i += 32) tab[i] = 0u;
+  __syncwarp();
+}
+
+enum { ITEM_OK = 0, ITEM_OVERFLOW = 1, ITEM_BAD = 2 };
+
+// Generates the ordered legal afterstate list of one item into frontier level `out_lvl` (n_out nodes).
+template <int CAP, bool GLOBAL>
+__device__ int generate(const Frontier<CAP, GLOBAL>& F, uint32_t* tab, const uint32_t* rootw, int player, int d0, int d1,
+                        int lane, int& out_lvl, int& n_out) {
+  // ---- root ------------------------------------------------------------------------------------------
+  const int ob = player * 6, pb = (1 - player) * 6;
+  uint32_t bad = 0;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) bad |= rootw[i] & 0xf0f0f0f0u;
+  const uint32_t w12 = rootw[12];
+  bad |= w12 & 0xf0f0f0f0u;
+  if (bad || d0 < 1 || d0 > 6 || d1 < 1 || d1 > 6) return ITEM_BAD;
+  Node root;
+  root.k0 = bytes_to_nib4(rootw[ob + 0]) | (bytes_to_nib4(rootw[ob + 1]) << 16);
+  root.k1 = bytes_to_nib4(rootw[ob + 2]) | (bytes_to_nib4(rootw[ob + 3]) << 16);
+  root.k2 = bytes_to_nib4(rootw[ob + 4]) | (bytes_to_nib4(rootw[ob + 5]) << 16);
+  const uint32_t own_bar = (w12 >> (8 * player)) & 15u, own_off = (w12 >> (16 + 8 * player)) & 15u;
+  root.k3 = (own_bar << 24) | (own_off << 28);
+  root.m0 = root.m1 = 0u;
+  Root r;
+  r.player = player;
+  r.dirsign = player == 0 ? 1 : -1;
+  r.home = player == 0 ? 0xfc0000u : 0x00003fu;
+  {
+    uint32_t oc = 0;
+    if (lane < 24) oc = (rootw[pb + (lane >> 2)] >> ((lane & 3) * 8)) & 0xffu;
+    r.blocked = __ballot_sync(BG_FULL, oc >= 2) & 0xffffffu;
+    r.blot = __ballot_sync(BG_FULL, oc == 1) & 0xffffffu;
+    uint32_t total = own_bar + own_off;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const uint32_t w = rootw[ob + i];
+      total += (w & 0xff) + ((w >> 8) & 0xff) + ((w >> 16) & 0xff) + (w >> 24);
+    }
+    r.valid15 = total == 15u;
+  }
+  uint32_t am;
+  if (d0 == d1) {
+    // ---- doubles: BFS by ply with per-ply dedup (handle_move_types.py:84-193) ------------------------
+    int cur = 0, n_cur = 1;
+    if (lane == 0) {
+      F.st(0, 0, 0, root.k0);
+      F.st(0, 1, 0, root.k1);
+      F.st(0, 2, 0, root.k2);
+      F.st(0, 3, 0, root.k3);
+      F.st(0, 4, 0, 0u);
+      F.st(0, 5, 0, 0u);
+    }
+    __syncwarp();
+    int depth_done = 0;
+    for (int depth = 0; depth < 4; ++depth) {
+      clear_table<CAP>(tab, lane);
+      int n_next = 0;
+      for (int j = 0; j < n_cur; ++j) {
+        const Node p = load_node(F, cur, j);
+        Node c;
+        const bool v = expand(p, r, d0, depth, lane, c);
+        if (!append(F, tab, cur ^ 1, n_next, v, c, lane, am)) return ITEM_OVERFLOW;
+      }
+      if (n_next == 0) break;
+      cur ^= 1;
+      n_cur = n_next;
+      depth_done = depth + 1;
+    }
+    out_lvl = cur;
+    n_out = depth_done == 0 ? 0 : n_cur;
+    return ITEM_OK;
+  }
+  // ---- non-doubles: literal two-order control flow (generate_all_moves.py:25-53, handle_move_types.py:7-81)
+  const int hi = d0 > d1 ? d0 : d1, lo = d0 > d1 ? d1 : d0;
+  clear_table<CAP>(tab, lane);
+  int n_res = 0;      // result list lives in level 1
+  bool has2 = false;  // a two-sub-move entry was appended
+  for (int order = 0; order < 2; ++order) {
+    const int dA = order == 0 ? hi : lo, dB = order == 0 ? lo : hi;
+    Node c1;
+    const bool v1 = expand(root, r, dA, 0, lane, c1);
+    const uint32_t b1 = __ballot_sync(BG_FULL, v1);
+    const int n1 = __popc(b1);
+    if (v1) {  // first-die boards are pairwise distinct: compact into level 0 without dedup
+      const int pos = __popc(b1 & ((1u << lane) - 1u));
+      F.st(0, 0, pos, c1.k0);
+      F.st(0, 1, pos, c1.k1);
+      F.st(0, 2, pos, c1.k2);
+      F.st(0, 3, pos, c1.k3);
+      F.st(0, 4, pos, c1.m0);
+      F.st(0, 5, pos, c1.m1);
+    }
+    __syncwarp();
+    bool any2 = false;
+    for (int j = 0; j < n1; ++j) {
+      const Node p = load_node(F, 0, j);
+      Node c;
+      const bool v = expand(p, r, dB, 1, lane, c);
+      any2 |= __any_sync(BG_FULL, v);
+      if (!append(F, tab, 1, n_res, v, c, lane, am)) return ITEM_OVERFLOW;
+      has2 |= am != 0u;
+    }
+    if (!any2 && n1 > 0) {  // singles, in first-die order (handle_move_types.py:70-81)
+      Node s;
+      const bool v = lane < n1;
+      if (v) s = load_node(F, 0, lane);
+      if (!append(F, tab, 1, n_res, v, s, lane, am)) return ITEM_OVERFLOW;
+    }
+    // quirk Q1 (generate_all_moves.py:40-50): reverse order skipped iff exactly one 1-sub-move result
+    if (order == 0 && n_res == 1 && !has2) break;
+  }
+  // max-sub-moves filter (generate_all_moves.py:69-90), order preserving, into level 0
+  int n_f = 0;
+  for (int base = 0; base < n_res; base += 32) {
+    const int i = base + lane;
+    Node e;
+    bool keep = false;
+    if (i < n_res) {
+      e = load_node(F, 1, i);
+      const bool len2 = (e.m0 >> 27) & 1u;
+      keep = len2 == has2;
+    }
+    const uint32_t bk = __ballot_sync(BG_FULL, keep);
+    if (keep) {
+      const int pos = n_f + __popc(bk & ((1u << lane) - 1u));
+      F.st(0, 0, pos, e.k0);
+      F.st(0, 1, pos, e.k1);
+      F.st(0, 2, pos, e.k2);
+      F.st(0, 3, pos, e.k3);
+      F.st(0, 4, pos, e.m0);
+      F.st(0, 5, pos, e.m1);
+    }
+    n_f += __popc(bk);
+  }
+  __syncwarp();
+  out_lvl = 0;
+  n_out = n_f;
+  return ITEM_OK;
+}
+
+template <int CAP, bool GLOBAL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_movegen(MovegenParams P) {
+  extern __shared__ uint32_t smem[];
+  constexpr int FRONT_WORDS = GLOBAL ? 0 : 2 * NF * CAP;
+  constexpr int PER_WARP = FRONT_WORDS + 2 * CAP + 16;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t* my = smem + wib * PER_WARP;
+  Frontier<CAP, GLOBAL> F;
+  if constexpr (GLOBAL)
+    F.base = P.gfront + (size_t)(blockIdx.x * WARPS + wib) * (2 * NF * CAP);
+  else
+    F.base = my;
+  uint32_t* tab = my + FRONT_WORDS;
+  uint32_t* rootw = tab + 2 * CAP;
+
+  const int64_t n_items = P.in_list ? (int64_t)(*P.in_count) : P.B;
+  while (true) {
+    int t0 = 0;
+    if (lane == 0) t0 = atomicAdd(P.item_counter, P.grab);
+    t0 = __shfl_sync(BG_FULL, t0, 0);
+    if (t0 >= n_items) break;
+    for (int g = 0; g < P.grab; ++g) {
+      const int64_t t = (int64_t)t0 + g;
+      if (t >= n_items) break;
+      const int item = P.in_list ? P.in_list[t] : (int)t;
+      __syncwarp();
+      if (lane < 13) rootw[lane] = reinterpret_cast<const uint32_t*>(P.boards)[(int64_t)item * 13 + lane];
+      __syncwarp();
+      const int player = P.players[item] & 1;
+      const int d0 = P.rolls[2 * (int64_t)item], d1 = P.rolls[2 * (int64_t)item + 1];
+      int lvl = 0, n = 0;
+      const int rc = generate<CAP, GLOBAL>(F, tab, rootw, player, d0, d1, lane, lvl, n);
+      if (rc == ITEM_OVERFLOW) {
+        if (lane == 0) {
+          if (P.ovf_list) {
+            const int q = atomicAdd(P.ovf_count, 1);
+            P.ovf_list[q] = item;
+          } else {
+            P.out_count[item] = -1;
+            P.out_offsets[item] = -1;
+            atomicMin(P.status, BG_ERR_CAPACITY);
+          }
+        }
+        continue;
+      }
+      if (rc == ITEM_BAD) {
+        if (lane == 0) {
+          P.out_count[item] = 0;
+          P.out_offsets[item] = -1;
+          atomicMin(P.status, BG_ERR_INVARIANT);
+        }
+        continue;
+      }
+      // ---- emit --------------------------------------------------------------------------------------
+      const int n_keep = n < P.item_cap ? n : P.item_cap;
+      long long base = 0;
+      if (lane == 0) {
+        base = n_keep ? (long long)atomicAdd(P.pool_cursor, (unsigned long long)n_keep) : 0ll;
+        if (base + n_keep > P.pool_cap) {
+          base = -1;
+          atomicMin(P.status, BG_ERR_CAPACITY);
+        }
+        P.out_count[item] = n;
+        P.out_offsets[item] = base;
+      }
+      base = __shfl_sync(BG_FULL, base, 0);
+      if (base < 0 || n_keep == 0) continue;
+      uint32_t* ob = reinterpret_cast<uint32_t*>(P.out_boards) + base * 13;
+      const uint32_t w12 = rootw[12];
+      const uint32_t opp_bar = (w12 >> (8 * (1 - player))) & 0xffu, opp_off = (w12 >> (16 + 8 * (1 - player))) & 0xffu;
+      for (int tt = lane; tt < n_keep * 13; tt += 32) {
+        const int b = tt / 13, w = tt - b * 13;
+        uint32_t word;
+        if (w < 12) {
+          const int side = w >= 6, q = w - side * 6;
+          if (side == player) {
+            const uint32_t kw = F.ld(lvl, q >> 1, b);
+            word = nib4_to_bytes((kw >> (16 * (q & 1))) & 0xffffu);
+          } else {
+            const uint32_t hb = (F.ld(lvl, 3, b) >> (4 * q)) & 0xfu;
+            word = rootw[w] - bits4_to_bytes(hb);
+          }
+        } else {
+          const uint32_t k3 = F.ld(lvl, 3, b);
+          const uint32_t ownbar = (k3 >> 24) & 15u, ownoff = k3 >> 28, ob2 = opp_bar + __popc(k3 & 0xffffffu);
+          word = player == 0 ? (ownbar | (ob2 << 8) | (ownoff << 16) | (opp_off << 24))
+                             : (ob2 | (ownbar << 8) | (opp_off << 16) | (ownoff << 24));
+        }
+        ob[tt] = word;
+      }
+      if (P.out_owner)
+        for (int b = lane; b < n_keep; b += 32) P.out_owner[base + b] = item;
+      if (P.out_submoves) {
+        uint32_t* os = reinterpret_cast<uint32_t*>(P.out_submoves) + base * 3;
+        for (int b = lane; b < n_keep; b += 32) {
+          const uint32_t m[2] = {F.ld(lvl, 4, b), F.ld(lvl, 5, b)};
+          uint8_t by[12];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t sm = (m[q >> 1] >> (16 * (q & 1))) & 0xffffu;
+            const bool ok = (sm >> 11) & 1u;
+            by[3 * q] = ok ? (uint8_t)(sm & 31u) : 255;
+            by[3 * q + 1] = ok ? (uint8_t)((sm >> 5) & 31u) : 255;
+            by[3 * q + 2] = ok ? (uint8_t)((sm >> 10) & 1u) : 0;
+          }
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+            os[b * 3 + q] = by[4 * q] | (by[4 * q + 1] << 8) | (by[4 * q + 2] << 16) | ((uint32_t)by[4 * q + 3] << 24);
+        }
+      }
+    }
+  }
+}
+
+constexpr int T1_CAP = 128, T1_WARPS = 4, T1_CTAS_PER_SM = 7;
+constexpr int T2_CAP = 1024, T2_WARPS = 1, T2_CTAS_PER_SM = 3;
+constexpr int T3_CAP = 4096, T3_WARPS = 1, T3_CTAS_PER_SM = 2;
+constexpr int NUM_SMS = 148;
+
+constexpr size_t smem_bytes(int cap, bool global, int warps) {
+  return (size_t)warps * ((global ? 0 : 2 * NF * cap) + 2 * cap + 16) * 4;
+}
+
+constexpr int64_t HDR_BYTES = 256;
+constexpr int64_t GFRONT_BYTES = (int64_t)NUM_SMS * T3_CTAS_PER_SM * T3_WARPS * 2 * NF * T3_CAP * 4;
+
+}  // namespace
+
+int64_t movegen_workspace_bytes(int64_t B) {
+  int64_t lists = ((2 * B * 4 + 255) / 256) * 256;
+  return HDR_BYTES + lists + GFRONT_BYTES;
+}
+
+// workspace header layout (first HDR_BYTES): [0] u64 pool cursor, [8] i32 status, [12] i32 counter1,
+// [16] i32 counter2, [20] i32 counter3, [24] i32 ovf2 count, [28] i32 ovf3 count
+int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream) {
+  if (a.B < 0 || a.B >= (1ll << 31) || a.item_cap < 0 || a.pool_cap < 0) {
+    set_error("bg_movegen: bad sizes (B=%lld item_cap=%d pool_cap=%lld)", (long long)a.B, a.item_cap, (long long)a.pool_cap);
+    return BG_ERR_ARG;
+  }
+  if (a.workspace_bytes < movegen_workspace_bytes(a.B)) {
+    set_error("bg_movegen: workspace too small (%lld < %lld)", (long long)a.workspace_bytes,
+              (long long)movegen_workspace_bytes(a.B));
+    return BG_ERR_ARG;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_movegen<T1_CAP, false, T1_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem_bytes(T1_CAP, false, T1_WARPS));
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tier1)");
+    e = cudaFuncSetAttribute(k_movegen<T2_CAP, false, T2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem_bytes(T2_CAP, false, T2_WARPS));
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tier2)");
+    e = cudaFuncSetAttribute(k_movegen<T3_CAP, true, T3_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem_bytes(T3_CAP, true, T3_WARPS));
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tier3)");
+    attr_done = true;
+  }
+  char* ws = (char*)a.workspace;
+  cudaError_t e = cudaMemsetAsync(ws, 0, HDR_BYTES, stream);
+  if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(workspace)");
+  int64_t lists = ((2 * a.B * 4 + 255) / 256) * 256;
+  MovegenParams P;
+  P.boards = a.boards;
+  P.players = a.players;
+  P.rolls = a.rolls;
+  P.B = a.B;
+  P.item_cap = a.item_cap;
+  P.pool_cap = a.pool_cap;
+  P.out_boards = a.out_boards;
+  P.out_submoves = a.out_submoves;
+  P.out_owner = a.out_owner;
+  P.out_offsets = (long long*)a.out_offsets;
+  P.out_count = a.out_count;
+  P.pool_cursor = (unsigned long long*)ws;
+  P.status = (int32_t*)(ws + 8);
+  P.gfront = (uint32_t*)(ws + HDR_BYTES + lists);
+  int32_t* ctr = (int32_t*)(ws + 12);
+  int32_t* ovf2 = (int32_t*)(ws + HDR_BYTES);
+  int32_t* ovf3 = ovf2 + a.B;
+  int32_t* ovf2_n = (int32_t*)(ws + 24);
+  int32_t* ovf3_n = (int32_t*)(ws + 28);
+  if (a.B > 0) {
+    // tier 1
+    P.item_counter = ctr + 0;
+    P.in_list = nullptr;
+    P.in_count = nullptr;
+    P.ovf_list = ovf2;
+    P.ovf_count = ovf2_n;
+    P.grab = a.B > (1 << 20) ? 8 : 1;
+    int64_t want = (a.B + T1_WARPS - 1) / T1_WARPS;
+    int grid = (int)(want < (int64_t)NUM_SMS * T1_CTAS_PER_SM ? want : (int64_t)NUM_SMS * T1_CTAS_PER_SM);
+    k_movegen<T1_CAP, false, T1_WARPS><<<grid, T1_WARPS * 32, smem_bytes(T1_CAP, false, T1_WARPS), stream>>>(P);
+    // tier 2
+    P.item_counter = ctr + 1;
+    P.in_list = ovf2;
+    P.in_count = ovf2_n;
+    P.ovf_list = ovf3;
+    P.ovf_count = ovf3_n;
+    P.grab = 1;
+    k_movegen<T2_CAP, false, T2_WARPS>
+        <<<NUM_SMS * T2_CTAS_PER_SM, T2_WARPS * 32, smem_bytes(T2_CAP, false, T2_WARPS), stream>>>(P);
+    // tier 3
+    P.item_counter = ctr + 2;
+    P.in_list = ovf3;
+    P.in_count = ovf3_n;
+    P.ovf_list = nullptr;
+    P.ovf_count = nullptr;
+    k_movegen<T3_CAP, true, T3_WARPS>
+        <<<NUM_SMS * T3_CTAS_PER_SM, T3_WARPS * 32, smem_bytes(T3_CAP, true, T3_WARPS), stream>>>(P);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return check_cuda(e, "k_movegen launch");
+  if (a.out_total) {
+    e = cudaMemcpyAsync(a.out_total, ws, 8, cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) return check_cuda(e, "copy out_total");
+  }
+  if (a.out_status) {
+    e = cudaMemcpyAsync(a.out_status, ws + 8, 4, cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) return check_cuda(e, "copy out_status");
+  }
+  return BG_OK;
+}
+
+}  // namespace bg

@@ -1,0 +1,52 @@
+// movegen.cuh -- host-side launch interface of the move generator (see movegen.cu)
+#pragma once
+#include "bg_common.cuh"
+
+namespace bg {
+
+struct MovegenArgs {
+  const int8_t* boards;
+  const uint8_t* players;
+  const uint8_t* rolls;
+  int64_t B;
+  int32_t item_cap;
+  int64_t pool_cap;
+  int8_t* out_boards;
+  uint8_t* out_submoves;
+  int32_t* out_owner;
+  int64_t* out_offsets;
+  int32_t* out_count;
+  int64_t* out_total;
+  int32_t* out_status;
+  void* workspace;
+  int64_t workspace_bytes;
+};
+
+// kernel parameter block
+struct MovegenParams {
+  const int8_t* boards;
+  const uint8_t* players;
+  const uint8_t* rolls;
+  int64_t B;
+  int32_t item_cap;
+  int64_t pool_cap;
+  int8_t* out_boards;
+  uint8_t* out_submoves;
+  int32_t* out_owner;
+  long long* out_offsets;
+  int32_t* out_count;
+  unsigned long long* pool_cursor;
+  int32_t* status;
+  int32_t* item_counter;
+  const int32_t* in_list;
+  const int32_t* in_count;
+  int32_t* ovf_list;
+  int32_t* ovf_count;
+  uint32_t* gfront;
+  int32_t grab;
+};
+
+int64_t movegen_workspace_bytes(int64_t B);
+int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream);
+
+}  // namespace bg

