@@ -120,6 +120,83 @@ int32_t bg_select(const float* v, const int64_t* offsets /*[B]*/, const int32_t*
                   int64_t B, float temperature, uint64_t seed, uint64_t ctr, int64_t item_id_base,
                   int32_t* out_action /*[B]*/, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Stateful self-play arena: n_games concurrent games resident on one GPU.
+ * Replaces the reference's worker processes: Worker.play_episode (src/multi/worker.py:78-174) over
+ * BackgammonEnv.reset/step (src/environments/backgammon_env.py:92-329), Experience/Episode recording
+ * (src/environments/episode.py:5-84), the ExperienceQueue (src/multi/experience_queue.py:5-13) and the
+ * ParameterManager polling (src/multi/worker.py:66-76).  One opaque handle per device, one host thread per handle.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct bg_arena bg_arena;
+
+#define BG_GAME_ACTIVE 0  /* playing */
+#define BG_GAME_WAIT 1    /* episode finished, waiting for room in the episode ring (drain it) */
+#define BG_GAME_STOPPED 2 /* no auto-reset / dice tape exhausted / per-game error */
+
+/* bg_arena_stats layout (int64[BG_ARENA_NSTATS]); all counters are cumulative since bg_arena_reset */
+#define BG_ARENA_NSTATS 16
+#define BG_STAT_GAMES 0        /* finished episodes */
+#define BG_STAT_STEPS 1        /* env steps (plies incl. passes) of finished episodes */
+#define BG_STAT_DECISIONS 2    /* recorded experiences of finished episodes */
+#define BG_STAT_PASSES 3
+#define BG_STAT_AFTERSTATES 4  /* afterstates evaluated at decisions (sum of num_moves), all episodes */
+#define BG_STAT_WIN_REGULAR 5
+#define BG_STAT_WIN_GAMMON 6
+#define BG_STAT_WIN_BACKGAMMON 7
+#define BG_STAT_TRUNCATED 8    /* episodes that hit max_plies without a winner */
+#define BG_STAT_P1_WINS 9
+#define BG_STAT_WAIT_STEPS 10  /* game-steps spent waiting for ring space (actor idle) */
+#define BG_STAT_ERRORS 11      /* games stopped by a per-item move-generator overflow */
+
+/* ep_info layout (int32[BG_EP_INFO_INTS] per drained episode) */
+#define BG_EP_INFO_INTS 12
+/* [0] win_type (0 none/truncated, 1 regular, 2 gammon, 3 backgammon)  [1] winner (-1 none)  [2] env steps  [3] passes
+ * [4],[5] close_out_counts P1,P2  [6],[7] prime_reward_counts P1,P2  [8] players-seen mask  [9] global game id
+ * [10] episode serial of that game slot  [11] reserved */
+
+/* per-experience meta byte: bit0 mover (== observation flag), bit1 next-observation flag, bit2 done,
+ * bit3 close_out_reward, bit4 prime_reward */
+
+/*
+ * max_plies: reference MAX_TIMESTEPS = 300 (src/config/configuration.py:4); move_cap: max_legal_moves = 500
+ * (src/environments/backgammon_env.py:35).  game_id_base offsets the Philox streams so that sharding games over GPUs
+ * does not change any game's dice or sampled actions.  ring_*: capacity of the finished-episode ring (0 = default).
+ * auto_reset != 0: a finished game immediately starts its next episode.
+ */
+int32_t bg_arena_create(bg_arena** out, int32_t device, int64_t n_games, int32_t H, int32_t max_plies, int32_t move_cap,
+                        uint64_t seed, int64_t game_id_base, int64_t ring_experiences, int64_t ring_episodes,
+                        int32_t auto_reset);
+int32_t bg_arena_destroy(bg_arena* a);
+/* Publish a new packed weight blob (device pointer) + its version and sampling temperature
+ * (ParameterManager.set_parameters / get_temperature, src/multi/parameter_manager.py:79-111). Double buffered. */
+int32_t bg_arena_set_weights(bg_arena* a, const float* packed, int64_t version, float temperature /* <=0: greedy */,
+                             void* stream);
+/* Parity mode: dice come from tape[n_games][L][2] (host or device pointer, copied) in order, including the doubles
+ * rejected by the reset protocol; a game whose tape runs out stops.  NULL restores Philox dice. */
+int32_t bg_arena_set_dice_tape(bg_arena* a, const uint8_t* tape, int64_t L, void* stream);
+/* (Re)start every game: BackgammonEnv.reset (src/environments/backgammon_env.py:92-128); clears stats and the ring. */
+int32_t bg_arena_reset(bg_arena* a, void* stream);
+/* Advance every active game by n_plies env steps: movegen + fused eval + select + apply + record (lookahead must be 1).
+ * forced_action: optional device int32[n_games]; entries >= 0 override the policy's choice (env.step(action)). */
+int32_t bg_arena_step(bg_arena* a, int32_t n_plies, int32_t lookahead, const int32_t* forced_action, void* stream);
+/*
+ * Hand finished episodes to the learner (replaces ExperienceQueue.get, src/main.py:117): copies up to max_episodes whole
+ * episodes / max_experiences records, oldest first, into caller buffers in CSR form and frees their ring space.
+ * Record t of an episode: after_boards = board after the mover's move (== next_observation's board; the observation's
+ * board is the previous record's after_board, or the initial board for t = 0), Experience fields state_value = v,
+ * next_state_value = v_next, reward, done (meta).  n_moves/action/roll are optional traces (may be NULL).
+ * out_n: device int64[2] = {episodes, experiences} written.
+ */
+int32_t bg_arena_drain_episodes(bg_arena* a, int64_t max_episodes, int64_t max_experiences, int8_t* after_boards /*[.,52]*/,
+                                uint8_t* meta, float* reward, float* v, float* v_next, int16_t* n_moves, int16_t* action,
+                                uint8_t* roll /*[.,2]*/, int64_t* ep_offsets /*[max_episodes+1]*/,
+                                int32_t* ep_info /*[max_episodes,BG_EP_INFO_INTS]*/, int64_t* out_n /*[2]*/, void* stream);
+/* out: int64[BG_ARENA_NSTATS], host or device pointer (cudaMemcpyAsync on `stream`). */
+int32_t bg_arena_stats(bg_arena* a, int64_t* out, void* stream);
+/* Snapshot of the live games (any pointer may be NULL): boards[n,52], players[n], rolls[n,2], game_state[n]. */
+int32_t bg_arena_export_state(bg_arena* a, int8_t* boards, uint8_t* players, uint8_t* rolls, uint8_t* game_state,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

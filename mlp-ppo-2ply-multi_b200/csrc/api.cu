@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include "arena.cuh"
 #include "eval.cuh"
 #include "movegen.cuh"
 #include "select.cuh"
@@ -73,8 +74,8 @@ int32_t bg_movegen(const int8_t* boards, const uint8_t* players, const uint8_t* 
   BG_REQUIRE(workspace, "bg_movegen: workspace is null");
   int32_t rc = require_device();
   if (rc != BG_OK) return rc;
-  MovegenArgs a{boards,      players,   rolls,     B,          item_cap,  pool_cap,  out_boards,     out_submoves,
-                out_owner,   out_offsets, out_count, out_total, out_status, workspace, workspace_bytes};
+  MovegenArgs a{boards,    players,     rolls,     B,         item_cap,   pool_cap,  out_boards,      out_submoves,
+                out_owner, out_offsets, out_count, out_total, out_status, workspace, workspace_bytes, nullptr};
   return movegen_launch(a, (cudaStream_t)stream);
 }
 
@@ -123,6 +124,59 @@ int32_t bg_select(const float* v, const int64_t* offsets, const int32_t* counts,
   if (rc != BG_OK) return rc;
   SelectArgs a{v, offsets, counts, item_cap, B, temperature, seed, ctr, item_id_base, out_action};
   return select_launch(a, (cudaStream_t)stream);
+}
+
+/* ---- arena ---- */
+
+int32_t bg_arena_create(bg_arena** out, int32_t device, int64_t n_games, int32_t H, int32_t max_plies, int32_t move_cap, uint64_t seed,
+                        int64_t game_id_base, int64_t ring_experiences, int64_t ring_episodes, int32_t auto_reset) {
+  BG_REQUIRE(out, "bg_arena_create: out is null");
+  int32_t rc = require_device();
+  if (rc != BG_OK) return rc;
+  Arena* A = nullptr;
+  rc = arena_create(&A, device, n_games, H, max_plies, move_cap, seed, game_id_base, ring_experiences, ring_episodes, auto_reset);
+  *out = reinterpret_cast<bg_arena*>(A);
+  return rc;
+}
+
+int32_t bg_arena_destroy(bg_arena* a) { return arena_destroy(reinterpret_cast<Arena*>(a)); }
+
+int32_t bg_arena_set_weights(bg_arena* a, const float* packed, int64_t version, float temperature, void* stream) {
+  BG_REQUIRE(a && packed, "bg_arena_set_weights: null pointer");
+  return arena_set_weights(reinterpret_cast<Arena*>(a), packed, version, temperature, (cudaStream_t)stream);
+}
+
+int32_t bg_arena_set_dice_tape(bg_arena* a, const uint8_t* tape, int64_t L, void* stream) {
+  BG_REQUIRE(a, "bg_arena_set_dice_tape: null arena");
+  return arena_set_dice_tape(reinterpret_cast<Arena*>(a), tape, L, (cudaStream_t)stream);
+}
+
+int32_t bg_arena_reset(bg_arena* a, void* stream) {
+  BG_REQUIRE(a, "bg_arena_reset: null arena");
+  return arena_reset(reinterpret_cast<Arena*>(a), (cudaStream_t)stream);
+}
+
+int32_t bg_arena_step(bg_arena* a, int32_t n_plies, int32_t lookahead, const int32_t* forced_action, void* stream) {
+  BG_REQUIRE(a && n_plies >= 0, "bg_arena_step: bad arguments");
+  return arena_step(reinterpret_cast<Arena*>(a), n_plies, lookahead, forced_action, (cudaStream_t)stream);
+}
+
+int32_t bg_arena_drain_episodes(bg_arena* a, int64_t max_episodes, int64_t max_experiences, int8_t* after_boards, uint8_t* meta,
+                                float* reward, float* v, float* v_next, int16_t* n_moves, int16_t* action, uint8_t* roll,
+                                int64_t* ep_offsets, int32_t* ep_info, int64_t* out_n, void* stream) {
+  BG_REQUIRE(a, "bg_arena_drain_episodes: null arena");
+  return arena_drain(reinterpret_cast<Arena*>(a), max_episodes, max_experiences, after_boards, meta, reward, v, v_next, n_moves, action,
+                     roll, ep_offsets, ep_info, out_n, (cudaStream_t)stream);
+}
+
+int32_t bg_arena_stats(bg_arena* a, int64_t* out, void* stream) {
+  BG_REQUIRE(a && out, "bg_arena_stats: null pointer");
+  return arena_stats(reinterpret_cast<Arena*>(a), out, (cudaStream_t)stream);
+}
+
+int32_t bg_arena_export_state(bg_arena* a, int8_t* boards, uint8_t* players, uint8_t* rolls, uint8_t* game_state, void* stream) {
+  BG_REQUIRE(a, "bg_arena_export_state: null arena");
+  return arena_export_state(reinterpret_cast<Arena*>(a), boards, players, rolls, game_state, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -356,6 +356,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_movegen(MovegenParams P) {
       const int64_t t = (int64_t)t0 + g;
       if (t >= n_items) break;
       const int item = P.in_list ? P.in_list[t] : (int)t;
+      if (P.active && !P.active[item]) {
+        if (lane == 0) {
+          P.out_count[item] = 0;
+          P.out_offsets[item] = 0;
+        }
+        continue;
+      }
       __syncwarp();
       if (lane < 13) rootw[lane] = reinterpret_cast<const uint32_t*>(P.boards)[(int64_t)item * 13 + lane];
       __syncwarp();
@@ -509,6 +516,7 @@ int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream) {
   P.pool_cursor = (unsigned long long*)ws;
   P.status = (int32_t*)(ws + 8);
   P.gfront = (uint32_t*)(ws + HDR_BYTES + lists);
+  P.active = a.active;
   int32_t* ctr = (int32_t*)(ws + 12);
   int32_t* ovf2 = (int32_t*)(ws + HDR_BYTES);
   int32_t* ovf3 = ovf2 + a.B;

@@ -20,6 +20,7 @@ struct MovegenArgs {
   int32_t* out_status;
   void* workspace;
   int64_t workspace_bytes;
+  const uint8_t* active;  // optional [B]: items with active[i] == 0 are skipped (count 0)
 };
 
 // kernel parameter block
@@ -44,6 +45,7 @@ struct MovegenParams {
   int32_t* ovf_count;
   uint32_t* gfront;
   int32_t grab;
+  const uint8_t* active;
 };
 
 int64_t movegen_workspace_bytes(int64_t B);
