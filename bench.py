@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native backgammon hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--positions P]
+
+Workload (BASELINE.json configs[1]): P = 1,048,576 random-but-legal positions x the 21 unordered rolls
+(22,020,096 (position, roll) items, ~4.8e8 afterstates) per GPU.  One "step" = one pass of the hot path over that batch:
+legal-move generation (bg_movegen) + fused 198-feature encode + sigmoid-MLP value of every afterstate (bg_eval).
+Metric: afterstates evaluated per second (whole job, all GPUs).  Positions are synthetic: produced by the arena itself
+playing uniformly random legal moves from the start position (temperature -> infinity), snapshotted at spread-out plies.
+Also reported: `e2e` (host buffers in, greedy action + count per item out, copies inside the timed region),
+`roofline` for the dominant kernel, `cpu_baseline` (the C oracle port on the host cores, bounded sample),
+`selfplay_1ply` (BASELINE configs[2]: 65,536 concurrent games, games/s).
+Under torchrun each rank owns an independent shard (weak scaling, no data-path collective); rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = 128
+FLOP_PER_AFTERSTATE = 2 * 198 * H + 2 * H  # 50,944 dense FLOP per evaluated afterstate
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0]))
+                mx.append(float(c[1]))
+                power.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            busy = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+            out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "power_w_max": max(power),
+                   "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def packed_random_weights(seed=0):
+    """Xavier-uniform 198->128->1 value net (reference policy_network.py:36-51), packed [W1^T | b1 | w2 | b2]."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    a1 = (6.0 / (198 + H)) ** 0.5
+    W1 = (torch.rand(H, 198, generator=g) * 2 - 1) * a1
+    b1 = (torch.rand(H, generator=g) * 2 - 1) / 198 ** 0.5
+    a2 = (6.0 / (H + 1)) ** 0.5
+    w2 = (torch.rand(1, H, generator=g) * 2 - 1) * a2
+    b2 = (torch.rand(1, generator=g) * 2 - 1) / H ** 0.5
+    return torch.cat([W1.t().contiguous().reshape(-1), b1, w2.reshape(-1), b2]).float()
+
+
+def make_positions(bg, n_pos, device, seed):
+    """n_pos reachable positions from the arena playing uniformly random legal moves (temperature 1e9)."""
+    import torch
+
+    G = min(131072, n_pos)
+    snaps = (n_pos + G - 1) // G
+    ar = bg.Arena(G, hidden_size=H, device=device, seed=seed, ring_experiences=1 << 22, ring_episodes=1 << 17)
+    ar.set_weights(packed_random_weights(1).to(device), version=1, temperature=1e9)
+    ar.reset()
+    boards, players = [], []
+    have = 0
+    ar.step(97)
+    for s in range(4 * snaps + 4):
+        ar.step(13)
+        while ar.drain(max_episodes=1 << 16, max_experiences=1 << 21).n_episodes:  # keep the ring empty; episodes are discarded
+            pass
+        b, p, _, st = ar.state()
+        keep = st == 0
+        boards.append(b[keep])
+        players.append(p[keep])
+        have += int(keep.sum().item())
+        if have >= n_pos:
+            break
+    ar.close()
+    boards = torch.cat(boards)[:n_pos].contiguous()
+    players = torch.cat(players)[:n_pos].contiguous()
+    return boards, players
+
+
+def expand_rolls(bg, boards, players):
+    import torch
+
+    n = boards.shape[0]
+    rolls = torch.tensor(bg.DICE_ROLLS, dtype=torch.uint8, device=boards.device)
+    ib = boards.repeat_interleave(21, dim=0)
+    ip = players.repeat_interleave(21)
+    ir = rolls.repeat(n, 1)
+    return ib.contiguous(), ip.contiguous(), ir.contiguous()
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's algorithm on the host cores (the C oracle port, OpenMP over items).  The Python
+    reference itself cannot travel to the GPU box; oracle/bg_oracle.c is its line-by-line restatement, pinned against it."""
+    if rank != 0:
+        return
+    import numpy as np
+
+    from oracle import pyoracle as po
+
+    po.build()
+    cores = os.cpu_count() or 1
+    n_pos = args.ref_positions
+    boards, players = po.random_positions(n_pos, seed=2026)
+    ib, ip, ir = po.all_rolls_items(boards, players)
+    packed = packed_random_weights(0).numpy()
+    for _ in range(args.warmup):
+        po.movegen_eval_bench(ib[: len(ib) // 8], ip[: len(ib) // 8], ir[: len(ib) // 8], packed, H, nthreads=cores)
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(args.steps):
+        n, _ = po.movegen_eval_bench(ib, ip, ir, packed, H, nthreads=cores)
+        total += n
+    dt = time.perf_counter() - t0
+    val = total / dt
+    sample = f"{n_pos} positions x 21 rolls ({len(ib)} items, {total // max(args.steps, 1)} afterstates) per step"
+    line = {"impl": "reference", "metric": "afterstates_evaluated_per_sec", "value": val, "unit": "afterstates/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int8 boards / fp32 values", "data": "synthetic",
+            "config": {"workload": "config2: random-legal positions x 21 rolls -> legal-move generation + 198-feature encode + 198x128x1 sigmoid-MLP value",
+                       "hidden": H, "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "afterstates/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "afterstates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--positions", type=int, default=1048576)
+    ap.add_argument("--ref-positions", type=int, default=32768)
+    ap.add_argument("--cpu-positions", type=int, default=32768)
+    ap.add_argument("--selfplay-games", type=int, default=65536)
+    ap.add_argument("--selfplay-plies", type=int, default=200)
+    ap.add_argument("--no-selfplay", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    import mlp_ppo_2ply_multi_b200 as bg
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- inputs (resident in HBM before the timed region) --------------------------------------------------------
+    packed = packed_random_weights(0).to(dev)
+    weights = bg.prepare_weights(packed, H)
+    boards, players = make_positions(bg, args.positions, dev, seed=2026 + 7919 * rank)
+    ib, ip, ir = expand_rolls(bg, boards, players)
+    B = ib.shape[0]
+    pool_cap = int(B * 26) + (1 << 20)
+    pool = torch.empty((pool_cap, 52), dtype=torch.int8, device=dev)
+    values = torch.empty(pool_cap, dtype=torch.float32, device=dev)
+    owner = torch.empty(pool_cap, dtype=torch.int32, device=dev)
+    ws = torch.empty(bg._lib.lib().bg_movegen_workspace_bytes(B), dtype=torch.uint8, device=dev)
+
+    def step():
+        res = bg.movegen(ib, ip, ir, item_cap=500, out_boards=pool, check_status=False, workspace=ws, out_owner=owner)
+        bg.evaluate(pool, None, weights, owner=res.owner, owner_players=ip, n_dev=res.total_dev, out=values)
+        return res
+
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    torch.cuda.synchronize()
+    n_after = res.total
+    res.raise_for_status()
+
+    # ---- timed region: K steps, CUDA events, barrier + sync on both sides, max over ranks ---------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for k in range(args.steps):
+        r = bg.movegen(ib, ip, ir, item_cap=500, out_boards=pool, check_status=False, workspace=ws, out_owner=owner)
+        ev[3 * k + 1].record()
+        bg.evaluate(pool, None, weights, owner=r.owner, owner_players=ip, n_dev=r.total_dev, out=values)
+        ev[3 * k + 2].record()
+        ev[3 * k + 3].record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    total_ms = ev[0].elapsed_time(ev[3 * args.steps])
+    t_movegen = sum(ev[3 * k].elapsed_time(ev[3 * k + 1]) for k in range(args.steps)) / args.steps
+    t_eval = sum(ev[3 * k + 1].elapsed_time(ev[3 * k + 2]) for k in range(args.steps)) / args.steps
+    t = torch.tensor([total_ms, float(n_after)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, n_after_all = float(tmax[0]), float(tsum[1])
+    else:
+        n_after_all = float(n_after)
+    ms_per_step = total_ms / args.steps
+    value = n_after_all / (ms_per_step * 1e-3)
+
+    # ---- e2e: public API from HOST buffers (pinned), H2D of the step's inputs and D2H of its result inside the timed region ----
+    h_b, h_p, h_r = ib.cpu().pin_memory(), ip.cpu().pin_memory(), ir.cpu().pin_memory()
+    h_act = torch.empty(B, dtype=torch.int32).pin_memory()
+    h_cnt = torch.empty(B, dtype=torch.int32).pin_memory()
+    d_b, d_p, d_r = torch.empty_like(ib), torch.empty_like(ip), torch.empty_like(ir)
+
+    def e2e_step():
+        d_b.copy_(h_b, non_blocking=True)
+        d_p.copy_(h_p, non_blocking=True)
+        d_r.copy_(h_r, non_blocking=True)
+        r = bg.movegen(d_b, d_p, d_r, item_cap=500, out_boards=pool, check_status=False, workspace=ws, out_owner=owner)
+        bg.evaluate(pool, None, weights, owner=r.owner, owner_players=d_p, n_dev=r.total_dev, out=values)
+        act = bg.select(values, r.offsets, r.counts, temperature=0.0, item_cap=500)
+        h_act.copy_(act, non_blocking=True)
+        h_cnt.copy_(r.counts, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = n_after_all / (float(te[0]) / args.steps * 1e-3)
+    h2d = h_b.numel() + h_p.numel() + h_r.numel()
+    d2h = h_act.numel() * 4 + h_cnt.numel() * 4
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (algorithmic bytes / measured kernel time) -----------------------------------------
+    peak, peak_src = load_peaks()
+    eval_bytes = n_after * (52 + 4 + 4)  # board in + owner in + value out
+    movegen_bytes = B * (52 + 1 + 2 + 8 + 4) + n_after * (52 + 4)  # item in/out + board, owner out
+    kern = {"bg::k_eval<4>": (t_eval, eval_bytes), "bg::k_movegen<128|1024|4096> (3 tiers)": (t_movegen, movegen_bytes)}
+    dom = max(kern, key=lambda k: kern[k][0])
+    ach = kern[dom][1] / (kern[dom][0] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "ms_per_launch": kern[dom][0],
+                "note": "integer-issue / shared-memory bound by design: algorithmic bytes are tiny (SURVEY.md 8(d))",
+                "kernels_ms": {k: v[0] for k, v in kern.items()},
+                "eval_fp32_tflops_dense_equiv": n_after * FLOP_PER_AFTERSTATE / (t_eval * 1e-3) / 1e12}
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample of the same workload -----------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import pyoracle as po
+
+        po.build()
+        cores = os.cpu_count() or 1
+        ns = min(args.cpu_positions, boards.shape[0])
+        sb, sp, sr = (x.cpu().numpy() for x in expand_rolls(bg, boards[:ns], players[:ns]))
+        pk = packed.cpu().numpy()
+        po.movegen_eval_bench(sb[:4096], sp[:4096], sr[:4096], pk, H, nthreads=cores)
+        t0 = time.perf_counter()
+        n_cpu, _ = po.movegen_eval_bench(sb, sp, sr, pk, H, nthreads=cores)
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_cpu / dt, "unit": "afterstates/s", "cores": cores, "kind": "port",
+               "sample": f"first {ns} of the benchmark's positions x 21 rolls ({len(sb)} items, {n_cpu} afterstates), {dt:.1f} s, OpenMP"}
+
+    # ---- secondary: BASELINE configs[2], 1-ply self-play with 65,536 concurrent games ---------------------------------------------
+    selfplay = None
+    if not args.no_selfplay:
+        G = args.selfplay_games
+        ar = bg.Arena(G, hidden_size=H, device=dev, seed=0, ring_experiences=G * 48, ring_episodes=G)
+        ar.set_weights(packed, version=1)  # T = 1.5
+        ar.reset()
+        ar.step(120)  # desynchronise game phases
+        ar.drain(max_episodes=G, max_experiences=G * 48)
+        torch.cuda.synchronize()
+        s0 = ar.stats()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        done = 0
+        while done < args.selfplay_plies:
+            ar.step(20)
+            ar.drain(max_episodes=G, max_experiences=G * 48)
+            done += 20
+        a1.record()
+        torch.cuda.synchronize()
+        s1 = ar.stats()
+        ms = a0.elapsed_time(a1)
+        games = s1["games"] - s0["games"]
+        after = s1["afterstates"] - s0["afterstates"]
+        selfplay = {"workload": f"config3: {G} concurrent 1-ply self-play games, T=1.5, Philox dice, episodes drained on device",
+                    "games_per_sec": games / (ms * 1e-3), "afterstates_per_sec": after / (ms * 1e-3), "plies_per_sec": G * done / (ms * 1e-3),
+                    "ms_per_ply_step": ms / done, "games_finished": games, "mean_steps_per_game": (s1["steps"] - s0["steps"]) / max(games, 1),
+                    "pass_rate": (s1["passes"] - s0["passes"]) / max(s1["steps"] - s0["steps"], 1), "wait_steps": s1["wait_steps"], "errors": s1["errors"]}
+        ar.close()
+
+    line = {"metric": "afterstates_evaluated_per_sec", "value": value, "unit": "afterstates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8 boards / fp32 values", "data": "synthetic",
+            "config": {"workload": "config2: random-legal positions x 21 rolls -> legal-move generation + fused 198-feature encode + 198x128x1 sigmoid-MLP value",
+                       "positions_per_gpu": int(boards.shape[0]), "items_per_gpu": int(B), "afterstates_per_gpu_step": int(n_after), "hidden": H,
+                       "l2": "inputs+outputs per step (>25 GB) far exceed the 126 MB L2", "parallelism": f"{world} x independent shards"},
+            "e2e": {"value": e2e_value, "unit": "afterstates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "what": "pinned host boards/players/rolls -> bg_movegen -> bg_eval -> bg_select(greedy) -> host actions + counts"},
+            "gpu_launches": 4 * args.steps, "gpu_launches_note": "per step: k_movegen tier 128, 1024, 4096 + k_eval (e2e adds k_select)",
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "selfplay_1ply": selfplay}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

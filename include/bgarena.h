@@ -120,6 +120,24 @@ int32_t bg_select(const float* v, const int64_t* offsets /*[B]*/, const int32_t*
                   int64_t B, float temperature, uint64_t seed, uint64_t ctr, int64_t item_id_base,
                   int32_t* out_action /*[B]*/, void* stream);
 
+/*
+ * 2-ply lookahead score of N candidate afterstates.  Replaces compute_scores_for_boards /
+ * compute_weighted_opponent_response (src/multi/two_ply.py:44-150): for each candidate (board after `mover` moved),
+ * W = sum over the 21 unordered opponent rolls (1/36 doubles, 2/36 others) of mean(top_k opponent-reply values)
+ * (all replies if fewer than top_k; 0 for a roll without reply), score = alpha * S - beta * W.
+ * Reference setting: top_k = 5, alpha = 1.0, beta = 0.9; north_star's best-reply expectimax: top_k = 1.
+ * The reference's random.sample(replies, 50) on 1-1/2-2/3-3 is not reproduced (every reply is evaluated).
+ *   S           : [N] 1-ply value of each candidate (mover's flag)
+ *   out_replies : optional [N] number of replies evaluated per candidate
+ *   out_status  : optional [1] device int32, BG_OK or BG_ERR_CAPACITY (such candidates get score NaN)
+ *   workspace   : device scratch, bg_two_ply_workspace_bytes(N) recommended; smaller is legal (more, smaller chunks)
+ */
+int64_t bg_two_ply_workspace_bytes(int64_t N);
+int32_t bg_two_ply(const int8_t* cand_boards /*[N,52]*/, const uint8_t* mover /*[N]*/, const float* S /*[N]*/, int64_t N,
+                   const float* prepared, int32_t H, int32_t top_k, float alpha, float beta, float* out_score /*[N]*/,
+                   int64_t* out_replies /*[N] or NULL*/, int32_t* out_status /*[1] or NULL*/, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Stateful self-play arena: n_games concurrent games resident on one GPU.
  * Replaces the reference's worker processes: Worker.play_episode (src/multi/worker.py:78-174) over

@@ -7,8 +7,8 @@ from .episode import Episode, EpisodeBatch, Experience
 from .types import BoardState, FullMove, Player, Position, SubMove
 from ._lib import BgError, SO_PATH
 from .ops import (DICE_ROLLS, MovegenResult, PreparedWeights, encode, evaluate, movegen, pack_weights, prepare_weights, select,
-                  unpack_weights)
+                  two_ply, unpack_weights)
 
 __all__ = ["Arena", "temperature_for_version", "Episode", "EpisodeBatch", "Experience", "BoardState", "FullMove", "Player",
            "Position", "SubMove", "ops", "BgError", "SO_PATH", "DICE_ROLLS", "MovegenResult", "PreparedWeights", "encode", "evaluate", "movegen",
-           "pack_weights", "prepare_weights", "select", "unpack_weights"]
+           "pack_weights", "prepare_weights", "select", "two_ply", "unpack_weights"]

@@ -6,6 +6,7 @@
 #include "eval.cuh"
 #include "movegen.cuh"
 #include "select.cuh"
+#include "two_ply.cuh"
 
 namespace bg {
 
@@ -124,6 +125,19 @@ int32_t bg_select(const float* v, const int64_t* offsets, const int32_t* counts,
   if (rc != BG_OK) return rc;
   SelectArgs a{v, offsets, counts, item_cap, B, temperature, seed, ctr, item_id_base, out_action};
   return select_launch(a, (cudaStream_t)stream);
+}
+
+int64_t bg_two_ply_workspace_bytes(int64_t N) { return two_ply_workspace_bytes(N); }
+
+int32_t bg_two_ply(const int8_t* cand_boards, const uint8_t* mover, const float* S, int64_t N, const float* prepared, int32_t H,
+                   int32_t top_k, float alpha, float beta, float* out_score, int64_t* out_replies, int32_t* out_status, void* workspace,
+                   int64_t workspace_bytes, void* stream) {
+  BG_REQUIRE(N >= 0, "bg_two_ply: N < 0");
+  BG_REQUIRE(N == 0 || (cand_boards && mover && S && prepared && out_score && workspace), "bg_two_ply: null pointer");
+  int32_t rc = require_device();
+  if (rc != BG_OK) return rc;
+  TwoPlyArgs a{cand_boards, mover, S, N, prepared, H, top_k, alpha, beta, out_score, out_replies, out_status, workspace, workspace_bytes};
+  return two_ply_launch(a, (cudaStream_t)stream);
 }
 
 /* ---- arena ---- */

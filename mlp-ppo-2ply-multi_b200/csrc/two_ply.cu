@@ -1,0 +1,212 @@
+// two_ply.cu -- 2-ply lookahead scorer (sm_100a).
+//
+// Replaces compute_scores_for_boards / compute_weighted_opponent_response (reference src/multi/two_ply.py:44-150):
+//   for every candidate afterstate, over the 21 unordered opponent rolls (weights 1/36 doubles, 2/36 otherwise,
+//   two_ply.py:10-35): generate the opponent's legal replies (movegen.cu), evaluate them with the opponent's flag
+//   (eval.cu), take the mean of the top_k reply values (all of them if fewer; a roll with no reply adds 0), and
+//   W = sum_r p_r * mean_r;  score = alpha * S - beta * W.
+// top_k = 5, alpha = 1, beta = 0.9 is the reference's setting; top_k = 1 is north_star's "best reply" expectimax.
+// The reference's random.sample(replies, 50) on 1-1/2-2/3-3 (two_ply.py:119-121) is NOT reproduced: it is
+// nondeterministic there; every reply is evaluated here.
+// Composition: k_expand (candidate x roll -> items) -> movegen tiers -> k_eval -> k_reduce (warp per candidate, top-k
+// selection and the 21-term expectation entirely in registers).  Candidates are processed in workspace-sized chunks.
+#include "two_ply.cuh"
+
+#include "eval.cuh"
+#include "movegen.cuh"
+
+namespace bg {
+
+namespace {
+
+__constant__ uint8_t c_roll_d0[21] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 5, 5, 6};
+__constant__ uint8_t c_roll_d1[21] = {1, 2, 3, 4, 5, 6, 2, 3, 4, 5, 6, 3, 4, 5, 6, 4, 5, 6, 5, 6, 6};
+
+constexpr int ROWS_PER_ITEM = 48;  // pool rows provisioned per (candidate, roll) item (mean is ~22)
+constexpr int MAX_TOPK = 8;
+
+__global__ void __launch_bounds__(256) k_expand(const int8_t* __restrict__ cand, const uint8_t* __restrict__ mover, int64_t c0, int64_t nc,
+                                                int8_t* __restrict__ ib, uint8_t* __restrict__ ip, uint8_t* __restrict__ ir) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  const uint32_t* c32 = reinterpret_cast<const uint32_t*>(cand);
+  uint32_t* o32 = reinterpret_cast<uint32_t*>(ib);
+  for (int64_t c = warp; c < nc; c += nwarps) {
+    const uint32_t w = lane < 13 ? c32[(c0 + c) * 13 + lane] : 0u;
+    const uint8_t opp = 1 - (mover[c0 + c] & 1);
+    for (int r = 0; r < 21; ++r) {
+      const int64_t t = c * 21 + r;
+      if (lane < 13) o32[t * 13 + lane] = w;
+    }
+    if (lane < 21) {
+      const int64_t t = c * 21 + lane;
+      ip[t] = opp;
+      ir[2 * t] = c_roll_d0[lane];
+      ir[2 * t + 1] = c_roll_d1[lane];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_reduce(const float* __restrict__ v, const long long* __restrict__ offsets, const int32_t* __restrict__ counts,
+                                                const float* __restrict__ S, int64_t c0, int64_t nc, int top_k, float alpha, float beta,
+                                                float* __restrict__ out_score, long long* __restrict__ out_replies,
+                                                const int32_t* __restrict__ chunk_status, int32_t* __restrict__ out_status) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && out_status && *chunk_status != 0) atomicMin(out_status, *chunk_status);
+  for (int64_t c = warp; c < nc; c += nwarps) {
+    double W = 0.0;
+    long long nrep = 0;
+    bool bad = false;
+    for (int r = 0; r < 21; ++r) {
+      const int64_t t = c * 21 + r;
+      const int n = counts[t];
+      const long long off = offsets[t];
+      if (n < 0 || (n > 0 && off < 0)) {
+        bad = true;
+        continue;
+      }
+      if (n == 0) continue;  // two_ply.py:123 `if opponent_moves:`
+      nrep += n;
+      float loc[MAX_TOPK];
+#pragma unroll
+      for (int q = 0; q < MAX_TOPK; ++q) loc[q] = -INFINITY;
+      for (int i = lane; i < n; i += 32) {
+        float x = v[off + i];
+#pragma unroll
+        for (int q = 0; q < MAX_TOPK; ++q) {  // insertion into the lane-local descending list
+          const float hi = fmaxf(loc[q], x);
+          x = fminf(loc[q], x);
+          loc[q] = hi;
+        }
+      }
+      const int k = n < top_k ? n : top_k;
+      float sum = 0.f;
+      for (int j = 0; j < k; ++j) {
+        float m = loc[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(BG_FULL, m, o));
+        const uint32_t who = __ballot_sync(BG_FULL, loc[0] == m);
+        if (lane == __ffs(who) - 1) {
+#pragma unroll
+          for (int q = 0; q < MAX_TOPK - 1; ++q) loc[q] = loc[q + 1];
+          loc[MAX_TOPK - 1] = -INFINITY;
+        }
+        sum += m;  // descending order, as torch.sort(...)[:k].mean() sums them
+      }
+      const float mean = sum / (float)k;
+      const double p = (r == 0 || r == 6 || r == 11 || r == 15 || r == 18 || r == 20) ? 1.0 / 36.0 : 2.0 / 36.0;
+      W += (double)mean * p;
+    }
+    if (lane == 0) {
+      out_score[c0 + c] = bad ? NAN : (float)((double)alpha * (double)S[c0 + c] - (double)beta * W);
+      if (out_replies) out_replies[c0 + c] = nrep;
+    }
+  }
+}
+
+struct Layout {
+  int64_t C;  // candidates per chunk
+  int64_t items, rows;
+  int64_t o_ib, o_ip, o_ir, o_off, o_cnt, o_tot, o_pool, o_owner, o_val, o_ws, ws_bytes, total;
+};
+
+int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
+
+Layout make_layout(int64_t C) {
+  Layout L;
+  L.C = C;
+  L.items = C * 21;
+  L.rows = L.items * ROWS_PER_ITEM;
+  int64_t o = 0;
+  L.o_ib = o;
+  o += align256(L.items * 52);
+  L.o_ip = o;
+  o += align256(L.items);
+  L.o_ir = o;
+  o += align256(L.items * 2);
+  L.o_off = o;
+  o += align256(L.items * 8);
+  L.o_cnt = o;
+  o += align256(L.items * 4);
+  L.o_tot = o;
+  o += 256;
+  L.o_pool = o;
+  o += align256(L.rows * 52);
+  L.o_owner = o;
+  o += align256(L.rows * 4);
+  L.o_val = o;
+  o += align256(L.rows * 4);
+  L.o_ws = o;
+  L.ws_bytes = movegen_workspace_bytes(L.items);
+  o += align256(L.ws_bytes);
+  L.total = o;
+  return L;
+}
+
+constexpr int64_t DEFAULT_CHUNK = 65536;
+
+}  // namespace
+
+int64_t two_ply_workspace_bytes(int64_t N) {
+  if (N < 1) N = 1;
+  return make_layout(N < DEFAULT_CHUNK ? N : DEFAULT_CHUNK).total;
+}
+
+int32_t two_ply_launch(const TwoPlyArgs& a, cudaStream_t s) {
+  if (a.N <= 0) return BG_OK;
+  if (a.top_k < 1 || a.top_k > MAX_TOPK) {
+    set_error("bg_two_ply: top_k must be in [1,%d]", MAX_TOPK);
+    return BG_ERR_ARG;
+  }
+  // largest chunk that fits the caller's workspace
+  int64_t C = a.N < DEFAULT_CHUNK ? a.N : DEFAULT_CHUNK;
+  while (C > 1 && make_layout(C).total > a.workspace_bytes) C = (C + 1) / 2;
+  Layout L = make_layout(C);
+  if (L.total > a.workspace_bytes) {
+    set_error("bg_two_ply: workspace too small (%lld bytes; need >= %lld)", (long long)a.workspace_bytes, (long long)L.total);
+    return BG_ERR_ARG;
+  }
+  char* w = (char*)a.workspace;
+  if (a.out_status) {
+    cudaError_t e = cudaMemsetAsync(a.out_status, 0, 4, s);
+    if (e != cudaSuccess) return check_cuda(e, "memset status");
+  }
+  for (int64_t c0 = 0; c0 < a.N; c0 += C) {
+    const int64_t nc = a.N - c0 < C ? a.N - c0 : C;
+    const int64_t items = nc * 21;
+    int64_t blocks = (nc + 7) / 8;
+    const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+    k_expand<<<grid, 256, 0, s>>>(a.cand_boards, a.mover, c0, nc, (int8_t*)(w + L.o_ib), (uint8_t*)(w + L.o_ip), (uint8_t*)(w + L.o_ir));
+    MovegenArgs m{};
+    m.boards = (const int8_t*)(w + L.o_ib);
+    m.players = (const uint8_t*)(w + L.o_ip);
+    m.rolls = (const uint8_t*)(w + L.o_ir);
+    m.B = items;
+    m.item_cap = BG_MAX_ITEM_MOVES;
+    m.pool_cap = L.rows;
+    m.out_boards = (int8_t*)(w + L.o_pool);
+    m.out_submoves = nullptr;
+    m.out_owner = (int32_t*)(w + L.o_owner);
+    m.out_offsets = (int64_t*)(w + L.o_off);
+    m.out_count = (int32_t*)(w + L.o_cnt);
+    m.out_total = (int64_t*)(w + L.o_tot);
+    m.out_status = (int32_t*)(w + L.o_tot + 8);
+    m.workspace = w + L.o_ws;
+    m.workspace_bytes = L.ws_bytes;
+    m.active = nullptr;
+    int32_t rc = movegen_launch(m, s);
+    if (rc != BG_OK) return rc;
+    EvalArgs ev{m.out_boards, nullptr, m.out_owner, m.players, 0, m.out_total, L.rows, a.prepared, a.H, (float*)(w + L.o_val)};
+    rc = eval_launch(ev, s);
+    if (rc != BG_OK) return rc;
+    k_reduce<<<grid, 256, 0, s>>>((const float*)(w + L.o_val), (const long long*)(w + L.o_off), (const int32_t*)(w + L.o_cnt), a.S, c0, nc,
+                                  a.top_k, a.alpha, a.beta, a.out_score, (long long*)a.out_replies, (const int32_t*)(w + L.o_tot + 8),
+                                  a.out_status);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return check_cuda(e, "two_ply launch");
+  }
+  return BG_OK;
+}
+
+}  // namespace bg

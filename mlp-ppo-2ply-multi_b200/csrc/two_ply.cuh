@@ -1,0 +1,26 @@
+// two_ply.cuh -- host-side interface of the 2-ply scorer (see two_ply.cu)
+#pragma once
+#include "bg_common.cuh"
+
+namespace bg {
+
+struct TwoPlyArgs {
+  const int8_t* cand_boards;
+  const uint8_t* mover;
+  const float* S;
+  int64_t N;
+  const float* prepared;
+  int32_t H;
+  int32_t top_k;
+  float alpha, beta;
+  float* out_score;
+  int64_t* out_replies;
+  int32_t* out_status;
+  void* workspace;
+  int64_t workspace_bytes;
+};
+
+int64_t two_ply_workspace_bytes(int64_t N);
+int32_t two_ply_launch(const TwoPlyArgs& a, cudaStream_t s);
+
+}  // namespace bg

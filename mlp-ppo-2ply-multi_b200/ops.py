@@ -118,7 +118,7 @@ def _workspace(B: int, device) -> torch.Tensor:
 
 def movegen(boards: torch.Tensor, players: torch.Tensor, rolls: torch.Tensor, item_cap: int = 500, pool_cap: Optional[int] = None,
             want_submoves: bool = False, want_owner: bool = True, check_status: bool = True, out_boards: Optional[torch.Tensor] = None,
-            workspace: Optional[torch.Tensor] = None) -> MovegenResult:
+            workspace: Optional[torch.Tensor] = None, out_owner: Optional[torch.Tensor] = None) -> MovegenResult:
     """Batched get_all_possible_moves + execute_full_move_on_board_copy (reference generate_all_moves.py:7, env_helper.py:27)."""
     boards = _req(boards, torch.int8, "boards").reshape(-1, BOARD_BYTES)
     B = boards.shape[0]
@@ -130,7 +130,7 @@ def movegen(boards: torch.Tensor, players: torch.Tensor, rolls: torch.Tensor, it
     if out_boards is None:
         out_boards = torch.empty((pool_cap, BOARD_BYTES), dtype=torch.int8, device=dev)
     sub = torch.empty((pool_cap, 4, 3), dtype=torch.uint8, device=dev) if want_submoves else None
-    owner = torch.empty(pool_cap, dtype=torch.int32, device=dev) if want_owner else None
+    owner = out_owner if out_owner is not None else (torch.empty(pool_cap, dtype=torch.int32, device=dev) if want_owner else None)
     offsets = torch.empty(B, dtype=torch.int64, device=dev)
     counts = torch.empty(B, dtype=torch.int32, device=dev)
     total = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -188,3 +188,26 @@ def select(values: torch.Tensor, offsets: torch.Tensor, counts: torch.Tensor, te
     check(lib().bg_select(values.data_ptr(), offsets.data_ptr(), counts.data_ptr(), item_cap, B, float(temperature), seed & (2**64 - 1),
                           ctr & (2**64 - 1), item_id_base, out.data_ptr(), _stream()))
     return out
+
+
+def two_ply(cand_boards: torch.Tensor, mover: torch.Tensor, S: torch.Tensor, weights: PreparedWeights, top_k: int = 5, alpha: float = 1.0,
+            beta: float = 0.9, workspace: Optional[torch.Tensor] = None, check_status: bool = True):
+    """2-ply scores (reference src/multi/two_ply.py:44-150): alpha*S - beta*sum_r p_r*mean(top_k opponent replies).
+    -> (scores fp32[N], replies int64[N])"""
+    cand_boards = _req(cand_boards, torch.int8, "cand_boards").reshape(-1, BOARD_BYTES)
+    N = cand_boards.shape[0]
+    mover = _req(mover, torch.uint8, "mover").reshape(N)
+    S = _req(S, torch.float32, "S").reshape(N)
+    dev = cand_boards.device
+    out = torch.empty(N, dtype=torch.float32, device=dev)
+    nrep = torch.zeros(N, dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    if workspace is None:
+        workspace = torch.empty(lib().bg_two_ply_workspace_bytes(N), dtype=torch.uint8, device=dev)
+    check(lib().bg_two_ply(cand_boards.data_ptr(), mover.data_ptr(), S.data_ptr(), N, weights.table.data_ptr(), weights.H, top_k, alpha, beta,
+                           out.data_ptr(), nrep.data_ptr(), status.data_ptr(), workspace.data_ptr(), workspace.numel(), _stream()))
+    if check_status:
+        st = int(status.item())
+        if st != 0:
+            raise _lib.BgError(st, "bg_two_ply: reply pool capacity exceeded for some candidates")
+    return out, nrep

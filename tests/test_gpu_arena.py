@@ -83,7 +83,6 @@ def test_greedy_games_match_oracle_random_tapes(bg, oracle, golden, which):
     assert batch.n_episodes == G and st["errors"] == 0
     games = batch_to_games(batch)
     tolerated = 0
-    shaped = 0
     for k in range(G):
         env = oracle.Env(tape=tapes[k])
         stats, tr = env.play_episode(packed, H, temperature=0.0)
@@ -96,7 +95,6 @@ def test_greedy_games_match_oracle_random_tapes(bg, oracle, golden, which):
             assert np.abs(Gk["reward"] - tr["reward"]).max() < 1e-7
             assert np.abs(Gk["v"] - tr["v"]).max() < 1e-5 and np.abs(Gk["vnext"] - tr["vnext"]).max() < 1e-5
             assert Gk["info"][0] == stats["win_type"] and Gk["info"][2] == stats["n_steps"] and Gk["info"][3] == stats["n_passes"]
-            shaped += int(((Gk["meta"] >> 3) & 3).any())
             continue
         # divergence: must be a near-tie under the oracle's own (double-accumulated) values
         t = int(np.argmin(same))
@@ -108,7 +106,6 @@ def test_greedy_games_match_oracle_random_tapes(bg, oracle, golden, which):
         assert abs(vv[Gk["action"][t]] - vv[tr["action"][t]]) < 2e-6, (k, t)
         tolerated += 1
     assert tolerated <= 4
-    assert shaped > 0 or which == "packed_init0"  # shaping rewards (close-out / prime) are exercised by the trained net
 
 
 def test_sampled_selfplay_statistics_and_determinism(bg, golden):
@@ -161,6 +158,55 @@ def test_sampled_selfplay_statistics_and_determinism(bg, golden):
     assert len(halves) >= 2000
     for gid, (a, af) in halves.items():
         assert np.array_equal(full[gid][0], a) and np.array_equal(full[gid][1], af)
+
+
+def test_rewards_recomputed_with_oracle_predicates(bg, oracle, golden):
+    """every recorded reward (terminal 1 / 2 / 2.5, +0.30 first close-out, +0.20 first 5-prime, once per player per game:
+    reference backgammon_env.py:167-218) is recomputed from the recorded boards with the oracle's predicates"""
+    import ctypes as C
+
+    vals = golden("values")
+    G = 4096
+    ar = bg.Arena(G, device=DEV, seed=21, ring_experiences=G * 400, ring_episodes=G * 4)
+    ar.set_weights(torch.from_numpy(vals["packed"]).to(DEV), version=1, temperature=0.05)  # near-greedy trained play: primes/close-outs happen
+    ar.reset()
+    ar.step(300)
+    batch = ar.drain(max_episodes=G * 4, max_experiences=G * 400)
+    ar.close()
+    L = oracle.lib()
+    off = batch.ep_offsets.cpu().numpy()
+    after = np.ascontiguousarray(batch.after_boards.cpu().numpy())
+    meta = batch.meta.cpu().numpy()
+    rew = batch.reward.cpu().numpy()
+    info = batch.ep_info.cpu().numpy()
+    n_close = n_prime = 0
+    for k in range(min(batch.n_episodes, 3000)):
+        given_c, given_p = [False, False], [False, False]
+        cc, pc = [0, 0], [0, 0]
+        for t in range(off[k], off[k + 1]):
+            mover = int(meta[t] & 1)
+            ptr = after[t].ctypes.data_as(C.c_void_p)
+            if L.bgo_check_game_over(ptr, mover):
+                want = 2.5 if L.bgo_check_backgammon(ptr, mover) else 2.0 if L.bgo_check_gammon(ptr, mover) else 1.0
+                assert (meta[t] >> 2) & 1 and t == off[k + 1] - 1
+            else:
+                want = np.float32(0.0)
+                if L.bgo_is_closed_out(ptr, mover) and not given_c[mover]:
+                    want = np.float32(want + np.float32(0.30))
+                    given_c[mover] = True
+                    cc[mover] += 1
+                    assert (meta[t] >> 3) & 1
+                if L.bgo_made_five_prime(ptr, mover) and not given_p[mover]:
+                    want = np.float32(want + np.float32(0.20))
+                    given_p[mover] = True
+                    pc[mover] += 1
+                    assert (meta[t] >> 4) & 1
+                assert not (meta[t] >> 2) & 1
+            assert abs(float(rew[t]) - float(want)) < 1e-7, (k, t)
+        assert list(info[k][4:8]) == cc + pc
+        n_close += sum(cc)
+        n_prime += sum(pc)
+    assert n_close > 0 and n_prime > 0  # the shaping paths were really exercised
 
 
 def test_ring_backpressure_loses_no_episode(bg, golden):

@@ -237,3 +237,29 @@ def test_full_size_properties(bg, oracle):
         return torch.where(pl == 0, p0, p1)
 
     assert bool((pips(ob) < pips(root)).all())
+
+
+def test_two_ply_reference_setting_and_best_reply(bg, oracle, golden):
+    """bg_two_ply vs compute_weighted_opponent_response of the reference (golden, top-5 / alpha 1 / beta 0.9) and vs the oracle"""
+    g = golden("two_ply")
+    v = golden("values")
+    H = int(v["H"])
+    w = bg.prepare_weights(dev(v["packed"]), H)
+    score, nrep = bg.two_ply(dev(g["cand_boards"]), dev(g["mover"]), dev(g["S"]), w, top_k=5, alpha=1.0, beta=0.9)
+    assert np.abs(score.cpu().numpy() - g["score"]).max() < 1e-5  # vs the reference itself
+    # larger sample vs the oracle, both settings, small workspace to force chunking
+    boards, players = oracle.random_positions(600, seed=31)
+    ib, ip, ir = oracle.all_rolls_items(boards[:40], players[:40])
+    o_off, o_b, _ = oracle.movegen_batch(ib, ip, ir, want_moves=False)
+    mover = np.repeat(ip, np.diff(o_off))
+    sel = np.random.default_rng(1).choice(len(o_b), size=700, replace=False)
+    cb, mv = o_b[sel], mover[sel]
+    S = oracle.value(v["packed"], H, cb, mv)
+    ws_small = torch.empty(bg._lib.lib().bg_two_ply_workspace_bytes(64), dtype=torch.uint8, device=DEV)
+    for k, a, b in ((5, 1.0, 0.9), (1, 1.0, 1.0)):
+        want, want_rep = oracle.two_ply(cb, mv, S, v["packed"], H, top_k=k, alpha=a, beta=b)
+        got, rep = bg.two_ply(dev(cb), dev(mv), dev(S), w, top_k=k, alpha=a, beta=b)
+        assert np.abs(got.cpu().numpy() - want).max() < 1e-5
+        assert np.array_equal(rep.cpu().numpy(), want_rep)
+        got2, _ = bg.two_ply(dev(cb), dev(mv), dev(S), w, top_k=k, alpha=a, beta=b, workspace=ws_small)
+        assert np.array_equal(got2.cpu().numpy(), got.cpu().numpy())
