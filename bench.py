@@ -226,12 +226,12 @@ def main():
     pool_cap = int(B * 26) + (1 << 20)
     pool = torch.empty((pool_cap, 52), dtype=torch.int8, device=dev)
     values = torch.empty(pool_cap, dtype=torch.float32, device=dev)
-    owner = torch.empty(pool_cap, dtype=torch.int32, device=dev)
+    pflags = torch.empty(pool_cap, dtype=torch.uint8, device=dev)
     ws = torch.empty(bg._lib.lib().bg_movegen_workspace_bytes(B), dtype=torch.uint8, device=dev)
 
     def step():
-        res = bg.movegen(ib, ip, ir, item_cap=500, out_boards=pool, check_status=False, workspace=ws, out_owner=owner)
-        bg.evaluate(pool, None, weights, owner=res.owner, owner_players=ip, n_dev=res.total_dev, out=values)
+        res = bg.movegen(ib, ip, ir, item_cap=500, out_boards=pool, check_status=False, workspace=ws, want_owner=False, out_flags=pflags)
+        bg.evaluate(pool, res.flags, weights, n_dev=res.total_dev, out=values)
         return res
 
     for _ in range(max(args.warmup, 3)):
@@ -244,14 +244,19 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     barrier()
+    profiling = os.environ.get("BG_PROFILE") == "1"  # ncu --profile-from-start off: capture only the timed region
+    if profiling:
+        torch.cuda.profiler.start()
     ev[0].record()
     for k in range(args.steps):
-        r = bg.movegen(ib, ip, ir, item_cap=500, out_boards=pool, check_status=False, workspace=ws, out_owner=owner)
+        r = bg.movegen(ib, ip, ir, item_cap=500, out_boards=pool, check_status=False, workspace=ws, want_owner=False, out_flags=pflags)
         ev[3 * k + 1].record()
-        bg.evaluate(pool, None, weights, owner=r.owner, owner_players=ip, n_dev=r.total_dev, out=values)
+        bg.evaluate(pool, r.flags, weights, n_dev=r.total_dev, out=values)
         ev[3 * k + 2].record()
         ev[3 * k + 3].record()
     barrier()
+    if profiling:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop() if sampler else None
     total_ms = ev[0].elapsed_time(ev[3 * args.steps])
     t_movegen = sum(ev[3 * k].elapsed_time(ev[3 * k + 1]) for k in range(args.steps)) / args.steps
@@ -278,8 +283,8 @@ def main():
         d_b.copy_(h_b, non_blocking=True)
         d_p.copy_(h_p, non_blocking=True)
         d_r.copy_(h_r, non_blocking=True)
-        r = bg.movegen(d_b, d_p, d_r, item_cap=500, out_boards=pool, check_status=False, workspace=ws, out_owner=owner)
-        bg.evaluate(pool, None, weights, owner=r.owner, owner_players=d_p, n_dev=r.total_dev, out=values)
+        r = bg.movegen(d_b, d_p, d_r, item_cap=500, out_boards=pool, check_status=False, workspace=ws, want_owner=False, out_flags=pflags)
+        bg.evaluate(pool, r.flags, weights, n_dev=r.total_dev, out=values)
         act = bg.select(values, r.offsets, r.counts, temperature=0.0, item_cap=500)
         h_act.copy_(act, non_blocking=True)
         h_cnt.copy_(r.counts, non_blocking=True)
@@ -307,8 +312,8 @@ def main():
 
     # ---- roofline of the dominant kernel (algorithmic bytes / measured kernel time) -----------------------------------------
     peak, peak_src = load_peaks()
-    eval_bytes = n_after * (52 + 4 + 4)  # board in + owner in + value out
-    movegen_bytes = B * (52 + 1 + 2 + 8 + 4) + n_after * (52 + 4)  # item in/out + board, owner out
+    eval_bytes = n_after * (52 + 1 + 4)  # board in + flag in + value out
+    movegen_bytes = B * (52 + 1 + 2 + 8 + 4) + n_after * (52 + 1)  # item in/out + board, flag out
     kern = {"bg::k_eval<4>": (t_eval, eval_bytes), "bg::k_movegen<128|1024|4096> (3 tiers)": (t_movegen, movegen_bytes)}
     dom = max(kern, key=lambda k: kern[k][0])
     ach = kern[dom][1] / (kern[dom][0] * 1e-3) / 1e9

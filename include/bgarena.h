@@ -72,6 +72,7 @@ int64_t bg_movegen_workspace_bytes(int64_t B);
  *   pool_cap     : capacity of out_boards / out_submoves / out_owner in afterstates.
  *   out_submoves : optional (may be NULL) [pool_cap,4,3] the FullMove sub-move sequences.
  *   out_owner    : optional (may be NULL) [pool_cap] item index owning each pool slot.
+ *   out_flags    : optional (may be NULL) [pool_cap] the item's player for each slot (the flag bg_eval needs for afterstates).
  *   out_total    : [1] device int64, number of pool slots used.
  *   out_status   : [1] device int32, BG_OK or BG_ERR_CAPACITY (pool or BG_MAX_ITEM_MOVES exceeded; the
  *                  offending items get out_offsets = -1).
@@ -79,7 +80,7 @@ int64_t bg_movegen_workspace_bytes(int64_t B);
 int32_t bg_movegen(const int8_t* boards /*[B,52]*/, const uint8_t* players /*[B]*/, const uint8_t* rolls /*[B,2]*/,
                    int64_t B, int32_t item_cap, int64_t pool_cap, int8_t* out_boards /*[pool_cap,52]*/,
                    uint8_t* out_submoves /*[pool_cap,4,3] or NULL*/, int32_t* out_owner /*[pool_cap] or NULL*/,
-                   int64_t* out_offsets /*[B]*/, int32_t* out_count /*[B]*/, int64_t* out_total /*[1]*/,
+                   uint8_t* out_flags /*[pool_cap] or NULL*/, int64_t* out_offsets /*[B]*/, int32_t* out_count /*[B]*/, int64_t* out_total /*[1]*/,
                    int32_t* out_status /*[1]*/, void* workspace, int64_t workspace_bytes, void* stream);
 
 /*

@@ -30,7 +30,7 @@ SIGNATURES = {
     "bg_last_error": (C.c_char_p, []),
     "bg_device_count": (_i32, []),
     "bg_movegen_workspace_bytes": (_i64, [_i64]),
-    "bg_movegen": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "bg_movegen": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "bg_encode": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "bg_prepared_weights_bytes": (_i64, [_i32]),
     "bg_prepare_weights": (_i32, [_vp, _i32, _vp, _vp]),

@@ -66,8 +66,8 @@ int32_t bg_device_count(void) {
 int64_t bg_movegen_workspace_bytes(int64_t B) { return movegen_workspace_bytes(B < 0 ? 0 : B); }
 
 int32_t bg_movegen(const int8_t* boards, const uint8_t* players, const uint8_t* rolls, int64_t B, int32_t item_cap,
-                   int64_t pool_cap, int8_t* out_boards, uint8_t* out_submoves, int32_t* out_owner, int64_t* out_offsets,
-                   int32_t* out_count, int64_t* out_total, int32_t* out_status, void* workspace, int64_t workspace_bytes,
+                   int64_t pool_cap, int8_t* out_boards, uint8_t* out_submoves, int32_t* out_owner, uint8_t* out_flags,
+                   int64_t* out_offsets, int32_t* out_count, int64_t* out_total, int32_t* out_status, void* workspace, int64_t workspace_bytes,
                    void* stream) {
   BG_REQUIRE(B >= 0, "bg_movegen: B < 0");
   BG_REQUIRE(B == 0 || (boards && players && rolls && out_offsets && out_count), "bg_movegen: null input/output pointer");
@@ -76,7 +76,7 @@ int32_t bg_movegen(const int8_t* boards, const uint8_t* players, const uint8_t* 
   int32_t rc = require_device();
   if (rc != BG_OK) return rc;
   MovegenArgs a{boards,    players,     rolls,     B,         item_cap,   pool_cap,  out_boards,      out_submoves,
-                out_owner, out_offsets, out_count, out_total, out_status, workspace, workspace_bytes, nullptr};
+                out_owner, out_flags, out_offsets, out_count, out_total, out_status, workspace, workspace_bytes, nullptr};
   return movegen_launch(a, (cudaStream_t)stream);
 }
 

@@ -524,7 +524,7 @@ struct Arena {
   // per-step scratch
   int8_t* pool = nullptr;
   int64_t pool_cap = 0;
-  int32_t* owner = nullptr;
+  uint8_t* pflags = nullptr;
   int64_t* offsets = nullptr;
   int32_t* counts = nullptr;
   int64_t* total = nullptr;
@@ -630,7 +630,7 @@ int32_t arena_create(Arena** out, int32_t device, int64_t n_games, int32_t H, in
   A->pool_cap = n_games * 128 < n_games * (int64_t)move_cap ? n_games * 128 : n_games * (int64_t)move_cap;
   if (A->pool_cap < 65536) A->pool_cap = n_games * (int64_t)move_cap < 65536 ? n_games * (int64_t)move_cap : 65536;
   AL(A->pool, (size_t)A->pool_cap * BG_BOARD_BYTES);
-  AL(A->owner, (size_t)A->pool_cap);
+  AL(A->pflags, (size_t)A->pool_cap);
   AL(A->offsets, G);
   AL(A->counts, G);
   AL(A->total, 2);
@@ -726,7 +726,8 @@ int32_t arena_step(Arena* A, int32_t n_plies, int32_t lookahead, const int32_t* 
     m.pool_cap = A->pool_cap;
     m.out_boards = A->pool;
     m.out_submoves = nullptr;
-    m.out_owner = A->owner;
+    m.out_owner = nullptr;
+    m.out_flags = A->pflags;
     m.out_offsets = A->offsets;
     m.out_count = A->counts;
     m.out_total = A->total;
@@ -735,7 +736,7 @@ int32_t arena_step(Arena* A, int32_t n_plies, int32_t lookahead, const int32_t* 
     m.workspace_bytes = A->ws_bytes;
     m.active = A->active;
     TRY(movegen_launch(m, s));
-    EvalArgs ev{A->pool, nullptr, A->owner, A->D.player, 0, A->total, A->pool_cap, A->prepared[A->cur_w], A->H, A->v_pool};
+    EvalArgs ev{A->pool, A->pflags, nullptr, nullptr, 0, A->total, A->pool_cap, A->prepared[A->cur_w], A->H, A->v_pool};
     TRY(eval_launch(ev, s));
     EvalArgs ec{reinterpret_cast<const int8_t*>(A->D.board), A->D.player, nullptr, nullptr, C.G, nullptr, C.G, A->prepared[A->cur_w], A->H, A->v_cur};
     TRY(eval_launch(ec, s));

@@ -19,7 +19,7 @@ namespace {
 __constant__ float c_off15[16];  // (float)(n / 15.0), reference immutable_board.py:117,120
 
 constexpr int NUM_SMS = 148;
-constexpr int EVAL_THREADS = 256;
+constexpr int EVAL_THREADS = 512;
 
 // prepared layout: rows [0,192): (pl*24+pt)*4 + k  (k=0: r0, 1: r0+r1, 2: r0+r1+r2, 3: 0.5*r3)
 //                  rows 192..197: 0.5*W[192], W[193], 0.5*W[194], W[195], W[196], W[197]; then b1[H], w2[H], b2
@@ -111,36 +111,62 @@ __device__ __forceinline__ int unit_index(int lane, int q) {
     return q * 32 + lane;
 }
 
+// Row gather for one board.  `list` (per-warp shared scratch) receives the table-row offsets (in floats) of every
+// occupied (player, point) pair, compacted across lanes with ballot/popc, padded to a multiple of 4 with the all-zero row;
+// the warp then streams them four rows at a time (independent 512-byte conflict-free reads, H=128).
 template <int HPL>
-__device__ __forceinline__ void accumulate_side(Acc<HPL>& z, const float* T, int H, uint32_t cnt, int lane) {
-  // cnt: this lane's checker count at point `lane` (lanes >= 24 hold 0)
-  const uint32_t ge1 = __ballot_sync(BG_FULL, cnt >= 1), ge2 = __ballot_sync(BG_FULL, cnt >= 2),
-                 ge3 = __ballot_sync(BG_FULL, cnt >= 3), gt3 = __ballot_sync(BG_FULL, cnt > 3);
-  uint32_t m = ge1;
-  while (m) {
-    const int p = __ffs(m) - 1;
-    m &= m - 1;
-    const int k = ((ge2 >> p) & 1) + ((ge3 >> p) & 1);
-    add_row<HPL>(z, T + (p * 4 + k) * H, lane);
+__device__ __forceinline__ void gather_rows(Acc<HPL>& z, const float* sT, uint32_t* list, uint32_t c0, uint32_t c1, int lane) {
+  constexpr int H = HPL * 32;
+  constexpr uint32_t ZROW = 201 * H;  // zero row placed after the table (+pad) in shared memory
+  const uint32_t occ0 = __ballot_sync(BG_FULL, c0 > 0), occ1 = __ballot_sync(BG_FULL, c1 > 0);
+  const uint32_t gt0 = __ballot_sync(BG_FULL, c0 > 3), gt1 = __ballot_sync(BG_FULL, c1 > 3);
+  const uint32_t lt = (1u << lane) - 1u;
+  const int n0 = __popc(occ0), n = n0 + __popc(occ1);
+  __syncwarp();
+  if (c0 > 0) list[__popc(occ0 & lt)] = (uint32_t)((lane * 4 + (int)min(c0, 3u) - 1) * H);
+  if (c1 > 0) list[n0 + __popc(occ1 & lt)] = (uint32_t)((96 + lane * 4 + (int)min(c1, 3u) - 1) * H);
+  if (lane < 3) list[n + lane] = ZROW;
+  __syncwarp();
+  for (int j = 0; j < n; j += 4) {
+    const uint32_t r0 = list[j], r1 = list[j + 1], r2 = list[j + 2], r3 = list[j + 3];
+    Acc<HPL> a, b, c, d;
+#pragma unroll
+    for (int q = 0; q < HPL; ++q) a.a[q] = b.a[q] = c.a[q] = d.a[q] = 0.f;
+    add_row<HPL>(a, sT + r0, lane);
+    add_row<HPL>(b, sT + r1, lane);
+    add_row<HPL>(c, sT + r2, lane);
+    add_row<HPL>(d, sT + r3, lane);
+#pragma unroll
+    for (int q = 0; q < HPL; ++q) z.a[q] = (((z.a[q] + a.a[q]) + b.a[q]) + c.a[q]) + d.a[q];
   }
-  m = gt3;
+  // counts above 3: (c - 3) * (0.5 * W[.,3])
+  uint32_t m = gt0;
   while (m) {
     const int p = __ffs(m) - 1;
     m &= m - 1;
-    const int c = __shfl_sync(BG_FULL, (int)cnt, p);
-    fma_row<HPL>(z, (float)(c - 3), T + (p * 4 + 3) * H, lane);
+    const int c = __shfl_sync(BG_FULL, (int)c0, p);
+    fma_row<HPL>(z, (float)(c - 3), sT + (p * 4 + 3) * H, lane);
+  }
+  m = gt1;
+  while (m) {
+    const int p = __ffs(m) - 1;
+    m &= m - 1;
+    const int c = __shfl_sync(BG_FULL, (int)c1, p);
+    fma_row<HPL>(z, (float)(c - 3), sT + (96 + p * 4 + 3) * H, lane);
   }
 }
 
 template <int HPL>
-__global__ void __launch_bounds__(EVAL_THREADS) k_eval(const int8_t* __restrict__ boards, const uint8_t* __restrict__ flags,
-                                                      const int32_t* __restrict__ owner, const uint8_t* __restrict__ owner_players,
-                                                      int64_t N_host, const int64_t* __restrict__ N_dev, int64_t max_N,
-                                                      const float* __restrict__ prep, float* __restrict__ out_v) {
+__global__ void __launch_bounds__(EVAL_THREADS, (HPL <= 4 ? 2 : 1))
+    k_eval(const int8_t* __restrict__ boards, const uint8_t* __restrict__ flags, const int32_t* __restrict__ owner,
+           const uint8_t* __restrict__ owner_players, int64_t N_host, const int64_t* __restrict__ N_dev, int64_t max_N,
+           const float* __restrict__ prep, float* __restrict__ out_v) {
   constexpr int H = HPL * 32;
   extern __shared__ __align__(16) float sT[];
   const int n_floats = 200 * H + 1;
   for (int i = threadIdx.x; i < n_floats; i += blockDim.x) sT[i] = prep[i];
+  for (int i = threadIdx.x; i < H; i += blockDim.x) sT[201 * H + i] = 0.f;  // zero row
+  uint32_t* lists = reinterpret_cast<uint32_t*>(sT + 202 * H);
   __syncthreads();
   const float* sb1 = sT + 198 * H;
   const float* sw2 = sb1 + H;
@@ -148,6 +174,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval(const int8_t* __restrict_
   int64_t N = N_dev ? *N_dev : N_host;
   if (N > max_N) N = max_N;
   const int lane = threadIdx.x & 31;
+  uint32_t* list = lists + (threadIdx.x >> 5) * 56;
   const int64_t warp = (int64_t)blockIdx.x * (EVAL_THREADS / 32) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (EVAL_THREADS / 32);
   const uint32_t* b32 = reinterpret_cast<const uint32_t*>(boards);
@@ -157,13 +184,17 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval(const int8_t* __restrict_
     w2r[q] = sw2[unit_index<HPL>(lane, q)];
     b1r[q] = sb1[unit_index<HPL>(lane, q)];
   }
+  // lanes 0..12 fetch the board words, lane 13 the flag; the next board is prefetched while this one is evaluated
+  auto fetch = [&](int64_t j) -> uint32_t {
+    if (lane < 13) return __ldg(b32 + j * 13 + lane);
+    if (lane == 13) return flags ? (uint32_t)flags[j] : (uint32_t)owner_players[owner[j]];
+    return 0u;
+  };
+  uint32_t nxt = warp < N ? fetch(warp) : 0u;
   for (int64_t i = warp; i < N; i += nwarps) {
-    const uint32_t myw = lane < 13 ? __ldg(b32 + i * 13 + lane) : 0u;
-    int flag;
-    if (flags)
-      flag = flags[i];
-    else
-      flag = owner_players[owner[i]];
+    const uint32_t myw = nxt;
+    if (i + nwarps < N) nxt = fetch(i + nwarps);
+    const int flag = (int)__shfl_sync(BG_FULL, myw, 13);
     const uint32_t wa = __shfl_sync(BG_FULL, myw, lane >> 2);
     const uint32_t wb = __shfl_sync(BG_FULL, myw, 6 + (lane >> 2));
     const uint32_t w12 = __shfl_sync(BG_FULL, myw, 12);
@@ -172,8 +203,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval(const int8_t* __restrict_
     Acc<HPL> z;
 #pragma unroll
     for (int q = 0; q < HPL; ++q) z.a[q] = b1r[q];
-    accumulate_side<HPL>(z, sT, H, c0, lane);
-    accumulate_side<HPL>(z, sT + 96 * H, H, c1, lane);
+    gather_rows<HPL>(z, sT, list, c0, c1, lane);
     const uint32_t bar0 = w12 & 0xffu, bar1 = (w12 >> 8) & 0xffu, off0 = (w12 >> 16) & 0xffu, off1 = w12 >> 24;
     if (bar0) fma_row<HPL>(z, (float)bar0, sT + 192 * H, lane);
     if (off0) fma_row<HPL>(z, c_off15[off0 & 15u], sT + 193 * H, lane);
@@ -240,7 +270,7 @@ int32_t init_constants() {
 template <int HPL>
 int32_t launch_eval_t(const EvalArgs& a, cudaStream_t stream) {
   constexpr int H = HPL * 32;
-  const size_t smem = ((size_t)(200 * H + 1) * 4 + 15) / 16 * 16;
+  const size_t smem = (size_t)(202 * H) * 4 + (EVAL_THREADS / 32) * 56 * 4;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k_eval<HPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

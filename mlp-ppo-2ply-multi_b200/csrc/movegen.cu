@@ -16,7 +16,7 @@
 //     distinct intermediate board once (the reference re-expands ~5x-8x duplicates).
 //   * non-doubles keep the reference's literal control flow (both die orders, singles only when an order has
 //     no two-move play, quirk Q1 skip, shared seen-set, max-length filter).
-//   * three capacity tiers (128 / 1024 nodes per ply in shared memory, 4096 in L2-resident global scratch);
+//   * three capacity tiers (128 / 512 nodes per ply in shared memory, 4096 in L2-resident global scratch);
 //     an item overflowing a tier is queued for the next one.  Overflowing the last tier is BG_ERR_CAPACITY.
 #include "movegen.cuh"
 
@@ -26,11 +26,10 @@ namespace bg {
 
 namespace {
 
-constexpr int NF = 6;  // words per node: k0..k3 key, m0 m1 sub-move history
-
-template <int CAP, bool GLOBAL>
+template <int CAP, bool GLOBAL, bool MOVES>
 struct Frontier {
-  uint32_t* base;  // [2][NF][CAP]
+  static constexpr int NF = MOVES ? 6 : 4;  // words per node: k0..k3 key (+ m0 m1 sub-move history)
+  uint32_t* base;                           // [2][NF][CAP]
   __device__ __forceinline__ uint32_t ld(int lvl, int f, int pos) const {
     if constexpr (GLOBAL)
       return __ldcg(base + (lvl * NF + f) * CAP + pos);
@@ -47,11 +46,11 @@ struct Frontier {
 
 struct Root {
   int player;
-  int dirsign;        // +1 / -1
-  uint32_t blocked;   // opponent >= 2 (24 bits)
-  uint32_t blot;      // opponent == 1 (24 bits)
-  uint32_t home;      // mover's home mask
-  bool valid15;       // mover has exactly 15 checkers (conditions.py:191-194)
+  int dirsign;       // +1 / -1
+  uint32_t blocked;  // opponent >= 2 (24 bits)
+  uint32_t blot;     // opponent == 1 (24 bits)
+  uint32_t home;     // mover's home mask
+  bool valid15;      // mover has exactly 15 checkers (conditions.py:191-194)
 };
 
 struct Node {
@@ -127,63 +126,32 @@ __device__ __forceinline__ bool expand(const Node& p, const Root& r, int die, in
   return true;
 }
 
-// First-occurrence dedup + ordered append of this chunk's valid nodes into level `lvl`.
-// Within one chunk all valid keys are distinct (children of one parent via distinct moves, or distinct
-// frontier nodes), so only earlier chunks can hold a duplicate.  Returns false on capacity overflow.
-template <int CAP, bool GLOBAL>
-__device__ __forceinline__ bool append(const Frontier<CAP, GLOBAL>& F, uint32_t* tab, int lvl, int& n, bool valid,
-                                       const Node& c, int lane, uint32_t& appended_mask) {
-  constexpr uint32_t TMASK = 2 * CAP - 1;
-  const uint32_t h = mix32(c.k0, c.k1, c.k2, c.k3);
-  const uint32_t fp = h >> 16;
-  uint32_t idx = h & TMASK;
-  bool found = false;
-  if (valid) {
-    while (true) {
-      const uint32_t s = tab[idx];
-      if (!s) break;
-      if ((s >> 16) == fp) {
-        const int pp = (int)(s & 0xffffu) - 1;
-        if (F.ld(lvl, 0, pp) == c.k0 && F.ld(lvl, 1, pp) == c.k1 && F.ld(lvl, 2, pp) == c.k2 &&
-            F.ld(lvl, 3, pp) == c.k3) {
-          found = true;
-          break;
-        }
-      }
-      idx = (idx + 1) & TMASK;
-    }
-  }
-  const bool isnew = valid && !found;
-  const uint32_t bal = __ballot_sync(BG_FULL, isnew);
-  appended_mask = bal;
-  const int cnt = __popc(bal);
-  if (n + cnt > CAP) return false;
-  if (isnew) {
-    const int pos = n + __popc(bal & ((1u << lane) - 1u));
-    F.st(lvl, 0, pos, c.k0);
-    F.st(lvl, 1, pos, c.k1);
-    F.st(lvl, 2, pos, c.k2);
-    F.st(lvl, 3, pos, c.k3);
-    F.st(lvl, 4, pos, c.m0);
-    F.st(lvl, 5, pos, c.m1);
-    const uint32_t word = (fp << 16) | (uint32_t)(pos + 1);
-    while (atomicCAS(&tab[idx], 0u, word) != 0u) idx = (idx + 1) & TMASK;
-  }
-  n += cnt;
-  __syncwarp();
-  return true;
-}
-
-template <int CAP, bool GLOBAL>
-__device__ __forceinline__ Node load_node(const Frontier<CAP, GLOBAL>& F, int lvl, int pos) {
+template <int CAP, bool GLOBAL, bool MOVES>
+__device__ __forceinline__ Node load_node(const Frontier<CAP, GLOBAL, MOVES>& F, int lvl, int pos) {
   Node p;
   p.k0 = F.ld(lvl, 0, pos);
   p.k1 = F.ld(lvl, 1, pos);
   p.k2 = F.ld(lvl, 2, pos);
   p.k3 = F.ld(lvl, 3, pos);
-  p.m0 = F.ld(lvl, 4, pos);
-  p.m1 = F.ld(lvl, 5, pos);
+  if constexpr (MOVES) {
+    p.m0 = F.ld(lvl, 4, pos);
+    p.m1 = F.ld(lvl, 5, pos);
+  } else {
+    p.m0 = p.m1 = 0u;
+  }
   return p;
+}
+
+template <int CAP, bool GLOBAL, bool MOVES>
+__device__ __forceinline__ void store_node(const Frontier<CAP, GLOBAL, MOVES>& F, int lvl, int pos, const Node& c) {
+  F.st(lvl, 0, pos, c.k0);
+  F.st(lvl, 1, pos, c.k1);
+  F.st(lvl, 2, pos, c.k2);
+  F.st(lvl, 3, pos, c.k3);
+  if constexpr (MOVES) {
+    F.st(lvl, 4, pos, c.m0);
+    F.st(lvl, 5, pos, c.m1);
+  }
 }
 
 template <int CAP>
@@ -194,11 +162,82 @@ __device__ __forceinline__ void clear_table(uint32_t* tab, int lane) {
 }
 
 enum { ITEM_OK = 0, ITEM_OVERFLOW = 1, ITEM_BAD = 2 };
+enum { MODE_EXPAND = 0, MODE_IDENTITY = 1 };
 
-// Generates the ordered legal afterstate list of one item into frontier level `out_lvl` (n_out nodes).
-template <int CAP, bool GLOBAL>
-__device__ int generate(const Frontier<CAP, GLOBAL>& F, uint32_t* tab, const uint32_t* rootw, int player, int d0, int d1,
-                        int lane, int& out_lvl, int& n_out) {
+// THE inner loop (kept out of line so the kernel has exactly one copy of it: the fully inlined variant was 55 KB of
+// SASS and stalled on instruction fetch).  For each parent src[src_off + j], j < n_src, in order: expand by `die`
+// (lane == move slot; MODE_IDENTITY re-emits the parent itself) and append the valid children to dst[...n_dst) in slot
+// order.  With dedup, a child whose key is already in `tab` is dropped (first occurrence wins); within one parent all
+// children are distinct, so only earlier parents / earlier calls can hold a duplicate.
+// Returns false on capacity overflow.  flags: bit0 some child was valid, bit1 some child was appended.
+template <int CAP, bool GLOBAL, bool MOVES>
+__device__ __noinline__ bool expand_level(const Frontier<CAP, GLOBAL, MOVES> F, uint32_t* tab, const Root r, int src_lvl, int src_off,
+                                          int n_src, int dst_lvl, int& n_dst, bool dedup, int mode, int die, int depth, uint32_t& flags) {
+  constexpr uint32_t TMASK = 2 * CAP - 1;
+  const int lane = threadIdx.x & 31;
+  int n = n_dst;
+  uint32_t fl = 0;
+  for (int j = 0; j < n_src; ++j) {
+    const Node p = load_node(F, src_lvl, src_off + j);
+    Node c;
+    bool valid;
+    if (mode == MODE_EXPAND) {
+      valid = expand(p, r, die, depth, lane, c);
+    } else {
+      valid = lane == 0;
+      c = p;
+    }
+    uint32_t idx = 0, fp = 0;
+    bool found = false;
+    if (dedup && valid) {
+      const uint32_t h = mix32(c.k0, c.k1, c.k2, c.k3);
+      fp = h >> 16;
+      idx = h & TMASK;
+      while (true) {
+        const uint32_t s = tab[idx];
+        if (!s) break;
+        if ((s >> 16) == fp) {
+          const int pp = (int)(s & 0xffffu) - 1;
+          if (F.ld(dst_lvl, 0, pp) == c.k0 && F.ld(dst_lvl, 1, pp) == c.k1 && F.ld(dst_lvl, 2, pp) == c.k2 &&
+              F.ld(dst_lvl, 3, pp) == c.k3) {
+            found = true;
+            break;
+          }
+        }
+        idx = (idx + 1) & TMASK;
+      }
+    }
+    const bool isnew = valid && !found;
+    const uint32_t bv = __ballot_sync(BG_FULL, valid);
+    const uint32_t bal = __ballot_sync(BG_FULL, isnew);
+    fl |= (bv ? 1u : 0u) | (bal ? 2u : 0u);
+    const int cnt = __popc(bal);
+    if (n + cnt > CAP) return false;
+    if (isnew) {
+      const int pos = n + __popc(bal & ((1u << lane) - 1u));
+      store_node(F, dst_lvl, pos, c);
+      if (dedup) {
+        const uint32_t word = (fp << 16) | (uint32_t)(pos + 1);
+        while (atomicCAS(&tab[idx], 0u, word) != 0u) idx = (idx + 1) & TMASK;
+      }
+    }
+    n += cnt;
+    __syncwarp();
+  }
+  n_dst = n;
+  flags = fl;
+  return true;
+}
+
+// Result of one item: up to two index ranges [a0,a1) ++ [b0,b1) of frontier level `lvl`, in output order.
+struct ItemOut {
+  int lvl, a0, a1, b0, b1;
+};
+
+// Generates the ordered legal afterstate list of one item.
+template <int CAP, bool GLOBAL, bool MOVES>
+__device__ __forceinline__ int generate(const Frontier<CAP, GLOBAL, MOVES>& F, uint32_t* tab, const uint32_t* rootw, int player, int d0,
+                                        int d1, int lane, ItemOut& out) {
   // ---- root ------------------------------------------------------------------------------------------
   const int ob = player * 6, pb = (1 - player) * 6;
   uint32_t bad = 0;
@@ -231,114 +270,75 @@ __device__ int generate(const Frontier<CAP, GLOBAL>& F, uint32_t* tab, const uin
     }
     r.valid15 = total == 15u;
   }
-  uint32_t am;
-  if (d0 == d1) {
+  if (lane == 0) store_node(F, 0, 0, root);
+  __syncwarp();
+  uint32_t fl;
+  const bool doubles = d0 == d1;
+  const int hi = d0 > d1 ? d0 : d1, lo = d0 > d1 ? d1 : d0;
+  clear_table<CAP>(tab, lane);
+  if (doubles) {
     // ---- doubles: BFS by ply with per-ply dedup (handle_move_types.py:84-193) ------------------------
-    int cur = 0, n_cur = 1;
-    if (lane == 0) {
-      F.st(0, 0, 0, root.k0);
-      F.st(0, 1, 0, root.k1);
-      F.st(0, 2, 0, root.k2);
-      F.st(0, 3, 0, root.k3);
-      F.st(0, 4, 0, 0u);
-      F.st(0, 5, 0, 0u);
-    }
-    __syncwarp();
-    int depth_done = 0;
+    int cur = 0, n_cur = 1, depth_done = 0;
     for (int depth = 0; depth < 4; ++depth) {
-      clear_table<CAP>(tab, lane);
+      if (depth) clear_table<CAP>(tab, lane);
       int n_next = 0;
-      for (int j = 0; j < n_cur; ++j) {
-        const Node p = load_node(F, cur, j);
-        Node c;
-        const bool v = expand(p, r, d0, depth, lane, c);
-        if (!append(F, tab, cur ^ 1, n_next, v, c, lane, am)) return ITEM_OVERFLOW;
-      }
+      if (!expand_level(F, tab, r, cur, 0, n_cur, cur ^ 1, n_next, true, MODE_EXPAND, d0, depth, fl)) return ITEM_OVERFLOW;
       if (n_next == 0) break;
       cur ^= 1;
       n_cur = n_next;
       depth_done = depth + 1;
     }
-    out_lvl = cur;
-    n_out = depth_done == 0 ? 0 : n_cur;
+    out.lvl = cur;
+    out.a0 = 0;
+    out.a1 = depth_done == 0 ? 0 : n_cur;
+    out.b0 = out.b1 = 0;
     return ITEM_OK;
   }
-  // ---- non-doubles: literal two-order control flow (generate_all_moves.py:25-53, handle_move_types.py:7-81)
-  const int hi = d0 > d1 ? d0 : d1, lo = d0 > d1 ? d1 : d0;
-  clear_table<CAP>(tab, lane);
-  int n_res = 0;      // result list lives in level 1
-  bool has2 = false;  // a two-sub-move entry was appended
+  // ---- non-doubles: literal two-order control flow (generate_all_moves.py:25-53, handle_move_types.py:7-81) ----
+  // level 0: root at [0], the first-die boards at [1, 1+n1); level 1: the result list (shared seen-set `tab`).
+  // Entries are appended in two phases (one per die order), each of uniform length (2 sub-moves, or 1 when the order
+  // has no two-move play), so the max-sub-moves filter (generate_all_moves.py:69-90) is a choice of phase ranges.
+  int n_res = 0, n_a = 0, len_a = 0, len_b = 0;
   for (int order = 0; order < 2; ++order) {
     const int dA = order == 0 ? hi : lo, dB = order == 0 ? lo : hi;
-    Node c1;
-    const bool v1 = expand(root, r, dA, 0, lane, c1);
-    const uint32_t b1 = __ballot_sync(BG_FULL, v1);
-    const int n1 = __popc(b1);
-    if (v1) {  // first-die boards are pairwise distinct: compact into level 0 without dedup
-      const int pos = __popc(b1 & ((1u << lane) - 1u));
-      F.st(0, 0, pos, c1.k0);
-      F.st(0, 1, pos, c1.k1);
-      F.st(0, 2, pos, c1.k2);
-      F.st(0, 3, pos, c1.k3);
-      F.st(0, 4, pos, c1.m0);
-      F.st(0, 5, pos, c1.m1);
+    int n1 = 1;  // appended after the root; first-die boards are pairwise distinct -> no dedup
+    if (!expand_level(F, tab, r, 0, 0, 1, 0, n1, false, MODE_EXPAND, dA, 0, fl)) return ITEM_OVERFLOW;
+    n1 -= 1;
+    if (!expand_level(F, tab, r, 0, 1, n1, 1, n_res, true, MODE_EXPAND, dB, 1, fl)) return ITEM_OVERFLOW;
+    int len = 2;
+    if (!(fl & 1u)) {  // no two-move sequence in this order: singles, in first-die order (handle_move_types.py:70-81)
+      len = 1;
+      if (!expand_level(F, tab, r, 0, 1, n1, 1, n_res, true, MODE_IDENTITY, dA, 0, fl)) return ITEM_OVERFLOW;
     }
-    __syncwarp();
-    bool any2 = false;
-    for (int j = 0; j < n1; ++j) {
-      const Node p = load_node(F, 0, j);
-      Node c;
-      const bool v = expand(p, r, dB, 1, lane, c);
-      any2 |= __any_sync(BG_FULL, v);
-      if (!append(F, tab, 1, n_res, v, c, lane, am)) return ITEM_OVERFLOW;
-      has2 |= am != 0u;
+    if (order == 0) {
+      n_a = n_res;
+      len_a = len;
+      // quirk Q1 (generate_all_moves.py:40-50): reverse order skipped iff exactly one 1-sub-move result
+      if (n_res == 1 && len == 1) break;
+    } else {
+      len_b = len;
     }
-    if (!any2 && n1 > 0) {  // singles, in first-die order (handle_move_types.py:70-81)
-      Node s;
-      const bool v = lane < n1;
-      if (v) s = load_node(F, 0, lane);
-      if (!append(F, tab, 1, n_res, v, s, lane, am)) return ITEM_OVERFLOW;
-    }
-    // quirk Q1 (generate_all_moves.py:40-50): reverse order skipped iff exactly one 1-sub-move result
-    if (order == 0 && n_res == 1 && !has2) break;
   }
-  // max-sub-moves filter (generate_all_moves.py:69-90), order preserving, into level 0
-  int n_f = 0;
-  for (int base = 0; base < n_res; base += 32) {
-    const int i = base + lane;
-    Node e;
-    bool keep = false;
-    if (i < n_res) {
-      e = load_node(F, 1, i);
-      const bool len2 = (e.m0 >> 27) & 1u;
-      keep = len2 == has2;
-    }
-    const uint32_t bk = __ballot_sync(BG_FULL, keep);
-    if (keep) {
-      const int pos = n_f + __popc(bk & ((1u << lane) - 1u));
-      F.st(0, 0, pos, e.k0);
-      F.st(0, 1, pos, e.k1);
-      F.st(0, 2, pos, e.k2);
-      F.st(0, 3, pos, e.k3);
-      F.st(0, 4, pos, e.m0);
-      F.st(0, 5, pos, e.m1);
-    }
-    n_f += __popc(bk);
-  }
-  __syncwarp();
-  out_lvl = 0;
-  n_out = n_f;
+  // a phase that appended nothing has no entries and does not define the maximum
+  const int la = n_a > 0 ? len_a : 0, lb = n_res > n_a ? len_b : 0;
+  const int maxlen = la > lb ? la : lb;
+  out.lvl = 1;
+  out.a0 = 0;
+  out.a1 = la == maxlen ? n_a : 0;
+  out.b0 = n_a;
+  out.b1 = lb == maxlen ? n_res : n_a;
   return ITEM_OK;
 }
 
-template <int CAP, bool GLOBAL, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_movegen(MovegenParams P) {
+template <int CAP, bool GLOBAL, bool MOVES, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_movegen(MovegenParams P) {
   extern __shared__ uint32_t smem[];
+  constexpr int NF = MOVES ? 6 : 4;
   constexpr int FRONT_WORDS = GLOBAL ? 0 : 2 * NF * CAP;
   constexpr int PER_WARP = FRONT_WORDS + 2 * CAP + 16;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t* my = smem + wib * PER_WARP;
-  Frontier<CAP, GLOBAL> F;
+  Frontier<CAP, GLOBAL, MOVES> F;
   if constexpr (GLOBAL)
     F.base = P.gfront + (size_t)(blockIdx.x * WARPS + wib) * (2 * NF * CAP);
   else
@@ -368,8 +368,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_movegen(MovegenParams P) {
       __syncwarp();
       const int player = P.players[item] & 1;
       const int d0 = P.rolls[2 * (int64_t)item], d1 = P.rolls[2 * (int64_t)item + 1];
-      int lvl = 0, n = 0;
-      const int rc = generate<CAP, GLOBAL>(F, tab, rootw, player, d0, d1, lane, lvl, n);
+      ItemOut io;
+      const int rc = generate<CAP, GLOBAL, MOVES>(F, tab, rootw, player, d0, d1, lane, io);
       if (rc == ITEM_OVERFLOW) {
         if (lane == 0) {
           if (P.ovf_list) {
@@ -392,6 +392,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_movegen(MovegenParams P) {
         continue;
       }
       // ---- emit --------------------------------------------------------------------------------------
+      const int lvl = io.lvl, na = io.a1 - io.a0;
+      const int n = na + (io.b1 - io.b0);
       const int n_keep = n < P.item_cap ? n : P.item_cap;
       long long base = 0;
       if (lane == 0) {
@@ -409,7 +411,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_movegen(MovegenParams P) {
       const uint32_t w12 = rootw[12];
       const uint32_t opp_bar = (w12 >> (8 * (1 - player))) & 0xffu, opp_off = (w12 >> (16 + 8 * (1 - player))) & 0xffu;
       for (int tt = lane; tt < n_keep * 13; tt += 32) {
-        const int b = tt / 13, w = tt - b * 13;
+        const int bo = tt / 13, w = tt - bo * 13;
+        const int b = bo < na ? io.a0 + bo : io.b0 + (bo - na);
         uint32_t word;
         if (w < 12) {
           const int side = w >= 6, q = w - side * 6;
@@ -430,9 +433,12 @@ __global__ void __launch_bounds__(WARPS * 32) k_movegen(MovegenParams P) {
       }
       if (P.out_owner)
         for (int b = lane; b < n_keep; b += 32) P.out_owner[base + b] = item;
-      if (P.out_submoves) {
+      if (P.out_flags)
+        for (int b = lane; b < n_keep; b += 32) P.out_flags[base + b] = (uint8_t)player;
+      if constexpr (MOVES) {
         uint32_t* os = reinterpret_cast<uint32_t*>(P.out_submoves) + base * 3;
-        for (int b = lane; b < n_keep; b += 32) {
+        for (int bo = lane; bo < n_keep; bo += 32) {
+          const int b = bo < na ? io.a0 + bo : io.b0 + (bo - na);
           const uint32_t m[2] = {F.ld(lvl, 4, b), F.ld(lvl, 5, b)};
           uint8_t by[12];
 #pragma unroll
@@ -445,24 +451,73 @@ __global__ void __launch_bounds__(WARPS * 32) k_movegen(MovegenParams P) {
           }
 #pragma unroll
           for (int q = 0; q < 3; ++q)
-            os[b * 3 + q] = by[4 * q] | (by[4 * q + 1] << 8) | (by[4 * q + 2] << 16) | ((uint32_t)by[4 * q + 3] << 24);
+            os[bo * 3 + q] = by[4 * q] | (by[4 * q + 1] << 8) | (by[4 * q + 2] << 16) | ((uint32_t)by[4 * q + 3] << 24);
         }
       }
     }
   }
 }
 
-constexpr int T1_CAP = 128, T1_WARPS = 4, T1_CTAS_PER_SM = 7;
-constexpr int T2_CAP = 1024, T2_WARPS = 1, T2_CTAS_PER_SM = 3;
-constexpr int T3_CAP = 4096, T3_WARPS = 1, T3_CTAS_PER_SM = 2;
+// capacity tiers: nodes per ply.  T1/T2 keep the frontiers in shared memory, T3 in L2-resident global scratch.
+constexpr int T1_CAP = 128, T1_WARPS = 4, T1_CTAS_PER_SM = 8;
+constexpr int T2_CAP = 512, T2_WARPS = 2, T2_CTAS_PER_SM = 4;
+constexpr int T3_CAP = 4096, T3_WARPS = 2, T3_CTAS_PER_SM = 3;
 constexpr int NUM_SMS = 148;
 
-constexpr size_t smem_bytes(int cap, bool global, int warps) {
-  return (size_t)warps * ((global ? 0 : 2 * NF * cap) + 2 * cap + 16) * 4;
+constexpr size_t smem_bytes(int cap, bool global, bool moves, int warps) {
+  return (size_t)warps * ((global ? 0 : 2 * (moves ? 6 : 4) * cap) + 2 * cap + 16) * 4;
 }
 
 constexpr int64_t HDR_BYTES = 256;
-constexpr int64_t GFRONT_BYTES = (int64_t)NUM_SMS * T3_CTAS_PER_SM * T3_WARPS * 2 * NF * T3_CAP * 4;
+constexpr int64_t GFRONT_BYTES = (int64_t)NUM_SMS * T3_CTAS_PER_SM * T3_WARPS * 2 * 6 * T3_CAP * 4;
+
+template <bool MOVES>
+int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* ovf2, int32_t* ovf3, int32_t* ovf2_n, int32_t* ovf3_n,
+                     cudaStream_t stream) {
+  auto k1 = k_movegen<T1_CAP, false, MOVES, T1_WARPS, T1_CTAS_PER_SM>;
+  auto k2 = k_movegen<T2_CAP, false, MOVES, T2_WARPS, T2_CTAS_PER_SM>;
+  auto k3 = k_movegen<T3_CAP, true, MOVES, T3_WARPS, T3_CTAS_PER_SM>;
+  constexpr size_t s1 = smem_bytes(T1_CAP, false, MOVES, T1_WARPS), s2 = smem_bytes(T2_CAP, false, MOVES, T2_WARPS),
+                   s3 = smem_bytes(T3_CAP, true, MOVES, T3_WARPS);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tier1)");
+    e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tier2)");
+    e = cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tier3)");
+    attr_done = true;
+  }
+  // tier 1: every item
+  P.item_counter = ctr + 0;
+  P.in_list = nullptr;
+  P.in_count = nullptr;
+  P.ovf_list = ovf2;
+  P.ovf_count = ovf2_n;
+  P.grab = B > (1 << 20) ? 8 : 1;
+  int64_t want = (B + T1_WARPS - 1) / T1_WARPS;
+  int grid = (int)(want < (int64_t)NUM_SMS * T1_CTAS_PER_SM ? want : (int64_t)NUM_SMS * T1_CTAS_PER_SM);
+  k1<<<grid, T1_WARPS * 32, s1, stream>>>(P);
+  // tier 2: items that overflowed 128 nodes in some ply
+  P.item_counter = ctr + 1;
+  P.in_list = ovf2;
+  P.in_count = ovf2_n;
+  P.ovf_list = ovf3;
+  P.ovf_count = ovf3_n;
+  P.grab = 1;
+  k2<<<NUM_SMS * T2_CTAS_PER_SM, T2_WARPS * 32, s2, stream>>>(P);
+  // tier 3: items that overflowed 512 nodes
+  P.item_counter = ctr + 2;
+  P.in_list = ovf3;
+  P.in_count = ovf3_n;
+  P.ovf_list = nullptr;
+  P.ovf_count = nullptr;
+  k3<<<NUM_SMS * T3_CTAS_PER_SM, T3_WARPS * 32, s3, stream>>>(P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return check_cuda(e, "k_movegen launch");
+  return BG_OK;
+}
 
 }  // namespace
 
@@ -483,20 +538,6 @@ int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream) {
               (long long)movegen_workspace_bytes(a.B));
     return BG_ERR_ARG;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e;
-    e = cudaFuncSetAttribute(k_movegen<T1_CAP, false, T1_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem_bytes(T1_CAP, false, T1_WARPS));
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tier1)");
-    e = cudaFuncSetAttribute(k_movegen<T2_CAP, false, T2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem_bytes(T2_CAP, false, T2_WARPS));
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tier2)");
-    e = cudaFuncSetAttribute(k_movegen<T3_CAP, true, T3_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem_bytes(T3_CAP, true, T3_WARPS));
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tier3)");
-    attr_done = true;
-  }
   char* ws = (char*)a.workspace;
   cudaError_t e = cudaMemsetAsync(ws, 0, HDR_BYTES, stream);
   if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(workspace)");
@@ -511,6 +552,7 @@ int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream) {
   P.out_boards = a.out_boards;
   P.out_submoves = a.out_submoves;
   P.out_owner = a.out_owner;
+  P.out_flags = a.out_flags;
   P.out_offsets = (long long*)a.out_offsets;
   P.out_count = a.out_count;
   P.pool_cursor = (unsigned long long*)ws;
@@ -523,36 +565,11 @@ int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream) {
   int32_t* ovf2_n = (int32_t*)(ws + 24);
   int32_t* ovf3_n = (int32_t*)(ws + 28);
   if (a.B > 0) {
-    // tier 1
-    P.item_counter = ctr + 0;
-    P.in_list = nullptr;
-    P.in_count = nullptr;
-    P.ovf_list = ovf2;
-    P.ovf_count = ovf2_n;
-    P.grab = a.B > (1 << 20) ? 8 : 1;
-    int64_t want = (a.B + T1_WARPS - 1) / T1_WARPS;
-    int grid = (int)(want < (int64_t)NUM_SMS * T1_CTAS_PER_SM ? want : (int64_t)NUM_SMS * T1_CTAS_PER_SM);
-    k_movegen<T1_CAP, false, T1_WARPS><<<grid, T1_WARPS * 32, smem_bytes(T1_CAP, false, T1_WARPS), stream>>>(P);
-    // tier 2
-    P.item_counter = ctr + 1;
-    P.in_list = ovf2;
-    P.in_count = ovf2_n;
-    P.ovf_list = ovf3;
-    P.ovf_count = ovf3_n;
-    P.grab = 1;
-    k_movegen<T2_CAP, false, T2_WARPS>
-        <<<NUM_SMS * T2_CTAS_PER_SM, T2_WARPS * 32, smem_bytes(T2_CAP, false, T2_WARPS), stream>>>(P);
-    // tier 3
-    P.item_counter = ctr + 2;
-    P.in_list = ovf3;
-    P.in_count = ovf3_n;
-    P.ovf_list = nullptr;
-    P.ovf_count = nullptr;
-    k_movegen<T3_CAP, true, T3_WARPS>
-        <<<NUM_SMS * T3_CTAS_PER_SM, T3_WARPS * 32, smem_bytes(T3_CAP, true, T3_WARPS), stream>>>(P);
+    // the sub-move history (2 extra words per node) is only carried when the caller asks for the FullMove sequences
+    int32_t rc = a.out_submoves ? launch_tiers<true>(P, a.B, ctr, ovf2, ovf3, ovf2_n, ovf3_n, stream)
+                                : launch_tiers<false>(P, a.B, ctr, ovf2, ovf3, ovf2_n, ovf3_n, stream);
+    if (rc != BG_OK) return rc;
   }
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return check_cuda(e, "k_movegen launch");
   if (a.out_total) {
     e = cudaMemcpyAsync(a.out_total, ws, 8, cudaMemcpyDeviceToDevice, stream);
     if (e != cudaSuccess) return check_cuda(e, "copy out_total");

@@ -14,6 +14,7 @@ struct MovegenArgs {
   int8_t* out_boards;
   uint8_t* out_submoves;
   int32_t* out_owner;
+  uint8_t* out_flags;  // optional [pool_cap]: mover (== feature flag player) of each row
   int64_t* out_offsets;
   int32_t* out_count;
   int64_t* out_total;
@@ -34,6 +35,7 @@ struct MovegenParams {
   int8_t* out_boards;
   uint8_t* out_submoves;
   int32_t* out_owner;
+  uint8_t* out_flags;
   long long* out_offsets;
   int32_t* out_count;
   unsigned long long* pool_cursor;

@@ -134,7 +134,7 @@ Layout make_layout(int64_t C) {
   L.o_pool = o;
   o += align256(L.rows * 52);
   L.o_owner = o;
-  o += align256(L.rows * 4);
+  o += align256(L.rows);
   L.o_val = o;
   o += align256(L.rows * 4);
   L.o_ws = o;
@@ -187,7 +187,8 @@ int32_t two_ply_launch(const TwoPlyArgs& a, cudaStream_t s) {
     m.pool_cap = L.rows;
     m.out_boards = (int8_t*)(w + L.o_pool);
     m.out_submoves = nullptr;
-    m.out_owner = (int32_t*)(w + L.o_owner);
+    m.out_owner = nullptr;
+    m.out_flags = (uint8_t*)(w + L.o_owner);
     m.out_offsets = (int64_t*)(w + L.o_off);
     m.out_count = (int32_t*)(w + L.o_cnt);
     m.out_total = (int64_t*)(w + L.o_tot);
@@ -197,7 +198,7 @@ int32_t two_ply_launch(const TwoPlyArgs& a, cudaStream_t s) {
     m.active = nullptr;
     int32_t rc = movegen_launch(m, s);
     if (rc != BG_OK) return rc;
-    EvalArgs ev{m.out_boards, nullptr, m.out_owner, m.players, 0, m.out_total, L.rows, a.prepared, a.H, (float*)(w + L.o_val)};
+    EvalArgs ev{m.out_boards, m.out_flags, nullptr, nullptr, 0, m.out_total, L.rows, a.prepared, a.H, (float*)(w + L.o_val)};
     rc = eval_launch(ev, s);
     if (rc != BG_OK) return rc;
     k_reduce<<<grid, 256, 0, s>>>((const float*)(w + L.o_val), (const long long*)(w + L.o_off), (const int32_t*)(w + L.o_cnt), a.S, c0, nc,

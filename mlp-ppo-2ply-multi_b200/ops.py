@@ -76,6 +76,7 @@ class MovegenResult:
     boards: torch.Tensor  # int8 [pool_cap, 52]; valid rows: union of item segments
     submoves: Optional[torch.Tensor]  # uint8 [pool_cap, 4, 3] or None
     owner: Optional[torch.Tensor]  # int32 [pool_cap] item index of each row
+    flags: Optional[torch.Tensor]  # uint8 [pool_cap] the item's player per row (feature flag of the afterstate)
     offsets: torch.Tensor  # int64 [B] segment start per item (-1 if the item failed)
     counts: torch.Tensor  # int32 [B] TRUE number of legal moves (may exceed item_cap)
     total_dev: torch.Tensor  # int64 [1] rows used
@@ -118,7 +119,8 @@ def _workspace(B: int, device) -> torch.Tensor:
 
 def movegen(boards: torch.Tensor, players: torch.Tensor, rolls: torch.Tensor, item_cap: int = 500, pool_cap: Optional[int] = None,
             want_submoves: bool = False, want_owner: bool = True, check_status: bool = True, out_boards: Optional[torch.Tensor] = None,
-            workspace: Optional[torch.Tensor] = None, out_owner: Optional[torch.Tensor] = None) -> MovegenResult:
+            workspace: Optional[torch.Tensor] = None, out_owner: Optional[torch.Tensor] = None, want_flags: bool = True,
+            out_flags: Optional[torch.Tensor] = None) -> MovegenResult:
     """Batched get_all_possible_moves + execute_full_move_on_board_copy (reference generate_all_moves.py:7, env_helper.py:27)."""
     boards = _req(boards, torch.int8, "boards").reshape(-1, BOARD_BYTES)
     B = boards.shape[0]
@@ -131,15 +133,16 @@ def movegen(boards: torch.Tensor, players: torch.Tensor, rolls: torch.Tensor, it
         out_boards = torch.empty((pool_cap, BOARD_BYTES), dtype=torch.int8, device=dev)
     sub = torch.empty((pool_cap, 4, 3), dtype=torch.uint8, device=dev) if want_submoves else None
     owner = out_owner if out_owner is not None else (torch.empty(pool_cap, dtype=torch.int32, device=dev) if want_owner else None)
+    flags = out_flags if out_flags is not None else (torch.empty(pool_cap, dtype=torch.uint8, device=dev) if want_flags else None)
     offsets = torch.empty(B, dtype=torch.int64, device=dev)
     counts = torch.empty(B, dtype=torch.int32, device=dev)
     total = torch.zeros(1, dtype=torch.int64, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     ws = workspace if workspace is not None else _workspace(B, dev)
     check(lib().bg_movegen(boards.data_ptr(), players.data_ptr(), rolls.data_ptr(), B, item_cap, pool_cap, out_boards.data_ptr(),
-                           _ptr(sub), _ptr(owner), offsets.data_ptr(), counts.data_ptr(), total.data_ptr(), status.data_ptr(),
+                           _ptr(sub), _ptr(owner), _ptr(flags), offsets.data_ptr(), counts.data_ptr(), total.data_ptr(), status.data_ptr(),
                            ws.data_ptr(), ws.numel(), _stream()))
-    res = MovegenResult(out_boards, sub, owner, offsets, counts, total, status, item_cap)
+    res = MovegenResult(out_boards, sub, owner, flags, offsets, counts, total, status, item_cap)
     if check_status:
         res.raise_for_status()
     return res

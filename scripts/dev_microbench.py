@@ -25,7 +25,7 @@ for rolls_name, sel in (("all21", slice(None)), ("nondoubles", None), ("doubles"
         b_, p_, r_ = dib, dip, dir_
     for it in range(3):
         e0 = ev(); res = bg.movegen(b_, p_, r_, item_cap=4096, out_boards=out_boards, check_status=False); e1 = ev()
-        v = bg.evaluate(out_boards, None, w, owner=res.owner, owner_players=p_, n_dev=res.total_dev); e2 = ev()
+        v = bg.evaluate(out_boards, res.flags, w, n_dev=res.total_dev); e2 = ev()
         torch.cuda.synchronize()
     tot = res.total
     tm, te = e0.elapsed_time(e1), e1.elapsed_time(e2)
