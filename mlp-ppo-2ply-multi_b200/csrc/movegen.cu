@@ -10,10 +10,12 @@
 //     root-constant except for hit blots, so the key identifies the resulting board exactly (no hash-only dedup).
 //   * breadth-first by ply: the frontier of unique nodes after k sub-moves is kept ordered by the
 //     lexicographically smallest sub-move index sequence that reaches it.  Expanding frontier nodes in order,
-//     children in the reference's one-die order (lane == move slot: 0..23 point moves ascending, 24 bar entry,
+//     children in the reference's one-die order (move slots: 0..23 point moves ascending, 24 bar entry,
 //     25 bear-off of the farthest checker, 26 exact bear-off), with first-occurrence dedup through a
 //     shared-memory hash set, reproduces the reference's DFS first-occurrence order while visiting each
 //     distinct intermediate board once (the reference re-expands ~5x-8x duplicates).
+//   * inside a ply the work is lane-per-candidate: move sets are slot bitmasks computed lane-per-parent, and the
+//     (parent, move) pairs are flattened over the warp so that every lane builds one child per round.
 //   * non-doubles keep the reference's literal control flow (both die orders, singles only when an order has
 //     no two-move play, quirk Q1 skip, shared seen-set, max-length filter).
 //   * three capacity tiers (128 / 512 nodes per ply in shared memory, 4096 in L2-resident global scratch);
@@ -57,42 +59,68 @@ struct Node {
   uint32_t k0, k1, k2, k3, m0, m1;
 };
 
-// One-die expansion of `p` for this lane's move slot (reference get_moves_with_one_die order == slot order).
-__device__ __forceinline__ bool expand(const Node& p, const Root& r, int die, int depth, int lane, Node& c) {
-  const uint32_t pk[3] = {p.k0, p.k1, p.k2};
-  uint32_t cnt = 0;
-  if (lane < 24) cnt = (pk[lane >> 3] >> ((lane & 7) * 4)) & 15u;
-  const uint32_t occ = __ballot_sync(BG_FULL, cnt > 0) & 0xffffffu;
+// 24 nibbles (3 words) -> 24-bit occupancy mask (bit p set iff nibble p != 0)
+__device__ __forceinline__ uint32_t nib_occupancy(uint32_t w) {  // 8 nibbles -> 8 bits
+  uint32_t t = w | (w >> 1);
+  t |= t >> 2;
+  t &= 0x11111111u;                    // bit 4i = nibble i non-zero
+  t = (t | (t >> 3)) & 0x03030303u;    // byte b: bits 0,1 = nibbles 2b, 2b+1
+  t = (t | (t >> 6)) & 0x000f000fu;    // half h: bits 0..3 = nibbles 4h..4h+3
+  return (t | (t >> 12)) & 0xffu;
+}
+
+// One-die move set of node `p` as a slot mask, in the reference's get_moves_with_one_die order (slot order):
+//   bits 0..23 in-board move from that point, 24 bar entry, 25 bear-off of the farthest checker, 26 exact bear-off;
+//   bits 27..31 carry `last` (the farthest checker's point) for slot 25.
+__device__ __forceinline__ uint32_t move_mask(const Node& p, const Root& r, int die) {
+  const uint32_t occ = nib_occupancy(p.k0) | (nib_occupancy(p.k1) << 8) | (nib_occupancy(p.k2) << 16);
   const uint32_t bar = (p.k3 >> 24) & 15u, off = p.k3 >> 28;
-  const uint32_t blot = r.blot & ~p.k3;
-  bool valid = false;
-  int s = lane, e = 0;
-  if (off == 15u) {
-    // GAME_OVER: no moves (conditions.py:16-17)
-  } else if (bar > 0) {  // ON_BAR (get_moves_one_die.py:86-130)
-    if (lane == 24) {
-      e = r.player == 0 ? die - 1 : 24 - die;
-      valid = !((r.blocked >> e) & 1u);
-    }
-  } else {
-    if (lane < 24) {  // NORMAL (:40-83) and in-home moves of BEAR_OFF (:164-189)
-      e = lane + r.dirsign * die;
-      valid = cnt > 0 && e >= 0 && e < 24 && !((r.blocked >> (e & 31)) & 1u);
-    } else if (r.valid15 && (occ & ~r.home) == 0) {  // BEAR_OFF (:192-249)
-      const int last = r.player == 0 ? (occ ? __ffs(occ) - 1 : 18) : (occ ? 31 - __clz(occ) : 5);
-      if (lane == 25) {
-        s = last;
-        e = 25;
-        valid = r.player == 0 ? (last + die >= 24) : (last - die < 0);
-      } else if (lane == 26) {
-        const int ps = r.player == 0 ? 24 - die : die - 1;
-        s = ps;
-        e = 25;
-        valid = ps != last && ((occ >> ps) & 1u);
-      }
+  if (off == 15u) return 0u;  // GAME_OVER (conditions.py:16-17)
+  if (bar > 0) {              // ON_BAR (get_moves_one_die.py:86-130)
+    const int e = r.player == 0 ? die - 1 : 24 - die;
+    return ((r.blocked >> e) & 1u) ? 0u : (1u << 24);
+  }
+  // NORMAL (:40-83) / in-home moves of BEAR_OFF (:164-189): destination on the board and not blocked
+  uint32_t vm = r.player == 0 ? (occ & ~(r.blocked >> die) & ((1u << (24 - die)) - 1u))
+                              : (occ & ~(r.blocked << die) & (0xffffffu & ~((1u << die) - 1u)));
+  uint32_t last = 0;
+  if (r.valid15 && (occ & ~r.home) == 0) {  // BEAR_OFF (:192-249)
+    last = r.player == 0 ? (occ ? __ffs(occ) - 1 : 18) : (occ ? 31 - __clz(occ) : 5);
+    const bool far_off = r.player == 0 ? ((int)last + die >= 24) : ((int)last - die < 0);
+    const uint32_t ps = r.player == 0 ? 24 - die : die - 1;
+    if (far_off) vm |= 1u << 25;
+    if (ps != last && ((occ >> ps) & 1u)) vm |= 1u << 26;
+  }
+  return vm | (last << 27);
+}
+
+// n-th (0-based) set bit of m
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
+  int pos = 0;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    const int c = __popc((m >> pos) & ((1u << s) - 1u));
+    if (c <= n) {
+      n -= c;
+      pos += s;
     }
   }
-  if (!valid) return false;
+  return pos;
+}
+
+// apply the move in `slot` of parent p (immutable_board.py:183-258 on the packed key)
+__device__ __forceinline__ void make_child(const Node& p, const Root& r, int slot, uint32_t last, int die, int depth, Node& c) {
+  int s, e;
+  if (slot < 24) {
+    s = slot;
+    e = slot + r.dirsign * die;
+  } else if (slot == 24) {
+    s = 24;
+    e = r.player == 0 ? die - 1 : 24 - die;
+  } else {
+    s = slot == 25 ? (int)last : (r.player == 0 ? 24 - die : die - 1);
+    e = 25;
+  }
   uint32_t k[3] = {p.k0, p.k1, p.k2};
   uint32_t k3 = p.k3;
   uint32_t hit = 0;
@@ -113,7 +141,7 @@ __device__ __forceinline__ bool expand(const Node& p, const Root& r, int die, in
     k[0] += we == 0 ? de : 0u;
     k[1] += we == 1 ? de : 0u;
     k[2] += we == 2 ? de : 0u;
-    hit = (blot >> e) & 1u;
+    hit = ((r.blot & ~p.k3) >> e) & 1u;
     k3 |= hit << e;
   }
   const uint32_t sm = (uint32_t)s | ((uint32_t)e << 5) | (hit << 10) | (1u << 11);
@@ -123,7 +151,6 @@ __device__ __forceinline__ bool expand(const Node& p, const Root& r, int die, in
   c.k3 = k3;
   c.m0 = depth < 2 ? (p.m0 | (sm << (16 * depth))) : p.m0;
   c.m1 = depth < 2 ? p.m1 : (p.m1 | (sm << (16 * (depth - 2))));
-  return true;
 }
 
 template <int CAP, bool GLOBAL, bool MOVES>
@@ -165,64 +192,127 @@ enum { ITEM_OK = 0, ITEM_OVERFLOW = 1, ITEM_BAD = 2 };
 enum { MODE_EXPAND = 0, MODE_IDENTITY = 1 };
 
 // THE inner loop (kept out of line so the kernel has exactly one copy of it: the fully inlined variant was 55 KB of
-// SASS and stalled on instruction fetch).  For each parent src[src_off + j], j < n_src, in order: expand by `die`
-// (lane == move slot; MODE_IDENTITY re-emits the parent itself) and append the valid children to dst[...n_dst) in slot
-// order.  With dedup, a child whose key is already in `tab` is dropped (first occurrence wins); within one parent all
-// children are distinct, so only earlier parents / earlier calls can hold a duplicate.
-// Returns false on capacity overflow.  flags: bit0 some child was valid, bit1 some child was appended.
+// SASS and stalled on instruction fetch).  Expands the parents src[src_off .. src_off+n_src) by `die` and appends their
+// children to dst[.. n_dst) IN CANONICAL ORDER (parent order, then the reference's one-die move order).
+//   1. lane-per-parent: each lane derives its parent's move set as a slot bitmask (pure bit arithmetic);
+//   2. lane-per-candidate: the (parent, move) pairs of up to 32 parents are flattened (warp scan + shuffle binary
+//      search + n-th-set-bit), so every lane builds one child per round regardless of how few moves a parent has;
+//   3. dedup, first occurrence wins: equal children inside a round are resolved with match.any on the key hash
+//      (verified on the full 128-bit key; a fingerprint collision falls back to one-lane-at-a-time rounds), earlier rounds
+//      and earlier calls through the shared-memory open-addressing set `tab`;
+//   4. survivors are appended by ballot compaction (order preserving) and inserted with one CAS each.
+// MODE_IDENTITY re-emits the parents themselves (the reference's single-move fallback).
+// Returns false on capacity overflow.  flags: bit0 some child existed, bit1 some child was appended.
 template <int CAP, bool GLOBAL, bool MOVES>
 __device__ __noinline__ bool expand_level(const Frontier<CAP, GLOBAL, MOVES> F, uint32_t* tab, const Root r, int src_lvl, int src_off,
                                           int n_src, int dst_lvl, int& n_dst, bool dedup, int mode, int die, int depth, uint32_t& flags) {
   constexpr uint32_t TMASK = 2 * CAP - 1;
   const int lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
   int n = n_dst;
   uint32_t fl = 0;
-  for (int j = 0; j < n_src; ++j) {
-    const Node p = load_node(F, src_lvl, src_off + j);
-    Node c;
-    bool valid;
-    if (mode == MODE_EXPAND) {
-      valid = expand(p, r, die, depth, lane, c);
-    } else {
-      valid = lane == 0;
-      c = p;
+  for (int pb = 0; pb < n_src; pb += 32) {
+    // ---- 1. move sets of up to 32 parents ---------------------------------------------------------------------------
+    uint32_t vmw = 0;
+    if (pb + lane < n_src) {
+      if (mode == MODE_EXPAND) {
+        Node p;
+        p.k0 = F.ld(src_lvl, 0, src_off + pb + lane);
+        p.k1 = F.ld(src_lvl, 1, src_off + pb + lane);
+        p.k2 = F.ld(src_lvl, 2, src_off + pb + lane);
+        p.k3 = F.ld(src_lvl, 3, src_off + pb + lane);
+        vmw = move_mask(p, r, die);
+      } else {
+        vmw = 1u;
+      }
     }
-    uint32_t idx = 0, fp = 0;
-    bool found = false;
-    if (dedup && valid) {
-      const uint32_t h = mix32(c.k0, c.k1, c.k2, c.k3);
-      fp = h >> 16;
-      idx = h & TMASK;
-      while (true) {
-        const uint32_t s = tab[idx];
-        if (!s) break;
-        if ((s >> 16) == fp) {
-          const int pp = (int)(s & 0xffffu) - 1;
-          if (F.ld(dst_lvl, 0, pp) == c.k0 && F.ld(dst_lvl, 1, pp) == c.k1 && F.ld(dst_lvl, 2, pp) == c.k2 &&
-              F.ld(dst_lvl, 3, pp) == c.k3) {
-            found = true;
-            break;
+    const int cnt = __popc(vmw & 0x7ffffffu);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(BG_FULL, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const int total = __shfl_sync(BG_FULL, inc, 31);
+    const int exc = inc - cnt;
+    if (total) fl |= 1u;
+    // ---- 2..4. rounds of 32 candidates ------------------------------------------------------------------------------------
+    for (int b0 = 0; b0 < total; b0 += 32) {
+      const int t = b0 + lane;
+      const bool cv = t < total;
+      int q = 0;  // owner parent lane: number of parents whose inclusive end <= t
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) {
+        const int v = __shfl_sync(BG_FULL, inc, (q + sft - 1) & 31);
+        if (v <= t && q + sft <= 32) q += sft;
+      }
+      q &= 31;
+      const int rank = t - __shfl_sync(BG_FULL, exc, q);
+      const uint32_t vq = __shfl_sync(BG_FULL, vmw, q);
+      Node c;
+      c.k0 = c.k1 = c.k2 = c.k3 = c.m0 = c.m1 = 0u;
+      if (cv) {
+        const Node p = load_node(F, src_lvl, src_off + pb + q);
+        if (mode == MODE_EXPAND)
+          make_child(p, r, nth_set_bit(vq & 0x7ffffffu, rank), vq >> 27, die, depth, c);
+        else
+          c = p;
+      }
+      uint32_t h = 0, fp = 0;
+      bool dup = false, collide = false;
+      if (dedup) {
+        h = mix32(c.k0, c.k1, c.k2, c.k3);
+        fp = h >> 16;
+        // equal children inside this round: lowest lane of each hash group leads, the others compare against it
+        const uint32_t grp = __match_any_sync(BG_FULL, cv ? h : (0x80000000u ^ (uint32_t)lane ^ (h & 0u)));
+        const uint32_t cvm = __ballot_sync(BG_FULL, cv);
+        const int leader = __ffs(grp & cvm) - 1;
+        const int ls = leader < 0 ? lane : leader;
+        const uint32_t l0 = __shfl_sync(BG_FULL, c.k0, ls), l1 = __shfl_sync(BG_FULL, c.k1, ls), l2 = __shfl_sync(BG_FULL, c.k2, ls),
+                       l3 = __shfl_sync(BG_FULL, c.k3, ls);
+        const bool same = l0 == c.k0 && l1 == c.k1 && l2 == c.k2 && l3 == c.k3;
+        dup = cv && ls != lane && same;
+        collide = cv && ls != lane && !same;
+      }
+      // normally one pass over all lanes; after a 32-bit hash collision inside the round, one lane per pass (exact)
+      const bool slow = __any_sync(BG_FULL, collide);
+      const int npass = slow ? 32 : 1;
+      for (int pass = 0; pass < npass; ++pass) {
+        const bool act = cv && (slow ? lane == pass : !dup);
+        uint32_t idx = h & TMASK;
+        bool found = false;
+        if (dedup && act) {
+          while (true) {
+            const uint32_t sw = tab[idx];
+            if (!sw) break;
+            if ((sw >> 16) == fp) {
+              const int pp = (int)(sw & 0xffffu) - 1;
+              if (F.ld(dst_lvl, 0, pp) == c.k0 && F.ld(dst_lvl, 1, pp) == c.k1 && F.ld(dst_lvl, 2, pp) == c.k2 &&
+                  F.ld(dst_lvl, 3, pp) == c.k3) {
+                found = true;
+                break;
+              }
+            }
+            idx = (idx + 1) & TMASK;
           }
         }
-        idx = (idx + 1) & TMASK;
+        const bool isnew = act && !found;
+        const uint32_t bal = __ballot_sync(BG_FULL, isnew);
+        const int add = __popc(bal);
+        if (add) fl |= 2u;
+        if (n + add > CAP) return false;
+        if (isnew) {
+          const int pos = n + __popc(bal & lt);
+          store_node(F, dst_lvl, pos, c);
+          if (dedup) {
+            const uint32_t word = (fp << 16) | (uint32_t)(pos + 1);
+            while (atomicCAS(&tab[idx], 0u, word) != 0u) idx = (idx + 1) & TMASK;
+          }
+        }
+        n += add;
+        __syncwarp();
       }
     }
-    const bool isnew = valid && !found;
-    const uint32_t bv = __ballot_sync(BG_FULL, valid);
-    const uint32_t bal = __ballot_sync(BG_FULL, isnew);
-    fl |= (bv ? 1u : 0u) | (bal ? 2u : 0u);
-    const int cnt = __popc(bal);
-    if (n + cnt > CAP) return false;
-    if (isnew) {
-      const int pos = n + __popc(bal & ((1u << lane) - 1u));
-      store_node(F, dst_lvl, pos, c);
-      if (dedup) {
-        const uint32_t word = (fp << 16) | (uint32_t)(pos + 1);
-        while (atomicCAS(&tab[idx], 0u, word) != 0u) idx = (idx + 1) & TMASK;
-      }
-    }
-    n += cnt;
-    __syncwarp();
   }
   n_dst = n;
   flags = fl;

@@ -1,0 +1,107 @@
+"""CPU tests (gloo, world_size 2) of the multi-GPU host logic: game sharding, the weight-blob broadcast that replaces
+ParameterManager polling, and the statistics reduction.  The data path itself has no collective (games are independent)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import mlp_ppo_2ply_multi_b200 as bg
+    from mlp_ppo_2ply_multi_b200 import distributed as bgd
+
+    torch.manual_seed(100 + rank)  # ranks start from DIFFERENT weights
+    pm = bg.ParameterManager(hidden_size=128)
+    if rank == 0:
+        net = bg.BackgammonPolicyNetwork()
+        pm.set_parameters(net.state_dict())  # trainer rank publishes -> one broadcast
+        pm.set_parameters(net.state_dict())
+    else:
+        pm.sync_from_source()
+        pm.sync_from_source()
+    packed = bg.pack_weights(pm.get_parameters())
+    n_local, base = bgd.shard_games(65536 + 1, rank, world)
+    stats = bgd.all_reduce_stats({"games": 10 + rank, "steps": 1000 * (rank + 1), "afterstates": 7})
+    w, ver, temp = bgd.broadcast_weights(packed * (rank + 1), 5 + rank, 1.25 - rank, src=0)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), packed=packed.numpy(), version=pm.get_version(), temperature=pm.get_temperature(),
+             n_local=n_local, base=base, games=stats["games"], steps=stats["steps"], after=stats["afterstates"], w=w.numpy(), ver=ver, temp=temp)
+    dist.destroy_process_group()
+
+
+def test_two_rank_weight_broadcast_sharding_and_stats(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = (np.load(tmp_path / f"r{r}.npz") for r in range(world))
+    assert np.array_equal(r0["packed"], r1["packed"])  # both ranks hold the trainer rank's weights
+    assert int(r0["version"]) == int(r1["version"]) == 3
+    assert float(r0["temperature"]) == float(r1["temperature"]) == pytest.approx(1.5 - 1.0 * 2 / 4000)
+    assert int(r0["n_local"]) + int(r1["n_local"]) == 65537 and int(r0["base"]) == 0 and int(r1["base"]) == int(r0["n_local"])
+    assert int(r0["games"]) == int(r1["games"]) == 21 and int(r0["steps"]) == 3000 and int(r1["after"]) == 14
+    assert np.array_equal(r0["w"], r1["w"]) and int(r1["ver"]) == 5 and float(r1["temp"]) == 1.25
+
+
+def test_shard_games_partition():
+    from mlp_ppo_2ply_multi_b200.distributed import shard_games
+
+    for total, world in ((65536, 8), (10, 4), (7, 8), (1, 1)):
+        parts = [shard_games(total, r, world) for r in range(world)]
+        assert sum(n for n, _ in parts) == total
+        pos = 0
+        for n, b in parts:
+            assert b == pos
+            pos += n
+
+
+def test_temperature_schedule_matches_reference_formula():
+    import mlp_ppo_2ply_multi_b200 as bg
+
+    # reference src/multi/parameter_manager.py:93-111 with INITIAL 1.5, FINAL 0.5, MAX_UPDATES 4000
+    assert bg.temperature_for_version(0) == 1.5 and bg.temperature_for_version(1) == 1.5
+    assert bg.temperature_for_version(2001) == pytest.approx(1.0)
+    assert bg.temperature_for_version(4001) == 0.5 and bg.temperature_for_version(10**6) == 0.5
+
+
+def test_episode_record_semantics():
+    import mlp_ppo_2ply_multi_b200 as bg
+
+    ep = bg.Episode()
+    e = bg.Experience(torch.zeros(198), 0.5, torch.tensor(0.3), False, torch.ones(198), 0.7)
+    ep.add_experience(e, {"current_player": bg.Player.PLAYER1, "close_out_reward": True})
+    ep.add_experience(bg.Experience(torch.zeros(198), 0.1, torch.tensor(1.0), True, torch.ones(198), 0.2),
+                      {"current_player": bg.Player.PLAYER2, "win_type": "gammon", "winner": bg.Player.PLAYER2})
+    assert ep.win_type == "gammon" and ep.close_out_counts == {bg.Player.PLAYER1: 1, bg.Player.PLAYER2: 0}
+    assert ep.prime_reward_counts == {bg.Player.PLAYER1: 0, bg.Player.PLAYER2: 0}
+    ep.to_numpy()
+    assert isinstance(ep.experiences[0].observation, np.ndarray) and isinstance(ep.experiences[0].state_value, float)
+    ep.to_tensor()
+    x = ep.experiences[1]
+    assert x.observation.dtype == torch.float32 and x.state_value.dtype == torch.float32 and x.done.dtype == torch.int64  # bool -> int64 as in the reference
+
+
+def test_policy_network_state_dict_contract():
+    import mlp_ppo_2ply_multi_b200 as bg
+
+    net = bg.BackgammonPolicyNetwork()
+    sd = net.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {"fc1.weight": (128, 198), "fc1.bias": (128,), "value_head.weight": (1, 128),
+                                                          "value_head.bias": (1,)}
+    x = torch.rand(5, 198)
+    want = (torch.sigmoid(x @ sd["fc1.weight"].t() + sd["fc1.bias"]) @ sd["value_head.weight"].t() + sd["value_head.bias"]).squeeze(-1)
+    assert torch.allclose(net(x), want, atol=1e-6)
+    packed = bg.pack_weights(sd)
+    assert packed.numel() == 200 * 128 + 1
+    back = bg.unpack_weights(packed, 128)
+    assert all(torch.equal(back[k], sd[k]) for k in sd)
