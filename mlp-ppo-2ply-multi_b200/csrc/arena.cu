@@ -56,7 +56,8 @@ struct ArenaDev {
   int64_t* ep_start;  // [EPS] absolute experience cursor of the episode's first record
   int32_t* ep_len;    // [EPS]
   int32_t* ep_info;   // [EPS][BG_EP_INFO_INTS]
-  unsigned long long* ring;  // [0] head (eps<<40 | exps), [1] tail_eps, [2] tail_exps, [3] plan n_take, [4] plan end_exps
+  unsigned long long* ring;  // [0] head (eps<<40 | exps), [1] tail_eps, [2] tail_exps, [3] plan n_take, [4] plan end_exps,
+                             // [5] end of the successful reservations, [6] limit eps, [7] limit exps
   // stats
   unsigned long long* stats;  // [BG_ARENA_NSTATS]
   // tape
@@ -149,22 +150,18 @@ __device__ __forceinline__ bool finalize_episode(const ArenaDev& D, const ArenaC
   int ok = 1;
   if (lane == 0) {
     if (n > 0) {
-      unsigned long long cur = *((volatile unsigned long long*)&D.ring[0]);
-      while (true) {
-        const unsigned long long eps = cur >> 40, exps = cur & ((1ull << 40) - 1);
-        const unsigned long long tail_eps = *((volatile unsigned long long*)&D.ring[1]);
-        const unsigned long long tail_exps = *((volatile unsigned long long*)&D.ring[2]);
-        if (eps + 1 - tail_eps > (unsigned long long)C.EPS || exps + n - tail_exps > (unsigned long long)C.E) {
-          ok = 0;
-          break;
-        }
-        const unsigned long long nxt = ((eps + 1) << 40) | (exps + n);
-        const unsigned long long old = atomicCAS(&D.ring[0], cur, nxt);
-        if (old == cur) {
-          slot = cur;
-          break;
-        }
-        cur = old;
+      // One fetch-add per finished episode (a CAS loop serialised ~700 finishing warps per step).  The capacity test is
+      // a threshold on the pre-add cursor (room for one more episode of the MAXIMUM length), hence monotone: the
+      // successful reservations are a prefix of the cursor sequence, and ring[5] tracks where that prefix ends;
+      // ring_repair() rolls the cursor back over the failed suffix before the ring is used again.
+      const unsigned long long inc = (1ull << 40) | (unsigned long long)n;
+      const unsigned long long cur = atomicAdd(&D.ring[0], inc);
+      const unsigned long long eps = cur >> 40, exps = cur & ((1ull << 40) - 1);
+      if (eps + 1 > D.ring[6] || exps + (unsigned long long)C.P > D.ring[7]) {
+        ok = 0;
+      } else {
+        slot = cur;
+        atomicMax(&D.ring[5], cur + inc);
       }
     }
   }
@@ -207,13 +204,16 @@ __device__ __forceinline__ bool finalize_episode(const ArenaDev& D, const ArenaC
     inf[11] = 0;
   }
   const int64_t src = g * C.P;
+  const int64_t d0 = (int64_t)(x0 % (unsigned long long)C.E);
   for (int t = lane; t < n * 13; t += 32) {
     const int e = t / 13, w = t - e * 13;
-    const int64_t dst = (int64_t)((x0 + e) % (unsigned long long)C.E);
+    int64_t dst = d0 + e;
+    if (dst >= C.E) dst -= C.E;
     D.fp_after[dst * 13 + w] = D.xb_after[(src + e) * 13 + w];
   }
   for (int e = lane; e < n; e += 32) {
-    const int64_t dst = (int64_t)((x0 + e) % (unsigned long long)C.E);
+    int64_t dst = d0 + e;
+    if (dst >= C.E) dst -= C.E;
     D.fp_v[dst] = D.xb_v[src + e];
     D.fp_vnext[dst] = D.xb_vnext[src + e];
     D.fp_reward[dst] = D.xb_reward[src + e];
@@ -404,14 +404,28 @@ __global__ void __launch_bounds__(256) k_apply(ArenaDev D, ArenaCfg C, const uin
   }
 }
 
-__global__ void k_active_mask(const uint8_t* __restrict__ gstate, int64_t G, uint8_t* __restrict__ active) {
-  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < G; g += (int64_t)gridDim.x * blockDim.x)
-    active[g] = gstate[g] == BG_GAME_ACTIVE;
+// ring cursor repair + per-step limits (see finalize_episode); executed by ONE thread before the ring is used
+__device__ __forceinline__ void ring_repair(const ArenaDev& D, const ArenaCfg& C) {
+  unsigned long long head = D.ring[0];
+  const unsigned long long good = D.ring[5];
+  if (head > good) head = good;  // drop reservations that failed the capacity test
+  D.ring[0] = head;
+  D.ring[5] = head;
+  D.ring[6] = D.ring[1] + (unsigned long long)C.EPS;  // tails only move in drain (stream ordered)
+  D.ring[7] = D.ring[2] + (unsigned long long)C.E;
+}
+
+__global__ void k_prologue(ArenaDev D, ArenaCfg C, uint8_t* __restrict__ active) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) ring_repair(D, C);
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < C.G; g += (int64_t)gridDim.x * blockDim.x)
+    active[g] = D.gstate[g] == BG_GAME_ACTIVE;
 }
 
 // ---- drain ------------------------------------------------------------------------------------------------------
 __global__ void k_drain_plan(ArenaDev D, ArenaCfg C, int64_t max_eps, int64_t max_exps) {
   __shared__ unsigned long long s_n, s_end;
+  if (threadIdx.x == 0) ring_repair(D, C);
+  __syncthreads();
   const unsigned long long head = D.ring[0];
   const unsigned long long head_eps = head >> 40;
   const unsigned long long tail_eps = D.ring[1], tail_exps = D.ring[2];
@@ -471,13 +485,16 @@ __global__ void __launch_bounds__(256) k_drain_copy(ArenaDev D, ArenaCfg C, Drai
     if (lane == 0) O.ep_offsets[k] = o0;
     if (lane < BG_EP_INFO_INTS) O.ep_info[k * BG_EP_INFO_INTS + lane] = D.ep_info[slot * BG_EP_INFO_INTS + lane];
     uint32_t* oa = reinterpret_cast<uint32_t*>(O.after);
+    const int64_t s0 = (int64_t)(x0 % (unsigned long long)C.E);
     for (int t = lane; t < n * 13; t += 32) {
       const int e = t / 13, w = t - e * 13;
-      const int64_t src = (int64_t)((x0 + e) % (unsigned long long)C.E);
+      int64_t src = s0 + e;
+      if (src >= C.E) src -= C.E;
       oa[(o0 + e) * 13 + w] = D.fp_after[src * 13 + w];
     }
     for (int e = lane; e < n; e += 32) {
-      const int64_t src = (int64_t)((x0 + e) % (unsigned long long)C.E);
+      int64_t src = s0 + e;
+      if (src >= C.E) src -= C.E;
       O.meta[o0 + e] = D.fp_meta[src];
       O.reward[o0 + e] = D.fp_reward[src];
       O.v[o0 + e] = D.fp_v[src];
@@ -716,7 +733,7 @@ int32_t arena_step(Arena* A, int32_t n_plies, int32_t lookahead, const int32_t* 
   }
   const ArenaCfg& C = A->C;
   for (int ply = 0; ply < n_plies; ++ply) {
-    k_active_mask<<<(int)((C.G + 255) / 256 < 1184 ? (C.G + 255) / 256 : 1184), 256, 0, s>>>(A->D.gstate, C.G, A->active);
+    k_prologue<<<(int)((C.G + 255) / 256 < 1184 ? (C.G + 255) / 256 : 1184), 256, 0, s>>>(A->D, A->C, A->active);
     MovegenArgs m{};
     m.boards = reinterpret_cast<const int8_t*>(A->D.board);
     m.players = A->D.player;
@@ -740,7 +757,7 @@ int32_t arena_step(Arena* A, int32_t n_plies, int32_t lookahead, const int32_t* 
     TRY(eval_launch(ev, s));
     EvalArgs ec{reinterpret_cast<const int8_t*>(A->D.board), A->D.player, nullptr, nullptr, C.G, nullptr, C.G, A->prepared[A->cur_w], A->H, A->v_cur};
     TRY(eval_launch(ec, s));
-    k_apply<<<grid_for(C.G), 256, 0, s>>>(A->D, A->C, reinterpret_cast<const uint32_t*>(A->pool), (const long long*)A->offsets, A->counts,
+    k_apply<<<(int)((C.G + 7) / 8), 256, 0, s>>>(A->D, A->C, reinterpret_cast<const uint32_t*>(A->pool), (const long long*)A->offsets, A->counts,
                                           A->v_pool, A->v_cur, forced_action, A->temperature);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return check_cuda(e, "k_apply launch");

@@ -111,13 +111,12 @@ __device__ __forceinline__ int unit_index(int lane, int q) {
     return q * 32 + lane;
 }
 
-// Row gather for one board.  `list` (per-warp shared scratch) receives the table-row offsets (in floats) of every
-// occupied (player, point) pair, compacted across lanes with ballot/popc, padded to a multiple of 4 with the all-zero row;
-// the warp then streams them four rows at a time (independent 512-byte conflict-free reads, H=128).
+// Row gather for one board.  `list` (per-warp shared scratch, 16-byte aligned) receives the table-row offsets (in floats)
+// of every occupied (player, point) pair, compacted across lanes with ballot/popc; the warp then streams them four rows at a
+// time (one broadcast 16-byte read of four offsets, then four independent 512-byte conflict-free row reads at H=128).
 template <int HPL>
 __device__ __forceinline__ void gather_rows(Acc<HPL>& z, const float* sT, uint32_t* list, uint32_t c0, uint32_t c1, int lane) {
   constexpr int H = HPL * 32;
-  constexpr uint32_t ZROW = 201 * H;  // zero row placed after the table (+pad) in shared memory
   const uint32_t occ0 = __ballot_sync(BG_FULL, c0 > 0), occ1 = __ballot_sync(BG_FULL, c1 > 0);
   const uint32_t gt0 = __ballot_sync(BG_FULL, c0 > 3), gt1 = __ballot_sync(BG_FULL, c1 > 3);
   const uint32_t lt = (1u << lane) - 1u;
@@ -125,20 +124,16 @@ __device__ __forceinline__ void gather_rows(Acc<HPL>& z, const float* sT, uint32
   __syncwarp();
   if (c0 > 0) list[__popc(occ0 & lt)] = (uint32_t)((lane * 4 + (int)min(c0, 3u) - 1) * H);
   if (c1 > 0) list[n0 + __popc(occ1 & lt)] = (uint32_t)((96 + lane * 4 + (int)min(c1, 3u) - 1) * H);
-  if (lane < 3) list[n + lane] = ZROW;
   __syncwarp();
-  for (int j = 0; j < n; j += 4) {
-    const uint32_t r0 = list[j], r1 = list[j + 1], r2 = list[j + 2], r3 = list[j + 3];
-    Acc<HPL> a, b, c, d;
-#pragma unroll
-    for (int q = 0; q < HPL; ++q) a.a[q] = b.a[q] = c.a[q] = d.a[q] = 0.f;
-    add_row<HPL>(a, sT + r0, lane);
-    add_row<HPL>(b, sT + r1, lane);
-    add_row<HPL>(c, sT + r2, lane);
-    add_row<HPL>(d, sT + r3, lane);
-#pragma unroll
-    for (int q = 0; q < HPL; ++q) z.a[q] = (((z.a[q] + a.a[q]) + b.a[q]) + c.a[q]) + d.a[q];
+  int j = 0;
+  for (; j + 4 <= n; j += 4) {
+    const uint4 r = *reinterpret_cast<const uint4*>(list + j);
+    add_row<HPL>(z, sT + r.x, lane);
+    add_row<HPL>(z, sT + r.y, lane);
+    add_row<HPL>(z, sT + r.z, lane);
+    add_row<HPL>(z, sT + r.w, lane);
   }
+  for (; j < n; ++j) add_row<HPL>(z, sT + list[j], lane);
   // counts above 3: (c - 3) * (0.5 * W[.,3])
   uint32_t m = gt0;
   while (m) {
@@ -165,7 +160,6 @@ __global__ void __launch_bounds__(EVAL_THREADS, (HPL <= 4 ? 2 : 1))
   extern __shared__ __align__(16) float sT[];
   const int n_floats = 200 * H + 1;
   for (int i = threadIdx.x; i < n_floats; i += blockDim.x) sT[i] = prep[i];
-  for (int i = threadIdx.x; i < H; i += blockDim.x) sT[201 * H + i] = 0.f;  // zero row
   uint32_t* lists = reinterpret_cast<uint32_t*>(sT + 202 * H);
   __syncthreads();
   const float* sb1 = sT + 198 * H;
@@ -178,11 +172,14 @@ __global__ void __launch_bounds__(EVAL_THREADS, (HPL <= 4 ? 2 : 1))
   const int64_t warp = (int64_t)blockIdx.x * (EVAL_THREADS / 32) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (EVAL_THREADS / 32);
   const uint32_t* b32 = reinterpret_cast<const uint32_t*>(boards);
-  float w2r[HPL], b1r[HPL];
+  // per-lane constants: w2 and the two possible initial accumulators b1 + W[196 + flag] (the flag row is always present)
+  float w2r[HPL], bf0[HPL], bf1[HPL];
 #pragma unroll
   for (int q = 0; q < HPL; ++q) {
-    w2r[q] = sw2[unit_index<HPL>(lane, q)];
-    b1r[q] = sb1[unit_index<HPL>(lane, q)];
+    const int u = unit_index<HPL>(lane, q);
+    w2r[q] = sw2[u];
+    bf0[q] = sb1[u] + sT[196 * H + u];
+    bf1[q] = sb1[u] + sT[197 * H + u];
   }
   // lanes 0..12 fetch the board words, lane 13 the flag; the next board is prefetched while this one is evaluated
   auto fetch = [&](int64_t j) -> uint32_t {
@@ -202,14 +199,13 @@ __global__ void __launch_bounds__(EVAL_THREADS, (HPL <= 4 ? 2 : 1))
     const uint32_t c1 = lane < 24 ? (wb >> ((lane & 3) * 8)) & 0xffu : 0u;
     Acc<HPL> z;
 #pragma unroll
-    for (int q = 0; q < HPL; ++q) z.a[q] = b1r[q];
+    for (int q = 0; q < HPL; ++q) z.a[q] = (flag & 1) ? bf1[q] : bf0[q];
     gather_rows<HPL>(z, sT, list, c0, c1, lane);
     const uint32_t bar0 = w12 & 0xffu, bar1 = (w12 >> 8) & 0xffu, off0 = (w12 >> 16) & 0xffu, off1 = w12 >> 24;
     if (bar0) fma_row<HPL>(z, (float)bar0, sT + 192 * H, lane);
     if (off0) fma_row<HPL>(z, c_off15[off0 & 15u], sT + 193 * H, lane);
     if (bar1) fma_row<HPL>(z, (float)bar1, sT + 194 * H, lane);
     if (off1) fma_row<HPL>(z, c_off15[off1 & 15u], sT + 195 * H, lane);
-    add_row<HPL>(z, sT + (196 + (flag & 1)) * H, lane);
     float v = 0.f;
 #pragma unroll
     for (int q = 0; q < HPL; ++q) {
