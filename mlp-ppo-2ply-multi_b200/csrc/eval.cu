@@ -287,7 +287,12 @@ int32_t launch_eval_t(const EvalArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
-int64_t prepared_weights_bytes(int32_t H) { return ((int64_t)(200 * H + 1) * 4 + 255) / 256 * 256; }
+// generic table (200 * H + 1 floats, padded to 256 B) followed, for H == 128, by the table of the two-boards-per-warp kernel
+static int64_t generic_table_bytes(int32_t H) { return ((int64_t)(200 * H + 1) * 4 + 255) / 256 * 256; }
+
+int64_t prepared_weights_bytes(int32_t H) {
+  return generic_table_bytes(H) + (H == 128 ? (eval128_table_floats() * 4 + 255) / 256 * 256 : 0);
+}
 
 int32_t prepare_weights_launch(const float* packed, int32_t H, float* prepared, cudaStream_t stream) {
   if (H < 32 || H > 256 || H % 32) {
@@ -297,6 +302,7 @@ int32_t prepare_weights_launch(const float* packed, int32_t H, float* prepared, 
   k_prepare<<<64, 256, 0, stream>>>(packed, H, prepared);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return check_cuda(e, "k_prepare launch");
+  if (H == 128) return eval128_prepare(packed, prepared + generic_table_bytes(H) / 4, stream);
   return BG_OK;
 }
 
@@ -310,6 +316,7 @@ int32_t eval_launch(const EvalArgs& a, cudaStream_t stream) {
     return BG_ERR_ARG;
   }
   if ((a.N_dev ? a.max_N : a.N) <= 0) return BG_OK;
+  if (a.H == 128) return eval128_launch(a, a.prepared + generic_table_bytes(128) / 4, stream);
   int32_t rc = init_constants();
   if (rc != BG_OK) return rc;
   switch (a.H / 32) {

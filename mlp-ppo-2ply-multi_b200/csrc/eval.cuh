@@ -20,6 +20,10 @@ struct EvalArgs {
 int64_t prepared_weights_bytes(int32_t H);
 int32_t prepare_weights_launch(const float* packed, int32_t H, float* prepared, cudaStream_t stream);
 int32_t eval_launch(const EvalArgs& a, cudaStream_t stream);
+// H == 128 production kernel (eval128.cu); its table is appended to the generic prepared table
+int64_t eval128_table_floats();
+int32_t eval128_prepare(const float* packed, float* t128, cudaStream_t stream);
+int32_t eval128_launch(const EvalArgs& a, const float* t128, cudaStream_t stream);
 int32_t encode_launch(const int8_t* boards, const uint8_t* flags, int64_t N, float* out, cudaStream_t stream);
 
 }  // namespace bg
