@@ -166,6 +166,7 @@ typedef struct bg_arena bg_arena;
 #define BG_STAT_P1_WINS 9
 #define BG_STAT_WAIT_STEPS 10  /* game-steps spent waiting for ring space (actor idle) */
 #define BG_STAT_ERRORS 11      /* games stopped by a per-item move-generator overflow */
+#define BG_STAT_REPLIES 12     /* opponent replies evaluated by the 2-ply lookahead */
 
 /* ep_info layout (int32[BG_EP_INFO_INTS] per drained episode) */
 #define BG_EP_INFO_INTS 12
@@ -195,7 +196,13 @@ int32_t bg_arena_set_weights(bg_arena* a, const float* packed, int64_t version, 
 int32_t bg_arena_set_dice_tape(bg_arena* a, const uint8_t* tape, int64_t L, void* stream);
 /* (Re)start every game: BackgammonEnv.reset (src/environments/backgammon_env.py:92-128); clears stats and the ring. */
 int32_t bg_arena_reset(bg_arena* a, void* stream);
-/* Advance every active game by n_plies env steps: movegen + fused eval + select + apply + record (lookahead must be 1).
+/* 2-ply policy parameters used by bg_arena_step(lookahead = 2) (src/multi/two_ply.py:44-90 and its commented-out integration
+ * :153-193).  n_candidates = 4, top_k = 5, alpha = 1.0, beta = 0.9 is the reference's setting (decisions with fewer than
+ * n_candidates legal moves fall back to the 1-ply policy); n_candidates = 0 scores EVERY legal afterstate (north_star's
+ * expectimax with top_k = 1), which reads one counter back to the host per ply. */
+int32_t bg_arena_set_lookahead(bg_arena* a, int32_t n_candidates, int32_t top_k, float alpha, float beta);
+/* Advance every active game by n_plies env steps: movegen + fused eval (+ 2-ply rescoring when lookahead == 2) + select +
+ * apply + record.  lookahead is 1 or 2.
  * forced_action: optional device int32[n_games]; entries >= 0 override the policy's choice (env.step(action)). */
 int32_t bg_arena_step(bg_arena* a, int32_t n_plies, int32_t lookahead, const int32_t* forced_action, void* stream);
 /*

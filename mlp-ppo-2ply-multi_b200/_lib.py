@@ -44,6 +44,7 @@ SIGNATURES = {
     "bg_arena_set_weights": (_i32, [_vp, _vp, _i64, _f32, _vp]),
     "bg_arena_set_dice_tape": (_i32, [_vp, _vp, _i64, _vp]),
     "bg_arena_reset": (_i32, [_vp, _vp]),
+    "bg_arena_set_lookahead": (_i32, [_vp, _i32, _i32, _f32, _f32]),
     "bg_arena_step": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "bg_arena_drain_episodes": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bg_arena_stats": (_i32, [_vp, _vp, _vp]),

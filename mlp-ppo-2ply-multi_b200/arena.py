@@ -27,7 +27,7 @@ MAX_UPDATES = 4000
 MAX_LEGAL_MOVES = 500  # src/environments/backgammon_env.py:35
 
 STAT_NAMES = ["games", "steps", "decisions", "passes", "afterstates", "win_regular", "win_gammon", "win_backgammon", "truncated",
-              "p1_wins", "wait_steps", "errors"]
+              "p1_wins", "wait_steps", "errors", "replies"]
 EP_INFO_INTS = 12
 
 
@@ -97,6 +97,12 @@ class Arena:
     # -- play ---------------------------------------------------------------------------------------------------------
     def reset(self):
         check(lib().bg_arena_reset(self._h, self._stream()))
+
+    def set_lookahead(self, n_candidates: int = 4, top_k: int = 5, alpha: float = 1.0, beta: float = 0.9):
+        """2-ply policy parameters for step(lookahead=2).  Defaults = the reference's compute_scores_for_boards setting
+        (src/multi/two_ply.py:44-90: top-4 candidates, mean of the top-5 replies, 1.0 * S - 0.9 * W); n_candidates=0 scores every
+        legal afterstate (north_star expectimax, use top_k=1)."""
+        check(lib().bg_arena_set_lookahead(self._h, int(n_candidates), int(top_k), float(alpha), float(beta)))
 
     def step(self, n_plies: int = 1, forced_action: Optional[torch.Tensor] = None, lookahead: int = 1):
         fa = None

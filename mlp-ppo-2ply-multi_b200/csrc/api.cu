@@ -136,7 +136,7 @@ int32_t bg_two_ply(const int8_t* cand_boards, const uint8_t* mover, const float*
   BG_REQUIRE(N == 0 || (cand_boards && mover && S && prepared && out_score && workspace), "bg_two_ply: null pointer");
   int32_t rc = require_device();
   if (rc != BG_OK) return rc;
-  TwoPlyArgs a{cand_boards, mover, S, N, prepared, H, top_k, alpha, beta, out_score, out_replies, out_status, workspace, workspace_bytes};
+  TwoPlyArgs a{cand_boards, mover, S, N, prepared, H, top_k, alpha, beta, out_score, out_replies, out_status, workspace, workspace_bytes, nullptr, nullptr};
   return two_ply_launch(a, (cudaStream_t)stream);
 }
 
@@ -168,6 +168,11 @@ int32_t bg_arena_set_dice_tape(bg_arena* a, const uint8_t* tape, int64_t L, void
 int32_t bg_arena_reset(bg_arena* a, void* stream) {
   BG_REQUIRE(a, "bg_arena_reset: null arena");
   return arena_reset(reinterpret_cast<Arena*>(a), (cudaStream_t)stream);
+}
+
+int32_t bg_arena_set_lookahead(bg_arena* a, int32_t n_candidates, int32_t top_k, float alpha, float beta) {
+  BG_REQUIRE(a, "bg_arena_set_lookahead: null arena");
+  return arena_set_lookahead(reinterpret_cast<Arena*>(a), n_candidates, top_k, alpha, beta);
 }
 
 int32_t bg_arena_step(bg_arena* a, int32_t n_plies, int32_t lookahead, const int32_t* forced_action, void* stream) {

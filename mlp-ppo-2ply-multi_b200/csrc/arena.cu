@@ -15,6 +15,7 @@
 #include "eval.cuh"
 #include "movegen.cuh"
 #include "select.cuh"
+#include "two_ply.cuh"
 
 namespace bg {
 
@@ -231,7 +232,8 @@ __device__ __forceinline__ bool finalize_episode(const ArenaDev& D, const ArenaC
 __global__ void __launch_bounds__(256) k_apply(ArenaDev D, ArenaCfg C, const uint32_t* __restrict__ pool, const long long* __restrict__ offsets,
                                                const int32_t* __restrict__ counts, const float* __restrict__ v_pool,
                                                const float* __restrict__ v_cur, const int32_t* __restrict__ forced_action,
-                                               float temperature) {
+                                               float temperature, const float* __restrict__ sel_score, const int32_t* __restrict__ sel_idx,
+                                               const int32_t* __restrict__ sel_n, int sel_c, const float* __restrict__ pool_score) {
   __shared__ uint32_t sb[8][16];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t* bw = sb[wib];
@@ -286,7 +288,12 @@ __global__ void __launch_bounds__(256) k_apply(ArenaDev D, ArenaCfg C, const uin
           uint32_t r[4];
           Philox::gen(C.seed ^ KEY_ACT, (uint64_t)(C.gid_base + g), ((uint64_t)serial << 20) | (uint64_t)(uint32_t)step, r);
           const float u = (float)(r[0] >> 8) * (1.0f / 16777216.0f);
-          a = warp_select(v_pool + off, n, temperature, u, lane);
+          if (sel_n && sel_n[g] > 0) {  // 2-ply over the top candidates: pick among their scores, map back to the action index
+            const int al = warp_select(sel_score + g * sel_c, sel_n[g], temperature, u, lane);
+            a = sel_idx[g * sel_c + al];
+          } else {
+            a = warp_select((pool_score ? pool_score : v_pool) + off, n, temperature, u, lane);
+          }
         }
         if (lane < 13) bw[lane] = pool[(off + a) * 13 + lane];
         __syncwarp();
@@ -401,6 +408,67 @@ __global__ void __launch_bounds__(256) k_apply(ArenaDev D, ArenaCfg C, const uin
         atomicAdd(&D.stats[BG_STAT_WAIT_STEPS], 1ull);
       }
     }
+  }
+}
+
+// 2-ply, reference setting (src/multi/two_ply.py:153-193, the commented-out integration): when a decision has at least
+// `C` legal moves, the C best 1-ply candidates (torch.topk order: descending value, lowest index first on ties) are rescored
+// by bg_two_ply and the action is drawn among them; otherwise the 1-ply policy is used.  Warp per game.
+__global__ void __launch_bounds__(256) k_pick_candidates(ArenaDev D, ArenaCfg Cc, const uint32_t* __restrict__ pool, const long long* __restrict__ offsets,
+                                                         const int32_t* __restrict__ counts, const float* __restrict__ v_pool, int C,
+                                                         uint32_t* __restrict__ cand_boards, uint8_t* __restrict__ cand_mover,
+                                                         uint8_t* __restrict__ cand_active, float* __restrict__ cand_S, int32_t* __restrict__ cand_idx,
+                                                         int32_t* __restrict__ sel_n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t g = warp; g < Cc.G; g += nwarps) {
+    int n = counts[g];
+    if (n > Cc.move_cap) n = Cc.move_cap;
+    const long long off = offsets[g];
+    const bool use = D.gstate[g] == BG_GAME_ACTIVE && n >= C && off >= 0;
+    if (!use) {
+      if (lane == 0) sel_n[g] = 0;
+      if (lane < C) cand_active[g * C + lane] = 0;
+      continue;
+    }
+    int chosen[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) chosen[c] = -1;
+    for (int c = 0; c < C; ++c) {
+      float best = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int i = lane; i < n; i += 32) {
+        bool taken = false;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) taken |= chosen[q] == i;
+        const float x = v_pool[off + i];
+        if (!taken && (bi == 0x7fffffff || x > best)) {
+          best = x;
+          bi = i;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(BG_FULL, best, o);
+        const int oi = __shfl_xor_sync(BG_FULL, bi, o);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) {
+          best = ob;
+          bi = oi;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q == c) chosen[q] = bi;
+      const int64_t slot = g * C + c;
+      if (lane < 13) cand_boards[slot * 13 + lane] = pool[(off + bi) * 13 + lane];
+      if (lane == 0) {
+        cand_mover[slot] = D.player[g];
+        cand_active[slot] = 1;
+        cand_S[slot] = best;
+        cand_idx[slot] = bi;
+      }
+    }
+    if (lane == 0) sel_n[g] = C;
   }
 }
 
@@ -552,6 +620,21 @@ struct Arena {
   void* ws = nullptr;
   int64_t ws_bytes = 0;
   uint8_t* tape_dev = nullptr;
+  // 2-ply lookahead (bg_arena_set_lookahead); scratch is allocated on first use
+  int32_t la_cands = 4, la_topk = 5;  // reference: top-4 candidates, mean of the top-5 replies, alpha 1.0, beta 0.9
+  float la_alpha = 1.0f, la_beta = 0.9f;
+  int8_t* cand_boards = nullptr;
+  uint8_t* cand_mover = nullptr;
+  uint8_t* cand_active = nullptr;
+  float* cand_S = nullptr;
+  float* cand_score = nullptr;
+  int32_t* cand_idx = nullptr;
+  int32_t* sel_n = nullptr;
+  float* pool_score = nullptr;
+  int32_t* tp_status = nullptr;
+  void* tp_ws = nullptr;
+  int64_t tp_ws_bytes = 0;
+  int64_t tp_cands_alloc = 0;
   std::vector<void*> allocs;
 };
 
@@ -722,16 +805,54 @@ int32_t arena_reset(Arena* A, cudaStream_t s) {
   return BG_OK;
 }
 
+int32_t arena_set_lookahead(Arena* A, int32_t n_candidates, int32_t top_k, float alpha, float beta) {
+  if (n_candidates < 0 || n_candidates > 8 || n_candidates == 1 || top_k < 1 || top_k > 8) {
+    set_error("bg_arena_set_lookahead: n_candidates must be 0 (all) or 2..8, top_k in 1..8");
+    return BG_ERR_ARG;
+  }
+  A->la_cands = n_candidates;
+  A->la_topk = top_k;
+  A->la_alpha = alpha;
+  A->la_beta = beta;
+  return BG_OK;
+}
+
+static int32_t ensure_two_ply_scratch(Arena* A) {
+  const int64_t G = A->C.G;
+  const int64_t n_cand = A->la_cands > 0 ? G * A->la_cands : A->pool_cap;
+  if (A->tp_cands_alloc >= n_cand && A->tp_ws) return BG_OK;
+  int32_t rc;
+#define AL2(ptr, count) \
+  if ((rc = dmalloc(A, &(ptr), (count))) != BG_OK) return rc
+  AL2(A->cand_boards, (size_t)G * 8 * BG_BOARD_BYTES);
+  AL2(A->cand_mover, (size_t)G * 8);
+  AL2(A->cand_active, (size_t)G * 8);
+  AL2(A->cand_S, (size_t)G * 8);
+  AL2(A->cand_score, (size_t)G * 8);
+  AL2(A->cand_idx, (size_t)G * 8);
+  AL2(A->sel_n, (size_t)G);
+  AL2(A->pool_score, (size_t)A->pool_cap);
+  AL2(A->tp_status, 4);
+  A->tp_ws_bytes = two_ply_workspace_bytes(n_cand);
+  uint8_t* w = nullptr;
+  AL2(w, (size_t)A->tp_ws_bytes);
+  A->tp_ws = w;
+#undef AL2
+  A->tp_cands_alloc = A->pool_cap > G * 8 ? A->pool_cap : G * 8;
+  return BG_OK;
+}
+
 int32_t arena_step(Arena* A, int32_t n_plies, int32_t lookahead, const int32_t* forced_action, cudaStream_t s) {
   if (A->cur_w < 0) {
     set_error("bg_arena_step: no weights set (call bg_arena_set_weights first)");
     return BG_ERR_ARG;
   }
-  if (lookahead != 1) {
-    set_error("bg_arena_step: lookahead must be 1 (2-ply is exposed through bg_two_ply)");
+  if (lookahead != 1 && lookahead != 2) {
+    set_error("bg_arena_step: lookahead must be 1 or 2");
     return BG_ERR_ARG;
   }
   const ArenaCfg& C = A->C;
+  if (lookahead == 2) TRY(ensure_two_ply_scratch(A));
   for (int ply = 0; ply < n_plies; ++ply) {
     k_prologue<<<(int)((C.G + 255) / 256 < 1184 ? (C.G + 255) / 256 : 1184), 256, 0, s>>>(A->D, A->C, A->active);
     MovegenArgs m{};
@@ -757,8 +878,54 @@ int32_t arena_step(Arena* A, int32_t n_plies, int32_t lookahead, const int32_t* 
     TRY(eval_launch(ev, s));
     EvalArgs ec{reinterpret_cast<const int8_t*>(A->D.board), A->D.player, nullptr, nullptr, C.G, nullptr, C.G, A->prepared[A->cur_w], A->H, A->v_cur};
     TRY(eval_launch(ec, s));
+    const float* sel_score = nullptr;
+    const int32_t* sel_idx = nullptr;
+    const int32_t* sel_n = nullptr;
+    const float* pool_score = nullptr;
+    if (lookahead == 2) {
+      TwoPlyArgs t{};
+      t.prepared = A->prepared[A->cur_w];
+      t.H = A->H;
+      t.top_k = A->la_topk;
+      t.alpha = A->la_alpha;
+      t.beta = A->la_beta;
+      t.out_replies = nullptr;
+      t.out_status = A->tp_status;
+      t.workspace = A->tp_ws;
+      t.workspace_bytes = A->tp_ws_bytes;
+      t.reply_counter = A->D.stats + BG_STAT_REPLIES;
+      if (A->la_cands > 0) {  // reference setting: rescore the top-C candidates of each decision with >= C moves
+        k_pick_candidates<<<grid_for(C.G), 256, 0, s>>>(A->D, A->C, reinterpret_cast<const uint32_t*>(A->pool), (const long long*)A->offsets,
+                                                        A->counts, A->v_pool, A->la_cands, reinterpret_cast<uint32_t*>(A->cand_boards),
+                                                        A->cand_mover, A->cand_active, A->cand_S, A->cand_idx, A->sel_n);
+        t.cand_boards = A->cand_boards;
+        t.mover = A->cand_mover;
+        t.S = A->cand_S;
+        t.N = C.G * A->la_cands;
+        t.out_score = A->cand_score;
+        t.cand_active = A->cand_active;
+        TRY(two_ply_launch(t, s));
+        sel_score = A->cand_score;
+        sel_idx = A->cand_idx;
+        sel_n = A->sel_n;
+      } else {  // north-star setting: every legal afterstate is a candidate (needs this ply's afterstate count on the host)
+        int64_t total = 0;
+        cudaError_t e = cudaMemcpyAsync(&total, A->total, sizeof(total), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return check_cuda(e, "read afterstate count");
+        if (total > A->pool_cap) total = A->pool_cap;
+        t.cand_boards = A->pool;
+        t.mover = A->pflags;
+        t.S = A->v_pool;
+        t.N = total;
+        t.out_score = A->pool_score;
+        TRY(two_ply_launch(t, s));
+        pool_score = A->pool_score;
+      }
+    }
     k_apply<<<(int)((C.G + 7) / 8), 256, 0, s>>>(A->D, A->C, reinterpret_cast<const uint32_t*>(A->pool), (const long long*)A->offsets, A->counts,
-                                          A->v_pool, A->v_cur, forced_action, A->temperature);
+                                                  A->v_pool, A->v_cur, forced_action, A->temperature, sel_score, sel_idx, sel_n, A->la_cands,
+                                                  pool_score);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return check_cuda(e, "k_apply launch");
   }

@@ -14,6 +14,7 @@ int32_t arena_destroy(Arena* A);
 int32_t arena_set_weights(Arena* A, const float* packed_dev, int64_t version, float temperature, cudaStream_t s);
 int32_t arena_set_dice_tape(Arena* A, const uint8_t* tape, int64_t L, cudaStream_t s);
 int32_t arena_reset(Arena* A, cudaStream_t s);
+int32_t arena_set_lookahead(Arena* A, int32_t n_candidates, int32_t top_k, float alpha, float beta);
 int32_t arena_step(Arena* A, int32_t n_plies, int32_t lookahead, const int32_t* forced_action, cudaStream_t s);
 int32_t arena_drain(Arena* A, int64_t max_eps, int64_t max_exps, int8_t* after, uint8_t* meta, float* reward, float* v, float* vnext,
                     int16_t* nmoves, int16_t* action, uint8_t* roll, int64_t* ep_offsets, int32_t* ep_info, int64_t* out_n, cudaStream_t s);

@@ -25,8 +25,9 @@ __constant__ uint8_t c_roll_d1[21] = {1, 2, 3, 4, 5, 6, 2, 3, 4, 5, 6, 3, 4, 5, 
 constexpr int ROWS_PER_ITEM = 48;  // pool rows provisioned per (candidate, roll) item (mean is ~22)
 constexpr int MAX_TOPK = 8;
 
-__global__ void __launch_bounds__(256) k_expand(const int8_t* __restrict__ cand, const uint8_t* __restrict__ mover, int64_t c0, int64_t nc,
-                                                int8_t* __restrict__ ib, uint8_t* __restrict__ ip, uint8_t* __restrict__ ir) {
+__global__ void __launch_bounds__(256) k_expand(const int8_t* __restrict__ cand, const uint8_t* __restrict__ mover, const uint8_t* __restrict__ cand_active,
+                                                int64_t c0, int64_t nc, int8_t* __restrict__ ib, uint8_t* __restrict__ ip, uint8_t* __restrict__ ir,
+                                                uint8_t* __restrict__ iactive) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
   const uint32_t* c32 = reinterpret_cast<const uint32_t*>(cand);
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(256) k_expand(const int8_t* __restrict__ cand,
     if (lane < 21) {
       const int64_t t = c * 21 + lane;
       ip[t] = opp;
+      iactive[t] = cand_active ? cand_active[c0 + c] : (uint8_t)1;
       ir[2 * t] = c_roll_d0[lane];
       ir[2 * t + 1] = c_roll_d1[lane];
     }
@@ -50,7 +52,8 @@ __global__ void __launch_bounds__(256) k_expand(const int8_t* __restrict__ cand,
 __global__ void __launch_bounds__(256) k_reduce(const float* __restrict__ v, const long long* __restrict__ offsets, const int32_t* __restrict__ counts,
                                                 const float* __restrict__ S, int64_t c0, int64_t nc, int top_k, float alpha, float beta,
                                                 float* __restrict__ out_score, long long* __restrict__ out_replies,
-                                                const int32_t* __restrict__ chunk_status, int32_t* __restrict__ out_status) {
+                                                const int32_t* __restrict__ chunk_status, int32_t* __restrict__ out_status,
+                                                unsigned long long* __restrict__ reply_counter) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
   if (blockIdx.x == 0 && threadIdx.x == 0 && out_status && *chunk_status != 0) atomicMin(out_status, *chunk_status);
@@ -101,6 +104,7 @@ __global__ void __launch_bounds__(256) k_reduce(const float* __restrict__ v, con
     if (lane == 0) {
       out_score[c0 + c] = bad ? NAN : (float)((double)alpha * (double)S[c0 + c] - (double)beta * W);
       if (out_replies) out_replies[c0 + c] = nrep;
+      if (reply_counter && nrep) atomicAdd(reply_counter, (unsigned long long)nrep);
     }
   }
 }
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(256) k_reduce(const float* __restrict__ v, con
 struct Layout {
   int64_t C;  // candidates per chunk
   int64_t items, rows;
-  int64_t o_ib, o_ip, o_ir, o_off, o_cnt, o_tot, o_pool, o_owner, o_val, o_ws, ws_bytes, total;
+  int64_t o_ib, o_ip, o_ir, o_act, o_off, o_cnt, o_tot, o_pool, o_owner, o_val, o_ws, ws_bytes, total;
 };
 
 int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
@@ -125,6 +129,8 @@ Layout make_layout(int64_t C) {
   o += align256(L.items);
   L.o_ir = o;
   o += align256(L.items * 2);
+  L.o_act = o;
+  o += align256(L.items);
   L.o_off = o;
   o += align256(L.items * 8);
   L.o_cnt = o;
@@ -177,7 +183,8 @@ int32_t two_ply_launch(const TwoPlyArgs& a, cudaStream_t s) {
     const int64_t items = nc * 21;
     int64_t blocks = (nc + 7) / 8;
     const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
-    k_expand<<<grid, 256, 0, s>>>(a.cand_boards, a.mover, c0, nc, (int8_t*)(w + L.o_ib), (uint8_t*)(w + L.o_ip), (uint8_t*)(w + L.o_ir));
+    k_expand<<<grid, 256, 0, s>>>(a.cand_boards, a.mover, a.cand_active, c0, nc, (int8_t*)(w + L.o_ib), (uint8_t*)(w + L.o_ip),
+                                  (uint8_t*)(w + L.o_ir), (uint8_t*)(w + L.o_act));
     MovegenArgs m{};
     m.boards = (const int8_t*)(w + L.o_ib);
     m.players = (const uint8_t*)(w + L.o_ip);
@@ -195,7 +202,7 @@ int32_t two_ply_launch(const TwoPlyArgs& a, cudaStream_t s) {
     m.out_status = (int32_t*)(w + L.o_tot + 8);
     m.workspace = w + L.o_ws;
     m.workspace_bytes = L.ws_bytes;
-    m.active = nullptr;
+    m.active = (const uint8_t*)(w + L.o_act);
     int32_t rc = movegen_launch(m, s);
     if (rc != BG_OK) return rc;
     EvalArgs ev{m.out_boards, m.out_flags, nullptr, nullptr, 0, m.out_total, L.rows, a.prepared, a.H, (float*)(w + L.o_val)};
@@ -203,7 +210,7 @@ int32_t two_ply_launch(const TwoPlyArgs& a, cudaStream_t s) {
     if (rc != BG_OK) return rc;
     k_reduce<<<grid, 256, 0, s>>>((const float*)(w + L.o_val), (const long long*)(w + L.o_off), (const int32_t*)(w + L.o_cnt), a.S, c0, nc,
                                   a.top_k, a.alpha, a.beta, a.out_score, (long long*)a.out_replies, (const int32_t*)(w + L.o_tot + 8),
-                                  a.out_status);
+                                  a.out_status, a.reply_counter);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return check_cuda(e, "two_ply launch");
   }

@@ -18,6 +18,8 @@ struct TwoPlyArgs {
   int32_t* out_status;
   void* workspace;
   int64_t workspace_bytes;
+  const uint8_t* cand_active = nullptr;            // optional [N]: inactive candidates are skipped (score = alpha * S)
+  unsigned long long* reply_counter = nullptr;     // optional device counter: += replies evaluated
 };
 
 int64_t two_ply_workspace_bytes(int64_t N);

@@ -257,3 +257,47 @@ def test_episode_batch_feeds_trainer_shaped_consumer(bg, oracle, golden):
         t += len(ep.experiences)
         for pl, c in ep.close_out_counts.items():
             assert c in (0, 1) and ep.prime_reward_counts[pl] in (0, 1)
+
+
+@pytest.mark.parametrize("n_cand,top_k,alpha,beta", [(4, 5, 1.0, 0.9), (0, 1, 1.0, 1.0)])
+def test_two_ply_lookahead_policy_matches_oracle(bg, oracle, golden, n_cand, top_k, alpha, beta):
+    """arena.step(lookahead=2), greedy: every game's move must be the argmax of the oracle's 2-ply scores over the reference's
+    candidate set (top-4 by 1-ply value when >= 4 legal moves, else the 1-ply argmax; or all afterstates for n_cand=0)"""
+    vals = golden("values")
+    packed, H = vals["packed"], int(vals["H"])
+    G = 192
+    ar = bg.Arena(G, device=DEV, seed=9, auto_reset=True)
+    ar.set_weights(torch.from_numpy(packed).to(DEV), version=1, temperature=0.0)
+    ar.set_lookahead(n_cand, top_k, alpha, beta)
+    ar.reset()
+    ar.step(6)  # get away from the opening with the 1-ply policy
+    checked = near = 0
+    for _ in range(5):
+        b0, p0, r0, s0 = (x.cpu().numpy() for x in ar.state())
+        ar.step(1, lookahead=2)
+        b1, p1, r1, s1 = (x.cpu().numpy() for x in ar.state())
+        for g in range(G):
+            ob, _ = oracle.legal_moves(b0[g], int(p0[g]), tuple(r0[g]))
+            ob = ob[:500]
+            n = len(ob)
+            if n == 0 or s0[g] != 0:
+                continue
+            v = oracle.value(packed, H, ob, np.full(n, p0[g], np.uint8))
+            if n_cand and n < n_cand:
+                scores, cand = v, np.arange(n)
+            else:
+                cand = np.argsort(-v, kind="stable")[:n_cand] if n_cand else np.arange(n)
+                scores, _ = oracle.two_ply(ob[cand], np.full(len(cand), p0[g], np.uint8), v[cand], packed, H, top_k=top_k, alpha=alpha, beta=beta)
+            srt = np.sort(scores)[::-1]
+            if len(srt) > 1 and srt[0] - srt[1] < 2e-5 or (n_cand and n > n_cand and abs(np.sort(v)[::-1][n_cand - 1] - np.sort(v)[::-1][n_cand]) < 2e-6):
+                near += 1
+                continue
+            want = ob[cand[int(np.argmax(scores))]]
+            finished = want[50 + int(p0[g])] >= 15
+            if finished:
+                continue  # the game was reset by auto_reset; terminal application is covered elsewhere
+            assert np.array_equal(b1[g], want), (g, n)
+            checked += 1
+    st = ar.stats()
+    ar.close()
+    assert checked > 500 and near < checked // 10 and st["replies"] > 0 and st["errors"] == 0
