@@ -181,10 +181,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--positions", type=int, default=1048576)
-    ap.add_argument("--ref-positions", type=int, default=32768)
-    ap.add_argument("--cpu-positions", type=int, default=32768)
+    ap.add_argument("--ref-positions", type=int, default=65536)
+    ap.add_argument("--cpu-positions", type=int, default=262144)
     ap.add_argument("--selfplay-games", type=int, default=65536)
     ap.add_argument("--selfplay-plies", type=int, default=200)
+    ap.add_argument("--selfplay2-plies", type=int, default=20)
     ap.add_argument("--no-selfplay", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -305,16 +306,11 @@ def main():
     h2d = h_b.numel() + h_p.numel() + h_r.numel()
     d2h = h_act.numel() * 4 + h_cnt.numel() * 4
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-
     # ---- roofline of the dominant kernel (algorithmic bytes / measured kernel time) -----------------------------------------
     peak, peak_src = load_peaks()
     eval_bytes = n_after * (52 + 1 + 4)  # board in + flag in + value out
     movegen_bytes = B * (52 + 1 + 2 + 8 + 4) + n_after * (52 + 1)  # item in/out + board, flag out
-    kern = {"bg::k_eval<4>": (t_eval, eval_bytes), "bg::k_movegen<128|1024|4096> (3 tiers)": (t_movegen, movegen_bytes)}
+    kern = {"bg::k_eval128": (t_eval, eval_bytes), "bg::k_movegen<128|512|4096> (3 tiers)": (t_movegen, movegen_bytes)}
     dom = max(kern, key=lambda k: kern[k][0])
     ach = kern[dom][1] / (kern[dom][0] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
@@ -325,7 +321,7 @@ def main():
 
     # ---- CPU baseline: the oracle port on the host cores, bounded sample of the same workload -----------------------------------
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and rank == 0 and world == 1:  # reported baseline, rank 0 at N=1 only
         from oracle import pyoracle as po
 
         po.build()
@@ -340,35 +336,63 @@ def main():
         cpu = {"value": n_cpu / dt, "unit": "afterstates/s", "cores": cores, "kind": "port",
                "sample": f"first {ns} of the benchmark's positions x 21 rolls ({len(sb)} items, {n_cpu} afterstates), {dt:.1f} s, OpenMP"}
 
-    # ---- secondary: BASELINE configs[2], 1-ply self-play with 65,536 concurrent games ---------------------------------------------
-    selfplay = None
-    if not args.no_selfplay:
-        G = args.selfplay_games
-        ar = bg.Arena(G, hidden_size=H, device=dev, seed=0, ring_experiences=G * 48, ring_episodes=G)
-        ar.set_weights(packed, version=1)  # T = 1.5
+    del pool, values, pflags, ws, d_b, d_p, d_r, ib, ip, ir
+    torch.cuda.empty_cache()
+
+    # ---- secondary: BASELINE configs[2] / configs[3], self-play with 65,536 concurrent games per GPU (all ranks, sharded by game id) ----
+    def run_selfplay(G, plies, lookahead, la=None, label=""):
+        n_local, base = G, rank * G  # weak scaling: G games per GPU, global game ids keep the Philox streams disjoint
+        ar = bg.Arena(n_local, hidden_size=H, device=dev, seed=0, game_id_base=base, ring_experiences=n_local * 48, ring_episodes=n_local)
+        ar.set_weights(packed, version=1)  # T = 1.5 (reference schedule at version 1)
+        if la is not None:
+            ar.set_lookahead(*la)
         ar.reset()
-        ar.step(120)  # desynchronise game phases
-        ar.drain(max_episodes=G, max_experiences=G * 48)
-        torch.cuda.synchronize()
+        ar.step(120)  # desynchronise game phases (1-ply)
+        ar.drain(max_episodes=n_local, max_experiences=n_local * 48)
+        barrier()
         s0 = ar.stats()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         done = 0
-        while done < args.selfplay_plies:
-            ar.step(20)
-            ar.drain(max_episodes=G, max_experiences=G * 48)
-            done += 20
+        chunk = 20 if lookahead == 1 else 5
+        while done < plies:
+            ar.step(chunk, lookahead=lookahead)
+            ar.drain(max_episodes=n_local, max_experiences=n_local * 48)
+            done += chunk
         a1.record()
-        torch.cuda.synchronize()
+        barrier()
         s1 = ar.stats()
-        ms = a0.elapsed_time(a1)
-        games = s1["games"] - s0["games"]
-        after = s1["afterstates"] - s0["afterstates"]
-        selfplay = {"workload": f"config3: {G} concurrent 1-ply self-play games, T=1.5, Philox dice, episodes drained on device",
-                    "games_per_sec": games / (ms * 1e-3), "afterstates_per_sec": after / (ms * 1e-3), "plies_per_sec": G * done / (ms * 1e-3),
-                    "ms_per_ply_step": ms / done, "games_finished": games, "mean_steps_per_game": (s1["steps"] - s0["steps"]) / max(games, 1),
-                    "pass_rate": (s1["passes"] - s0["passes"]) / max(s1["steps"] - s0["steps"], 1), "wait_steps": s1["wait_steps"], "errors": s1["errors"]}
         ar.close()
+        keys = ["games", "steps", "passes", "afterstates", "replies", "wait_steps", "errors"]
+        d = torch.tensor([float(s1[k] - s0[k]) for k in keys] + [a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            tot = d.clone()
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            mx = d.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            d = torch.cat([tot[:-1], mx[-1:]])
+        v = dict(zip(keys, d[:-1].tolist()))
+        ms = float(d[-1])
+        return {"workload": label, "games_per_sec": v["games"] / (ms * 1e-3), "afterstates_per_sec": v["afterstates"] / (ms * 1e-3),
+                "reply_evals_per_sec": v["replies"] / (ms * 1e-3), "plies_per_sec": world * G * done / (ms * 1e-3), "ms_per_ply_step": ms / done,
+                "games_finished": int(v["games"]), "mean_steps_per_game": v["steps"] / max(v["games"], 1.0),
+                "pass_rate": v["passes"] / max(v["steps"], 1.0), "wait_steps": int(v["wait_steps"]), "errors": int(v["errors"])}
+
+    selfplay = selfplay2 = selfplay2b = None
+    if not args.no_selfplay:
+        G = args.selfplay_games
+        selfplay = run_selfplay(G, args.selfplay_plies, 1, None,
+                                f"config3: {G} concurrent 1-ply self-play games per GPU, T=1.5, Philox dice, episodes drained on device")
+        selfplay2 = run_selfplay(G, args.selfplay2_plies, 2, (4, 5, 1.0, 0.9),
+                                 f"config4 (reference setting, two_ply.py): {G} games per GPU, top-4 candidates x 21 rolls, mean of top-5 replies, score = S - 0.9 W")
+        G2 = max(G // 8, 1)
+        selfplay2b = run_selfplay(G2, args.selfplay2_plies, 2, (0, 1, 1.0, 1.0),
+                                  f"config4 (north-star expectimax): {G2} games per GPU, ALL candidates x 21 rolls, best reply, score = S - W")
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     line = {"metric": "afterstates_evaluated_per_sec", "value": value, "unit": "afterstates/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -378,8 +402,9 @@ def main():
                        "l2": "inputs+outputs per step (>25 GB) far exceed the 126 MB L2", "parallelism": f"{world} x independent shards"},
             "e2e": {"value": e2e_value, "unit": "afterstates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "what": "pinned host boards/players/rolls -> bg_movegen -> bg_eval -> bg_select(greedy) -> host actions + counts"},
-            "gpu_launches": 4 * args.steps, "gpu_launches_note": "per step: k_movegen tier 128, 1024, 4096 + k_eval (e2e adds k_select)",
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "selfplay_1ply": selfplay}
+            "gpu_launches": 4 * args.steps, "gpu_launches_note": "per step: k_movegen tiers 128 / 512 / 4096 + k_eval128 (e2e adds k_select)",
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "selfplay_1ply": selfplay, "selfplay_2ply": selfplay2,
+            "selfplay_2ply_all_candidates": selfplay2b}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
