@@ -319,23 +319,6 @@ def main():
                 "kernels_ms": {k: v[0] for k, v in kern.items()},
                 "eval_fp32_tflops_dense_equiv": n_after * FLOP_PER_AFTERSTATE / (t_eval * 1e-3) / 1e12}
 
-    # ---- CPU baseline: the oracle port on the host cores, bounded sample of the same workload -----------------------------------
-    cpu = None
-    if not args.no_cpu_baseline and rank == 0 and world == 1:  # reported baseline, rank 0 at N=1 only
-        from oracle import pyoracle as po
-
-        po.build()
-        cores = os.cpu_count() or 1
-        ns = min(args.cpu_positions, boards.shape[0])
-        sb, sp, sr = (x.cpu().numpy() for x in expand_rolls(bg, boards[:ns], players[:ns]))
-        pk = packed.cpu().numpy()
-        po.movegen_eval_bench(sb[:4096], sp[:4096], sr[:4096], pk, H, nthreads=cores)
-        t0 = time.perf_counter()
-        n_cpu, _ = po.movegen_eval_bench(sb, sp, sr, pk, H, nthreads=cores)
-        dt = time.perf_counter() - t0
-        cpu = {"value": n_cpu / dt, "unit": "afterstates/s", "cores": cores, "kind": "port",
-               "sample": f"first {ns} of the benchmark's positions x 21 rolls ({len(sb)} items, {n_cpu} afterstates), {dt:.1f} s, OpenMP"}
-
     del pool, values, pflags, ws, d_b, d_p, d_r, ib, ip, ir
     torch.cuda.empty_cache()
 
@@ -388,6 +371,23 @@ def main():
         G2 = max(G // 8, 1)
         selfplay2b = run_selfplay(G2, args.selfplay2_plies, 2, (0, 1, 1.0, 1.0),
                                   f"config4 (north-star expectimax): {G2} games per GPU, ALL candidates x 21 rolls, best reply, score = S - W")
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample of the same workload -----------------------------------
+    cpu = None
+    if not args.no_cpu_baseline and rank == 0 and world == 1:  # reported baseline, rank 0 at N=1 only
+        from oracle import pyoracle as po
+
+        po.build()
+        cores = os.cpu_count() or 1
+        ns = min(args.cpu_positions, boards.shape[0])
+        sb, sp, sr = (x.cpu().numpy() for x in expand_rolls(bg, boards[:ns], players[:ns]))
+        pk = packed.cpu().numpy()
+        po.movegen_eval_bench(sb[:4096], sp[:4096], sr[:4096], pk, H, nthreads=cores)
+        t0 = time.perf_counter()
+        n_cpu, _ = po.movegen_eval_bench(sb, sp, sr, pk, H, nthreads=cores)
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_cpu / dt, "unit": "afterstates/s", "cores": cores, "kind": "port",
+               "sample": f"first {ns} of the benchmark's positions x 21 rolls ({len(sb)} items, {n_cpu} afterstates), {dt:.1f} s, OpenMP"}
 
     if rank != 0:
         if dist is not None:

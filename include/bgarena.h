@@ -110,6 +110,10 @@ int32_t bg_eval(const int8_t* boards /*[N,52]*/, const uint8_t* flags /*[N] or N
 int32_t bg_eval_indirect(const int8_t* boards, const uint8_t* flags, const int32_t* owner, const uint8_t* owner_players,
                          const int64_t* N_dev, int64_t max_N, const float* prepared, int32_t H, float* out_v, void* stream);
 
+/* Diagnostic for the tcgen05 evaluator (H = 128, batches >= 32768 rows with per-row flags; set BG_EVAL_PATH=ffma to force the
+ * FFMA kernel): synchronises and returns 0, or non-zero if one of its bounded mbarrier waits ever timed out. */
+int32_t bg_eval_tc_status(void);
+
 /*
  * Action selection over ragged value segments.  Replaces softmax(V/T) + Categorical.sample
  * (src/multi/worker.py:136-143) and, for temperature <= 0, torch.argmax (lowest index on ties,

@@ -127,6 +127,8 @@ int32_t bg_select(const float* v, const int64_t* offsets, const int32_t* counts,
   return select_launch(a, (cudaStream_t)stream);
 }
 
+int32_t bg_eval_tc_status(void) { return eval_tc_status(); }
+
 int64_t bg_two_ply_workspace_bytes(int64_t N) { return two_ply_workspace_bytes(N); }
 
 int32_t bg_two_ply(const int8_t* cand_boards, const uint8_t* mover, const float* S, int64_t N, const float* prepared, int32_t H,

@@ -12,6 +12,8 @@
 // tensor-core path would not).  Persistent CTAs keep the 100 KB table resident in shared memory.
 #include "eval.cuh"
 
+#include <stdlib.h>
+
 namespace bg {
 
 namespace {
@@ -290,8 +292,29 @@ int32_t launch_eval_t(const EvalArgs& a, cudaStream_t stream) {
 // generic table (200 * H + 1 floats, padded to 256 B) followed, for H == 128, by the table of the two-boards-per-warp kernel
 static int64_t generic_table_bytes(int32_t H) { return ((int64_t)(200 * H + 1) * 4 + 255) / 256 * 256; }
 
+static int64_t table128_bytes() { return (eval128_table_floats() * 4 + 255) / 256 * 256; }
+
 int64_t prepared_weights_bytes(int32_t H) {
-  return generic_table_bytes(H) + (H == 128 ? (eval128_table_floats() * 4 + 255) / 256 * 256 : 0);
+  return generic_table_bytes(H) + (H == 128 ? table128_bytes() + eval_tc_image_bytes() : 0);
+}
+
+// which H == 128 evaluator: BG_EVAL_PATH = "tc" (tcgen05 for batches >= 32768 rows, default), "ffma" (always eval128)
+static int tc_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("BG_EVAL_PATH");
+    mode = (e && e[0] == 'f') ? 0 : 1;
+  }
+  return mode;
+}
+
+static int32_t* g_tc_err = nullptr;
+
+int32_t eval_tc_status() {
+  if (!g_tc_err) return 0;
+  int32_t h = 0;
+  if (cudaMemcpy(&h, g_tc_err, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return h;
 }
 
 int32_t prepare_weights_launch(const float* packed, int32_t H, float* prepared, cudaStream_t stream) {
@@ -302,7 +325,11 @@ int32_t prepare_weights_launch(const float* packed, int32_t H, float* prepared, 
   k_prepare<<<64, 256, 0, stream>>>(packed, H, prepared);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return check_cuda(e, "k_prepare launch");
-  if (H == 128) return eval128_prepare(packed, prepared + generic_table_bytes(H) / 4, stream);
+  if (H == 128) {
+    int32_t rc = eval128_prepare(packed, prepared + generic_table_bytes(H) / 4, stream);
+    if (rc != BG_OK) return rc;
+    return eval_tc_prepare(packed, reinterpret_cast<uint8_t*>(prepared) + generic_table_bytes(H) + table128_bytes(), stream);
+  }
   return BG_OK;
 }
 
@@ -316,7 +343,18 @@ int32_t eval_launch(const EvalArgs& a, cudaStream_t stream) {
     return BG_ERR_ARG;
   }
   if ((a.N_dev ? a.max_N : a.N) <= 0) return BG_OK;
-  if (a.H == 128) return eval128_launch(a, a.prepared + generic_table_bytes(128) / 4, stream);
+  if (a.H == 128) {
+    const int64_t bound = a.N_dev ? a.max_N : a.N;
+    if (tc_mode() == 1 && a.flags && bound >= 32768) {
+      if (!g_tc_err) {
+        cudaError_t e = cudaMalloc(&g_tc_err, 4);
+        if (e == cudaSuccess) e = cudaMemset(g_tc_err, 0, 4);
+        if (e != cudaSuccess) return check_cuda(e, "cudaMalloc(tc status)");
+      }
+      return eval_tc_launch(a, reinterpret_cast<const uint8_t*>(a.prepared) + generic_table_bytes(128) + table128_bytes(), g_tc_err, stream);
+    }
+    return eval128_launch(a, a.prepared + generic_table_bytes(128) / 4, stream);
+  }
   int32_t rc = init_constants();
   if (rc != BG_OK) return rc;
   switch (a.H / 32) {

@@ -24,6 +24,11 @@ int32_t eval_launch(const EvalArgs& a, cudaStream_t stream);
 int64_t eval128_table_floats();
 int32_t eval128_prepare(const float* packed, float* t128, cudaStream_t stream);
 int32_t eval128_launch(const EvalArgs& a, const float* t128, cudaStream_t stream);
+// H == 128 tensor-core (tcgen05 / TMEM) kernel (eval_tc.cu); its operand image follows the eval128 table
+int64_t eval_tc_image_bytes();
+int32_t eval_tc_prepare(const float* packed, uint8_t* img, cudaStream_t stream);
+int32_t eval_tc_launch(const EvalArgs& a, const uint8_t* img, int32_t* err_flag, cudaStream_t stream);
+int32_t eval_tc_status();  // synchronising: 0 ok, != 0 a bounded mbarrier wait timed out in k_eval_tc
 int32_t encode_launch(const int8_t* boards, const uint8_t* flags, int64_t N, float* out, cudaStream_t stream);
 
 }  // namespace bg
