@@ -164,27 +164,39 @@ __global__ void __launch_bounds__(THREADS, 1)
     const uint32_t full = smem_u32(&bars[g]), done = smem_u32(&bars[2 + g]);
     const uint32_t* b32 = reinterpret_cast<const uint32_t*>(boards);
     uint32_t it = 0;
-    for (int64_t t = (int64_t)blockIdx.x * 2 + g; t < n_tiles; t += (int64_t)gridDim.x * 2, ++it) {
+    // board words of the CURRENT tile live in registers; the next tile's are fetched before waiting on the tensor core
+    uint32_t bw[13];
+    uint32_t flag = 0;
+    auto fetch = [&](int64_t tile) {
+      const int64_t i = tile * 128 + row;
+      if (tile < n_tiles && i < N) {
+#pragma unroll
+        for (int w = 0; w < 13; ++w) bw[w] = __ldg(b32 + i * 13 + w);
+        flag = flags[i] & 1u;
+      } else {
+#pragma unroll
+        for (int w = 0; w < 13; ++w) bw[w] = 0u;
+        flag = 0u;
+      }
+    };
+    const int64_t tstride = (int64_t)gridDim.x * 2;
+    fetch((int64_t)blockIdx.x * 2 + g);
+    for (int64_t t = (int64_t)blockIdx.x * 2 + g; t < n_tiles; t += tstride, ++it) {
       const int64_t i = t * 128 + row;
       const bool valid = i < N;
-      // ---- build this board's bf16 feature row, 8 TMEM columns (= one K16 step = two points) at a time ----
-      uint32_t w12 = 0, flag = 0;
-      if (valid) {
-        w12 = __ldg(b32 + i * 13 + 12);
-        flag = flags[i] & 1u;
-      }
-#pragma unroll 1
+      // ---- build this board's bf16 feature row, 8 TMEM columns (= one K16 step = four points) at a time ----
+#pragma unroll
       for (int wd = 0; wd < 12; ++wd) {  // board word wd: 4 points -> 16 features -> 8 columns
-        const uint32_t bw = valid ? __ldg(b32 + i * 13 + wd) : 0u;
         uint32_t r[8];
-        point_words(bw & 0xffu, r[0], r[1]);
-        point_words((bw >> 8) & 0xffu, r[2], r[3]);
-        point_words((bw >> 16) & 0xffu, r[4], r[5]);
-        point_words(bw >> 24, r[6], r[7]);
+        point_words(bw[wd] & 0xffu, r[0], r[1]);
+        point_words((bw[wd] >> 8) & 0xffu, r[2], r[3]);
+        point_words((bw[wd] >> 16) & 0xffu, r[4], r[5]);
+        point_words(bw[wd] >> 24, r[6], r[7]);
         tmem_st8(tA + wd * 8, r);
       }
       {
         const uint32_t ONE = 0x3f80u;
+        const uint32_t w12 = bw[12];
         const uint32_t bar0 = w12 & 0xffu, bar1 = (w12 >> 8) & 0xffu, off0 = (w12 >> 16) & 15u, off1 = (w12 >> 24) & 15u;
         const uint32_t hb0 = __bfloat16_as_ushort(__float2bfloat16_rn((float)bar0 * 0.5f));
         const uint32_t hb1 = __bfloat16_as_ushort(__float2bfloat16_rn((float)bar1 * 0.5f));
@@ -204,6 +216,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(full);
+      fetch(t + tstride);  // overlaps the MMAs
       // ---- wait for the 39 MMAs of this tile, then the epilogue straight out of TMEM ----
       if (!mbar_wait(done, it & 1u)) {
         if (lane == 0) atomicExch(err, 1);
@@ -217,9 +230,14 @@ __global__ void __launch_bounds__(THREADS, 1)
         tmem_ld32(tD + c0, z);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float s = rcp_approx(1.0f + ex2_approx(__uint_as_float(z[c]) * -1.4426950408889634f));
-          v = fmaf(sW2[c0 + c], s, v);
+        for (int c = 0; c < 32; c += 2) {
+          // two sigmoids per reciprocal: 1/(1+a) = (1+b) * r, 1/(1+b) = (1+a) * r with r = 1/((1+a)(1+b));
+          // z is clamped at -40 (sigmoid < 5e-18) so the product stays finite
+          const float a1 = 1.0f + ex2_approx(fmaxf(__uint_as_float(z[c]), -40.f) * -1.4426950408889634f);
+          const float b1 = 1.0f + ex2_approx(fmaxf(__uint_as_float(z[c + 1]), -40.f) * -1.4426950408889634f);
+          const float r = rcp_approx(a1 * b1);
+          v = fmaf(sW2[c0 + c], b1 * r, v);
+          v = fmaf(sW2[c0 + c + 1], a1 * r, v);
         }
       }
       if (valid) out_v[i] = v + sW2[H];
