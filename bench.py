@@ -310,7 +310,7 @@ def main():
     peak, peak_src = load_peaks()
     eval_bytes = n_after * (52 + 1 + 4)  # board in + flag in + value out
     movegen_bytes = B * (52 + 1 + 2 + 8 + 4) + n_after * (52 + 1)  # item in/out + board, flag out
-    kern = {"bg::k_eval128": (t_eval, eval_bytes), "bg::k_movegen<128|512|4096> (3 tiers)": (t_movegen, movegen_bytes)}
+    kern = {"bg::k_eval_tc (tcgen05, H=128)": (t_eval, eval_bytes), "bg::k_movegen<128|512|4096> (3 tiers)": (t_movegen, movegen_bytes)}
     dom = max(kern, key=lambda k: kern[k][0])
     ach = kern[dom][1] / (kern[dom][0] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
@@ -318,6 +318,17 @@ def main():
                 "note": "integer-issue / shared-memory bound by design: algorithmic bytes are tiny (SURVEY.md 8(d))",
                 "kernels_ms": {k: v[0] for k, v in kern.items()},
                 "eval_fp32_tflops_dense_equiv": n_after * FLOP_PER_AFTERSTATE / (t_eval * 1e-3) / 1e12}
+    # the evaluator is a tensor-core kernel: 3 bf16 splits x (2 * 208 * 128) FLOP per afterstate actually issued to tcgen05
+    tc_flops = n_after * 3 * 2 * 208 * H
+    tpeak = None
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        tpeak = float(json.load(open(pk)).get("bf16_tflops", 0.0)) or None
+    tpeak, tsrc = (tpeak, "measured (MEASURED_PEAKS.json bf16_tflops, burst)") if tpeak else (1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)")
+    tach = tc_flops / (t_eval * 1e-3) / 1e12
+    roofline_eval = {"bound": "tensor", "kernel": "bg::k_eval_tc (tcgen05, H=128)", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s",
+                     "frac": tach / tpeak, "traffic": None, "peak_source": tsrc, "ms_per_launch": t_eval,
+                     "note": "bf16 FLOPs issued: 3 weight splits x 2*208*128 per afterstate (fp32-exact layer 1); dense fp32-equivalent is 1/3.27 of this"}
 
     del pool, values, pflags, ws, d_b, d_p, d_r, ib, ip, ir
     torch.cuda.empty_cache()
@@ -403,7 +414,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "afterstates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "what": "pinned host boards/players/rolls -> bg_movegen -> bg_eval -> bg_select(greedy) -> host actions + counts"},
             "gpu_launches": 4 * args.steps, "gpu_launches_note": "per step: k_movegen tiers 128 / 512 / 4096 + k_eval128 (e2e adds k_select)",
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "selfplay_1ply": selfplay, "selfplay_2ply": selfplay2,
+            "roofline": roofline, "roofline_eval": roofline_eval, "cpu_baseline": cpu, "clocks": clocks, "selfplay_1ply": selfplay, "selfplay_2ply": selfplay2,
             "selfplay_2ply_all_candidates": selfplay2b}
     print(json.dumps(line), flush=True)
     if dist is not None:

@@ -28,22 +28,32 @@ namespace bg {
 
 namespace {
 
+// dynamic shared memory, addressed through this accessor everywhere (also inside the out-of-line level expansion) so that
+// the compiler keeps shared-space loads/stores (LDS/STS) instead of generic ones
+__device__ __forceinline__ uint32_t* dyn_smem() {
+  extern __shared__ uint32_t bg_dyn_smem[];
+  return bg_dyn_smem;
+}
+
 template <int CAP, bool GLOBAL, bool MOVES>
 struct Frontier {
   static constexpr int NF = MOVES ? 6 : 4;  // words per node: k0..k3 key (+ m0 m1 sub-move history)
-  uint32_t* base;                           // [2][NF][CAP]
+  uint32_t* gbase;                          // GLOBAL: [2][NF][CAP] in L2-resident scratch
+  uint32_t soff;                            // !GLOBAL: word offset of [2][NF][CAP] in dynamic shared memory
+  uint32_t toff;                            // word offset of the hash table [2 * CAP] in dynamic shared memory
   __device__ __forceinline__ uint32_t ld(int lvl, int f, int pos) const {
     if constexpr (GLOBAL)
-      return __ldcg(base + (lvl * NF + f) * CAP + pos);
+      return __ldcg(gbase + (lvl * NF + f) * CAP + pos);
     else
-      return base[(lvl * NF + f) * CAP + pos];
+      return dyn_smem()[soff + (lvl * NF + f) * CAP + pos];
   }
   __device__ __forceinline__ void st(int lvl, int f, int pos, uint32_t v) const {
     if constexpr (GLOBAL)
-      __stcg(base + (lvl * NF + f) * CAP + pos, v);
+      __stcg(gbase + (lvl * NF + f) * CAP + pos, v);
     else
-      base[(lvl * NF + f) * CAP + pos] = v;
+      dyn_smem()[soff + (lvl * NF + f) * CAP + pos] = v;
   }
+  __device__ __forceinline__ uint32_t* table() const { return dyn_smem() + toff; }
 };
 
 struct Root {
@@ -204,9 +214,10 @@ enum { MODE_EXPAND = 0, MODE_IDENTITY = 1 };
 // MODE_IDENTITY re-emits the parents themselves (the reference's single-move fallback).
 // Returns false on capacity overflow.  flags: bit0 some child existed, bit1 some child was appended.
 template <int CAP, bool GLOBAL, bool MOVES>
-__device__ __noinline__ bool expand_level(const Frontier<CAP, GLOBAL, MOVES> F, uint32_t* tab, const Root r, int src_lvl, int src_off,
+__device__ __noinline__ bool expand_level(const Frontier<CAP, GLOBAL, MOVES> F, const Root r, int src_lvl, int src_off,
                                           int n_src, int dst_lvl, int& n_dst, bool dedup, int mode, int die, int depth, uint32_t& flags) {
   constexpr uint32_t TMASK = 2 * CAP - 1;
+  uint32_t* const tab = F.table();
   const int lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
   int n = n_dst;
@@ -326,7 +337,7 @@ struct ItemOut {
 
 // Generates the ordered legal afterstate list of one item.
 template <int CAP, bool GLOBAL, bool MOVES>
-__device__ __forceinline__ int generate(const Frontier<CAP, GLOBAL, MOVES>& F, uint32_t* tab, const uint32_t* rootw, int player, int d0,
+__device__ __forceinline__ int generate(const Frontier<CAP, GLOBAL, MOVES>& F, const uint32_t* rootw, int player, int d0,
                                         int d1, int lane, ItemOut& out) {
   // ---- root ------------------------------------------------------------------------------------------
   const int ob = player * 6, pb = (1 - player) * 6;
@@ -363,6 +374,7 @@ __device__ __forceinline__ int generate(const Frontier<CAP, GLOBAL, MOVES>& F, u
   if (lane == 0) store_node(F, 0, 0, root);
   __syncwarp();
   uint32_t fl;
+  uint32_t* const tab = F.table();
   const bool doubles = d0 == d1;
   const int hi = d0 > d1 ? d0 : d1, lo = d0 > d1 ? d1 : d0;
   clear_table<CAP>(tab, lane);
@@ -372,7 +384,7 @@ __device__ __forceinline__ int generate(const Frontier<CAP, GLOBAL, MOVES>& F, u
     for (int depth = 0; depth < 4; ++depth) {
       if (depth) clear_table<CAP>(tab, lane);
       int n_next = 0;
-      if (!expand_level(F, tab, r, cur, 0, n_cur, cur ^ 1, n_next, true, MODE_EXPAND, d0, depth, fl)) return ITEM_OVERFLOW;
+      if (!expand_level(F, r, cur, 0, n_cur, cur ^ 1, n_next, true, MODE_EXPAND, d0, depth, fl)) return ITEM_OVERFLOW;
       if (n_next == 0) break;
       cur ^= 1;
       n_cur = n_next;
@@ -392,13 +404,13 @@ __device__ __forceinline__ int generate(const Frontier<CAP, GLOBAL, MOVES>& F, u
   for (int order = 0; order < 2; ++order) {
     const int dA = order == 0 ? hi : lo, dB = order == 0 ? lo : hi;
     int n1 = 1;  // appended after the root; first-die boards are pairwise distinct -> no dedup
-    if (!expand_level(F, tab, r, 0, 0, 1, 0, n1, false, MODE_EXPAND, dA, 0, fl)) return ITEM_OVERFLOW;
+    if (!expand_level(F, r, 0, 0, 1, 0, n1, false, MODE_EXPAND, dA, 0, fl)) return ITEM_OVERFLOW;
     n1 -= 1;
-    if (!expand_level(F, tab, r, 0, 1, n1, 1, n_res, true, MODE_EXPAND, dB, 1, fl)) return ITEM_OVERFLOW;
+    if (!expand_level(F, r, 0, 1, n1, 1, n_res, true, MODE_EXPAND, dB, 1, fl)) return ITEM_OVERFLOW;
     int len = 2;
     if (!(fl & 1u)) {  // no two-move sequence in this order: singles, in first-die order (handle_move_types.py:70-81)
       len = 1;
-      if (!expand_level(F, tab, r, 0, 1, n1, 1, n_res, true, MODE_IDENTITY, dA, 0, fl)) return ITEM_OVERFLOW;
+      if (!expand_level(F, r, 0, 1, n1, 1, n_res, true, MODE_IDENTITY, dA, 0, fl)) return ITEM_OVERFLOW;
     }
     if (order == 0) {
       n_a = n_res;
@@ -422,19 +434,16 @@ __device__ __forceinline__ int generate(const Frontier<CAP, GLOBAL, MOVES>& F, u
 
 template <int CAP, bool GLOBAL, bool MOVES, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_movegen(MovegenParams P) {
-  extern __shared__ uint32_t smem[];
   constexpr int NF = MOVES ? 6 : 4;
   constexpr int FRONT_WORDS = GLOBAL ? 0 : 2 * NF * CAP;
   constexpr int PER_WARP = FRONT_WORDS + 2 * CAP + 16;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  uint32_t* my = smem + wib * PER_WARP;
   Frontier<CAP, GLOBAL, MOVES> F;
-  if constexpr (GLOBAL)
-    F.base = P.gfront + (size_t)(blockIdx.x * WARPS + wib) * (2 * NF * CAP);
-  else
-    F.base = my;
-  uint32_t* tab = my + FRONT_WORDS;
-  uint32_t* rootw = tab + 2 * CAP;
+  F.soff = (uint32_t)(wib * PER_WARP);
+  F.toff = F.soff + FRONT_WORDS;
+  F.gbase = nullptr;
+  if constexpr (GLOBAL) F.gbase = P.gfront + (size_t)(blockIdx.x * WARPS + wib) * (2 * NF * CAP);
+  uint32_t* const rootw = dyn_smem() + F.toff + 2 * CAP;
 
   const int64_t n_items = P.in_list ? (int64_t)(*P.in_count) : P.B;
   while (true) {
@@ -459,7 +468,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_movegen(MovegenParams P) {
       const int player = P.players[item] & 1;
       const int d0 = P.rolls[2 * (int64_t)item], d1 = P.rolls[2 * (int64_t)item + 1];
       ItemOut io;
-      const int rc = generate<CAP, GLOBAL, MOVES>(F, tab, rootw, player, d0, d1, lane, io);
+      const int rc = generate<CAP, GLOBAL, MOVES>(F, rootw, player, d0, d1, lane, io);
       if (rc == ITEM_OVERFLOW) {
         if (lane == 0) {
           if (P.ovf_list) {
@@ -497,29 +506,36 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_movegen(MovegenParams P) {
       }
       base = __shfl_sync(BG_FULL, base, 0);
       if (base < 0 || n_keep == 0) continue;
+      // Boards are rebuilt lane-per-board into a shared staging area (13-word rows: odd stride, conflict free) and then
+      // copied out with fully coalesced word stores.  Staging reuses memory that is dead after generation: the frontier
+      // level that does not hold the result (shared tiers) or the hash table (global tier).
       uint32_t* ob = reinterpret_cast<uint32_t*>(P.out_boards) + base * 13;
+      uint32_t* const stage = GLOBAL ? F.table() : dyn_smem() + F.soff + (lvl ^ 1) * NF * CAP;
       const uint32_t w12 = rootw[12];
       const uint32_t opp_bar = (w12 >> (8 * (1 - player))) & 0xffu, opp_off = (w12 >> (16 + 8 * (1 - player))) & 0xffu;
-      for (int tt = lane; tt < n_keep * 13; tt += 32) {
-        const int bo = tt / 13, w = tt - bo * 13;
-        const int b = bo < na ? io.a0 + bo : io.b0 + (bo - na);
-        uint32_t word;
-        if (w < 12) {
-          const int side = w >= 6, q = w - side * 6;
-          if (side == player) {
-            const uint32_t kw = F.ld(lvl, q >> 1, b);
-            word = nib4_to_bytes((kw >> (16 * (q & 1))) & 0xffffu);
-          } else {
-            const uint32_t hb = (F.ld(lvl, 3, b) >> (4 * q)) & 0xfu;
-            word = rootw[w] - bits4_to_bytes(hb);
-          }
-        } else {
-          const uint32_t k3 = F.ld(lvl, 3, b);
+      const int ownw = player * 6, oppw = (1 - player) * 6;
+      for (int b0 = 0; b0 < n_keep; b0 += 32) {
+        const int bo = b0 + lane;
+        __syncwarp();
+        if (bo < n_keep) {
+          const int b = bo < na ? io.a0 + bo : io.b0 + (bo - na);
+          const uint32_t k0 = F.ld(lvl, 0, b), k1 = F.ld(lvl, 1, b), k2 = F.ld(lvl, 2, b), k3 = F.ld(lvl, 3, b);
+          uint32_t* row = stage + lane * 13;
+          row[ownw + 0] = nib4_to_bytes(k0 & 0xffffu);
+          row[ownw + 1] = nib4_to_bytes(k0 >> 16);
+          row[ownw + 2] = nib4_to_bytes(k1 & 0xffffu);
+          row[ownw + 3] = nib4_to_bytes(k1 >> 16);
+          row[ownw + 4] = nib4_to_bytes(k2 & 0xffffu);
+          row[ownw + 5] = nib4_to_bytes(k2 >> 16);
+#pragma unroll
+          for (int q = 0; q < 6; ++q) row[oppw + q] = rootw[oppw + q] - bits4_to_bytes((k3 >> (4 * q)) & 0xfu);
           const uint32_t ownbar = (k3 >> 24) & 15u, ownoff = k3 >> 28, ob2 = opp_bar + __popc(k3 & 0xffffffu);
-          word = player == 0 ? (ownbar | (ob2 << 8) | (ownoff << 16) | (opp_off << 24))
-                             : (ob2 | (ownbar << 8) | (opp_off << 16) | (ownoff << 24));
+          row[12] = player == 0 ? (ownbar | (ob2 << 8) | (ownoff << 16) | (opp_off << 24))
+                                : (ob2 | (ownbar << 8) | (opp_off << 16) | (ownoff << 24));
         }
-        ob[tt] = word;
+        __syncwarp();
+        const int nw = (n_keep - b0 < 32 ? n_keep - b0 : 32) * 13;
+        for (int tt = lane; tt < nw; tt += 32) ob[b0 * 13 + tt] = stage[tt];
       }
       if (P.out_owner)
         for (int b = lane; b < n_keep; b += 32) P.out_owner[base + b] = item;
