@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_movegen(MovegenParams P) {
 
 // capacity tiers: nodes per ply.  T1/T2 keep the frontiers in shared memory, T3 in L2-resident global scratch.
 constexpr int T1_CAP = 128, T1_WARPS = 4, T1_CTAS_PER_SM = 8;
-constexpr int T2_CAP = 512, T2_WARPS = 2, T2_CTAS_PER_SM = 4;
+constexpr int T2_CAP = 512, T2_WARPS = 1, T2_CTAS_PER_SM = 10;
 constexpr int T3_CAP = 4096, T3_WARPS = 2, T3_CTAS_PER_SM = 3;
 constexpr int NUM_SMS = 148;
 
