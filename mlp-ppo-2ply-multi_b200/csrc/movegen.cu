@@ -330,6 +330,23 @@ __device__ __noinline__ bool expand_level(const Frontier<CAP, GLOBAL, MOVES> F, 
   return true;
 }
 
+// Children of the ROOT for one die, lane == move slot (no flattening needed for a single parent, no dedup: the children of one
+// node are pairwise distinct).  Stored compactly, in slot order, at dst[dst_pos ...); returns their number.
+template <int CAP, bool GLOBAL, bool MOVES>
+__device__ __forceinline__ int expand_root(const Frontier<CAP, GLOBAL, MOVES>& F, const Root& r, const Node& root, int die, int dst_lvl,
+                                           int dst_pos, int lane) {
+  const uint32_t vm = move_mask(root, r, die);
+  const bool valid = lane < 27 && ((vm >> lane) & 1u);
+  const uint32_t bal = __ballot_sync(BG_FULL, valid);
+  if (valid) {
+    Node c;
+    make_child(root, r, lane, vm >> 27, die, 0, c);
+    store_node(F, dst_lvl, dst_pos + __popc(bal & ((1u << lane) - 1u)), c);
+  }
+  __syncwarp();
+  return __popc(bal);
+}
+
 // Result of one item: up to two index ranges [a0,a1) ++ [b0,b1) of frontier level `lvl`, in output order.
 struct ItemOut {
   int lvl, a0, a1, b0, b1;
@@ -380,15 +397,19 @@ __device__ __forceinline__ int generate(const Frontier<CAP, GLOBAL, MOVES>& F, c
   clear_table<CAP>(tab, lane);
   if (doubles) {
     // ---- doubles: BFS by ply with per-ply dedup (handle_move_types.py:84-193) ------------------------
-    int cur = 0, n_cur = 1, depth_done = 0;
-    for (int depth = 0; depth < 4; ++depth) {
-      if (depth) clear_table<CAP>(tab, lane);
-      int n_next = 0;
-      if (!expand_level(F, r, cur, 0, n_cur, cur ^ 1, n_next, true, MODE_EXPAND, d0, depth, fl)) return ITEM_OVERFLOW;
-      if (n_next == 0) break;
-      cur ^= 1;
-      n_cur = n_next;
-      depth_done = depth + 1;
+    int cur = 1, depth_done = 0;
+    int n_cur = expand_root(F, r, root, d0, 1, 0, lane);
+    if (n_cur > 0) {
+      depth_done = 1;
+      for (int depth = 1; depth < 4; ++depth) {
+        if (depth > 1) clear_table<CAP>(tab, lane);
+        int n_next = 0;
+        if (!expand_level(F, r, cur, 0, n_cur, cur ^ 1, n_next, true, MODE_EXPAND, d0, depth, fl)) return ITEM_OVERFLOW;
+        if (n_next == 0) break;
+        cur ^= 1;
+        n_cur = n_next;
+        depth_done = depth + 1;
+      }
     }
     out.lvl = cur;
     out.a0 = 0;
@@ -403,9 +424,7 @@ __device__ __forceinline__ int generate(const Frontier<CAP, GLOBAL, MOVES>& F, c
   int n_res = 0, n_a = 0, len_a = 0, len_b = 0;
   for (int order = 0; order < 2; ++order) {
     const int dA = order == 0 ? hi : lo, dB = order == 0 ? lo : hi;
-    int n1 = 1;  // appended after the root; first-die boards are pairwise distinct -> no dedup
-    if (!expand_level(F, r, 0, 0, 1, 0, n1, false, MODE_EXPAND, dA, 0, fl)) return ITEM_OVERFLOW;
-    n1 -= 1;
+    const int n1 = expand_root(F, r, root, dA, 0, 1, lane);  // stored after the root; pairwise distinct -> no dedup
     if (!expand_level(F, r, 0, 1, n1, 1, n_res, true, MODE_EXPAND, dB, 1, fl)) return ITEM_OVERFLOW;
     int len = 2;
     if (!(fl & 1u)) {  // no two-move sequence in this order: singles, in first-die order (handle_move_types.py:70-81)
