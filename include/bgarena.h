@@ -227,6 +227,45 @@ int32_t bg_arena_stats(bg_arena* a, int64_t* out, void* stream);
 int32_t bg_arena_export_state(bg_arena* a, int8_t* boards, uint8_t* players, uint8_t* rolls, uint8_t* game_state,
                               void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * TD(0) learner: the consumer of the arena's episodes.
+ * Replaces Trainer.__init__ / Trainer.update (src/agents/trainer.py:11-46, 48-166): for each episode IN ORDER one forward
+ * pass over its T observations, targets r_t + gamma * V(x_{t+1}) (last target r_T), mse loss, backward,
+ * clip_grad_norm_(grad_clip), one torch.optim.Adam step (betas 0.9/0.999, eps 1e-8).  The whole batch runs as one
+ * persistent thread-block cluster with the optimiser state in shared memory; results agree with the reference trainer to
+ * fp32 rounding (tests/golden/learner.npz: |dW| <= 1e-5 after 400 sequential steps).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct bg_learner bg_learner;
+
+#define BG_LEARNER_NMETRICS 6
+/* per-episode metrics row (the quantities trainer.py:141-151 accumulates): [0] loss  [1] mean |TD error|
+ * [2] gradient norm after clipping  [3] mean predicted value  [4] reward sum  [5] length T */
+#define BG_LEARNER_MAX_T 320 /* longest episode accepted (reference MAX_TIMESTEPS = 300) */
+
+/* reference defaults: lr = 1e-3, gamma = 0.99, grad_clip = 1.0 (src/config/configuration.py:17-21); grad_clip <= 0 disables clipping.
+ * Parameters start at zero: call bg_learner_set_parameters before the first update. */
+int32_t bg_learner_create(bg_learner** out, int32_t device, int32_t H, float lr, float gamma, float grad_clip);
+int32_t bg_learner_destroy(bg_learner* l);
+/* Load a packed weight blob (device pointer; Trainer.__init__'s load_state_dict, trainer.py:21-24).
+ * reset_optimizer != 0 also zeroes the Adam moments and the step count (a fresh torch.optim.Adam). */
+int32_t bg_learner_set_parameters(bg_learner* l, const float* packed, int32_t reset_optimizer, void* stream);
+/* Copy the current packed weights out (device pointer): what Trainer hands to ParameterManager.set_parameters (trainer.py:166);
+ * feed it to bg_arena_set_weights. */
+int32_t bg_learner_get_parameters(bg_learner* l, float* packed_out, void* stream);
+/* Adam moments in packed order and the step count (device pointers, any may be NULL). */
+int32_t bg_learner_get_optimizer(bg_learner* l, float* exp_avg, float* exp_avg_sq, int64_t* step, void* stream);
+/*
+ * One Trainer.update over n_episodes episodes in CSR form (ep_offsets[n_episodes+1], device).
+ *   records == 0: boards[N,52] / flags[N] are the OBSERVATIONS (board the decision was made on, player to move).
+ *   records == 1: boards / flags are bg_arena_drain_episodes' after_boards / meta exactly as drained: experience t's
+ *                 observation board is record t-1's after_board (the initial board for t = 0), its flag is meta bit 0.
+ *   out_metrics : optional [n_episodes, BG_LEARNER_NMETRICS].
+ *   out_status  : optional [1] device int32: BG_OK, or BG_ERR_CAPACITY if an episode was longer than BG_LEARNER_MAX_T
+ *                 (such episodes, and empty ones, are skipped without an optimiser step).
+ */
+int32_t bg_learner_update(bg_learner* l, const int8_t* boards, const uint8_t* flags, const float* reward, const int64_t* ep_offsets,
+                          int64_t n_episodes, int32_t records, float* out_metrics, int32_t* out_status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,12 @@ SIGNATURES = {
     "bg_arena_drain_episodes": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bg_arena_stats": (_i32, [_vp, _vp, _vp]),
     "bg_arena_export_state": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "bg_learner_create": (_i32, [_vp, _i32, _i32, _f32, _f32, _f32]),
+    "bg_learner_destroy": (_i32, [_vp]),
+    "bg_learner_set_parameters": (_i32, [_vp, _vp, _i32, _vp]),
+    "bg_learner_get_parameters": (_i32, [_vp, _vp, _vp]),
+    "bg_learner_get_optimizer": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "bg_learner_update": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
 }
 
 

@@ -4,6 +4,7 @@
 
 #include "arena.cuh"
 #include "eval.cuh"
+#include "learner.cuh"
 #include "movegen.cuh"
 #include "select.cuh"
 #include "two_ply.cuh"
@@ -198,6 +199,44 @@ int32_t bg_arena_stats(bg_arena* a, int64_t* out, void* stream) {
 int32_t bg_arena_export_state(bg_arena* a, int8_t* boards, uint8_t* players, uint8_t* rolls, uint8_t* game_state, void* stream) {
   BG_REQUIRE(a, "bg_arena_export_state: null arena");
   return arena_export_state(reinterpret_cast<Arena*>(a), boards, players, rolls, game_state, (cudaStream_t)stream);
+}
+
+/* ---- learner ---- */
+
+int32_t bg_learner_create(bg_learner** out, int32_t device, int32_t H, float lr, float gamma, float grad_clip) {
+  BG_REQUIRE(out, "bg_learner_create: out is null");
+  BG_REQUIRE(lr > 0.f && gamma >= 0.f, "bg_learner_create: bad hyper-parameters");
+  int32_t rc = require_device();
+  if (rc != BG_OK) return rc;
+  Learner* L = nullptr;
+  rc = learner_create(&L, device, H, lr, gamma, grad_clip);
+  *out = reinterpret_cast<bg_learner*>(L);
+  return rc;
+}
+
+int32_t bg_learner_destroy(bg_learner* l) { return learner_destroy(reinterpret_cast<Learner*>(l)); }
+
+int32_t bg_learner_set_parameters(bg_learner* l, const float* packed, int32_t reset_optimizer, void* stream) {
+  BG_REQUIRE(l && packed, "bg_learner_set_parameters: null pointer");
+  return learner_set_parameters(reinterpret_cast<Learner*>(l), packed, reset_optimizer, (cudaStream_t)stream);
+}
+
+int32_t bg_learner_get_parameters(bg_learner* l, float* packed_out, void* stream) {
+  BG_REQUIRE(l && packed_out, "bg_learner_get_parameters: null pointer");
+  return learner_get_parameters(reinterpret_cast<Learner*>(l), packed_out, (cudaStream_t)stream);
+}
+
+int32_t bg_learner_get_optimizer(bg_learner* l, float* exp_avg, float* exp_avg_sq, int64_t* step, void* stream) {
+  BG_REQUIRE(l, "bg_learner_get_optimizer: null learner");
+  return learner_get_optimizer(reinterpret_cast<Learner*>(l), exp_avg, exp_avg_sq, step, (cudaStream_t)stream);
+}
+
+int32_t bg_learner_update(bg_learner* l, const int8_t* boards, const uint8_t* flags, const float* reward, const int64_t* ep_offsets,
+                          int64_t n_episodes, int32_t records, float* out_metrics, int32_t* out_status, void* stream) {
+  BG_REQUIRE(l && n_episodes >= 0, "bg_learner_update: bad arguments");
+  BG_REQUIRE(n_episodes == 0 || (boards && flags && reward && ep_offsets), "bg_learner_update: null pointer");
+  return learner_update(reinterpret_cast<Learner*>(l), boards, flags, reward, ep_offsets, n_episodes, records, out_metrics, out_status,
+                        (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -77,18 +77,6 @@ struct ArenaCfg {
   int32_t auto_reset;
 };
 
-// word `lane` (0..12) of the start position, reference immutable_board.py:26-70: P1 {0:2, 11:5, 16:3, 18:5}, P2 {23:2, 12:5, 7:3, 5:5}
-__device__ __forceinline__ uint32_t initial_board_word(int lane) {
-  uint32_t v = 0;
-  if (lane == 0) v = 2u;                          // p0[0] = 2
-  if (lane == 2) v = 5u << 24;                    // p0[11] = 5
-  if (lane == 4) v = 3u | (5u << 16);             // p0[16] = 3, p0[18] = 5
-  if (lane == 6 + 1) v = (5u << 8) | (3u << 24);  // p1[5] = 5, p1[7] = 3
-  if (lane == 6 + 3) v = 5u;                      // p1[12] = 5
-  if (lane == 6 + 5) v = 2u << 24;                // p1[23] = 2
-  return v;
-}
-
 // one dice roll (reference backgammon_env.py:310-311); all lanes compute the same value
 __device__ __forceinline__ void roll_dice(const ArenaDev& D, const ArenaCfg& C, int64_t g, int64_t serial, int32_t& ctr, int& d0, int& d1,
                                           bool& exhausted) {

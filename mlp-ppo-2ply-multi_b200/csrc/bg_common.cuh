@@ -29,6 +29,18 @@ __device__ __forceinline__ uint32_t bits4_to_bytes(uint32_t h) {
   return (h & 1u) | ((h & 2u) << 7) | ((h & 4u) << 14) | ((h & 8u) << 21);
 }
 
+// word `lane` (0..12) of the start position, reference immutable_board.py:26-70: P1 {0:2, 11:5, 16:3, 18:5}, P2 {23:2, 12:5, 7:3, 5:5}
+__device__ __forceinline__ uint32_t initial_board_word(int lane) {
+  uint32_t v = 0;
+  if (lane == 0) v = 2u;                          // p0[0] = 2
+  if (lane == 2) v = 5u << 24;                    // p0[11] = 5
+  if (lane == 4) v = 3u | (5u << 16);             // p0[16] = 3, p0[18] = 5
+  if (lane == 6 + 1) v = (5u << 8) | (3u << 24);  // p1[5] = 5, p1[7] = 3
+  if (lane == 6 + 3) v = 5u;                      // p1[12] = 5
+  if (lane == 6 + 5) v = 2u << 24;                // p1[23] = 2
+  return v;
+}
+
 __device__ __forceinline__ uint32_t mix32(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   uint32_t h = a * 0x9E3779B1u;
   h = (h ^ (h >> 15)) + b * 0x85EBCA77u;

@@ -26,21 +26,29 @@ class ParameterManager:
         self._lock = threading.Lock()
         self._version = 1
         self._hidden = hidden_size
-        self._params = {k: v.detach().cpu().clone() for k, v in BackgammonPolicyNetwork(hidden_size=hidden_size).state_dict().items()}
+        # the packed fp32 blob [W1^T | b1 | w2 | b2] is the source of truth (CPU or device tensor); state dicts are views of it
+        self._packed = ops.pack_weights(BackgammonPolicyNetwork(hidden_size=hidden_size).state_dict()).detach().cpu()
         self._arenas: List = []
         self.src_rank = src_rank
         self.process_group = process_group
 
     # ---- reference surface -----------------------------------------------------------------------------------------
     def get_parameters(self, device=None):
-        return {k: v.clone().to(device) if device is not None else v.clone() for k, v in self._params.items()}
+        sd = ops.unpack_weights(self._packed, self._hidden)
+        return {k: v.to(device if device is not None else "cpu") for k, v in sd.items()}
 
     def get_version(self) -> int:
         return self._version
 
     def set_parameters(self, new_state_dict):
+        self.set_packed(ops.pack_weights(new_state_dict), new_state_dict["fc1.weight"].shape[0])
+
+    def set_packed(self, packed: torch.Tensor, hidden_size: Optional[int] = None):
+        """set_parameters for an already packed (device) blob: what the CUDA learner hands over, no host round trip."""
         with self._lock:
-            self._params = {k: v.detach().cpu().clone() for k, v in new_state_dict.items()}
+            if hidden_size is not None:
+                self._hidden = int(hidden_size)
+            self._packed = packed.detach().to(torch.float32).reshape(-1).clone()
             self._version += 1
         self.publish()
 
@@ -59,14 +67,14 @@ class ParameterManager:
         """Send the current weights (+version, temperature) to every subscribed arena; across ranks with one broadcast."""
         if not self._arenas and not self._distributed():
             return
-        dev = self._arenas[0].device if self._arenas else torch.device("cpu")
-        blob = torch.cat([ops.pack_weights(self._params).to(torch.float32), torch.tensor([float(self._version), self.get_temperature()])]).to(dev)
         if self._distributed():
+            dev = self._arenas[0].device if self._arenas else self._packed.device
+            blob = torch.cat([self._packed.to(dev), torch.tensor([float(self._version), self.get_temperature()], device=dev)])
             torch.distributed.broadcast(blob, src=self.src_rank, group=self.process_group)
             self._version = int(blob[-2].item())
-            self._params = {k: v.cpu() for k, v in ops.unpack_weights(blob[:-2], self._hidden).items()}
+            self._packed = blob[:-2].clone()
         for a in self._arenas:
-            a.set_weights(blob[:-2].to(a.device), version=self._version, temperature=float(blob[-1].item()))
+            a.set_weights(self._packed.to(a.device), version=self._version, temperature=self.get_temperature())
 
     def sync_from_source(self):
         """Non-source ranks call this where the source rank calls set_parameters()/publish() (collective)."""

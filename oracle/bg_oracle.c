@@ -967,3 +967,165 @@ void bgo_random_positions(int64_t n, uint64_t seed, int8_t* out_boards, uint8_t*
     bgo_env_destroy(e);
   }
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* learner: Trainer.update (src/agents/trainer.py:48-166)                                     */
+/* ------------------------------------------------------------------------------------------ */
+
+/* The reference processes the episodes of a batch SEQUENTIALLY: for each episode one forward pass over its
+ * T observations (trainer.py:104-108), TD(0) targets r_t + gamma * V(x_{t+1}).detach() with the last target = r_T
+ * (:110-115), loss = mse (:118), backward (:121-122), clip_grad_norm_(1.0) (:125-128), the logged gradient norm of the
+ * clipped gradients (:131-136) and one torch.optim.Adam step (lr 1e-3, betas (0.9, 0.999), eps 1e-8, :27-29,139).
+ * The arithmetic (matmul, mse, clip, Adam) is PyTorch's; its fp32 summation order is unspecified, so this
+ * restatement accumulates every gradient sum in double and rounds once to fp32 (the neutral anchor), and keeps
+ * parameters and Adam moments in fp32 with torch's operation order (torch/optim/adam.py _single_tensor_adam:
+ * lerp, mul+addcmul, sqrt/bias_correction2_sqrt + eps, addcdiv with step_size = lr / bias_correction1). */
+struct bgo_learner {
+  int H;
+  int64_t n_params;
+  float* p; /* packed [W1t(198,H) | b1 | w2 | b2] */
+  float* m;
+  float* v;
+  int64_t step;
+  float lr, gamma, grad_clip;
+};
+
+bgo_learner* bgo_learner_create(const float* packed, int H, float lr, float gamma, float grad_clip) {
+  bgo_learner* L = (bgo_learner*)calloc(1, sizeof(bgo_learner));
+  L->H = H;
+  L->n_params = (int64_t)(BGO_NFEAT + 2) * H + 1;
+  L->p = (float*)malloc(sizeof(float) * (size_t)L->n_params);
+  L->m = (float*)calloc((size_t)L->n_params, sizeof(float));
+  L->v = (float*)calloc((size_t)L->n_params, sizeof(float));
+  memcpy(L->p, packed, sizeof(float) * (size_t)L->n_params);
+  L->lr = lr;
+  L->gamma = gamma;
+  L->grad_clip = grad_clip;
+  return L;
+}
+
+void bgo_learner_destroy(bgo_learner* L) {
+  if (!L) return;
+  free(L->p);
+  free(L->m);
+  free(L->v);
+  free(L);
+}
+
+void bgo_learner_get(const bgo_learner* L, float* packed, float* m, float* v, int64_t* step) {
+  if (packed) memcpy(packed, L->p, sizeof(float) * (size_t)L->n_params);
+  if (m) memcpy(m, L->m, sizeof(float) * (size_t)L->n_params);
+  if (v) memcpy(v, L->v, sizeof(float) * (size_t)L->n_params);
+  if (step) *step = L->step;
+}
+
+/* sub-range [lo,hi) of the packed vector is one torch parameter: sum of squares in double */
+static double sumsq(const double* g, int64_t lo, int64_t hi) {
+  double s = 0.0;
+  for (int64_t i = lo; i < hi; ++i) s += g[i] * g[i];
+  return s;
+}
+
+void bgo_learner_update(bgo_learner* L, const int8_t* obs_boards, const uint8_t* obs_flags, const float* reward,
+                        const int64_t* ep_offsets, int64_t n_eps, float* out_metrics) {
+  const int H = L->H;
+  const int64_t NP = L->n_params;
+  const int64_t oB1 = (int64_t)BGO_NFEAT * H, oW2 = oB1 + H, oB2 = oW2 + H;
+  double* g = (double*)malloc(sizeof(double) * (size_t)NP);
+  for (int64_t e = 0; e < n_eps; ++e) {
+    const int64_t lo = ep_offsets[e], T = ep_offsets[e + 1] - lo;
+    float* met = out_metrics ? out_metrics + e * BGO_LEARNER_NMETRICS : NULL;
+    if (T <= 0) { /* the reference would fail on torch.stack([]); never produced by the worker (worker.py:149-158) */
+      if (met) memset(met, 0, sizeof(float) * BGO_LEARNER_NMETRICS);
+      continue;
+    }
+    float* x = (float*)malloc(sizeof(float) * (size_t)T * BGO_NFEAT);
+    double* h = (double*)malloc(sizeof(double) * (size_t)T * (size_t)H);
+    float* Y = (float*)malloc(sizeof(float) * (size_t)T);
+    float* tgt = (float*)malloc(sizeof(float) * (size_t)T);
+    const float* W1t = L->p;
+    const float* b1 = L->p + oB1;
+    const float* w2 = L->p + oW2;
+    /* forward (policy_network.py:53-70) */
+    for (int64_t t = 0; t < T; ++t) {
+      bgo_features((const bgo_board*)(obs_boards + (lo + t) * BGO_BOARD_BYTES), obs_flags[lo + t], x + t * BGO_NFEAT);
+      double* ht = h + t * H;
+      for (int j = 0; j < H; ++j) ht[j] = (double)b1[j];
+      for (int f = 0; f < BGO_NFEAT; ++f) {
+        float xf = x[t * BGO_NFEAT + f];
+        if (xf != 0.0f)
+          for (int j = 0; j < H; ++j) ht[j] += (double)xf * (double)W1t[(int64_t)f * H + j];
+      }
+      double y = (double)L->p[oB2];
+      for (int j = 0; j < H; ++j) {
+        ht[j] = 1.0 / (1.0 + exp(-ht[j]));
+        y += (double)w2[j] * ht[j];
+      }
+      Y[t] = (float)y;
+    }
+    /* targets (trainer.py:110-115) and loss (:118) */
+    double loss = 0.0, tdabs = 0.0, ysum = 0.0, rsum = 0.0;
+    for (int64_t t = 0; t < T; ++t) {
+      tgt[t] = reward[lo + t];
+      if (t + 1 < T) tgt[t] = tgt[t] + L->gamma * Y[t + 1];
+      double d = (double)Y[t] - (double)tgt[t];
+      loss += d * d;
+      tdabs += fabs((double)tgt[t] - (double)Y[t]);
+      ysum += (double)Y[t];
+      rsum += (double)reward[lo + t];
+    }
+    loss /= (double)T;
+    /* backward of mean((Y - tgt)^2) through value_head, sigmoid, fc1 */
+    memset(g, 0, sizeof(double) * (size_t)NP);
+    for (int64_t t = 0; t < T; ++t) {
+      double dY = 2.0 * ((double)Y[t] - (double)tgt[t]) / (double)T;
+      const double* ht = h + t * H;
+      g[oB2] += dY;
+      for (int j = 0; j < H; ++j) {
+        g[oW2 + j] += dY * ht[j];
+        double dz = dY * (double)w2[j] * ht[j] * (1.0 - ht[j]);
+        g[oB1 + j] += dz;
+        for (int f = 0; f < BGO_NFEAT; ++f) {
+          float xf = x[t * BGO_NFEAT + f];
+          if (xf != 0.0f) g[(int64_t)f * H + j] += dz * (double)xf;
+        }
+      }
+    }
+    /* torch.nn.utils.clip_grad_norm_ (trainer.py:125-128): norm of the per-parameter norms, coef = max_norm / (norm + 1e-6)
+     * clamped to 1, gradients always multiplied by it */
+    double total = sqrt(sumsq(g, 0, oB1) + sumsq(g, oB1, oW2) + sumsq(g, oW2, oB2) + sumsq(g, oB2, NP));
+    float coef = 1.0f;
+    if (L->grad_clip > 0.0f) {
+      coef = L->grad_clip / ((float)total + 1e-6f);
+      if (coef > 1.0f) coef = 1.0f;
+    }
+    /* Adam (torch/optim/adam.py, defaults of trainer.py:27-29) */
+    L->step += 1;
+    const double beta1 = 0.9, beta2 = 0.999, eps = 1e-8;
+    const double bc1 = 1.0 - pow(beta1, (double)L->step), bc2 = 1.0 - pow(beta2, (double)L->step);
+    const float step_size = (float)((double)L->lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    double gn2 = 0.0;
+    for (int64_t i = 0; i < NP; ++i) {
+      float gi = (float)g[i] * coef;
+      gn2 += (double)gi * (double)gi;
+      L->m[i] = L->m[i] + (float)(1.0 - beta1) * (gi - L->m[i]);
+      L->v[i] = L->v[i] * (float)beta2 + (float)(1.0 - beta2) * gi * gi;
+      float denom = sqrtf(L->v[i]) / bc2_sqrt + (float)eps;
+      L->p[i] = L->p[i] - step_size * (L->m[i] / denom);
+    }
+    if (met) {
+      met[0] = (float)loss;                 /* loss.item()                       trainer.py:148 */
+      met[1] = (float)(tdabs / (double)T);  /* TD_error.abs().mean()             :142-144 */
+      met[2] = (float)sqrt(gn2);            /* norm of the clipped gradients     :131-136 */
+      met[3] = (float)(ysum / (double)T);   /* Y_values.mean()                   :149 */
+      met[4] = (float)rsum;                 /* rewards.sum()                     :150 */
+      met[5] = (float)T;                    /* seq_len                           :151 */
+    }
+    free(x);
+    free(h);
+    free(Y);
+    free(tgt);
+  }
+  free(g);
+}

@@ -310,3 +310,72 @@ def all_rolls_items(boards, players):
     ip = np.repeat(np.asarray(players, np.uint8), 21)
     ir = np.tile(rolls, (n, 1))
     return ib, ip, ir
+
+
+LEARNER_NMETRICS = 6
+
+
+class Learner:
+    """oracle restatement of Trainer.update (reference src/agents/trainer.py:48-166)"""
+
+    def __init__(self, packed, H, lr=1e-3, gamma=0.99, grad_clip=1.0):
+        L = lib()
+        L.bgo_learner_create.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, C.c_float]
+        L.bgo_learner_create.restype = C.c_void_p
+        L.bgo_learner_destroy.argtypes = [C.c_void_p]
+        L.bgo_learner_update.argtypes = [C.c_void_p, C.POINTER(C.c_int8), C.POINTER(C.c_uint8), C.POINTER(C.c_float),
+                                         C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_float)]
+        L.bgo_learner_get.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int64)]
+        packed = np.ascontiguousarray(packed, np.float32)
+        self.H = H
+        self.n_params = 200 * H + 1
+        assert packed.size == self.n_params
+        self._l = L.bgo_learner_create(_p(packed, C.c_float), H, lr, gamma, grad_clip)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_l", None):
+                lib().bgo_learner_destroy(self._l)
+                self._l = None
+        except Exception:  # interpreter shutdown
+            pass
+
+    def update(self, obs_boards, obs_flags, reward, ep_offsets) -> np.ndarray:
+        """-> per-episode metrics float32 [E, 6] (loss, mean |td|, clipped grad norm, mean V, reward sum, length)"""
+        obs_boards = np.ascontiguousarray(obs_boards, np.int8).reshape(-1, 52)
+        obs_flags = np.ascontiguousarray(obs_flags, np.uint8)
+        reward = np.ascontiguousarray(reward, np.float32)
+        ep_offsets = np.ascontiguousarray(ep_offsets, np.int64)
+        E = ep_offsets.size - 1
+        met = np.zeros((E, LEARNER_NMETRICS), np.float32)
+        lib().bgo_learner_update(self._l, _p(obs_boards, C.c_int8), _p(obs_flags, C.c_uint8), _p(reward, C.c_float),
+                                 _p(ep_offsets, C.c_int64), E, _p(met, C.c_float))
+        return met
+
+    def state(self):
+        """-> (packed, exp_avg, exp_avg_sq, step)"""
+        p, m, v = (np.zeros(self.n_params, np.float32) for _ in range(3))
+        st = C.c_int64()
+        lib().bgo_learner_get(self._l, _p(p, C.c_float), _p(m, C.c_float), _p(v, C.c_float), C.byref(st))
+        return p, m, v, st.value
+
+
+def selfplay_episodes(packed, H, n_games, temperature=1.5, seed=0, max_steps=300):
+    """n_games oracle self-play episodes in the learner's CSR form:
+    (obs_boards int8[N,52], obs_flags uint8[N], reward fp32[N], ep_offsets int64[E+1], win_types int32[E])."""
+    obs, flg, rew, off, wins = [], [], [], [0], []
+    for g in range(n_games):
+        env = Env(seed=seed * 1000003 + g)
+        st, tr = env.play_episode(packed, H, temperature=temperature, rng_seed=seed * 7919 + g + 1, max_steps=max_steps)
+        n = len(tr["reward"])
+        if n == 0:
+            continue
+        ob = np.empty((n, 52), np.int8)
+        ob[0] = initial_board()
+        ob[1:] = tr["after"][:-1]
+        obs.append(ob)
+        flg.append(tr["player"].astype(np.uint8))
+        rew.append(tr["reward"].astype(np.float32))
+        off.append(off[-1] + n)
+        wins.append(st["win_type"])
+    return np.concatenate(obs), np.concatenate(flg), np.concatenate(rew), np.array(off, np.int64), np.array(wins, np.int32)
