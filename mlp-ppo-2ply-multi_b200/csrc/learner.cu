@@ -11,6 +11,7 @@
 // row bitmask per feature (backward), so neither the [T,198] feature matrix nor any activation ever exists in HBM.
 // Everything is deterministic: all sums run in a fixed order (no atomics).
 #include <cooperative_groups.h>
+#include <cuda_bf16.h>
 #include <math.h>
 #include <stdio.h>
 
@@ -26,7 +27,6 @@ namespace {
 constexpr int NF = 198;
 constexpr int NROW = 200;  // per hidden unit: 198 fc1 weights, b1, w2 (row f of the packed [W1t | b1 | w2] matrix)
 constexpr int TMAX = 320;  // experiences per episode the kernel accepts (reference MAX_TIMESTEPS = 300)
-constexpr int LHALF = 20;  // sparse-list capacity per (row, player half): <= 15 point features + bar + off + flag = 18
 constexpr int NT = 256;
 constexpr int MAXCL = 8;
 
@@ -60,37 +60,40 @@ struct LearnerArgs {
 
 constexpr int EC = 512;   // episodes whose offsets are staged in shared memory at a time
 constexpr int NSC = NT;   // Adam bias-correction scalars precomputed for this many steps at a time
-constexpr int FI = 4;     // rows in flight per thread in the forward pass
+constexpr int LROW = 40;  // sparse-row capacity: <= 15 + 15 point features, 2 bar, 2 off, 1 flag = 35
+constexpr int TW = TMAX / 32;
 
 template <int UPC>
 struct Smem {
-  float P[NROW * UPC], M[NROW * UPC], V[NROW * UPC], G[NROW * UPC];
-  float hs[TMAX * UPC];        // sigmoid activations, then dL/dz
+  float P[NROW * UPC], M[NROW * UPC], V[NROW * UPC];
+  alignas(16) float hs[TMAX * UPC];  // dL/dz of the episode, [t][unit]
   float ypart[MAXCL * TMAX];   // ypart[c][t]: CTA c's partial of V(x_t), pushed by CTA c
   float Y[TMAX], dY[TMAX], rew[TMAX];
-  float pr[2][NT];             // per-thread partials of the w2 / b1 gradients
-  float2 sc[NSC];              // (lr / bias_correction1, sqrt(bias_correction2)) for the next NSC optimiser steps
+  alignas(16) float pr[2][NT / 32][UPC];  // per-warp partials of the w2 / b1 gradients
+  float2 sc[NSC];              // (lr / bias_correction1, 1 / sqrt(bias_correction2)) for the next NSC optimiser steps
   int64_t offs[EC + 1];
   float npart[MAXCL];          // per-CTA sums of squared gradients, pushed by each CTA
   float red[8][8];
   float red2[8];
-  float vtab[32];              // feature value codes: 0 -> 1, k (1..15) -> k/2, 16+k -> k/15
-  float extab[16];             // value of a point's 4th feature by checker count: max(c - 3, 0) / 2
+  float vtab[32];              // list value codes: 0 -> 1, k (1..15) -> k/2, 16+k -> k/15
+  float ftab[4][16];           // feature value by board byte: [0] 1, [1] max(c-3,0)/2, [2] c/2, [3] c/15
   float b2[4];                 // b2 and its Adam moments (replicated in every CTA, updated identically)
   uint32_t brd[2][TMAX * 13];  // observation boards, double buffered: episode e+1 is fetched while e is processed
-  uint16_t list[TMAX * 2 * LHALF];  // sparse rows: feature index | value code << 8, one sub-list per player half
-  uint8_t lcnt[TMAX * 2];
+  uint32_t nz[NF * TW];        // nz[f][w] bit b: feature f of row 32w+b is non-zero
+  uint16_t list[TMAX * LROW];  // sparse rows: feature index | value code << 8
+  uint8_t lcnt[TMAX];
   uint8_t flg[TMAX];
 };
 
 static_assert(sizeof(Smem<32>) <= 232448, "k_td0_update<32> exceeds the 227 KB of shared memory a CTA can opt into");
 
-__device__ __forceinline__ void adam_step(float& p, float& m, float& v, float g, float step_size, float bc2_sqrt) {
+__device__ __forceinline__ float adam1(float p, float& m, float& v, float g, float step_size, float inv_bc2_sqrt) {
   // torch/optim/adam.py _single_tensor_adam: lerp, mul + addcmul, sqrt / bias_correction2_sqrt + eps, addcdiv
+  // (sqrt and the two divisions through the SFU approximations: relative error ~2e-7 of a 1e-3 step)
   m = m + 0.1f * (g - m);
   v = v * 0.999f + 0.001f * g * g;
-  const float denom = __fdividef(sqrtf(v), bc2_sqrt) + 1e-8f;
-  p = p - step_size * __fdividef(m, denom);
+  const float denom = fmaf(v > 0.f ? v * rsqrtf(v) : 0.f, inv_bc2_sqrt, 1e-8f);
+  return p - step_size * __fdividef(m, denom);
 }
 
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
@@ -101,6 +104,18 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
+// number of non-zero features of 4 board bytes packed in a word: sum over bytes of min(c, 4)
+__device__ __forceinline__ int word_entries(uint32_t w) {
+  const uint32_t s = __vsetgtu4(w, 0u) + __vsetgtu4(w, 0x01010101u) + __vsetgtu4(w, 0x02020202u) + __vsetgtu4(w, 0x03030303u);
+  return (int)__dp4a(s, 0x01010101u, 0u);
+}
+
+// Thread layout.  The CTA's UPC hidden units are split into QJ = UPC / 4 quads; a thread owns one quad (float4 weights) and
+// one of FL = NT / QJ lanes, which index ROWS in the forward pass and FEATURES in the backward pass and the Adam step.
+// Backward features are visited in the order o -> f(o): the 48 points' ">= 1" features first, then ">= 2", ">= 3", the
+// excess features, then bar/off/flag, b1 and w2, so that the 8 (or 4) lanes of a warp scan bitmasks of similar density.
+__device__ __forceinline__ int feature_of(int o) { return o < 192 ? (o % 48) * 4 + o / 48 : o; }
+
 template <int UPC>
 __global__ void __launch_bounds__(NT, 1) k_td0_update(const LearnerArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -108,10 +123,12 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update(const LearnerArgs a) {
   const int CL = (int)cluster.num_blocks();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<UPC>& S = *reinterpret_cast<Smem<UPC>*>(smem_raw);
-  constexpr int RL = NT / UPC;   // row lanes (forward) / point lanes (backward)
-  constexpr int NPT = 48 / RL;   // board points per thread in the fc1 gradient
+  constexpr int QJ = UPC / 4;
+  constexpr int FL = NT / QJ;
+  constexpr int MAXR = TMAX / FL;             // rows per thread (forward)
+  constexpr int KF = (NROW + FL - 1) / FL;    // features per thread (backward / Adam)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int j = tid % UPC, r = tid / UPC;
+  const int jq = tid % QJ, fl = tid / QJ;
   const int H = a.H;
   const int64_t iB2 = (int64_t)NROW * H;
 
@@ -130,16 +147,30 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update(const LearnerArgs a) {
     const int k = tid & 15;
     // reference immutable_board.py:99-112: (c-3)/2 and bar/2 are exact; off/15 is a double division stored to fp32
     S.vtab[tid] = tid == 0 ? 1.0f : tid < 16 ? 0.5f * (float)k : (float)((double)k / 15.0);
-    if (tid < 16) S.extab[tid] = tid > 3 ? 0.5f * (float)(tid - 3) : 0.0f;
+  }
+  if (tid < 64) {
+    const int k = tid & 15, kind = tid >> 4;
+    S.ftab[kind][k] = kind == 0 ? 1.0f : kind == 1 ? (k > 3 ? 0.5f * (float)(k - 3) : 0.0f) : kind == 2 ? 0.5f * (float)k : (float)((double)k / 15.0);
   }
   const int64_t step0 = *a.step;
   int64_t kstep = 0;  // optimiser steps taken by this launch (thread-uniform)
   // torch/optim/adam.py: bias_correction = 1 - beta ** step in double; step_size = lr / bc1; bias_correction2_sqrt = sqrt(bc2)
   auto fill_scalars = [&]() {
     const double n = (double)(step0 + kstep + tid + 1);
-    S.sc[tid] = make_float2((float)((double)a.lr / (1.0 - pow(0.9, n))), (float)sqrt(1.0 - pow(0.999, n)));
+    S.sc[tid] = make_float2((float)((double)a.lr / (1.0 - pow(0.9, n))), 1.0f / (float)sqrt(1.0 - pow(0.999, n)));
   };
   fill_scalars();
+
+  // per-thread feature slots (constant over the launch): packed-row index, board byte and value table of each
+  int fF[KF], fBo[KF], fKind[KF];
+#pragma unroll
+  for (int k = 0; k < KF; ++k) {
+    const int o = fl + FL * k;
+    const int f = o < NROW ? feature_of(o) : -1;
+    fF[k] = f;
+    fBo[k] = f < 0 ? 0 : f < 192 ? (f >> 2) : f == 192 ? 48 : f == 193 ? 50 : f == 194 ? 49 : f == 195 ? 51 : 0;
+    fKind[k] = f < 0 ? 0 : f < 192 ? ((f & 3) == 3 ? 1 : 0) : f < 196 ? ((f & 1) ? 3 : 2) : 0;
+  }
   __syncthreads();
   cluster.sync();  // every CTA of the cluster is resident before the first DSMEM store
 
@@ -198,7 +229,9 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update(const LearnerArgs a) {
     while (e < c1) {
       PH(9);
       const int T = (int)(S.offs[e - c0 + 1] - S.offs[e - c0]);
-      const int8_t* brd8 = reinterpret_cast<const int8_t*>(S.brd[buf]);
+      const int nch = (T + 31) >> 5;
+      const uint32_t* brd32 = S.brd[buf];
+      const uint8_t* brd8 = reinterpret_cast<const uint8_t*>(S.brd[buf]);
 
       // ---- A: land the staged episode; start fetching the next one ----
       cp_async_wait_all();
@@ -214,81 +247,115 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update(const LearnerArgs a) {
       const int64_t e_next = next_valid(e + 1);
       if (e_next < c1) prefetch(e_next, buf ^ 1);
       PH(0);
-      // sparse feature rows for the forward pass: one (row, player half) task per thread
+      // sparse feature rows for the forward pass: one (row, player half) task per thread, predicated stores, no branches;
+      // player 2's half starts where player 1's ends (its length is counted with byte-SIMD compares)
       for (int task = tid; task < 2 * T; task += NT) {
         const int t = task >> 1, p = task & 1;
-        uint16_t* li = S.list + task * LHALF;
-        const int8_t* b = brd8 + t * 52;
+        const uint8_t* b = brd8 + t * 52;
+        const int fg = S.flg[t];
         int cnt = 0;
+        if (p) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) cnt += word_entries(brd32[t * 13 + k]);
+          cnt += (b[48] > 0) + (b[50] > 0) + (fg == 0);
+        }
+        uint16_t* li = S.list + t * LROW;
+#pragma unroll 4
         for (int pt = 0; pt < 24; ++pt) {
           const int c = b[p * 24 + pt];
-          if (c > 0) {
-            const int f0 = p * 96 + pt * 4;
-            li[cnt++] = (uint16_t)f0;
-            if (c > 1) li[cnt++] = (uint16_t)(f0 + 1);
-            if (c > 2) li[cnt++] = (uint16_t)(f0 + 2);
-            if (c > 3) li[cnt++] = (uint16_t)((f0 + 3) | ((c - 3) << 8));
-          }
+          const int f0 = p * 96 + pt * 4;
+          if (c > 0) li[cnt] = (uint16_t)f0;
+          if (c > 1) li[cnt + 1] = (uint16_t)(f0 + 1);
+          if (c > 2) li[cnt + 2] = (uint16_t)(f0 + 2);
+          if (c > 3) li[cnt + 3] = (uint16_t)((f0 + 3) | ((c - 3) << 8));
+          cnt += min(c, 4);
         }
         const int bar = b[48 + p], off = b[50 + p];
         if (bar > 0) li[cnt++] = (uint16_t)((192 + 2 * p) | (bar << 8));
         if (off > 0) li[cnt++] = (uint16_t)((193 + 2 * p) | ((16 + off) << 8));
-        if (S.flg[t] == p) li[cnt++] = (uint16_t)(196 + p);
-        S.lcnt[task] = (uint8_t)cnt;
+        if (fg == p) li[cnt++] = (uint16_t)(196 + p);
+        if (p) S.lcnt[t] = (uint8_t)cnt;
+      }
+      // row bitmasks per feature for the backward pass: one (32-row chunk, board byte) task per warp, lane == row
+      for (int task = warp; task < nch * 53; task += NT / 32) {
+        const int ch = task / 53, q = task - ch * 53;  // q < 48 points, 48..51 bar/off bytes, 52 the flag
+        const int t = ch * 32 + lane;
+        const bool valid = t < T;
+        if (q < 48) {
+          const int c = valid ? brd8[t * 52 + q] : 0;
+          const uint32_t m0 = __ballot_sync(BG_FULL, c > 0), m1 = __ballot_sync(BG_FULL, c > 1), m2 = __ballot_sync(BG_FULL, c > 2),
+                         m3 = __ballot_sync(BG_FULL, c > 3);
+          if (lane < 4) S.nz[(q * 4 + lane) * TW + ch] = lane == 0 ? m0 : lane == 1 ? m1 : lane == 2 ? m2 : m3;
+        } else if (q < 52) {
+          const int c = valid ? brd8[t * 52 + q] : 0;
+          const uint32_t m0 = __ballot_sync(BG_FULL, c > 0);
+          const int f = q == 48 ? 192 : q == 49 ? 194 : q == 50 ? 193 : 195;
+          if (lane == 0) S.nz[f * TW + ch] = m0;
+        } else {
+          const int fg = valid ? S.flg[t] : 2;
+          const uint32_t m0 = __ballot_sync(BG_FULL, fg == 0), m1 = __ballot_sync(BG_FULL, fg == 1);
+          if (lane < 2) S.nz[(196 + lane) * TW + ch] = lane == 0 ? m0 : m1;
+        }
       }
       __syncthreads();
       PH(1);
 
-      // ---- B: forward for this CTA's UPC hidden units (FI rows in flight per thread); push the value partials to every CTA ----
-      {
-        const float b1j = S.P[NF * UPC + j], w2j = S.P[(NF + 1) * UPC + j];
-        for (int t0 = 0; t0 < T; t0 += FI * RL) {
-          int tr[FI];
-          float z[FI];
+      // ---- B: forward for this thread's quad of hidden units over its rows (kept in registers); value partials to every CTA ----
+      float4 hreg[MAXR];
+      const float4 b1q = *reinterpret_cast<const float4*>(&S.P[NF * UPC + jq * 4]);
+      const float4 w2q = *reinterpret_cast<const float4*>(&S.P[(NF + 1) * UPC + jq * 4]);
 #pragma unroll
-          for (int i = 0; i < FI; ++i) {
-            tr[i] = t0 + r + i * RL;
-            z[i] = b1j;
-          }
-#pragma unroll
-          for (int p = 0; p < 2; ++p) {
-            int n[FI], nmax = 0;
-            const uint16_t* l[FI];
-#pragma unroll
-            for (int i = 0; i < FI; ++i) {
-              const bool vd = tr[i] < T;
-              n[i] = vd ? S.lcnt[tr[i] * 2 + p] : 0;
-              l[i] = S.list + ((vd ? tr[i] : 0) * 2 + p) * LHALF;
-              nmax = max(nmax, n[i]);
+      for (int k = 0; k < MAXR; k += 2) {
+        if (k * FL < T) {  // uniform
+          const int tA = fl + k * FL, tB = tA + FL;
+          const bool vA = tA < T, vB = tB < T;
+          const int nA = vA ? S.lcnt[tA] : 0, nB = vB ? S.lcnt[tB] : 0;
+          const uint16_t* lA = S.list + (vA ? tA : 0) * LROW;
+          const uint16_t* lB = S.list + (vB ? tB : 0) * LROW;
+          float4 zA = b1q, zB = b1q;
+          const int nmax = max(nA, nB);
+#pragma unroll 2
+          for (int q = 0; q < nmax; ++q) {
+            // unconditional loads (a stale entry past a row's count stays inside the shared-memory block) + select
+            const uint32_t eA = lA[q], eB = lB[q];
+            const float4 wA = *reinterpret_cast<const float4*>(&S.P[(eA & 255u) * UPC + jq * 4]);
+            const float4 wB = *reinterpret_cast<const float4*>(&S.P[(eB & 255u) * UPC + jq * 4]);
+            const float xA = q < nA ? S.vtab[(eA >> 8) & 31u] : 0.f, xB = q < nB ? S.vtab[(eB >> 8) & 31u] : 0.f;
+            if (q < nA) {
+              zA.x = fmaf(xA, wA.x, zA.x);
+              zA.y = fmaf(xA, wA.y, zA.y);
+              zA.z = fmaf(xA, wA.z, zA.z);
+              zA.w = fmaf(xA, wA.w, zA.w);
             }
-            for (int q = 0; q < nmax; ++q) {
-              // unconditional loads (a stale entry past a row's count stays inside the shared-memory block) + select: the FI
-              // chains overlap instead of serialising behind predicated branches
-              uint32_t en[FI];
-              float w[FI], x[FI];
-#pragma unroll
-              for (int i = 0; i < FI; ++i) en[i] = l[i][q];
-#pragma unroll
-              for (int i = 0; i < FI; ++i) {
-                w[i] = S.P[(en[i] & 255u) * UPC + j];
-                x[i] = S.vtab[(en[i] >> 8) & 31u];
-              }
-#pragma unroll
-              for (int i = 0; i < FI; ++i) z[i] = q < n[i] ? fmaf(x[i], w[i], z[i]) : z[i];
+            if (q < nB) {
+              zB.x = fmaf(xB, wB.x, zB.x);
+              zB.y = fmaf(xB, wB.y, zB.y);
+              zB.z = fmaf(xB, wB.z, zB.z);
+              zB.w = fmaf(xB, wB.w, zB.w);
             }
           }
+          float4 hA, hB;
+          hA.x = 1.0f / (1.0f + expf(-zA.x));
+          hA.y = 1.0f / (1.0f + expf(-zA.y));
+          hA.z = 1.0f / (1.0f + expf(-zA.z));
+          hA.w = 1.0f / (1.0f + expf(-zA.w));
+          hB.x = 1.0f / (1.0f + expf(-zB.x));
+          hB.y = 1.0f / (1.0f + expf(-zB.y));
+          hB.z = 1.0f / (1.0f + expf(-zB.z));
+          hB.w = 1.0f / (1.0f + expf(-zB.w));
+          hreg[k] = hA;
+          if (k + 1 < MAXR) hreg[k + 1] = hB;
+          float pA = vA ? fmaf(w2q.w, hA.w, fmaf(w2q.z, hA.z, fmaf(w2q.y, hA.y, w2q.x * hA.x))) : 0.f;
+          float pB = vB ? fmaf(w2q.w, hB.w, fmaf(w2q.z, hB.z, fmaf(w2q.y, hB.y, w2q.x * hB.x))) : 0.f;
 #pragma unroll
-          for (int i = 0; i < FI; ++i) {
-            const bool vd = tr[i] < T;
-            float part = 0.0f;
-            if (vd) {
-              const float h = 1.0f / (1.0f + expf(-z[i]));
-              S.hs[tr[i] * UPC + j] = h;
-              part = w2j * h;
-            }
-#pragma unroll
-            for (int o = UPC / 2; o > 0; o >>= 1) part += __shfl_xor_sync(BG_FULL, part, o);
-            if (vd && j < CL) cluster.map_shared_rank(S.ypart, j)[rank * TMAX + tr[i]] = part;
+          for (int o = QJ / 2; o > 0; o >>= 1) {
+            pA += __shfl_xor_sync(BG_FULL, pA, o);
+            pB += __shfl_xor_sync(BG_FULL, pB, o);
+          }
+          for (int c = jq; c < CL; c += QJ) {
+            float* dst = cluster.map_shared_rank(S.ypart, c) + rank * TMAX;
+            if (vA) dst[tA] = pA;
+            if (vB) dst[tB] = pB;
           }
         }
       }
@@ -329,20 +396,46 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update(const LearnerArgs a) {
       __syncthreads();
       PH(4);
 
-      // ---- D: dL/dz in place of the activations; w2 / b1 gradient partials per row lane ----
+      // ---- D: dL/dz from the activations still in registers; w2 / b1 gradient partials, reduced over the warp's row lanes ----
       {
-        float gw2 = 0.f, gb1 = 0.f;
-        const float w2j = S.P[(NF + 1) * UPC + j];
-#pragma unroll 4
-        for (int t = r; t < T; t += RL) {
-          const float h = S.hs[t * UPC + j], dy = S.dY[t];
-          gw2 = fmaf(dy, h, gw2);
-          const float dz = dy * w2j * h * (1.0f - h);
-          S.hs[t * UPC + j] = dz;
-          gb1 += dz;
+        float4 gw2 = make_float4(0.f, 0.f, 0.f, 0.f), gb1 = gw2;
+#pragma unroll
+        for (int k = 0; k < MAXR; ++k) {
+          const int t = fl + k * FL;
+          if (t < T) {
+            const float dy = S.dY[t];
+            const float4 h = hreg[k];
+            float4 dz;
+            gw2.x = fmaf(dy, h.x, gw2.x);
+            gw2.y = fmaf(dy, h.y, gw2.y);
+            gw2.z = fmaf(dy, h.z, gw2.z);
+            gw2.w = fmaf(dy, h.w, gw2.w);
+            dz.x = dy * w2q.x * h.x * (1.0f - h.x);
+            dz.y = dy * w2q.y * h.y * (1.0f - h.y);
+            dz.z = dy * w2q.z * h.z * (1.0f - h.z);
+            dz.w = dy * w2q.w * h.w * (1.0f - h.w);
+            *reinterpret_cast<float4*>(&S.hs[t * UPC + jq * 4]) = dz;
+            gb1.x += dz.x;
+            gb1.y += dz.y;
+            gb1.z += dz.z;
+            gb1.w += dz.w;
+          }
         }
-        S.pr[0][tid] = gw2;
-        S.pr[1][tid] = gb1;
+#pragma unroll
+        for (int o = QJ; o < 32; o <<= 1) {
+          gw2.x += __shfl_xor_sync(BG_FULL, gw2.x, o);
+          gw2.y += __shfl_xor_sync(BG_FULL, gw2.y, o);
+          gw2.z += __shfl_xor_sync(BG_FULL, gw2.z, o);
+          gw2.w += __shfl_xor_sync(BG_FULL, gw2.w, o);
+          gb1.x += __shfl_xor_sync(BG_FULL, gb1.x, o);
+          gb1.y += __shfl_xor_sync(BG_FULL, gb1.y, o);
+          gb1.z += __shfl_xor_sync(BG_FULL, gb1.z, o);
+          gb1.w += __shfl_xor_sync(BG_FULL, gb1.w, o);
+        }
+        if (lane < QJ) {
+          *reinterpret_cast<float4*>(&S.pr[0][warp][jq * 4]) = gw2;
+          *reinterpret_cast<float4*>(&S.pr[1][warp][jq * 4]) = gb1;
+        }
       }
       float msum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
       if (tid == 0) {
@@ -355,54 +448,55 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update(const LearnerArgs a) {
       __syncthreads();
       PH(5);
 
-      // ---- E: fc1 gradient, dense over the rows: this thread owns unit j of the 4 features of NPT board points (the thermometer
-      //         code makes each a predicated add of dL/dz), rows in ascending order; then the 6 bar/off/flag features ----
+      // ---- E: gradients of this thread's feature slots: a walk over the set bits of the feature's row mask, two rows per
+      //         iteration; b1 / w2 slots sum the warp partials.  Kept in registers for the Adam step ----
+      float4 g[KF];
       float ss = 0.f;
-      {
-        float acc[NPT][4];
 #pragma unroll
-        for (int i = 0; i < NPT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-        const int8_t* bp = brd8 + r * NPT;
-#pragma unroll 4
-        for (int t = 0; t < T; ++t) {
-          const float dz = S.hs[t * UPC + j];
-#pragma unroll
-          for (int i = 0; i < NPT; ++i) {
-            const int c = bp[t * 52 + i];
-            acc[i][0] += c > 0 ? dz : 0.f;
-            acc[i][1] += c > 1 ? dz : 0.f;
-            acc[i][2] += c > 2 ? dz : 0.f;
-            acc[i][3] = fmaf(S.extab[c], dz, acc[i][3]);  // exact 0 for c <= 3
+      for (int k = 0; k < KF; ++k) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = acc;
+        const int f = fF[k];
+        if (f >= 0 && f < NF) {
+          const uint32_t* nzf = S.nz + f * TW;
+          const float* tab = S.ftab[fKind[k]];
+          const uint8_t* bb = brd8 + fBo[k];
+          for (int w = 0; w < nch; ++w) {
+            uint32_t bits = nzf[w];
+            while (bits) {
+              const int t0 = w * 32 + __ffs(bits) - 1;
+              bits &= bits - 1;
+              const bool two = bits != 0;
+              const int t1 = two ? w * 32 + __ffs(bits) - 1 : t0;
+              bits &= bits - 1;
+              const float4 d0 = *reinterpret_cast<const float4*>(&S.hs[t0 * UPC + jq * 4]);
+              const float4 d1 = *reinterpret_cast<const float4*>(&S.hs[t1 * UPC + jq * 4]);
+              const float x0 = tab[bb[t0 * 52]];
+              const float x1 = two ? tab[bb[t1 * 52]] : 0.f;
+              acc.x = fmaf(x0, d0.x, acc.x);
+              acc.y = fmaf(x0, d0.y, acc.y);
+              acc.z = fmaf(x0, d0.z, acc.z);
+              acc.w = fmaf(x0, d0.w, acc.w);
+              acc2.x = fmaf(x1, d1.x, acc2.x);
+              acc2.y = fmaf(x1, d1.y, acc2.y);
+              acc2.z = fmaf(x1, d1.z, acc2.z);
+              acc2.w = fmaf(x1, d1.w, acc2.w);
+            }
+          }
+          acc.x += acc2.x;
+          acc.y += acc2.y;
+          acc.z += acc2.z;
+          acc.w += acc2.w;
+        } else if (f >= NF) {  // f == 198: b1, f == 199: w2 (fixed-order sum of the warp partials)
+          for (int w = 0; w < NT / 32; ++w) {
+            const float4 x = *reinterpret_cast<const float4*>(&S.pr[199 - f][w][jq * 4]);
+            acc.x += x.x;
+            acc.y += x.y;
+            acc.z += x.z;
+            acc.w += x.w;
           }
         }
-#pragma unroll
-        for (int i = 0; i < NPT; ++i)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            S.G[((r * NPT + i) * 4 + k) * UPC + j] = acc[i][k];
-            ss = fmaf(acc[i][k], acc[i][k], ss);
-          }
-      }
-      if (r < 6) {
-        const int f = 192 + r;
-        const int bo = f == 192 ? 48 : f == 193 ? 50 : f == 194 ? 49 : 51;
-        float acc = 0.f;
-        if (f < 196) {
-          const int base = (f & 1) ? 16 : 0;  // off/15 : bar/2
-          for (int t = 0; t < T; ++t) {
-            const int c = brd8[t * 52 + bo];
-            if (c > 0) acc = fmaf(S.vtab[base + c], S.hs[t * UPC + j], acc);
-          }
-        } else {
-          for (int t = 0; t < T; ++t) acc += S.flg[t] == f - 196 ? S.hs[t * UPC + j] : 0.f;
-        }
-        S.G[f * UPC + j] = acc;
-        ss = fmaf(acc, acc, ss);
-      } else if (r < 8) {  // r == 6: b1 gradient, r == 7: w2 gradient (fixed-order sum of the row-lane partials)
-        float g = 0.f;
-        for (int rr = 0; rr < RL; ++rr) g += S.pr[7 - r][rr * UPC + j];
-        S.G[(NF + r - 6) * UPC + j] = g;
-        ss = fmaf(g, g, ss);
+        g[k] = acc;
+        ss = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, fmaf(acc.w, acc.w, ss))));
       }
       if (tid == 0 && rank == 0) ss = fmaf(msum[4], msum[4], ss);  // b2 gradient, counted once
 #pragma unroll
@@ -418,16 +512,29 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update(const LearnerArgs a) {
       cluster.sync();
       PH(7);
 
-      // ---- F: clip_grad_norm_ (trainer.py:125-128) and the Adam step (:139) on this CTA's slice ----
+      // ---- F: clip_grad_norm_ (trainer.py:125-128) and the Adam step (:139) on this thread's slots ----
       float tot2 = 0.f;
       for (int c = 0; c < CL; ++c) tot2 += S.npart[c];
       const float total = sqrtf(tot2);
       float coef = 1.0f;
       if (a.grad_clip > 0.f) coef = fminf(1.0f, a.grad_clip / (total + 1e-6f));
       const float2 sc = S.sc[kstep & (NSC - 1)];
-      for (int s = tid; s < NROW * UPC; s += NT) adam_step(S.P[s], S.M[s], S.V[s], S.G[s] * coef, sc.x, sc.y);
+#pragma unroll
+      for (int k = 0; k < KF; ++k) {
+        if (fF[k] >= 0) {
+          const int s = fF[k] * UPC + jq * 4;
+          float4 p = *reinterpret_cast<float4*>(&S.P[s]), m = *reinterpret_cast<float4*>(&S.M[s]), v = *reinterpret_cast<float4*>(&S.V[s]);
+          p.x = adam1(p.x, m.x, v.x, g[k].x * coef, sc.x, sc.y);
+          p.y = adam1(p.y, m.y, v.y, g[k].y * coef, sc.x, sc.y);
+          p.z = adam1(p.z, m.z, v.z, g[k].z * coef, sc.x, sc.y);
+          p.w = adam1(p.w, m.w, v.w, g[k].w * coef, sc.x, sc.y);
+          *reinterpret_cast<float4*>(&S.P[s]) = p;
+          *reinterpret_cast<float4*>(&S.M[s]) = m;
+          *reinterpret_cast<float4*>(&S.V[s]) = v;
+        }
+      }
       if (tid == 0) {
-        adam_step(S.b2[0], S.b2[1], S.b2[2], msum[4] * coef, sc.x, sc.y);
+        S.b2[0] = adam1(S.b2[0], S.b2[1], S.b2[2], msum[4] * coef, sc.x, sc.y);
         if (rank == 0 && a.metrics) {
           float* mt = a.metrics + e * 6;
           mt[0] = msum[0] / (float)T;  // loss.item()
@@ -469,6 +576,511 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update(const LearnerArgs a) {
     *a.step = step0 + kstep;
   }
   cluster.sync();  // no CTA exits while a peer may still address its shared memory
+}
+
+// ================================================================================================================
+// H <= 128: the same algorithm with the two contractions on the tensor cores.
+//
+// Per CTA (16 hidden units) an episode is two small GEMMs: Z[T,16] = X[T,208] W[208,16] and G[208,16] = X^T[208,T] dZ[T,16].
+// X (the 198 features, a ones column that carries b1, zero padding) is exact in bf16 -- every feature is 0, 1, k/2 or a borne-off
+// count 0..15 whose 1/15 is folded into W -- and the fp32 operand of each product (W, dZ) is split into three bf16 pieces
+// (hi + mid + lo = the fp32 value), so every tensor-core product is exact and the fp32 accumulation matches a CUDA-core FMA
+// loop to rounding (parity with the reference trainer is tested to 1e-5 on every weight after 400 steps).  This replaces the
+// sparse, divergent, latency-bound row/bitmask walks of k_td0_update with ~250 warp-level mma.sync per episode and CTA; the
+// dense X tile costs one pass over the boards.  mma.sync (not tcgen05): the tiles are 16 units wide and the critical resource
+// is latency inside a 200-step sequential chain, not tensor throughput.
+// ================================================================================================================
+constexpr int KP = 208;  // K of the forward / M of the backward GEMM: 198 features, ones column (198), zero padding
+constexpr int XS = 216;  // X row stride in bf16 (432 B): the 8 row addresses of an ldmatrix fall in distinct 16-byte bank groups
+constexpr int WS = 24;   // row stride of the split W / dZ operands in bf16 (48 B), same property
+constexpr int RT = 128;  // rows per X tile; longer episodes take several tiles
+constexpr int UT = 16;   // hidden units per CTA
+
+struct SmemTC {
+  float P[NROW * UT], M[NROW * UT], V[NROW * UT];
+  float hs[TMAX * UT];         // sigmoid activations [t][unit]
+  float ypart[MAXCL * TMAX];
+  float Y[TMAX], dY[TMAX], rew[TMAX];
+  float2 sc[NSC];
+  int64_t offs[EC + 1];
+  alignas(16) float pr[NT / 32][UT];  // per-warp partials of the w2 gradient
+  uint2 xtab[16];              // the four bf16 thermometer features of a point holding c checkers
+  float npart[MAXCL];
+  float red[8][8];
+  float red2[8];
+  float b2[4];
+  alignas(16) uint32_t brd[2][TMAX * 13];
+  alignas(16) __nv_bfloat16 X[RT * XS];
+  alignas(16) __nv_bfloat16 Ws[3][KP * WS];  // W1 (+ b1 in row 198), three bf16 pieces, [feature][unit]
+  alignas(16) __nv_bfloat16 Ds[3][RT * WS];  // dL/dz of the current tile, three bf16 pieces, [row][unit]
+  uint8_t flg[TMAX];
+};
+static_assert(sizeof(SmemTC) <= 232448, "k_td0_update_tc exceeds the 227 KB of shared memory a CTA can opt into");
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// x = hi + mid + lo with three bf16 pieces (24 mantissa bits)
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(x);
+  float r = x - __bfloat162float(h);
+  m = __float2bfloat16_rn(r);
+  r -= __bfloat162float(m);
+  l = __float2bfloat16_rn(r);
+}
+// the same for a pair, through the packed converts: p[0..2] = (hi, mid, lo) pieces of (x0, x1) as bf16x2 words
+__device__ __forceinline__ void split3x2(float x0, float x1, uint32_t (&p)[3]) {
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    const __nv_bfloat162 b = __floats2bfloat162_rn(x0, x1);
+    p[s] = *reinterpret_cast<const uint32_t*>(&b);
+    x0 -= __uint_as_float(p[s] << 16);
+    x1 -= __uint_as_float(p[s] & 0xffff0000u);
+  }
+}
+template <int N>
+__device__ __forceinline__ void store_split2(__nv_bfloat16 (*dst)[N], int idx, float x0, float x1) {
+  uint32_t p[3];
+  split3x2(x0, x1, p);
+#pragma unroll
+  for (int s = 0; s < 3; ++s) *reinterpret_cast<uint32_t*>(&dst[s][idx]) = p[s];
+}
+
+__global__ void __launch_bounds__(NT, 1) k_td0_update_tc(const LearnerArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int CL = (int)cluster.num_blocks();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemTC& S = *reinterpret_cast<SmemTC*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;  // mma fragment coordinates: row group, column pair
+  const int H = a.H;
+  const int64_t iB2 = (int64_t)NROW * H;
+  const float k15 = 1.0f / 15.0f;
+
+  for (int s = tid; s < NROW * UT; s += NT) {
+    const int64_t gi = (int64_t)(s / UT) * H + rank * UT + (s % UT);
+    S.P[s] = a.params[gi];
+    S.M[s] = a.m[gi];
+    S.V[s] = a.v[gi];
+  }
+  if (tid == 0) {
+    S.b2[0] = a.params[iB2];
+    S.b2[1] = a.m[iB2];
+    S.b2[2] = a.v[iB2];
+  }
+  for (int i = tid; i < 3 * KP * WS / 2; i += NT) reinterpret_cast<uint32_t*>(&S.Ws[0][0])[i] = 0u;
+  if (tid < 16) {
+    const uint32_t one = 0x3F80u;  // bf16 1.0
+    const uint32_t ex = tid > 3 ? (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(0.5f * (float)(tid - 3))) : 0u;
+    S.xtab[tid] = make_uint2((tid > 0 ? one : 0u) | (tid > 1 ? one << 16 : 0u), (tid > 2 ? one : 0u) | (ex << 16));
+  }
+  const int64_t step0 = *a.step;
+  int64_t kstep = 0;
+  auto fill_scalars = [&]() {
+    const double n = (double)(step0 + kstep + tid + 1);
+    S.sc[tid] = make_float2((float)((double)a.lr / (1.0 - pow(0.9, n))), 1.0f / (float)sqrt(1.0 - pow(0.999, n)));
+  };
+  fill_scalars();
+  __syncthreads();
+  // operand image of the weights: rows 0..197 = W1^T (the two borne-off rows scaled by 1/15: X holds the count), row 198 = b1
+  for (int i = tid; i < (NF + 1) * (UT / 2); i += NT) {
+    const int f = i / (UT / 2), n = (i % (UT / 2)) * 2;
+    const float sc = (f == 193 || f == 195) ? k15 : 1.0f;
+    store_split2(S.Ws, f * WS + n, S.P[f * UT + n] * sc, S.P[f * UT + n + 1] * sc);
+  }
+  __syncthreads();
+  cluster.sync();
+
+  const uint32_t* gb32 = reinterpret_cast<const uint32_t*>(a.boards);
+  int64_t c0 = 0, c1 = 0;
+  auto next_valid = [&](int64_t e) {
+    for (; e < c1; ++e) {
+      const int64_t Tl = S.offs[e - c0 + 1] - S.offs[e - c0];
+      if (Tl > 0 && Tl <= TMAX) break;
+      if (rank == 0 && tid == 0) {
+        if (Tl > TMAX && a.status) *a.status = BG_ERR_CAPACITY;
+        if (a.metrics)
+          for (int k = 0; k < 6; ++k) a.metrics[e * 6 + k] = 0.0f;
+      }
+    }
+    return e;
+  };
+  uint8_t pf_flag[2] = {0, 0};
+  float pf_rew[2] = {0.f, 0.f};
+  auto prefetch = [&](int64_t e, int buf) {
+    const int64_t lo = S.offs[e - c0];
+    const int T = (int)(S.offs[e - c0 + 1] - lo);
+    for (int w = tid; w < T * 13; w += NT) {
+      const int t = w / 13, k = w - t * 13;
+      if (a.records && t == 0)
+        S.brd[buf][w] = initial_board_word(k);
+      else
+        cp_async4(&S.brd[buf][w], gb32 + (a.records ? lo + t - 1 : lo + t) * 13 + k);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int t = tid + i * NT;
+      if (t < T) {
+        pf_flag[i] = a.flags[lo + t] & 1;
+        pf_rew[i] = a.reward[lo + t];
+      }
+    }
+  };
+
+#ifdef BG_LEARNER_PROFILE
+  long long ph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long t_ = clock64();
+#endif
+  for (c0 = 0; c0 < a.n_eps; c0 += EC) {
+    c1 = c0 + EC < a.n_eps ? c0 + EC : a.n_eps;
+    __syncthreads();
+    for (int i = tid; i <= (int)(c1 - c0); i += NT) S.offs[i] = a.ep_offsets[c0 + i];
+    __syncthreads();
+    int buf = 0;
+    int64_t e = next_valid(c0);
+    if (e < c1) prefetch(e, buf);
+    while (e < c1) {
+      PH(9);
+      const int T = (int)(S.offs[e - c0 + 1] - S.offs[e - c0]);
+      const uint8_t* brd8 = reinterpret_cast<const uint8_t*>(S.brd[buf]);
+
+      // ---- A: land the staged episode; start fetching the next one ----
+      cp_async_wait_all();
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int t = tid + i * NT;
+        if (t < T) {
+          S.flg[t] = pf_flag[i];
+          S.rew[t] = pf_rew[i];
+        }
+      }
+      __syncthreads();
+      const int64_t e_next = next_valid(e + 1);
+      if (e_next < c1) prefetch(e_next, buf ^ 1);
+      PH(0);
+
+      // dense bf16 feature rows of the tile starting at row tb (rows >= T are zero); returns the tile's row count (multiple of 16)
+      auto decode_tile = [&](int tb) {
+        const int rows = min(RT, ((T - tb) + 15) & ~15);
+        for (int i = tid; i < rows * 12; i += NT) {  // (row, board word): four points = 16 thermometer features, two 16-byte stores
+          const int tr = i / 12, w = i - tr * 12;
+          const int t = tb + tr;
+          const uint32_t c4 = t < T ? S.brd[buf][t * 13 + w] : 0u;
+          const uint2 v0 = S.xtab[c4 & 15u], v1 = S.xtab[(c4 >> 8) & 15u], v2 = S.xtab[(c4 >> 16) & 15u], v3 = S.xtab[(c4 >> 24) & 15u];
+          uint4* dst = reinterpret_cast<uint4*>(&S.X[tr * XS + w * 16]);
+          dst[0] = make_uint4(v0.x, v0.y, v1.x, v1.y);
+          dst[1] = make_uint4(v2.x, v2.y, v3.x, v3.y);
+        }
+        for (int tr = tid; tr < rows; tr += NT) {  // bar/2, off count, flags, ones column, zero padding
+          const int t = tb + tr;
+          const bool vd = t < T;
+          const uint8_t* b = brd8 + t * 52;
+          auto bf = [](float x) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x)); };
+          uint4 v;
+          v.x = vd ? bf(0.5f * (float)b[48]) | (bf((float)b[50]) << 16) : 0u;
+          v.y = vd ? bf(0.5f * (float)b[49]) | (bf((float)b[51]) << 16) : 0u;
+          v.z = vd ? (S.flg[t] == 0 ? 0x3F80u : 0x3F80u << 16) : 0u;
+          v.w = vd ? 0x3F80u : 0u;
+          *reinterpret_cast<uint4*>(&S.X[tr * XS + 192]) = v;
+          *reinterpret_cast<uint4*>(&S.X[tr * XS + 200]) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        return rows;
+      };
+
+      // ---- B: forward, tile by tile: Z = X W on the tensor cores (three bf16 pieces of W), sigmoid, value partials to every CTA ----
+      const float2 w2a = *reinterpret_cast<const float2*>(&S.P[(NF + 1) * UT + 2 * q]);      // units 2q, 2q+1
+      const float2 w2b = *reinterpret_cast<const float2*>(&S.P[(NF + 1) * UT + 8 + 2 * q]);  // units 8+2q, 9+2q
+      for (int tb = 0; tb < T; tb += RT) {
+        if (tb) __syncthreads();  // previous tile's X fully consumed
+        const int rows = decode_tile(tb);
+        __syncthreads();
+        PH(1);
+        if (warp * 16 < rows) {
+          float ac3[3][2][4];  // one accumulator chain per bf16 piece and unit half: six independent mma chains
+#pragma unroll
+          for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) ac3[s][nt][0] = ac3[s][nt][1] = ac3[s][nt][2] = ac3[s][nt][3] = 0.f;
+          const __nv_bfloat16* xa = &S.X[(warp * 16 + (lane & 15)) * XS + (lane >> 4) * 8];
+          const int brow = ((lane >> 3) & 1) * 8 + (lane & 7), bcol = (lane >> 4) * 8;
+#pragma unroll
+          for (int ks = 0; ks < KP / 16; ++ks) {
+            uint32_t af[4];
+            ldsm_x4(af, xa + ks * 16);
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              uint32_t bfr[4];
+              ldsm_x4_t(bfr, &S.Ws[s][(ks * 16 + brow) * WS + bcol]);
+              mma_bf16(ac3[s][0], af, bfr[0], bfr[1]);
+              mma_bf16(ac3[s][1], af, bfr[2], bfr[3]);
+            }
+          }
+          float acc[2][4];
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[nt][k] = ac3[0][nt][k] + (ac3[1][nt][k] + ac3[2][nt][k]);  // small pieces first
+          // C fragment: rows g and g+8 of the warp's 16, units 2q,2q+1 (acc[0]) and 8+2q,9+2q (acc[1])
+          const int tA = tb + warp * 16 + g, tB = tA + 8;
+          float h[2][4];
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h[nt][k] = 1.0f / (1.0f + expf(-acc[nt][k]));
+          float pA = fmaf(w2b.y, h[1][1], fmaf(w2b.x, h[1][0], fmaf(w2a.y, h[0][1], w2a.x * h[0][0])));
+          float pB = fmaf(w2b.y, h[1][3], fmaf(w2b.x, h[1][2], fmaf(w2a.y, h[0][3], w2a.x * h[0][2])));
+          pA += __shfl_xor_sync(BG_FULL, pA, 1);
+          pB += __shfl_xor_sync(BG_FULL, pB, 1);
+          pA += __shfl_xor_sync(BG_FULL, pA, 2);
+          pB += __shfl_xor_sync(BG_FULL, pB, 2);
+          if (tA < T) {
+            *reinterpret_cast<float2*>(&S.hs[tA * UT + 2 * q]) = make_float2(h[0][0], h[0][1]);
+            *reinterpret_cast<float2*>(&S.hs[tA * UT + 8 + 2 * q]) = make_float2(h[1][0], h[1][1]);
+          }
+          if (tB < T) {
+            *reinterpret_cast<float2*>(&S.hs[tB * UT + 2 * q]) = make_float2(h[0][2], h[0][3]);
+            *reinterpret_cast<float2*>(&S.hs[tB * UT + 8 + 2 * q]) = make_float2(h[1][2], h[1][3]);
+          }
+          for (int c = q; c < CL; c += 4) {
+            float* dst = cluster.map_shared_rank(S.ypart, c) + rank * TMAX;
+            if (tA < T) dst[tA] = pA;
+            if (tB < T) dst[tB] = pB;
+          }
+        }
+      }
+      PH(2);
+      cluster.sync();
+      PH(3);
+
+      // ---- C: values, TD(0) targets (trainer.py:110-115), dL/dY of the mse loss (:118), metric sums ----
+      for (int t = tid; t < T; t += NT) {
+        float y = S.b2[0];
+        for (int c = 0; c < CL; ++c) y += S.ypart[c * TMAX + t];
+        S.Y[t] = y;
+      }
+      __syncthreads();
+      {
+        float r5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int t = tid; t < T; t += NT) {
+          const float y = S.Y[t];
+          float tg = S.rew[t];
+          if (t + 1 < T) tg = __fadd_rn(tg, __fmul_rn(a.gamma, S.Y[t + 1]));
+          const float d = y - tg;
+          const float dy = 2.0f * d / (float)T;
+          S.dY[t] = dy;
+          r5[0] += d * d;
+          r5[1] += fabsf(d);
+          r5[2] += y;
+          r5[3] += S.rew[t];
+          r5[4] += dy;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) r5[k] += __shfl_xor_sync(BG_FULL, r5[k], o);
+        }
+        if (lane == 0)
+          for (int k = 0; k < 5; ++k) S.red[warp][k] = r5[k];
+      }
+      __syncthreads();
+      PH(4);
+      float msum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      if (tid == 0) {
+        for (int k = 0; k < 5; ++k) {
+          float s = 0.f;
+          for (int w = 0; w < NT / 32; ++w) s += S.red[w][k];
+          msum[k] = s;
+        }
+      }
+
+      // ---- D + E: per tile, dL/dz split into three bf16 pieces, then G += X^T dZ on the tensor cores.  Warp w owns the feature
+      //             m-tiles w and w + 8 (16 features each) for both 8-unit halves; the result stays in registers for Adam ----
+      float G3[3][2][2][4];  // [piece][m-tile slot][unit half][fragment]
+#pragma unroll
+      for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) G3[s][i][nt][0] = G3[s][i][nt][1] = G3[s][i][nt][2] = G3[s][i][nt][3] = 0.f;
+      float2 gw2 = make_float2(0.f, 0.f);  // this thread's unit pair (2 * (tid % 8)), summed over its rows
+      const int np = (tid & 7) * 2;
+      const float2 w2p = *reinterpret_cast<const float2*>(&S.P[(NF + 1) * UT + np]);
+      for (int tb = 0; tb < T; tb += RT) {
+        int rows = min(RT, ((T - tb) + 15) & ~15);
+        if (T > RT) {  // the forward pass left another tile in X
+          __syncthreads();
+          rows = decode_tile(tb);
+        }
+        for (int i = tid; i < rows * 8; i += NT) {
+          const int tr = i >> 3, t = tb + tr;
+          float2 dz = make_float2(0.f, 0.f);
+          if (t < T) {
+            const float dy = S.dY[t];
+            const float2 h = *reinterpret_cast<const float2*>(&S.hs[t * UT + np]);
+            gw2.x = fmaf(dy, h.x, gw2.x);
+            gw2.y = fmaf(dy, h.y, gw2.y);
+            dz.x = dy * w2p.x * h.x * (1.0f - h.x);
+            dz.y = dy * w2p.y * h.y * (1.0f - h.y);
+          }
+          store_split2(S.Ds, tr * WS + np, dz.x, dz.y);
+        }
+        __syncthreads();
+        PH(5);
+        const int brow = ((lane >> 3) & 1) * 8 + (lane & 7), bcol = (lane >> 4) * 8;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int mt = warp + 8 * i;
+          if (mt < KP / 16) {
+            // A = X^T: stored [row t][feature]; sub-matrices (features 0-7 | 8-15) x (rows 0-7 | 8-15), loaded transposed
+            const __nv_bfloat16* xa = &S.X[((lane >> 4) * 8 + (lane & 7)) * XS + mt * 16 + ((lane >> 3) & 1) * 8];
+#pragma unroll 2
+            for (int ks = 0; ks < rows / 16; ++ks) {
+              uint32_t af[4];
+              ldsm_x4_t(af, xa + ks * 16 * XS);
+#pragma unroll
+              for (int s = 0; s < 3; ++s) {
+                uint32_t bfr[4];
+                ldsm_x4_t(bfr, &S.Ds[s][(ks * 16 + brow) * WS + bcol]);
+                mma_bf16(G3[s][i][0], af, bfr[0], bfr[1]);
+                mma_bf16(G3[s][i][1], af, bfr[2], bfr[3]);
+              }
+            }
+          }
+        }
+      }
+      // w2 gradient: reduce the unit-pair partials over the lanes that share tid % 8, then over the warps
+      gw2.x += __shfl_xor_sync(BG_FULL, gw2.x, 8);
+      gw2.y += __shfl_xor_sync(BG_FULL, gw2.y, 8);
+      gw2.x += __shfl_xor_sync(BG_FULL, gw2.x, 16);
+      gw2.y += __shfl_xor_sync(BG_FULL, gw2.y, 16);
+      if (lane < 8) *reinterpret_cast<float2*>(&S.pr[warp][np]) = gw2;
+      __syncthreads();
+      // fragment ownership: G[i][nt][2 * hh + k] is feature f = (warp + 8 i) * 16 + g + 8 hh, unit nt * 8 + 2 q + k
+      float G[2][2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) G[i][nt][k] = G3[0][i][nt][k] + (G3[1][i][nt][k] + G3[2][i][nt][k]);  // small pieces first
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int f = (warp + 8 * i) * 16 + g + 8 * hh;
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              float x = G[i][nt][2 * hh + k];
+              if (f == 193 || f == 195) x *= k15;
+              if (f == NF + 1) {  // w2: fixed-order sum of the warp partials
+                x = 0.f;
+                for (int w = 0; w < NT / 32; ++w) x += S.pr[w][nt * 8 + 2 * q + k];
+              }
+              if (f >= NROW) x = 0.f;
+              G[i][nt][2 * hh + k] = x;
+              ss = fmaf(x, x, ss);
+            }
+        }
+      if (tid == 0 && rank == 0) ss = fmaf(msum[4], msum[4], ss);  // b2 gradient, counted once
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(BG_FULL, ss, o);
+      if (lane == 0) S.red2[warp] = ss;
+      __syncthreads();
+      if (tid < CL) {
+        float s = 0.f;
+        for (int w = 0; w < NT / 32; ++w) s += S.red2[w];
+        cluster.map_shared_rank(S.npart, tid)[rank] = s;
+      }
+      PH(6);
+      cluster.sync();
+      PH(7);
+
+      // ---- F: clip_grad_norm_ (trainer.py:125-128), the Adam step (:139) and the new operand image of the touched weights ----
+      float tot2 = 0.f;
+      for (int c = 0; c < CL; ++c) tot2 += S.npart[c];
+      const float total = sqrtf(tot2);
+      float coef = 1.0f;
+      if (a.grad_clip > 0.f) coef = fminf(1.0f, a.grad_clip / (total + 1e-6f));
+      const float2 sc = S.sc[kstep & (NSC - 1)];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int f = (warp + 8 * i) * 16 + g + 8 * hh;
+          if (f < NROW) {
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+              const int s = f * UT + nt * 8 + 2 * q;
+              float2 p = *reinterpret_cast<float2*>(&S.P[s]), m = *reinterpret_cast<float2*>(&S.M[s]), v = *reinterpret_cast<float2*>(&S.V[s]);
+              p.x = adam1(p.x, m.x, v.x, G[i][nt][2 * hh] * coef, sc.x, sc.y);
+              p.y = adam1(p.y, m.y, v.y, G[i][nt][2 * hh + 1] * coef, sc.x, sc.y);
+              *reinterpret_cast<float2*>(&S.P[s]) = p;
+              *reinterpret_cast<float2*>(&S.M[s]) = m;
+              *reinterpret_cast<float2*>(&S.V[s]) = v;
+              if (f <= NF) {
+                const float wsc = (f == 193 || f == 195) ? k15 : 1.0f;
+                store_split2(S.Ws, f * WS + nt * 8 + 2 * q, p.x * wsc, p.y * wsc);
+              }
+            }
+          }
+        }
+      if (tid == 0) {
+        S.b2[0] = adam1(S.b2[0], S.b2[1], S.b2[2], msum[4] * coef, sc.x, sc.y);
+        if (rank == 0 && a.metrics) {
+          float* mt = a.metrics + e * 6;
+          mt[0] = msum[0] / (float)T;
+          mt[1] = msum[1] / (float)T;
+          mt[2] = total * coef;
+          mt[3] = msum[2] / (float)T;
+          mt[4] = msum[3];
+          mt[5] = (float)T;
+        }
+      }
+      kstep += 1;
+      __syncthreads();
+      if ((kstep & (NSC - 1)) == 0) {
+        fill_scalars();
+        __syncthreads();
+      }
+      PH(8);
+      e = e_next;
+      buf ^= 1;
+    }
+  }
+#ifdef BG_LEARNER_PROFILE
+  if (tid == 0 && rank == 0 && kstep)
+    printf("k_td0_update_tc cycles/episode: stage %lld decode %lld fwd %lld csync1 %lld targets %lld dzsplit %lld gradW %lld csync2 %lld adam %lld head %lld\n",
+           ph[0] / kstep, ph[1] / kstep, ph[2] / kstep, ph[3] / kstep, ph[4] / kstep, ph[5] / kstep, ph[6] / kstep, ph[7] / kstep,
+           ph[8] / kstep, ph[9] / kstep);
+#endif
+
+  for (int s = tid; s < NROW * UT; s += NT) {
+    const int64_t gi = (int64_t)(s / UT) * H + rank * UT + (s % UT);
+    a.params[gi] = S.P[s];
+    a.m[gi] = S.M[s];
+    a.v[gi] = S.V[s];
+  }
+  if (rank == 0 && tid == 0) {
+    a.params[iB2] = S.b2[0];
+    a.m[iB2] = S.b2[1];
+    a.v[iB2] = S.b2[2];
+    *a.step = step0 + kstep;
+  }
+  cluster.sync();
 }
 
 struct OptScalars {
@@ -559,15 +1171,13 @@ int32_t learner_get_optimizer(Learner* L, float* m_dev, float* v_dev, int64_t* s
   return check_cuda(e, "bg_learner_get_optimizer");
 }
 
-template <int UPC>
-static int32_t launch_update(Learner* L, const LearnerArgs& a, cudaStream_t s) {
-  const size_t smem = sizeof(Smem<UPC>);
+template <typename K>
+static int32_t launch_update(Learner* L, K kernel, size_t smem, unsigned CL, const LearnerArgs& a, cudaStream_t s) {
   if (!L->attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_td0_update<UPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_td0_update)");
     L->attr_set = true;
   }
-  const unsigned CL = (unsigned)(L->H / UPC);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CL);
   cfg.blockDim = dim3(NT);
@@ -580,7 +1190,7 @@ static int32_t launch_update(Learner* L, const LearnerArgs& a, cudaStream_t s) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  return check_cuda(cudaLaunchKernelEx(&cfg, k_td0_update<UPC>, a), "k_td0_update launch");
+  return check_cuda(cudaLaunchKernelEx(&cfg, kernel, a), "k_td0_update launch");
 }
 
 int32_t learner_update(Learner* L, const int8_t* boards, const uint8_t* flags_or_meta, const float* reward, const int64_t* ep_offsets,
@@ -598,7 +1208,9 @@ int32_t learner_update(Learner* L, const int8_t* boards, const uint8_t* flags_or
   if (n_eps == 0) return BG_OK;
   LearnerArgs a{boards, flags_or_meta, reward, ep_offsets, n_eps, records, L->params, L->m, L->v, &L->opt->step,
                 L->lr, L->gamma, L->grad_clip, out_metrics, out_status, L->H};
-  return L->H <= 128 ? launch_update<16>(L, a, s) : launch_update<32>(L, a, s);
+  // H <= 128: 16 units per CTA, contractions on the tensor cores; larger nets: 32 units per CTA, CUDA-core sparse walks
+  if (L->H <= 128) return launch_update(L, k_td0_update_tc, sizeof(SmemTC), (unsigned)(L->H / UT), a, s);
+  return launch_update(L, k_td0_update<32>, sizeof(Smem<32>), (unsigned)(L->H / 32), a, s);
 }
 
 }  // namespace bg

@@ -82,7 +82,7 @@ def test_learner_other_hidden_sizes_vs_oracle(bg, golden, oracle, H):
     # Adam's first steps move a weight by lr * g / (|g| + eps): a gradient that cancels to ~1e-8 turns an fp32-vs-double summation
     # difference into a visible step difference on that one weight, so with random N(0, 0.2) nets the bound is on almost all weights
     d = np.abs(L.packed().cpu().numpy() - O.state()[0])
-    assert d.max() < 1e-4 and (d > W_TOL).mean() < 1e-4
+    assert d.max() < 1e-4 and (d > W_TOL).sum() <= 8
     assert np.allclose(met, omet, rtol=2e-3, atol=2e-6)
 
 
