@@ -186,6 +186,8 @@ def main():
     ap.add_argument("--selfplay-games", type=int, default=65536)
     ap.add_argument("--selfplay-plies", type=int, default=200)
     ap.add_argument("--selfplay2-plies", type=int, default=20)
+    ap.add_argument("--td0-updates", type=int, default=50)
+    ap.add_argument("--cpu-selfplay-games", type=int, default=16384)
     ap.add_argument("--no-selfplay", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -383,6 +385,132 @@ def main():
         selfplay2b = run_selfplay(G2, args.selfplay2_plies, 2, (0, 1, 1.0, 1.0),
                                   f"config4 (north-star expectimax): {G2} games per GPU, ALL candidates x 21 rolls, best reply, score = S - W")
 
+    # ---- BASELINE configs[4]: full TD(0) loop -- arena self-play -> 200-episode Trainer.update -> weights published (one broadcast) ----
+    def run_td0_loop(G, n_updates):
+        pm = bg.ParameterManager(hidden_size=H)
+        ar = bg.Arena(G, hidden_size=H, device=dev, seed=1, game_id_base=rank * G, ring_experiences=G * 48, ring_episodes=G)
+        pm.subscribe(ar)
+        if rank == 0:
+            pm.set_packed(packed, H)  # collective when world > 1
+            tr = bg.Trainer(pm, device=dev)
+        else:
+            pm.sync_from_source()
+        ar.reset()
+        ar.step(120)
+        ar.drain(max_episodes=G, max_experiences=G * 48)
+
+        lstream = torch.cuda.Stream(device=dev)  # the learner kernel (one 8-CTA cluster) overlaps the next self-play ply
+        n_iter = [0]
+
+        def iteration(timed):
+            # ply u of every game (weights of update u-2) || learner update u-1 on its own stream; then publish update u-1,
+            # hand 200 fresh episodes to the learner, drop the surplus (the sequential learner is the bottleneck)
+            ar.step(1)
+            m = None
+            if rank == 0:
+                m = tr.finish()  # stream-ordered wait for update u-1, set_packed -> (broadcast) -> arena.set_weights
+                batch = ar.drain(max_episodes=200)
+                while batch.n_episodes < 200:  # not reached with tens of thousands of games in flight
+                    ar.step(1)
+                    batch = ar.drain(max_episodes=200)
+                lstream.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(lstream):
+                    if timed is not None:
+                        timed[0].record()
+                    tr.update_async(batch)
+                    if timed is not None:
+                        timed[1].record()
+            elif n_iter[0] > 0:  # rank 0 publishes update u-1 in iteration u: nothing to receive in the very first one
+                pm.sync_from_source()
+            n_iter[0] += 1
+            ar.drain(max_episodes=G, max_experiences=G * 48)
+            return m
+
+        for _ in range(3):
+            iteration(None)
+        barrier()
+        s0 = ar.stats()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_updates)]
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        last = None
+        for u in range(n_updates):
+            last = iteration(evs[u]) or last
+        if rank == 0:
+            last = tr.finish() or last
+        elif n_updates:
+            pm.sync_from_source()
+        a1.record()
+        barrier()
+        s1 = ar.stats()
+        ms = a0.elapsed_time(a1)
+        d = torch.tensor([float(s1["games"] - s0["games"]), float(s1["wait_steps"] - s0["wait_steps"]), ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            tot = d.clone()
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            mx = d.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            d = torch.cat([tot[:2], mx[2:]])
+        out = None
+        if rank == 0:
+            upd_ms = sum(x.elapsed_time(y) for x, y in evs) / n_updates
+            ms = float(d[2])
+            out = {"workload": f"config5: {G} self-play games per GPU -> Trainer.update on 200-episode batches (sequential TD(0)/Adam, rank 0) -> packed weights "
+                               f"published to every arena ({'one NCCL broadcast' if world > 1 else 'single GPU'}); surplus episodes dropped",
+                   "updates_per_sec": n_updates / (ms * 1e-3), "episodes_trained_per_sec": 200 * n_updates / (ms * 1e-3),
+                   "games_played_per_sec": float(d[0]) / (ms * 1e-3), "ms_per_update_kernel": upd_ms, "ms_per_iteration": ms / n_updates,
+                   "actor_wait_steps": int(d[1]), "weights_version": pm.get_version(), "temperature": pm.get_temperature(),
+                   "last_update": {k: v for k, v in last.items() if isinstance(v, float)}}
+        ar.close()
+        return out
+
+    # learner alone: one 200-episode update on a fixed drained batch (kernel time, CUDA events)
+    def run_learner():
+        if rank != 0:
+            return None
+        ar = bg.Arena(8192, hidden_size=H, device=dev, seed=2)
+        ar.set_weights(packed, version=1)
+        ar.reset()
+        while ar.stats()["games"] < 200:
+            ar.step(40)
+        batch = ar.drain(max_episodes=200)
+        ar.close()
+        L = bg.TD0Learner(H, dev)
+        L.set_parameters(packed, reset_optimizer=True)
+        for _ in range(3):
+            L.update_batch(batch, check_status=False)
+        torch.cuda.synchronize()
+        R = 10
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(R):
+            L.update_batch(batch, check_status=False)
+        a1.record()
+        torch.cuda.synchronize()
+        ms = a0.elapsed_time(a1) / R
+        out = {"workload": "Trainer.update on one 200-episode batch drained from the arena (sequential per-episode forward, TD(0) targets, backward, "
+                           "clip_grad_norm_, Adam), one kernel launch (k_td0_update_tc, 8-CTA cluster)",
+               "ms_per_update": ms, "episodes_per_sec": 200 / (ms * 1e-3), "experiences_per_sec": batch.n_experiences / (ms * 1e-3),
+               "us_per_optimizer_step": ms * 1e3 / 200, "experiences": int(batch.n_experiences)}
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import pyoracle as po
+
+            po.build()
+            ob, of = batch.observation_boards()
+            N = batch.n_experiences
+            O = po.Learner(packed.cpu().numpy(), H)
+            t0 = time.perf_counter()
+            O.update(ob[:N].cpu().numpy(), of[:N].cpu().numpy(), batch.reward[:N].cpu().numpy(), batch.ep_offsets[:201].cpu().numpy())
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": 200 / dt, "unit": "episodes/s", "cores": 1, "kind": "port",
+                                   "sample": f"the same 200 episodes through the C restatement of Trainer.update (inherently sequential), {dt:.2f} s"}
+        return out
+
+    learner = td0 = None
+    if not args.no_selfplay:
+        learner = run_learner()
+        td0 = run_td0_loop(args.selfplay_games, args.td0_updates)
+
     # ---- CPU baseline: the oracle port on the host cores, bounded sample of the same workload -----------------------------------
     cpu = None
     if not args.no_cpu_baseline and rank == 0 and world == 1:  # reported baseline, rank 0 at N=1 only
@@ -399,6 +527,14 @@ def main():
         dt = time.perf_counter() - t0
         cpu = {"value": n_cpu / dt, "unit": "afterstates/s", "cores": cores, "kind": "port",
                "sample": f"first {ns} of the benchmark's positions x 21 rolls ({len(sb)} items, {n_cpu} afterstates), {dt:.1f} s, OpenMP"}
+        if selfplay is not None:  # BASELINE configs[0]: the reference's CPU self-play loop (1-ply, T = 1.5), one game per thread at a time
+            ng = args.cpu_selfplay_games
+            t0 = time.perf_counter()
+            n_after, n_steps, n_dec = po.selfplay_bench(pk, H, 1.5, ng, seed=0, nthreads=cores)
+            dt = time.perf_counter() - t0
+            selfplay["cpu_baseline"] = {"value": ng / dt, "unit": "games/s", "cores": cores, "kind": "port", "afterstates_per_sec": n_after / dt,
+                                        "sample": f"{ng} complete 1-ply self-play games (T=1.5) through the C restatement of Worker.play_episode, "
+                                                  f"{n_steps / ng:.1f} plies/game, {dt:.1f} s, OpenMP over games"}
 
     if rank != 0:
         if dist is not None:
@@ -415,7 +551,7 @@ def main():
                     "what": "pinned host boards/players/rolls -> bg_movegen -> bg_eval -> bg_select(greedy) -> host actions + counts"},
             "gpu_launches": 4 * args.steps, "gpu_launches_note": "per step: k_movegen tiers 128 / 512 / 4096 + k_eval128 (e2e adds k_select)",
             "roofline": roofline, "roofline_eval": roofline_eval, "cpu_baseline": cpu, "clocks": clocks, "selfplay_1ply": selfplay, "selfplay_2ply": selfplay2,
-            "selfplay_2ply_all_candidates": selfplay2b}
+            "selfplay_2ply_all_candidates": selfplay2b, "learner": learner, "td0_loop": td0}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

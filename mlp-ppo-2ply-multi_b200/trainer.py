@@ -109,6 +109,7 @@ class TD0Learner:
         status = torch.zeros(1, dtype=torch.int32, device=self.device)
         check(lib().bg_learner_update(self._h, boards.data_ptr(), flags.data_ptr(), reward.data_ptr(), ep_offsets.data_ptr(), E, int(records),
                                       met.data_ptr(), status.data_ptr(), self._stream()))
+        self.last_status = status  # device int32[1]; read lazily by callers that must not synchronise here
         if check_status and int(status.item()) != 0:
             raise RuntimeError(f"bg_learner_update: an episode exceeded {MAX_T} experiences and was skipped")
         return met
@@ -138,27 +139,43 @@ class Trainer:
         self.batch_episode_size = MIN_EPISODES_TO_TRAIN
         self.logger = logger  # optional object with add_scalar/add_scalars (the reference's S3Logger surface); S3 is out of scope
         self.last_metrics: dict = {}
+        self._pending = None
 
     def update(self, episodes):
+        """Reference semantics (trainer.py:48-228): train on exactly 200 episodes, hand the new weights to the parameter manager,
+        return (and log) the batch metrics.  Blocks until the update has run."""
+        self.update_async(episodes)
+        return self.finish()
+
+    def update_async(self, episodes):
+        """Enqueue the update on the current CUDA stream without any host synchronisation; finish() publishes and reports.  Lets
+        the caller overlap the (8-SM) learner kernel with arena self-play on another stream."""
         n = episodes.n_episodes if isinstance(episodes, EpisodeBatch) else len(episodes)
         if n != self.batch_episode_size:
             raise ValueError(f"Expected {self.batch_episode_size} episodes, but got {n}.")
+        if self._pending is not None:
+            self.finish()
         start = time.time()
         self.total_episodes += n
+        dev = self.device
         if isinstance(episodes, EpisodeBatch):
-            met = self.learner.update_batch(episodes)
-            info = episodes.ep_info[:n].to("cpu")
-            wins = {name: int((info[:, 0] == k).sum()) for k, name in ((1, "regular"), (2, "gammon"), (3, "backgammon"))}
-            lens = (episodes.ep_offsets[1:n + 1] - episodes.ep_offsets[:n]).to("cpu")
+            met = self.learner.update_batch(episodes, check_status=False)
+            info = episodes.ep_info[:n].to(torch.float32)
+            lens = (episodes.ep_offsets[1:n + 1] - episodes.ep_offsets[:n]).to(torch.float32)
+            wins = torch.stack([(info[:, 0] == k).sum() for k in (1, 2, 3)]).to(torch.float32)
+            seen = torch.stack([((episodes.ep_info[:n, 8] >> p) & 1).sum() for p in (0, 1)]).to(torch.float32)
             # the reference adds the episode's count dict once per EXPERIENCE (trainer.py:88-100)
-            close = {p: int((info[:, 4 + p] * lens).sum()) for p in (0, 1) if int(((info[:, 8] >> p) & 1).sum())}
-            prime = {p: int((info[:, 6 + p] * lens).sum()) for p in (0, 1) if int(((info[:, 8] >> p) & 1).sum())}
+            close = torch.stack([(info[:, 4 + p] * lens).sum() for p in (0, 1)])
+            prime = torch.stack([(info[:, 6 + p] * lens).sum() for p in (0, 1)])
+            summary = torch.cat([met.mean(dim=0), wins, seen, close, prime, self.learner.last_status.to(torch.float32)])  # read back once, in finish()
+            host = None
         else:
-            obs = torch.stack([x.observation for ep in episodes for x in ep.experiences]).to(self.device)
-            rew = torch.stack([torch.as_tensor(x.reward, dtype=torch.float32).reshape(()) for ep in episodes for x in ep.experiences]).to(self.device)
-            off = torch.tensor([0] + [len(ep.experiences) for ep in episodes], dtype=torch.int64).cumsum(0).to(self.device)
+            obs = torch.stack([x.observation for ep in episodes for x in ep.experiences]).to(dev)
+            rew = torch.stack([torch.as_tensor(x.reward, dtype=torch.float32).reshape(()) for ep in episodes for x in ep.experiences]).to(dev)
+            off = torch.tensor([0] + [len(ep.experiences) for ep in episodes], dtype=torch.int64).cumsum(0).to(dev)
             boards, flags = features_to_boards(obs)
-            met = self.learner.update(boards, flags, rew.contiguous(), off)
+            met = self.learner.update(boards, flags, rew.contiguous(), off, check_status=False)
+            summary = torch.cat([met.mean(dim=0), self.learner.last_status.to(torch.float32)])
             wins = {"regular": 0, "gammon": 0, "backgammon": 0}
             close, prime = {}, {}
             for ep in episodes:
@@ -168,12 +185,34 @@ class Trainer:
                     close[pid] = close.get(pid, 0) + c * len(ep.experiences)
                 for pid, c in ep.prime_reward_counts.items():
                     prime[pid] = prime.get(pid, 0) + c * len(ep.experiences)
-        avg = met.mean(dim=0).tolist()  # trainer.py:157-163: totals / batch_size
-        # trainer.py:166 -- hand the new weights to the parameter manager (device blob when it can take one)
+            host = (wins, close, prime)
+        packed = self.learner.packed()
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(dev))
+        self._pending = (summary, host, packed, done, start, episodes)  # `episodes` kept alive until the kernel has consumed it
+
+    def finish(self):
+        """Wait (stream-ordered) for the pending update, hand its weights to the parameter manager (trainer.py:166) and return the
+        metrics the reference logs (trainer.py:195-228)."""
+        if self._pending is None:
+            return self.last_metrics
+        summary, host, packed, done, start, _ = self._pending
+        self._pending = None
+        torch.cuda.current_stream(self.device).wait_event(done)
         if hasattr(self.parameter_manager, "set_packed"):
-            self.parameter_manager.set_packed(self.learner.packed(), self.learner.H)
+            self.parameter_manager.set_packed(packed, self.learner.H)  # device blob: no host round trip, one broadcast when distributed
         else:
-            self.parameter_manager.set_parameters(self.learner.state_dict())
+            self.parameter_manager.set_parameters(ops.unpack_weights(packed, self.learner.H))
+        vals = summary.tolist()
+        if vals[-1] != 0:
+            raise RuntimeError(f"bg_learner_update: an episode exceeded {MAX_T} experiences and was skipped")
+        avg = vals[:6]  # trainer.py:157-163: totals / batch_size
+        if host is None:
+            wins = dict(zip(("regular", "gammon", "backgammon"), (int(x) for x in vals[6:9])))
+            close = {p: int(vals[11 + p]) for p in (0, 1) if vals[9 + p] > 0}
+            prime = {p: int(vals[13 + p]) for p in (0, 1) if vals[9 + p] > 0}
+        else:
+            wins, close, prime = host
         self.last_metrics = {
             "Loss/Training Loss": avg[0], "TD Error/Mean TD Error": avg[1], "Gradients/Gradient Norm": avg[2],
             "Values/Average Predicted Value": avg[3], "Rewards/Average Reward per Episode": avg[4],
