@@ -301,3 +301,28 @@ def test_two_ply_lookahead_policy_matches_oracle(bg, oracle, golden, n_cand, top
     st = ar.stats()
     ar.close()
     assert checked > 500 and near < checked // 10 and st["replies"] > 0 and st["errors"] == 0
+
+
+def test_match_runner(bg, golden):
+    """checkpoint-vs-checkpoint matches with the reference agent's greedy rule (play_versus_ai.py:165-195)"""
+    vals = golden("values")
+    H = int(vals["H"])
+    trained, init0 = torch.from_numpy(vals["packed"]), torch.from_numpy(vals["packed_init0"])
+    same = bg.play_match(trained, trained, n_games=2048, hidden_size=H, device=DEV, seed=11)
+    assert same["games"] == 2048 and same["unfinished"] < 20 and same["a_wins"] + same["b_wins"] + same["unfinished"] == 2048
+    assert 0.44 < same["a_win_rate"] < 0.56  # a net against itself with alternating seats: a coin flip (sigma ~ 1.1 %)
+    ab = bg.play_match(trained, init0, n_games=2048, hidden_size=H, device=DEV, seed=12)
+    ba = bg.play_match(init0, trained, n_games=2048, hidden_size=H, device=DEV, seed=13)
+    assert abs(ab["a_win_rate"] + ba["a_win_rate"] - 1.0) < 0.06  # swapping the roles mirrors the result
+    # seat bookkeeping: B = all-zero weights values every afterstate 0, so B always plays action 0 (first-index argmax); A does not
+    zero = torch.zeros_like(trained)
+    out = bg.play_match(trained, zero, n_games=512, hidden_size=H, device=DEV, seed=14, return_batch=True)
+    b = out["batch"]
+    N = b.n_experiences
+    off = b.ep_offsets[: b.n_episodes + 1].cpu().numpy()
+    gid = b.ep_info[: b.n_episodes, 9].cpu().numpy()
+    mover = (b.meta[:N] & 1).cpu().numpy()
+    action = b.action[:N].cpu().numpy()
+    a_seat = np.repeat(gid % 2, np.diff(off))  # A is PLAYER1 (0) in even games
+    assert (action[mover != a_seat] == 0).all()
+    assert (action[mover == a_seat] != 0).mean() > 0.5
