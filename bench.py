@@ -315,7 +315,13 @@ def main():
     kern = {"bg::k_eval_tc (tcgen05, H=128)": (t_eval, eval_bytes), "bg::k_movegen<128|512|4096> (3 tiers)": (t_movegen, movegen_bytes)}
     dom = max(kern, key=lambda k: kern[k][0])
     ach = kern[dom][1] / (kern[dom][0] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    # dram__bytes_read + dram__bytes_write per launch from one `ncu --set full` capture of this command at the full configuration
+    # (profiles/r01_ncu_fullsize_dram_traffic.txt); only valid for that configuration
+    full_cfg = int(boards.shape[0]) == 1048576
+    traffic = {"bg::k_eval_tc (tcgen05, H=128)": 27.62e9, "bg::k_movegen<128|512|4096> (3 tiers)": 27.2e9} if full_cfg else {}
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic.get(dom),
+                "traffic_source": "profiles/r01_ncu_fullsize_dram_traffic.txt (ncu --set full, same command; bytes per launch)" if full_cfg else None,
+                "algorithmic_bytes": kern[dom][1],
                 "peak_source": peak_src, "ms_per_launch": kern[dom][0],
                 "note": "integer-issue / shared-memory bound by design: algorithmic bytes are tiny (SURVEY.md 8(d))",
                 "kernels_ms": {k: v[0] for k, v in kern.items()},
@@ -329,7 +335,7 @@ def main():
     tpeak, tsrc = (tpeak, "measured (MEASURED_PEAKS.json bf16_tflops, burst)") if tpeak else (1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)")
     tach = tc_flops / (t_eval * 1e-3) / 1e12
     roofline_eval = {"bound": "tensor", "kernel": "bg::k_eval_tc (tcgen05, H=128)", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s",
-                     "frac": tach / tpeak, "traffic": None, "peak_source": tsrc, "ms_per_launch": t_eval,
+                     "frac": tach / tpeak, "traffic": traffic.get("bg::k_eval_tc (tcgen05, H=128)"), "peak_source": tsrc, "ms_per_launch": t_eval,
                      "note": "bf16 FLOPs issued: 3 weight splits x 2*208*128 per afterstate (fp32-exact layer 1); dense fp32-equivalent is 1/3.27 of this"}
 
     del pool, values, pflags, ws, d_b, d_p, d_r, ib, ip, ir

@@ -837,7 +837,7 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update_tc(const LearnerArgs a) {
 #pragma unroll
           for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) h[nt][k] = 1.0f / (1.0f + expf(-acc[nt][k]));
+            for (int k = 0; k < 4; ++k) h[nt][k] = __fdividef(1.0f, 1.0f + __expf(-acc[nt][k]));  // as in k_eval (|dV| <= 1e-5 holds)
           float pA = fmaf(w2b.y, h[1][1], fmaf(w2b.x, h[1][0], fmaf(w2a.y, h[0][1], w2a.x * h[0][0])));
           float pB = fmaf(w2b.y, h[1][3], fmaf(w2b.x, h[1][2], fmaf(w2a.y, h[0][3], w2a.x * h[0][2])));
           pA += __shfl_xor_sync(BG_FULL, pA, 1);
