@@ -280,20 +280,18 @@ def main():
     h_b, h_p, h_r = ib.cpu().pin_memory(), ip.cpu().pin_memory(), ir.cpu().pin_memory()
     h_act = torch.empty(B, dtype=torch.int32).pin_memory()
     h_cnt = torch.empty(B, dtype=torch.int32).pin_memory()
-    d_b, d_p, d_r = torch.empty_like(ib), torch.empty_like(ip), torch.empty_like(ir)
+    res = r = None
+    del pool, values, pflags, ws
+    torch.cuda.empty_cache()
+    n_chunks = 8 if B >= (1 << 20) else 2
+    pipe = bg.HostPipeline(weights, items_per_chunk=(B + n_chunks - 1) // n_chunks, device=dev, item_cap=500)
 
     def e2e_step():
-        d_b.copy_(h_b, non_blocking=True)
-        d_p.copy_(h_p, non_blocking=True)
-        d_r.copy_(h_r, non_blocking=True)
-        r = bg.movegen(d_b, d_p, d_r, item_cap=500, out_boards=pool, check_status=False, workspace=ws, want_owner=False, out_flags=pflags)
-        bg.evaluate(pool, r.flags, weights, n_dev=r.total_dev, out=values)
-        act = bg.select(values, r.offsets, r.counts, temperature=0.0, item_cap=500)
-        h_act.copy_(act, non_blocking=True)
-        h_cnt.copy_(r.counts, non_blocking=True)
+        pipe.run(h_b, h_p, h_r, h_act, h_cnt, temperature=0.0)  # chunked: copies of neighbouring chunks overlap the kernels
 
     e2e_step()
     barrier()
+    pipe.raise_for_status()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -307,6 +305,9 @@ def main():
     e2e_value = n_after_all / (float(te[0]) / args.steps * 1e-3)
     h2d = h_b.numel() + h_p.numel() + h_r.numel()
     d2h = h_act.numel() * 4 + h_cnt.numel() * 4
+    n_e2e_kernels = 5 * n_chunks  # movegen tiers (3) + eval + select per chunk
+    e2e_check = int((h_cnt.to(torch.int64).clamp(max=500)).sum().item())  # must reproduce the afterstate count of the resident path
+    del pipe
 
     # ---- roofline of the dominant kernel (algorithmic bytes / measured kernel time) -----------------------------------------
     peak, peak_src = load_peaks()
@@ -338,7 +339,7 @@ def main():
                      "frac": tach / tpeak, "traffic": traffic.get("bg::k_eval_tc (tcgen05, H=128)"), "peak_source": tsrc, "ms_per_launch": t_eval,
                      "note": "bf16 FLOPs issued: 3 weight splits x 2*208*128 per afterstate (fp32-exact layer 1); dense fp32-equivalent is 1/3.27 of this"}
 
-    del pool, values, pflags, ws, d_b, d_p, d_r, ib, ip, ir
+    del ib, ip, ir
     torch.cuda.empty_cache()
 
     # ---- secondary: BASELINE configs[2] / configs[3], self-play with 65,536 concurrent games per GPU (all ranks, sharded by game id) ----
@@ -554,8 +555,9 @@ def main():
                        "positions_per_gpu": int(boards.shape[0]), "items_per_gpu": int(B), "afterstates_per_gpu_step": int(n_after), "hidden": H,
                        "l2": "inputs+outputs per step (>25 GB) far exceed the 126 MB L2", "parallelism": f"{world} x independent shards"},
             "e2e": {"value": e2e_value, "unit": "afterstates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "what": "pinned host boards/players/rolls -> bg_movegen -> bg_eval -> bg_select(greedy) -> host actions + counts"},
-            "gpu_launches": 4 * args.steps, "gpu_launches_note": "per step: k_movegen tiers 128 / 512 / 4096 + k_eval128 (e2e adds k_select)",
+                    "what": f"bg.HostPipeline.run: pinned host boards/players/rolls -> {n_chunks} chunks on 2 streams (H2D, bg_movegen, bg_eval, bg_select(greedy), D2H) -> host actions + counts",
+                    "afterstates_check": e2e_check},
+            "gpu_launches": 4 * args.steps, "gpu_launches_note": f"timed region, per step: k_movegen tiers 128 / 512 / 4096 + k_eval_tc; the e2e region launches {n_e2e_kernels} per step (the same four + k_select, per chunk)",
             "roofline": roofline, "roofline_eval": roofline_eval, "cpu_baseline": cpu, "clocks": clocks, "selfplay_1ply": selfplay, "selfplay_2ply": selfplay2,
             "selfplay_2ply_all_candidates": selfplay2b, "learner": learner, "td0_loop": td0}
     print(json.dumps(line), flush=True)

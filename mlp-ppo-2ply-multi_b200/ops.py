@@ -214,3 +214,57 @@ def two_ply(cand_boards: torch.Tensor, mover: torch.Tensor, S: torch.Tensor, wei
         if st != 0:
             raise _lib.BgError(st, "bg_two_ply: reply pool capacity exceeded for some candidates")
     return out, nrep
+
+
+class HostPipeline:
+    """The per-decision hot path for HOST-resident batches: pinned (boards, players, rolls) in, (action, count) per item out.
+
+    The batch is cut into chunks that alternate between two CUDA streams, so chunk k+1's host->device copy and chunk k-1's
+    device->host copy overlap chunk k's kernels (bg_movegen -> bg_eval -> bg_select); all device buffers are allocated once.
+    This is the call a CPU-side caller of get_all_possible_moves + generate_all_board_features + policy_network.forward +
+    argmax/sample (reference worker.py:101-143) makes when its positions live in host memory."""
+
+    def __init__(self, weights: PreparedWeights, items_per_chunk: int = 1 << 21, device=None, item_cap: int = 500, rows_per_item: int = 26):
+        self.dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.weights, self.item_cap, self.Bc = weights, int(item_cap), int(items_per_chunk)
+        self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(2)]
+        cap = self.Bc * rows_per_item + (1 << 18)
+        self.buf = []
+        for _ in range(2):
+            self.buf.append(dict(
+                b=torch.empty((self.Bc, BOARD_BYTES), dtype=torch.int8, device=self.dev), p=torch.empty(self.Bc, dtype=torch.uint8, device=self.dev),
+                r=torch.empty((self.Bc, 2), dtype=torch.uint8, device=self.dev), pool=torch.empty((cap, BOARD_BYTES), dtype=torch.int8, device=self.dev),
+                flags=torch.empty(cap, dtype=torch.uint8, device=self.dev), v=torch.empty(cap, dtype=torch.float32, device=self.dev),
+                ws=torch.empty(lib().bg_movegen_workspace_bytes(self.Bc), dtype=torch.uint8, device=self.dev), status=[]))
+
+    def run(self, h_boards: torch.Tensor, h_players: torch.Tensor, h_rolls: torch.Tensor, h_actions: torch.Tensor, h_counts: torch.Tensor,
+            temperature: float = 0.0, seed: int = 0) -> None:
+        """All five tensors are pinned host tensors ([B,52] int8, [B] uint8, [B,2] uint8, [B] int32, [B] int32).  Returns after
+        enqueueing; the calling stream waits for both worker streams (synchronise it to read the results)."""
+        B = h_boards.shape[0]
+        cur = torch.cuda.current_stream(self.dev)
+        for s in self.streams:
+            s.wait_stream(cur)
+        for k, lo in enumerate(range(0, B, self.Bc)):
+            hi = min(B, lo + self.Bc)
+            n = hi - lo
+            d, s = self.buf[k & 1], self.streams[k & 1]
+            with torch.cuda.stream(s):
+                d["b"][:n].copy_(h_boards[lo:hi], non_blocking=True)
+                d["p"][:n].copy_(h_players[lo:hi], non_blocking=True)
+                d["r"][:n].copy_(h_rolls[lo:hi], non_blocking=True)
+                res = movegen(d["b"][:n], d["p"][:n], d["r"][:n], item_cap=self.item_cap, out_boards=d["pool"], check_status=False, workspace=d["ws"],
+                              want_owner=False, out_flags=d["flags"])
+                evaluate(d["pool"], res.flags, self.weights, n_dev=res.total_dev, out=d["v"])
+                act = select(d["v"], res.offsets, res.counts, temperature=temperature, seed=seed, item_cap=self.item_cap, item_id_base=lo)
+                h_actions[lo:hi].copy_(act, non_blocking=True)
+                h_counts[lo:hi].copy_(res.counts, non_blocking=True)
+                d["status"] = [res.status_dev]
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def raise_for_status(self):
+        for d in self.buf:
+            for st in d["status"]:
+                if int(st.item()) != 0:
+                    raise _lib.BgError(int(st.item()), "HostPipeline: bg_movegen reported a capacity/invariant problem")

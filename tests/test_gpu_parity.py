@@ -1,6 +1,8 @@
 """GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the
 same seeded inputs and against the golden vectors produced by the unmodified reference.  Bit-exact for boards / order /
 sub-moves / features; |dV| <= 1e-5 for values (north_star contract)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -293,3 +295,24 @@ def test_eval_tensor_core_and_ffma_kernels_agree_with_oracle(bg, oracle, golden,
     v_ff = np.concatenate([bg.evaluate(dev(o_b[i:i + 20000]), dev(flags[i:i + 20000]), w).cpu().numpy() for i in range(0, n, 20000)])
     assert np.abs(v_ff - ref).max() < 1e-5
     assert np.abs(v_ff - v_tc).max() < 2e-6
+
+
+def test_host_pipeline_equals_resident_path(bg, oracle):
+    """bg.HostPipeline (pinned host batch, chunks on two streams) must give the same counts and greedy actions as one resident call."""
+    boards, players = oracle.random_positions(6000, seed=31)
+    ib, ip, ir = oracle.all_rolls_items(boards, players)
+    B = ib.shape[0]
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "values.npz"))
+    w = bg.prepare_weights(torch.from_numpy(g["packed"]).to(DEV), int(g["H"]))
+    db, dp, dr = (torch.from_numpy(x).to(DEV) for x in (ib, ip, ir))
+    res = bg.movegen(db, dp, dr, item_cap=500)
+    v = bg.evaluate(res.boards, res.flags, w, n_dev=res.total_dev)
+    act = bg.select(v, res.offsets, res.counts, temperature=0.0)
+    hb, hp, hr = (torch.from_numpy(x).pin_memory() for x in (ib, ip, ir))
+    ha, hc = torch.full((B,), -7, dtype=torch.int32).pin_memory(), torch.full((B,), -7, dtype=torch.int32).pin_memory()
+    pipe = bg.HostPipeline(w, items_per_chunk=B // 5 + 1, device=DEV)  # 5 chunks, the last one ragged
+    for _ in range(2):  # buffers are reused across runs
+        pipe.run(hb, hp, hr, ha, hc, temperature=0.0)
+        torch.cuda.synchronize()
+        pipe.raise_for_status()
+        assert torch.equal(hc, res.counts.cpu()) and torch.equal(ha, act.cpu())
