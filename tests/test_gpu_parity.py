@@ -211,12 +211,12 @@ def test_select_greedy_and_distribution(bg):
 
 
 def test_full_size_properties(bg, oracle):
-    """BASELINE config-2 scale slice (131,072 positions x 21 rolls) through size-independent properties:
-    checker conservation, counts vs oracle, order-insensitive checksum vs oracle, dice-order symmetry."""
+    """BASELINE config-2 scale slice (131,072 positions x 21 rolls = 2.75 M items, 58 M afterstates): counts vs oracle, checker
+    conservation, pip monotonicity, and an order-sensitive 64-bit checksum of every item's afterstate list vs the oracle."""
     n_pos = 131072
     boards, players = oracle.random_positions(n_pos, seed=2026)
     ib, ip, ir = oracle.all_rolls_items(boards, players)
-    o_off, _, _ = oracle.movegen_batch(ib, ip, ir, want_moves=False)
+    o_off, o_boards, _ = oracle.movegen_batch(ib, ip, ir, want_moves=False)
     total = int(o_off[-1])
     res = bg.movegen(dev(ib), dev(ip), dev(ir), item_cap=4096, pool_cap=total + 4096, want_owner=True)
     assert res.total == total
@@ -239,6 +239,35 @@ def test_full_size_properties(bg, oracle):
         return torch.where(pl == 0, p0, p1)
 
     assert bool((pips(ob) < pips(root)).all())
+    del ob, root
+    # content AND order of all 58 M afterstates: a 64-bit checksum per item, sum_k (2k+1) * hash(board_k), vs the oracle
+    # ("boards, order, counts ... via 64-bit checksum per item")
+    coef = (np.arange(1, 14, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(1)
+    words = np.ascontiguousarray(o_boards).view(np.uint32).reshape(-1, 13)
+    counts = np.diff(o_off)
+    k = np.arange(total, dtype=np.int64) - np.repeat(o_off[:-1], counts)
+    contrib = np.empty(total, np.uint64)
+    CH = 1 << 22
+    for lo in range(0, total, CH):
+        hi = min(total, lo + CH)
+        h = (words[lo:hi].astype(np.uint64) * coef).sum(1, dtype=np.uint64)
+        h ^= h >> np.uint64(29)
+        contrib[lo:hi] = h * (2 * k[lo:hi] + 1).astype(np.uint64)
+    want = np.zeros(len(ib), np.uint64)
+    nz = counts > 0
+    want[nz] = np.add.reduceat(contrib, o_off[:-1][nz])  # CSR segments (empty items skipped: reduceat would repeat a neighbour)
+    got = torch.zeros(len(ib), dtype=torch.int64, device=DEV)
+    coef_t = torch.from_numpy(coef.view(np.int64)).to(DEV)
+    gw = res.boards[:total].view(torch.int32).reshape(-1, 13)
+    for lo in range(0, total, CH):
+        hi = min(total, lo + CH)
+        w64 = gw[lo:hi].to(torch.int64) & 0xFFFFFFFF
+        h = (w64 * coef_t).sum(1)
+        h = h ^ ((h >> 29) & ((1 << 35) - 1))  # logical shift
+        rows = torch.arange(lo, hi, device=DEV)
+        kk = rows - res.offsets[own[lo:hi]]
+        got.index_add_(0, own[lo:hi], h * (2 * kk + 1))
+    assert np.array_equal(got.cpu().numpy().view(np.uint64), want)
 
 
 def test_two_ply_reference_setting_and_best_reply(bg, oracle, golden):
