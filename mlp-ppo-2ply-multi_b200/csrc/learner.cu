@@ -630,15 +630,7 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// x = hi + mid + lo with three bf16 pieces (24 mantissa bits)
-__device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
-  h = __float2bfloat16_rn(x);
-  float r = x - __bfloat162float(h);
-  m = __float2bfloat16_rn(r);
-  r -= __bfloat162float(m);
-  l = __float2bfloat16_rn(r);
-}
-// the same for a pair, through the packed converts: p[0..2] = (hi, mid, lo) pieces of (x0, x1) as bf16x2 words
+// x = hi + mid + lo with three bf16 pieces (24 mantissa bits), for a pair, through the packed converts: p[0..2] = (hi, mid, lo) pieces of (x0, x1) as bf16x2 words
 __device__ __forceinline__ void split3x2(float x0, float x1, uint32_t (&p)[3]) {
 #pragma unroll
   for (int s = 0; s < 3; ++s) {
