@@ -394,6 +394,8 @@ def main():
 
     # ---- BASELINE configs[4]: full TD(0) loop -- arena self-play -> 200-episode Trainer.update -> weights published (one broadcast) ----
     def run_td0_loop(G, n_updates):
+        from mlp_ppo_2ply_multi_b200 import distributed as bgd
+
         pm = bg.ParameterManager(hidden_size=H)
         ar = bg.Arena(G, hidden_size=H, device=dev, seed=1, game_id_base=rank * G, ring_experiences=G * 48, ring_episodes=G)
         pm.subscribe(ar)
@@ -416,10 +418,16 @@ def main():
             m = None
             if rank == 0:
                 m = tr.finish()  # stream-ordered wait for update u-1, set_packed -> (broadcast) -> arena.set_weights
-                batch = ar.drain(max_episodes=200)
-                while batch.n_episodes < 200:  # not reached with tens of thousands of games in flight
-                    ar.step(1)
-                    batch = ar.drain(max_episodes=200)
+            elif n_iter[0] > 0:  # rank 0 publishes update u-1 in iteration u: nothing to receive in the very first one
+                pm.sync_from_source()
+            quota = 200 // world  # every rank's arena feeds the trainer, as every worker process feeds the reference's queue
+            batch = ar.drain(max_episodes=quota)
+            while batch.n_episodes < quota:  # not reached with tens of thousands of games in flight
+                ar.step(1)
+                batch = ar.drain(max_episodes=quota)
+            if world > 1:
+                batch = bgd.all_gather_episodes(batch, quota, quota * 300)  # one all_gather of ~1.3 MB in total
+            if rank == 0:
                 lstream.wait_stream(torch.cuda.current_stream(dev))
                 with torch.cuda.stream(lstream):
                     if timed is not None:
@@ -427,8 +435,6 @@ def main():
                     tr.update_async(batch)
                     if timed is not None:
                         timed[1].record()
-            elif n_iter[0] > 0:  # rank 0 publishes update u-1 in iteration u: nothing to receive in the very first one
-                pm.sync_from_source()
             n_iter[0] += 1
             ar.drain(max_episodes=G, max_experiences=G * 48)
             return m
@@ -463,7 +469,7 @@ def main():
             upd_ms = sum(x.elapsed_time(y) for x, y in evs) / n_updates
             ms = float(d[2])
             out = {"workload": f"config5: {G} self-play games per GPU -> Trainer.update on 200-episode batches (sequential TD(0)/Adam, rank 0) -> packed weights "
-                               f"published to every arena ({'one NCCL broadcast' if world > 1 else 'single GPU'}); surplus episodes dropped",
+                               f"published to every arena ({'episodes all-gathered from every rank, one NCCL broadcast of the weights' if world > 1 else 'single GPU'}); surplus episodes dropped",
                    "updates_per_sec": n_updates / (ms * 1e-3), "episodes_trained_per_sec": 200 * n_updates / (ms * 1e-3),
                    "games_played_per_sec": float(d[0]) / (ms * 1e-3), "ms_per_update_kernel": upd_ms, "ms_per_iteration": ms / n_updates,
                    "actor_wait_steps": int(d[1]), "weights_version": pm.get_version(), "temperature": pm.get_temperature(),

@@ -35,3 +35,64 @@ def all_reduce_stats(stats: Dict[str, int], device=None, group=None) -> Dict[str
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return dict(zip(STAT_NAMES, t.tolist()))
+
+
+_EP_FIELDS = (("after_boards", torch.int8, 52), ("meta", torch.uint8, 1), ("reward", torch.float32, 1), ("state_value", torch.float32, 1),
+              ("next_state_value", torch.float32, 1), ("n_moves", torch.int16, 1), ("action", torch.int16, 1), ("roll", torch.uint8, 2))
+
+
+def all_gather_episodes(batch, max_episodes: int, max_experiences: int, group=None):
+    """Config 5 (collective 3): every rank contributes its drained episodes (at most max_episodes /
+    max_experiences) and receives the concatenation in rank order as one EpisodeBatch -- what the trainer rank feeds to
+    Trainer.update.  ONE all_gather of a fixed-size byte buffer per rank (compact records: 72 B per experience, so 200 episodes
+    are ~1.3 MB in total); replaces the reference's ExperienceQueue.put from every worker process (src/multi/worker.py:60-64)."""
+    from .episode import EpisodeBatch
+
+    E, N = int(batch.n_episodes), int(batch.n_experiences)
+    if E > max_episodes or N > max_experiences:
+        raise ValueError(f"batch ({E} episodes, {N} experiences) exceeds the gather quota ({max_episodes}, {max_experiences})")
+    dev = batch.after_boards.device
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+    def pad_bytes(t, rows, cols, dtype, used):
+        buf = torch.zeros((rows, cols), dtype=dtype, device=dev)
+        if used:
+            buf[:used] = t[:used].reshape(used, cols)
+        return buf.reshape(-1).view(torch.uint8)
+
+    parts = [torch.tensor([E, N], dtype=torch.int64, device=dev).view(torch.uint8)]
+    parts += [pad_bytes(getattr(batch, name), max_experiences, cols, dt, N) for name, dt, cols in _EP_FIELDS]
+    parts.append(pad_bytes(batch.ep_offsets[: E + 1] if E else batch.ep_offsets[:1], max_episodes + 1, 1, torch.int64, E + 1))
+    parts.append(pad_bytes(batch.ep_info, max_episodes, batch.ep_info.shape[1], torch.int32, E))
+    mine = torch.cat(parts)
+    if world > 1:
+        allb = torch.empty((world, mine.numel()), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allb, mine, group=group) if dev.type == "cuda" else dist.all_gather(list(allb.unbind(0)), mine, group=group)
+    else:
+        allb = mine.reshape(1, -1)
+    cols_info = batch.ep_info.shape[1]
+    out = {name: [] for name, _, _ in _EP_FIELDS}
+    offs, infos, tot_e, tot_n = [torch.zeros(1, dtype=torch.int64, device=dev)], [], 0, 0
+    hdr = allb[:, :16].clone().view(torch.int64).reshape(world, 2).tolist()  # the one host read-back
+    for r in range(world):
+        row = allb[r]
+        e_r, n_r = hdr[r]
+        pos = 16
+        for name, dt, cols in _EP_FIELDS:
+            nb = max_experiences * cols * torch.empty(0, dtype=dt).element_size()
+            t = row[pos:pos + nb].clone().view(dt).reshape(max_experiences, cols)[:n_r]  # clone: aligned storage for the wider view
+            out[name].append(t if cols > 1 else t.reshape(-1))
+            pos += nb
+        nb = (max_episodes + 1) * 8
+        o = row[pos:pos + nb].clone().view(torch.int64)[: e_r + 1]
+        pos += nb
+        nb = max_episodes * cols_info * 4
+        infos.append(row[pos:pos + nb].clone().view(torch.int32).reshape(max_episodes, cols_info)[:e_r])
+        if e_r:
+            offs.append(o[1:] - o[0] + tot_n)
+        tot_e += e_r
+        tot_n += n_r
+    cat = {k: torch.cat(v) if v else None for k, v in out.items()}
+    return EpisodeBatch(tot_e, tot_n, cat["after_boards"].contiguous(), cat["meta"].contiguous(), cat["reward"].contiguous(),
+                        cat["state_value"].contiguous(), cat["next_state_value"].contiguous(), cat["n_moves"].contiguous(),
+                        cat["action"].contiguous(), cat["roll"].contiguous(), torch.cat(offs).contiguous(), torch.cat(infos).contiguous())

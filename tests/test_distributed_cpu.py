@@ -36,6 +36,21 @@ def _worker(rank, world, port, out_dir):
     n_local, base = bgd.shard_games(65536 + 1, rank, world)
     stats = bgd.all_reduce_stats({"games": 10 + rank, "steps": 1000 * (rank + 1), "afterstates": 7})
     w, ver, temp = bgd.broadcast_weights(packed * (rank + 1), 5 + rank, 1.25 - rank, src=0)
+    # collective 3: every rank's drained episodes gathered into one batch (here: synthetic CPU batches of different sizes)
+    from mlp_ppo_2ply_multi_b200.episode import EpisodeBatch
+
+    E, lens = 2 + rank, [3 + rank, 1, 4][: 2 + rank]
+    N = sum(lens)
+    g = torch.Generator().manual_seed(7 + rank)
+    eb = EpisodeBatch(E, N, torch.randint(0, 6, (N + 5, 52), generator=g, dtype=torch.int8), torch.randint(0, 32, (N + 5,), generator=g, dtype=torch.uint8),
+                      torch.rand(N + 5, generator=g), torch.rand(N + 5, generator=g), torch.rand(N + 5, generator=g),
+                      torch.randint(1, 50, (N + 5,), generator=g, dtype=torch.int16), torch.randint(0, 50, (N + 5,), generator=g, dtype=torch.int16),
+                      torch.randint(1, 7, (N + 5, 2), generator=g, dtype=torch.uint8), torch.tensor([0] + list(np.cumsum(lens)) + [0, 0], dtype=torch.int64),
+                      torch.full((E + 2, 12), 100 + rank, dtype=torch.int32))
+    merged = bgd.all_gather_episodes(eb, max_episodes=4, max_experiences=12)
+    np.savez(os.path.join(out_dir, f"ep{rank}.npz"), n=np.array([merged.n_episodes, merged.n_experiences]), off=merged.ep_offsets.numpy(),
+             after=merged.after_boards.numpy(), reward=merged.reward.numpy(), info=merged.ep_info.numpy(), roll=merged.roll.numpy(),
+             action=merged.action.numpy(), my_after=eb.after_boards[:N].numpy(), my_reward=eb.reward[:N].numpy())
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), packed=packed.numpy(), version=pm.get_version(), temperature=pm.get_temperature(),
              n_local=n_local, base=base, games=stats["games"], steps=stats["steps"], after=stats["afterstates"], w=w.numpy(), ver=ver, temp=temp)
     dist.destroy_process_group()
@@ -51,6 +66,13 @@ def test_two_rank_weight_broadcast_sharding_and_stats(tmp_path):
     assert int(r0["n_local"]) + int(r1["n_local"]) == 65537 and int(r0["base"]) == 0 and int(r1["base"]) == int(r0["n_local"])
     assert int(r0["games"]) == int(r1["games"]) == 21 and int(r0["steps"]) == 3000 and int(r1["after"]) == 14
     assert np.array_equal(r0["w"], r1["w"]) and int(r1["ver"]) == 5 and float(r1["temp"]) == 1.25
+    e0, e1 = (np.load(tmp_path / f"ep{r}.npz") for r in range(world))
+    for k in ("n", "off", "after", "reward", "info", "roll", "action"):
+        assert np.array_equal(e0[k], e1[k])  # every rank holds the same merged batch
+    assert e0["n"].tolist() == [5, 4 + 9] and e0["off"].tolist() == [0, 3, 4, 8, 9, 13]  # rank 0: episodes of 3, 1; rank 1: 4, 1, 4
+    assert np.array_equal(e0["after"], np.concatenate([e0["my_after"], e1["my_after"]]))
+    assert np.array_equal(e0["reward"], np.concatenate([e0["my_reward"], e1["my_reward"]]))
+    assert e0["info"][:, 0].tolist() == [100, 100, 101, 101, 101]
 
 
 def test_shard_games_partition():
