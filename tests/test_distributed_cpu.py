@@ -127,3 +127,50 @@ def test_policy_network_state_dict_contract():
     assert packed.numel() == 200 * 128 + 1
     back = bg.unpack_weights(packed, 128)
     assert all(torch.equal(back[k], sd[k]) for k in sd)
+
+
+def test_parameter_manager_surface_and_checkpoint_io(tmp_path, monkeypatch):
+    """ParameterManager: the reference's 4-method surface (parameter_manager.py:54-111) and .pth files in its checkpoint format."""
+    import mlp_ppo_2ply_multi_b200 as bg
+
+    monkeypatch.chdir(tmp_path)
+    pm = bg.ParameterManager(hidden_size=128)
+    assert pm.get_version() == 1 and pm.get_temperature() == 1.5
+    sd = pm.get_parameters()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {"fc1.weight": (128, 198), "fc1.bias": (128,), "value_head.weight": (1, 128),
+                                                          "value_head.bias": (1,)}
+    net = bg.BackgammonPolicyNetwork()
+    pm.set_parameters(net.state_dict())
+    assert pm.get_version() == 2 and pm.get_temperature() == pytest.approx(1.5 - 1.0 / 4000)
+    assert all(torch.equal(pm.get_parameters()[k], v) for k, v in net.state_dict().items())
+    path = pm.save_model("ckpt.pth")
+    loaded = torch.load(path, map_location="cpu")  # a plain state_dict, loadable by the reference's BackgammonPolicyNetwork
+    net2 = bg.BackgammonPolicyNetwork()
+    net2.load_state_dict(loaded)
+    pm2 = bg.ParameterManager(hidden_size=128)
+    pm2.load_model("ckpt.pth")
+    assert pm2.get_version() == 2 and all(torch.equal(pm2.get_parameters()[k], v) for k, v in net.state_dict().items())
+    # packed fast path == state-dict path
+    pm2.set_packed(bg.pack_weights(net2.state_dict()))
+    assert pm2.get_version() == 3 and torch.equal(bg.pack_weights(pm2.get_parameters()), bg.pack_weights(net.state_dict()))
+    with pytest.raises(NotImplementedError):
+        pm.save_model("x.pth", to_s3=True)
+
+
+def test_reference_checkpoints_load_unchanged(golden):
+    """The reference's shipped checkpoints (src/play/*.pth) load into BackgammonPolicyNetwork unchanged; the packed blob of the
+    2.1 M-episode one is the golden `packed` vector.  Needs /root/reference (build container only)."""
+    import glob
+
+    import mlp_ppo_2ply_multi_b200 as bg
+
+    files = sorted(glob.glob("/root/reference/src/play/*.pth"))
+    if not files:
+        pytest.skip("reference checkpoints not present on this machine")
+    for f in files:
+        sd = torch.load(f, map_location="cpu")
+        net = bg.BackgammonPolicyNetwork(hidden_size=sd["fc1.weight"].shape[0])
+        net.load_state_dict(sd)
+        assert bg.pack_weights(net.state_dict()).numel() == 200 * net.hidden_size + 1
+    sd = torch.load([f for f in files if f.endswith("backgammon_256_standard_episode_2100000.pth")][0], map_location="cpu")
+    assert np.array_equal(bg.pack_weights(sd).numpy(), golden("values")["packed"])
