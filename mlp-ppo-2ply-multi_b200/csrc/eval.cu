@@ -157,7 +157,7 @@ template <int HPL>
 __global__ void __launch_bounds__(EVAL_THREADS, (HPL <= 4 ? 2 : 1))
     k_eval(const int8_t* __restrict__ boards, const uint8_t* __restrict__ flags, const int32_t* __restrict__ owner,
            const uint8_t* __restrict__ owner_players, int64_t N_host, const int64_t* __restrict__ N_dev, int64_t max_N,
-           const float* __restrict__ prep, float* __restrict__ out_v) {
+           const float* __restrict__ prep, float* __restrict__ out_v, const int64_t* __restrict__ start_dev) {
   constexpr int H = HPL * 32;
   extern __shared__ __align__(16) float sT[];
   const int n_floats = 200 * H + 1;
@@ -169,6 +169,16 @@ __global__ void __launch_bounds__(EVAL_THREADS, (HPL <= 4 ? 2 : 1))
   const float b2 = sw2[H];
   int64_t N = N_dev ? *N_dev : N_host;
   if (N > max_N) N = max_N;
+  {  // optional device-side start row: shift the row-indexed arrays once, everything below is unchanged
+    int64_t start = start_dev ? *start_dev : 0;
+    if (start > N) start = N;
+    if (start < 0) start = 0;
+    boards += start * BG_BOARD_BYTES;
+    if (flags) flags += start;
+    if (owner) owner += start;
+    out_v += start;
+    N -= start;
+  }
   const int lane = threadIdx.x & 31;
   uint32_t* list = lists + (threadIdx.x >> 5) * 56;
   const int64_t warp = (int64_t)blockIdx.x * (EVAL_THREADS / 32) + (threadIdx.x >> 5);
@@ -281,7 +291,7 @@ int32_t launch_eval_t(const EvalArgs& a, cudaStream_t stream) {
   if (want < 1) want = 1;
   const int grid = (int)(want < (int64_t)NUM_SMS * ctas_per_sm ? want : (int64_t)NUM_SMS * ctas_per_sm);
   k_eval<HPL><<<grid, EVAL_THREADS, smem, stream>>>(a.boards, a.flags, a.owner, a.owner_players, a.N, a.N_dev, a.max_N, a.prepared,
-                                                    a.out_v);
+                                                    a.out_v, a.start_dev);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return check_cuda(e, "k_eval launch");
   return BG_OK;

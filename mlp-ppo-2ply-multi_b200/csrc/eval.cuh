@@ -15,6 +15,7 @@ struct EvalArgs {
   const float* prepared;
   int32_t H;
   float* out_v;
+  const int64_t* start_dev = nullptr;  // optional device counter: evaluate rows [*start_dev, N) only (rows before it are left untouched)
 };
 
 int64_t prepared_weights_bytes(int32_t H);

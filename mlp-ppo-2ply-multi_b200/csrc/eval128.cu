@@ -105,7 +105,7 @@ __device__ __forceinline__ void fma2(Acc8& z, float s, const float* row, int gl)
 __global__ void __launch_bounds__(THREADS, 1)
     k_eval128(const int8_t* __restrict__ boards, const uint8_t* __restrict__ flags, const int32_t* __restrict__ owner,
               const uint8_t* __restrict__ owner_players, int64_t N_host, const int64_t* __restrict__ N_dev, int64_t max_N,
-              const float* __restrict__ t128, float* __restrict__ out_v) {
+              const float* __restrict__ t128, float* __restrict__ out_v, const int64_t* __restrict__ start_dev) {
   extern __shared__ __align__(16) float sT[];
   {
     const float4* src = reinterpret_cast<const float4*>(t128);
@@ -117,6 +117,16 @@ __global__ void __launch_bounds__(THREADS, 1)
   const float b2 = t128[TABLE_ROWS * H];
   int64_t N = N_dev ? *N_dev : N_host;
   if (N > max_N) N = max_N;
+  {  // optional device-side start row: shift the row-indexed arrays once, everything below is unchanged
+    int64_t start = start_dev ? *start_dev : 0;
+    if (start > N) start = N;
+    if (start < 0) start = 0;
+    boards += start * BG_BOARD_BYTES;
+    if (flags) flags += start;
+    if (owner) owner += start;
+    out_v += start;
+    N -= start;
+  }
   const int lane = threadIdx.x & 31, gl = lane & 15, grp = lane >> 4, gb = grp << 4;
   const int wib = threadIdx.x >> 5;
   uint32_t* list = lists + (wib * 2 + grp) * (LIST_WORDS + ELIST_WORDS);
@@ -246,7 +256,7 @@ int32_t eval128_launch(const EvalArgs& a, const float* t128, cudaStream_t stream
   int64_t want = (bound + WARPS * 2 - 1) / (WARPS * 2);
   if (want < 1) want = 1;
   const int grid = (int)(want < NUM_SMS ? want : NUM_SMS);
-  k_eval128<<<grid, THREADS, smem, stream>>>(a.boards, a.flags, a.owner, a.owner_players, a.N, a.N_dev, a.max_N, t128, a.out_v);
+  k_eval128<<<grid, THREADS, smem, stream>>>(a.boards, a.flags, a.owner, a.owner_players, a.N, a.N_dev, a.max_N, t128, a.out_v, a.start_dev);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return check_cuda(e, "k_eval128 launch");
   return BG_OK;

@@ -124,7 +124,8 @@ __device__ __forceinline__ void point_words(uint32_t c, uint32_t& w0, uint32_t& 
 
 __global__ void __launch_bounds__(THREADS, 1)
     k_eval_tc(const int8_t* __restrict__ boards, const uint8_t* __restrict__ flags, int64_t N_host, const int64_t* __restrict__ N_dev,
-              int64_t max_N, const uint8_t* __restrict__ img, float* __restrict__ out_v, int32_t* __restrict__ err) {
+              int64_t max_N, const uint8_t* __restrict__ img, float* __restrict__ out_v, int32_t* __restrict__ err,
+              const int64_t* __restrict__ start_dev) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sB = smem;                                             // B operand image
   float* sW2 = reinterpret_cast<float*>(smem + B_BYTES);          // w2[128], b2
@@ -154,6 +155,15 @@ __global__ void __launch_bounds__(THREADS, 1)
 
   int64_t N = N_dev ? *N_dev : N_host;
   if (N > max_N) N = max_N;
+  {  // optional device-side start row: shift the row-indexed arrays once, everything below is unchanged
+    int64_t start = start_dev ? *start_dev : 0;
+    if (start > N) start = N;
+    if (start < 0) start = 0;
+    boards += start * BG_BOARD_BYTES;
+    if (flags) flags += start;
+    out_v += start;
+    N -= start;
+  }
   const int64_t n_tiles = (N + 127) / 128;
   // tile t of the grid is owned by CTA (t / 2) % gridDim.x, group t & 1
   if (warp < 8) {
@@ -325,7 +335,7 @@ int32_t eval_tc_launch(const EvalArgs& a, const uint8_t* img, int32_t* err_flag,
   int64_t want = (bound + 255) / 256;
   if (want < 1) want = 1;
   const int grid = (int)(want < NUM_SMS ? want : NUM_SMS);
-  k_eval_tc<<<grid, THREADS, smem, stream>>>(a.boards, a.flags, a.N, a.N_dev, a.max_N, img, a.out_v, err_flag);
+  k_eval_tc<<<grid, THREADS, smem, stream>>>(a.boards, a.flags, a.N, a.N_dev, a.max_N, img, a.out_v, err_flag, a.start_dev);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return check_cuda(e, "k_eval_tc launch");
   return BG_OK;

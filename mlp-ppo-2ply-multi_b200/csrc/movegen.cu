@@ -18,7 +18,7 @@
 //     (parent, move) pairs are flattened over the warp so that every lane builds one child per round.
 //   * non-doubles keep the reference's literal control flow (both die orders, singles only when an order has
 //     no two-move play, quirk Q1 skip, shared seen-set, max-length filter).
-//   * three capacity tiers (128 / 512 nodes per ply in shared memory, 4096 in L2-resident global scratch);
+//   * four capacity tiers (128 / 512 / 2048 nodes per ply in shared memory, 4096 in L2-resident global scratch);
 //     an item overflowing a tier is queued for the next one.  Overflowing the last tier is BG_ERR_CAPACITY.
 #include "movegen.cuh"
 
@@ -583,10 +583,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_movegen(MovegenParams P) {
   }
 }
 
-// capacity tiers: nodes per ply.  T1/T2 keep the frontiers in shared memory, T3 in L2-resident global scratch.
+// capacity tiers: nodes per ply.  T1-T3 keep the frontiers in shared memory, T4 in L2-resident global scratch.
 constexpr int T1_CAP = 128, T1_WARPS = 4, T1_CTAS_PER_SM = 8;
 constexpr int T2_CAP = 512, T2_WARPS = 1, T2_CTAS_PER_SM = 10;
-constexpr int T3_CAP = 4096, T3_WARPS = 2, T3_CTAS_PER_SM = 3;
+constexpr int T3_CAP = 2048, T3_WARPS = 1, T3_CTAS_PER_SM = 2;   // still in shared memory: the rare very wide doubles trees
+constexpr int T4_CAP = 4096, T4_WARPS = 2, T4_CTAS_PER_SM = 3;
 constexpr int NUM_SMS = 148;
 
 constexpr size_t smem_bytes(int cap, bool global, bool moves, int warps) {
@@ -594,16 +595,17 @@ constexpr size_t smem_bytes(int cap, bool global, bool moves, int warps) {
 }
 
 constexpr int64_t HDR_BYTES = 256;
-constexpr int64_t GFRONT_BYTES = (int64_t)NUM_SMS * T3_CTAS_PER_SM * T3_WARPS * 2 * 6 * T3_CAP * 4;
+constexpr int64_t GFRONT_BYTES = (int64_t)NUM_SMS * T4_CTAS_PER_SM * T4_WARPS * 2 * 6 * T4_CAP * 4;
 
 template <bool MOVES>
-int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* ovf2, int32_t* ovf3, int32_t* ovf2_n, int32_t* ovf3_n,
-                     cudaStream_t stream) {
+int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* const (&ovf)[3], int32_t* const (&ovf_n)[3], int64_t* tier1_total,
+                     cudaEvent_t tier1_event, cudaStream_t stream) {
   auto k1 = k_movegen<T1_CAP, false, MOVES, T1_WARPS, T1_CTAS_PER_SM>;
   auto k2 = k_movegen<T2_CAP, false, MOVES, T2_WARPS, T2_CTAS_PER_SM>;
-  auto k3 = k_movegen<T3_CAP, true, MOVES, T3_WARPS, T3_CTAS_PER_SM>;
+  auto k3 = k_movegen<T3_CAP, false, MOVES, T3_WARPS, T3_CTAS_PER_SM>;
+  auto k4 = k_movegen<T4_CAP, true, MOVES, T4_WARPS, T4_CTAS_PER_SM>;
   constexpr size_t s1 = smem_bytes(T1_CAP, false, MOVES, T1_WARPS), s2 = smem_bytes(T2_CAP, false, MOVES, T2_WARPS),
-                   s3 = smem_bytes(T3_CAP, true, MOVES, T3_WARPS);
+                   s3 = smem_bytes(T3_CAP, false, MOVES, T3_WARPS), s4 = smem_bytes(T4_CAP, true, MOVES, T4_WARPS);
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
@@ -612,33 +614,50 @@ int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* ovf2, in
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tier2)");
     e = cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tier3)");
+    e = cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s4);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tier4)");
     attr_done = true;
   }
   // tier 1: every item
   P.item_counter = ctr + 0;
   P.in_list = nullptr;
   P.in_count = nullptr;
-  P.ovf_list = ovf2;
-  P.ovf_count = ovf2_n;
+  P.ovf_list = ovf[0];
+  P.ovf_count = ovf_n[0];
   P.grab = B > (1 << 20) ? 8 : 1;
   int64_t want = (B + T1_WARPS - 1) / T1_WARPS;
   int grid = (int)(want < (int64_t)NUM_SMS * T1_CTAS_PER_SM ? want : (int64_t)NUM_SMS * T1_CTAS_PER_SM);
   k1<<<grid, T1_WARPS * 32, s1, stream>>>(P);
+  if (tier1_total) {
+    cudaError_t e = cudaMemcpyAsync(tier1_total, P.pool_cursor, 8, cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) return check_cuda(e, "copy tier1_total");
+  }
+  if (tier1_event) {
+    cudaError_t e = cudaEventRecord(tier1_event, stream);
+    if (e != cudaSuccess) return check_cuda(e, "record tier1_event");
+  }
   // tier 2: items that overflowed 128 nodes in some ply
   P.item_counter = ctr + 1;
-  P.in_list = ovf2;
-  P.in_count = ovf2_n;
-  P.ovf_list = ovf3;
-  P.ovf_count = ovf3_n;
+  P.in_list = ovf[0];
+  P.in_count = ovf_n[0];
+  P.ovf_list = ovf[1];
+  P.ovf_count = ovf_n[1];
   P.grab = 1;
   k2<<<NUM_SMS * T2_CTAS_PER_SM, T2_WARPS * 32, s2, stream>>>(P);
-  // tier 3: items that overflowed 512 nodes
+  // tier 3: items that overflowed 512 nodes (frontier still in shared memory, two warps per SM)
   P.item_counter = ctr + 2;
-  P.in_list = ovf3;
-  P.in_count = ovf3_n;
+  P.in_list = ovf[1];
+  P.in_count = ovf_n[1];
+  P.ovf_list = ovf[2];
+  P.ovf_count = ovf_n[2];
+  k3<<<NUM_SMS * T3_CTAS_PER_SM, T3_WARPS * 32, s3, stream>>>(P);
+  // tier 4: items that overflowed 2048 nodes (frontier in L2-resident global scratch)
+  P.item_counter = ctr + 3;
+  P.in_list = ovf[2];
+  P.in_count = ovf_n[2];
   P.ovf_list = nullptr;
   P.ovf_count = nullptr;
-  k3<<<NUM_SMS * T3_CTAS_PER_SM, T3_WARPS * 32, s3, stream>>>(P);
+  k4<<<NUM_SMS * T4_CTAS_PER_SM, T4_WARPS * 32, s4, stream>>>(P);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return check_cuda(e, "k_movegen launch");
   return BG_OK;
@@ -647,12 +666,12 @@ int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* ovf2, in
 }  // namespace
 
 int64_t movegen_workspace_bytes(int64_t B) {
-  int64_t lists = ((2 * B * 4 + 255) / 256) * 256;
+  int64_t lists = ((3 * B * 4 + 255) / 256) * 256;
   return HDR_BYTES + lists + GFRONT_BYTES;
 }
 
 // workspace header layout (first HDR_BYTES): [0] u64 pool cursor, [8] i32 status, [12] i32 counter1,
-// [16] i32 counter2, [20] i32 counter3, [24] i32 ovf2 count, [28] i32 ovf3 count
+// [16] i32 counter2, [20] i32 counter3, [24] i32 counter4, [32] [36] [40] i32 overflow-list counts of tiers 1-3
 int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream) {
   if (a.B < 0 || a.B >= (1ll << 31) || a.item_cap < 0 || a.pool_cap < 0) {
     set_error("bg_movegen: bad sizes (B=%lld item_cap=%d pool_cap=%lld)", (long long)a.B, a.item_cap, (long long)a.pool_cap);
@@ -666,7 +685,7 @@ int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream) {
   char* ws = (char*)a.workspace;
   cudaError_t e = cudaMemsetAsync(ws, 0, HDR_BYTES, stream);
   if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(workspace)");
-  int64_t lists = ((2 * a.B * 4 + 255) / 256) * 256;
+  int64_t lists = ((3 * a.B * 4 + 255) / 256) * 256;
   MovegenParams P;
   P.boards = a.boards;
   P.players = a.players;
@@ -685,14 +704,13 @@ int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream) {
   P.gfront = (uint32_t*)(ws + HDR_BYTES + lists);
   P.active = a.active;
   int32_t* ctr = (int32_t*)(ws + 12);
-  int32_t* ovf2 = (int32_t*)(ws + HDR_BYTES);
-  int32_t* ovf3 = ovf2 + a.B;
-  int32_t* ovf2_n = (int32_t*)(ws + 24);
-  int32_t* ovf3_n = (int32_t*)(ws + 28);
+  int32_t* const l0 = (int32_t*)(ws + HDR_BYTES);
+  int32_t* const ovf[3] = {l0, l0 + a.B, l0 + 2 * a.B};
+  int32_t* const ovf_n[3] = {(int32_t*)(ws + 32), (int32_t*)(ws + 36), (int32_t*)(ws + 40)};
   if (a.B > 0) {
     // the sub-move history (2 extra words per node) is only carried when the caller asks for the FullMove sequences
-    int32_t rc = a.out_submoves ? launch_tiers<true>(P, a.B, ctr, ovf2, ovf3, ovf2_n, ovf3_n, stream)
-                                : launch_tiers<false>(P, a.B, ctr, ovf2, ovf3, ovf2_n, ovf3_n, stream);
+    int32_t rc = a.out_submoves ? launch_tiers<true>(P, a.B, ctr, ovf, ovf_n, a.tier1_total, a.tier1_event, stream)
+                                : launch_tiers<false>(P, a.B, ctr, ovf, ovf_n, a.tier1_total, a.tier1_event, stream);
     if (rc != BG_OK) return rc;
   }
   if (a.out_total) {

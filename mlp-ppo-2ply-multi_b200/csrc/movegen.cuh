@@ -22,6 +22,10 @@ struct MovegenArgs {
   void* workspace;
   int64_t workspace_bytes;
   const uint8_t* active;  // optional [B]: items with active[i] == 0 are skipped (count 0)
+  // optional hook after the first (bulk) tier: the pool rows [0, *tier1_total) are final once tier1_event has fired, so a consumer on
+  // another stream can start on them while the tail tiers (few, heavy items) are still running
+  int64_t* tier1_total = nullptr;
+  cudaEvent_t tier1_event = nullptr;
 };
 
 // kernel parameter block
