@@ -233,8 +233,9 @@ def main():
     ws = torch.empty(bg._lib.lib().bg_movegen_workspace_bytes(B), dtype=torch.uint8, device=dev)
 
     def step():
-        res = bg.movegen(ib, ip, ir, item_cap=500, out_boards=pool, check_status=False, workspace=ws, want_owner=False, out_flags=pflags)
-        bg.evaluate(pool, res.flags, weights, n_dev=res.total_dev, out=values)
+        # one pass of the hot path over the batch: bg_movegen_eval = bg_movegen + bg_eval over the pool, the evaluation of the bulk
+        # tier's afterstates overlapping the generation of the tail tiers
+        res, _ = bg.movegen_evaluate(ib, ip, ir, weights, pool, pflags, values, workspace=ws, item_cap=500)
         return res
 
     for _ in range(max(args.warmup, 3)):
@@ -245,11 +246,23 @@ def main():
 
     # ---- timed region: K steps, CUDA events, barrier + sync on both sides, max over ranks ---------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     profiling = os.environ.get("BG_PROFILE") == "1"  # ncu --profile-from-start off: capture only the timed region
     if profiling:
         torch.cuda.profiler.start()
+    t_beg.record()
+    for k in range(args.steps):
+        step()
+    t_end.record()
+    barrier()
+    if profiling:
+        torch.cuda.profiler.stop()
+    clocks = sampler.stop() if sampler else None
+    total_ms_fused = t_beg.elapsed_time(t_end)
+    # per-kernel durations for the roofline: the same pass with the two operators issued back to back on one stream, so that CUDA
+    # events on that stream bracket each of them
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     ev[0].record()
     for k in range(args.steps):
         r = bg.movegen(ib, ip, ir, item_cap=500, out_boards=pool, check_status=False, workspace=ws, want_owner=False, out_flags=pflags)
@@ -258,10 +271,8 @@ def main():
         ev[3 * k + 2].record()
         ev[3 * k + 3].record()
     barrier()
-    if profiling:
-        torch.cuda.profiler.stop()
-    clocks = sampler.stop() if sampler else None
-    total_ms = ev[0].elapsed_time(ev[3 * args.steps])
+    total_ms = total_ms_fused
+    unfused_ms_per_step = ev[0].elapsed_time(ev[3 * args.steps]) / args.steps
     t_movegen = sum(ev[3 * k].elapsed_time(ev[3 * k + 1]) for k in range(args.steps)) / args.steps
     t_eval = sum(ev[3 * k + 1].elapsed_time(ev[3 * k + 2]) for k in range(args.steps)) / args.steps
     t = torch.tensor([total_ms, float(n_after)], dtype=torch.float64, device=dev)
@@ -305,7 +316,7 @@ def main():
     e2e_value = n_after_all / (float(te[0]) / args.steps * 1e-3)
     h2d = h_b.numel() + h_p.numel() + h_r.numel()
     d2h = h_act.numel() * 4 + h_cnt.numel() * 4
-    n_e2e_kernels = 6 * n_chunks  # movegen tiers (4) + eval + select per chunk
+    n_e2e_kernels = 7 * n_chunks  # movegen tiers (4) + eval (2) + select per chunk
     e2e_check = int((h_cnt.to(torch.int64).clamp(max=500)).sum().item())  # must reproduce the afterstate count of the resident path
     del pipe
 
@@ -563,7 +574,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "afterstates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "what": f"bg.HostPipeline.run: pinned host boards/players/rolls -> {n_chunks} chunks on 2 streams (H2D, bg_movegen, bg_eval, bg_select(greedy), D2H) -> host actions + counts",
                     "afterstates_check": e2e_check},
-            "gpu_launches": 5 * args.steps, "gpu_launches_note": f"timed region, per step: k_movegen tiers 128 / 512 / 2048 / 4096 + k_eval_tc; the e2e region launches {n_e2e_kernels} per step (the same five + k_select, per chunk)",
+            "gpu_launches": 6 * args.steps, "gpu_launches_note": f"timed region, per step (bg_movegen_eval): k_movegen tiers 128 / 512 / 2048 / 4096 + k_eval_tc twice (bulk-tier rows on the side stream, tail-tier rows after); unfused ms_per_step {unfused_ms_per_step:.2f}; the e2e region launches {n_e2e_kernels} per step (the same six + k_select, per chunk)",
             "roofline": roofline, "roofline_eval": roofline_eval, "cpu_baseline": cpu, "clocks": clocks, "selfplay_1ply": selfplay, "selfplay_2ply": selfplay2,
             "selfplay_2ply_all_candidates": selfplay2b, "learner": learner, "td0_loop": td0}
     print(json.dumps(line), flush=True)

@@ -110,6 +110,19 @@ int32_t bg_eval(const int8_t* boards /*[N,52]*/, const uint8_t* flags /*[N] or N
 int32_t bg_eval_indirect(const int8_t* boards, const uint8_t* flags, const int32_t* owner, const uint8_t* owner_players,
                          const int64_t* N_dev, int64_t max_N, const float* prepared, int32_t H, float* out_v, void* stream);
 
+/*
+ * Fused bg_movegen + bg_eval_indirect over the whole afterstate pool (what the per-decision hot path always does:
+ * worker.py:101-125 evaluates every legal afterstate).  Same results as the two calls; internally the evaluation of the rows
+ * written by the move generator's bulk tier runs on a library-owned high-priority stream while the tail tiers (the few very wide
+ * doubles trees) are still being generated on `stream`, which then evaluates only the rows they added and joins.
+ *   out_flags : required [pool_cap];  out_total : device int64[2] = {rows used, rows written by the bulk tier};  out_v : [pool_cap].
+ */
+int32_t bg_movegen_eval(const int8_t* boards /*[B,52]*/, const uint8_t* players /*[B]*/, const uint8_t* rolls /*[B,2]*/, int64_t B,
+                        int32_t item_cap, int64_t pool_cap, int8_t* out_boards /*[pool_cap,52]*/, uint8_t* out_flags /*[pool_cap]*/,
+                        int64_t* out_offsets /*[B]*/, int32_t* out_count /*[B]*/, int64_t* out_total /*[2]*/, int32_t* out_status /*[1]*/,
+                        void* workspace, int64_t workspace_bytes, const float* prepared, int32_t H, float* out_v /*[pool_cap]*/,
+                        void* stream);
+
 /* Diagnostic for the tcgen05 evaluator (H = 128, batches >= 32768 rows with per-row flags; set BG_EVAL_PATH=ffma to force the
  * FFMA kernel): synchronises and returns 0, or non-zero if one of its bounded mbarrier waits ever timed out. */
 int32_t bg_eval_tc_status(void);

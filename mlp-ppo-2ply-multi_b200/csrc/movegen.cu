@@ -599,7 +599,7 @@ constexpr int64_t GFRONT_BYTES = (int64_t)NUM_SMS * T4_CTAS_PER_SM * T4_WARPS * 
 
 template <bool MOVES>
 int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* const (&ovf)[3], int32_t* const (&ovf_n)[3], int64_t* tier1_total,
-                     cudaEvent_t tier1_event, cudaStream_t stream) {
+                     cudaEvent_t tier1_event, int32_t tier2_ctas, cudaStream_t stream) {
   auto k1 = k_movegen<T1_CAP, false, MOVES, T1_WARPS, T1_CTAS_PER_SM>;
   auto k2 = k_movegen<T2_CAP, false, MOVES, T2_WARPS, T2_CTAS_PER_SM>;
   auto k3 = k_movegen<T3_CAP, false, MOVES, T3_WARPS, T3_CTAS_PER_SM>;
@@ -643,7 +643,7 @@ int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* const (&
   P.ovf_list = ovf[1];
   P.ovf_count = ovf_n[1];
   P.grab = 1;
-  k2<<<NUM_SMS * T2_CTAS_PER_SM, T2_WARPS * 32, s2, stream>>>(P);
+  k2<<<NUM_SMS * (tier2_ctas > 0 && tier2_ctas < T2_CTAS_PER_SM ? tier2_ctas : T2_CTAS_PER_SM), T2_WARPS * 32, s2, stream>>>(P);
   // tier 3: items that overflowed 512 nodes (frontier still in shared memory, two warps per SM)
   P.item_counter = ctr + 2;
   P.in_list = ovf[1];
@@ -709,8 +709,8 @@ int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream) {
   int32_t* const ovf_n[3] = {(int32_t*)(ws + 32), (int32_t*)(ws + 36), (int32_t*)(ws + 40)};
   if (a.B > 0) {
     // the sub-move history (2 extra words per node) is only carried when the caller asks for the FullMove sequences
-    int32_t rc = a.out_submoves ? launch_tiers<true>(P, a.B, ctr, ovf, ovf_n, a.tier1_total, a.tier1_event, stream)
-                                : launch_tiers<false>(P, a.B, ctr, ovf, ovf_n, a.tier1_total, a.tier1_event, stream);
+    int32_t rc = a.out_submoves ? launch_tiers<true>(P, a.B, ctr, ovf, ovf_n, a.tier1_total, a.tier1_event, a.tier2_ctas_per_sm, stream)
+                                : launch_tiers<false>(P, a.B, ctr, ovf, ovf_n, a.tier1_total, a.tier1_event, a.tier2_ctas_per_sm, stream);
     if (rc != BG_OK) return rc;
   }
   if (a.out_total) {

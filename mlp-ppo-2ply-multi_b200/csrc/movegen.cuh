@@ -26,6 +26,9 @@ struct MovegenArgs {
   // another stream can start on them while the tail tiers (few, heavy items) are still running
   int64_t* tier1_total = nullptr;
   cudaEvent_t tier1_event = nullptr;
+  // optional: resident CTAs per SM of the second tier (0 = default).  A consumer that overlaps the tail tiers with another kernel
+  // lowers this so that both fit on an SM at the same time
+  int32_t tier2_ctas_per_sm = 0;
 };
 
 // kernel parameter block

@@ -180,6 +180,33 @@ def evaluate(boards: torch.Tensor, flags: Optional[torch.Tensor], weights: Prepa
     return out
 
 
+def movegen_evaluate(boards: torch.Tensor, players: torch.Tensor, rolls: torch.Tensor, weights: PreparedWeights, out_boards: torch.Tensor,
+                     out_flags: torch.Tensor, out_values: torch.Tensor, workspace: Optional[torch.Tensor] = None, item_cap: int = 500,
+                     check_status: bool = False):
+    """bg_movegen + bg_eval over the whole pool in one call (bg_movegen_eval): the evaluation of the bulk tier's afterstates overlaps the
+    generation of the tail tiers.  -> (MovegenResult, values) with values[row] valid for the pool rows of every item."""
+    boards = _req(boards, torch.int8, "boards").reshape(-1, BOARD_BYTES)
+    B = boards.shape[0]
+    players = _req(players, torch.uint8, "players").reshape(B)
+    rolls = _req(rolls, torch.uint8, "rolls").reshape(B, 2)
+    dev = boards.device
+    pool_cap = out_boards.shape[0]
+    if out_flags.numel() < pool_cap or out_values.numel() < pool_cap:
+        raise ValueError("out_flags / out_values must have pool_cap entries")
+    offsets = torch.empty(B, dtype=torch.int64, device=dev)
+    counts = torch.empty(B, dtype=torch.int32, device=dev)
+    total = torch.zeros(2, dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = workspace if workspace is not None else _workspace(B, dev)
+    check(lib().bg_movegen_eval(boards.data_ptr(), players.data_ptr(), rolls.data_ptr(), B, item_cap, pool_cap, out_boards.data_ptr(),
+                                out_flags.data_ptr(), offsets.data_ptr(), counts.data_ptr(), total.data_ptr(), status.data_ptr(), ws.data_ptr(),
+                                ws.numel(), weights.table.data_ptr(), weights.H, out_values.data_ptr(), _stream()))
+    res = MovegenResult(out_boards, None, None, out_flags, offsets, counts, total[:1], status, item_cap)
+    if check_status:
+        res.raise_for_status()
+    return res, out_values
+
+
 def select(values: torch.Tensor, offsets: torch.Tensor, counts: torch.Tensor, temperature: float, seed: int = 0, ctr: int = 0,
            item_cap: int = 500, item_id_base: int = 0) -> torch.Tensor:
     """softmax(V/T) sampling (reference worker.py:136-143) or, temperature <= 0, first-index argmax (play_versus_ai.py:188-195)."""
@@ -253,9 +280,8 @@ class HostPipeline:
                 d["b"][:n].copy_(h_boards[lo:hi], non_blocking=True)
                 d["p"][:n].copy_(h_players[lo:hi], non_blocking=True)
                 d["r"][:n].copy_(h_rolls[lo:hi], non_blocking=True)
-                res = movegen(d["b"][:n], d["p"][:n], d["r"][:n], item_cap=self.item_cap, out_boards=d["pool"], check_status=False, workspace=d["ws"],
-                              want_owner=False, out_flags=d["flags"])
-                evaluate(d["pool"], res.flags, self.weights, n_dev=res.total_dev, out=d["v"])
+                res, _ = movegen_evaluate(d["b"][:n], d["p"][:n], d["r"][:n], self.weights, d["pool"], d["flags"], d["v"], workspace=d["ws"],
+                                          item_cap=self.item_cap)
                 act = select(d["v"], res.offsets, res.counts, temperature=temperature, seed=seed, item_cap=self.item_cap, item_id_base=lo)
                 h_actions[lo:hi].copy_(act, non_blocking=True)
                 h_counts[lo:hi].copy_(res.counts, non_blocking=True)

@@ -345,3 +345,31 @@ def test_host_pipeline_equals_resident_path(bg, oracle):
         torch.cuda.synchronize()
         pipe.raise_for_status()
         assert torch.equal(hc, res.counts.cpu()) and torch.equal(ha, act.cpu())
+
+
+def test_fused_movegen_eval_equals_separate_calls(bg, oracle):
+    """bg_movegen_eval (evaluation of the bulk tier overlapping the tail tiers) == bg_movegen followed by bg_eval over the pool."""
+    boards, players = oracle.random_positions(20000, seed=41)
+    ib, ip, ir = oracle.all_rolls_items(boards, players)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "values.npz"))
+    w = bg.prepare_weights(torch.from_numpy(g["packed"]).to(DEV), int(g["H"]))
+    db, dp, dr = dev(ib), dev(ip), dev(ir)
+    ref = bg.movegen(db, dp, dr, item_cap=500, pool_cap=len(ib) * 30)
+    v_ref = bg.evaluate(ref.boards, ref.flags, w, n_dev=ref.total_dev)
+    cap = len(ib) * 30
+    pool = torch.empty((cap, 52), dtype=torch.int8, device=DEV)
+    flags = torch.empty(cap, dtype=torch.uint8, device=DEV)
+    vals = torch.full((cap,), float("nan"), device=DEV)
+    for _ in range(2):
+        res, v = bg.movegen_evaluate(db, dp, dr, w, pool, flags, vals, check_status=True)
+        torch.cuda.synchronize()
+        assert res.total == ref.total and torch.equal(res.counts, ref.counts)
+        # pool placement is run dependent: compare per item, in action order
+        o1, b1, _ = ref.canonical()
+        o2, b2, _ = res.canonical()
+        assert torch.equal(o1, o2) and torch.equal(b1, b2)
+        kept = torch.clamp(ref.counts.long(), max=500)
+        item = torch.repeat_interleave(torch.arange(len(ib), device=DEV), kept)
+        k = torch.arange(int(o1[-1]), device=DEV) - o1[item]
+        assert torch.equal(v_ref[ref.offsets[item] + k], v[res.offsets[item] + k])  # same kernels, same rows: bit-identical
+        assert not torch.isnan(v[: res.total]).any()
