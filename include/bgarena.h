@@ -246,7 +246,9 @@ int32_t bg_arena_export_state(bg_arena* a, int8_t* boards, uint8_t* players, uin
  * pass over its T observations, targets r_t + gamma * V(x_{t+1}) (last target r_T), mse loss, backward,
  * clip_grad_norm_(grad_clip), one torch.optim.Adam step (betas 0.9/0.999, eps 1e-8).  The whole batch runs as one
  * persistent thread-block cluster with the optimiser state in shared memory; results agree with the reference trainer to
- * fp32 rounding (tests/golden/learner.npz: |dW| <= 1e-5 after 400 sequential steps).
+ * fp32 rounding (tests/golden/learner.npz: |dW| <= 1e-5 after 400 sequential steps).  16 hidden units per CTA: H <= 128 uses a
+ * portable cluster (<= 8 CTAs), larger H a 10-16 CTA cluster (opt-in size); if the device refuses that, or with
+ * BG_LEARNER_PATH=cuda-core in the environment, a CUDA-core kernel with 32 units per CTA is used for H > 128.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct bg_learner bg_learner;
 

@@ -13,6 +13,8 @@
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 #include <stdio.h>
 
 #include <new>
@@ -28,7 +30,8 @@ constexpr int NF = 198;
 constexpr int NROW = 200;  // per hidden unit: 198 fc1 weights, b1, w2 (row f of the packed [W1t | b1 | w2] matrix)
 constexpr int TMAX = 320;  // experiences per episode the kernel accepts (reference MAX_TIMESTEPS = 300)
 constexpr int NT = 256;
-constexpr int MAXCL = 8;
+constexpr int MAXCL = 8;    // portable cluster size (k_td0_update<32>)
+constexpr int MAXCL_TC = 16;  // k_td0_update_tc: 16 units per CTA, so H = 256 needs 16 CTAs (non-portable cluster size, opt-in)
 
 #ifdef BG_LEARNER_PROFILE
 #define PH(k)                                      \
@@ -599,13 +602,13 @@ constexpr int UT = 16;   // hidden units per CTA
 struct SmemTC {
   float P[NROW * UT], M[NROW * UT], V[NROW * UT];
   float hs[TMAX * UT];         // sigmoid activations [t][unit]
-  float ypart[MAXCL * TMAX];
+  float ypart[MAXCL_TC * TMAX];
   float Y[TMAX], dY[TMAX], rew[TMAX];
   float2 sc[NSC];
   int64_t offs[EC + 1];
   alignas(16) float pr[NT / 32][UT];  // per-warp partials of the w2 gradient
   uint2 xtab[16];              // the four bf16 thermometer features of a point holding c checkers
-  float npart[MAXCL];
+  float npart[MAXCL_TC];
   float red[8][8];
   float red2[8];
   float b2[4];
@@ -1088,7 +1091,7 @@ struct Learner {
   float lr, gamma, grad_clip;
   float *params, *m, *v;
   OptScalars* opt;
-  bool attr_set;
+  int path;  // 0 undecided, 1 tensor-core kernel (16 units per CTA), 2 sparse CUDA-core kernel (32 units per CTA)
 };
 
 int32_t learner_create(Learner** out, int32_t device, int32_t H, float lr, float gamma, float grad_clip) {
@@ -1106,7 +1109,7 @@ int32_t learner_create(Learner** out, int32_t device, int32_t H, float lr, float
   L->lr = lr;
   L->gamma = gamma;
   L->grad_clip = grad_clip;
-  L->attr_set = false;
+  L->path = 0;
   float* buf = nullptr;
   e = cudaMalloc(&buf, sizeof(float) * 3 * (size_t)L->n_params + sizeof(OptScalars) + 16);
   if (e != cudaSuccess) {
@@ -1164,25 +1167,55 @@ int32_t learner_get_optimizer(Learner* L, float* m_dev, float* v_dev, int64_t* s
 }
 
 template <typename K>
-static int32_t launch_update(Learner* L, K kernel, size_t smem, unsigned CL, const LearnerArgs& a, cudaStream_t s) {
-  if (!L->attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_td0_update)");
-    L->attr_set = true;
-  }
-  cudaLaunchConfig_t cfg = {};
+static void fill_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, size_t smem, unsigned CL, cudaStream_t s) {
+  cfg = {};
   cfg.gridDim = dim3(CL);
   cfg.blockDim = dim3(NT);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CL;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
+}
+
+template <typename K>
+static int32_t launch_update(K kernel, size_t smem, unsigned CL, const LearnerArgs& a, cudaStream_t s) {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute at[1];
+  fill_config<K>(cfg, at, smem, CL, s);
   return check_cuda(cudaLaunchKernelEx(&cfg, kernel, a), "k_td0_update launch");
+}
+
+// One-time choice of the kernel.  H <= 128: tensor-core kernel, portable cluster of H / 16 CTAs.  H > 128: the same kernel needs
+// 10-16 CTAs per cluster (non-portable size, allowed on B200 when a GPC can co-schedule them); if the device cannot place such a
+// cluster the CUDA-core kernel with 32 units per CTA (cluster of H / 32 <= 8) is used instead.
+static int32_t choose_path(Learner* L) {
+  if (L->path) return BG_OK;
+  cudaError_t e = cudaFuncSetAttribute(k_td0_update_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTC));
+  if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_td0_update_tc)");
+  e = cudaFuncSetAttribute(k_td0_update<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<32>));
+  if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_td0_update)");
+  const unsigned CL = (unsigned)(L->H / UT);
+  L->path = 1;
+  const char* force = getenv("BG_LEARNER_PATH");  // "cuda-core": force the 32-unit kernel (tests; only meaningful for H > 128)
+  if (CL > 8) {
+    L->path = 2;
+    if (force && !strcmp(force, "cuda-core")) return BG_OK;
+    e = cudaFuncSetAttribute(k_td0_update_tc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e == cudaSuccess) {
+      cudaLaunchConfig_t cfg;
+      cudaLaunchAttribute at[1];
+      fill_config<decltype(&k_td0_update_tc)>(cfg, at, sizeof(SmemTC), CL, nullptr);
+      int n = 0;
+      e = cudaOccupancyMaxActiveClusters(&n, k_td0_update_tc, &cfg);
+      if (e == cudaSuccess && n >= 1) L->path = 1;
+    }
+    cudaGetLastError();  // a refused opt-in is not an error: the 32-unit kernel handles these sizes
+  }
+  return BG_OK;
 }
 
 int32_t learner_update(Learner* L, const int8_t* boards, const uint8_t* flags_or_meta, const float* reward, const int64_t* ep_offsets,
@@ -1200,9 +1233,10 @@ int32_t learner_update(Learner* L, const int8_t* boards, const uint8_t* flags_or
   if (n_eps == 0) return BG_OK;
   LearnerArgs a{boards, flags_or_meta, reward, ep_offsets, n_eps, records, L->params, L->m, L->v, &L->opt->step,
                 L->lr, L->gamma, L->grad_clip, out_metrics, out_status, L->H};
-  // H <= 128: 16 units per CTA, contractions on the tensor cores; larger nets: 32 units per CTA, CUDA-core sparse walks
-  if (L->H <= 128) return launch_update(L, k_td0_update_tc, sizeof(SmemTC), (unsigned)(L->H / UT), a, s);
-  return launch_update(L, k_td0_update<32>, sizeof(Smem<32>), (unsigned)(L->H / 32), a, s);
+  int32_t rc = choose_path(L);
+  if (rc != BG_OK) return rc;
+  if (L->path == 1) return launch_update(k_td0_update_tc, sizeof(SmemTC), (unsigned)(L->H / UT), a, s);
+  return launch_update(k_td0_update<32>, sizeof(Smem<32>), (unsigned)(L->H / 32), a, s);
 }
 
 }  // namespace bg

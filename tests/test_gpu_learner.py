@@ -86,6 +86,14 @@ def test_learner_other_hidden_sizes_vs_oracle(bg, golden, oracle, H):
     assert np.allclose(met, omet, rtol=2e-3, atol=2e-6)
 
 
+def test_learner_cuda_core_fallback_kernel(bg, golden, oracle, monkeypatch):
+    """H > 128 normally runs the tensor-core kernel in a 10-16 CTA cluster; the 32-units-per-CTA CUDA-core kernel is the fallback when
+    the device refuses that cluster size.  Force it and check it against the oracle."""
+    monkeypatch.setenv("BG_LEARNER_PATH", "cuda-core")
+    test_learner_other_hidden_sizes_vs_oracle(bg, golden, oracle, 256)
+    test_learner_other_hidden_sizes_vs_oracle(bg, golden, oracle, 160)
+
+
 def test_learner_edge_cases(bg, golden, oracle):
     g = golden("learner")
     H = int(g["H"])
