@@ -43,6 +43,23 @@ static int32_t require_device() {
 
 using namespace bg;
 
+namespace {
+// per-device library-owned side stream (highest priority, so that the evaluator's CTAs are placed before the tail tiers' when both
+// become runnable at the end of the bulk tier)
+std::mutex g_fused_mu;
+SideCtx g_fused[64];
+
+int32_t fused_ctx(SideCtx** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 64) return check_cuda(e == cudaSuccess ? cudaErrorInvalidDevice : e, "cudaGetDevice");
+  std::lock_guard<std::mutex> lk(g_fused_mu);
+  int32_t rc = side_ctx_create(&g_fused[dev], true);
+  *out = &g_fused[dev];
+  return rc;
+}
+}  // namespace
+
 #define BG_REQUIRE(cond, msg)   \
   do {                          \
     if (!(cond)) {              \
@@ -142,39 +159,14 @@ int32_t bg_two_ply(const int8_t* cand_boards, const uint8_t* mover, const float*
   int32_t rc = require_device();
   if (rc != BG_OK) return rc;
   TwoPlyArgs a{cand_boards, mover, S, N, prepared, H, top_k, alpha, beta, out_score, out_replies, out_status, workspace, workspace_bytes, nullptr, nullptr};
+  SideCtx* c = nullptr;
+  if ((rc = fused_ctx(&c)) != BG_OK) return rc;
+  a.side = c;
   return two_ply_launch(a, (cudaStream_t)stream);
 }
 
 /* ---- fused move generation + evaluation ---- */
 
-namespace {
-// per-device side stream (highest priority, so that the evaluator's CTAs are placed before the tail tiers' when both become
-// runnable at the end of the bulk tier) and the fork / tier-1 / join events
-struct FusedCtx {
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_t1 = nullptr, ev_side = nullptr;
-};
-std::mutex g_fused_mu;
-FusedCtx g_fused[64];
-
-int32_t fused_ctx(FusedCtx** out) {
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess || dev < 0 || dev >= 64) return check_cuda(e == cudaSuccess ? cudaErrorInvalidDevice : e, "cudaGetDevice");
-  std::lock_guard<std::mutex> lk(g_fused_mu);
-  FusedCtx& c = g_fused[dev];
-  if (!c.side) {
-    int lo = 0, hi = 0;
-    e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, hi);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c.ev_t1, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c.ev_side, cudaEventDisableTiming);
-    if (e != cudaSuccess) return check_cuda(e, "fused side stream");
-  }
-  *out = &c;
-  return BG_OK;
-}
-}  // namespace
 
 int32_t bg_movegen_eval(const int8_t* boards, const uint8_t* players, const uint8_t* rolls, int64_t B, int32_t item_cap, int64_t pool_cap,
                         int8_t* out_boards, uint8_t* out_flags, int64_t* out_offsets, int32_t* out_count, int64_t* out_total /*[2]*/,
@@ -185,27 +177,13 @@ int32_t bg_movegen_eval(const int8_t* boards, const uint8_t* players, const uint
   BG_REQUIRE(out_boards && out_flags && out_total && out_v && prepared && workspace, "bg_movegen_eval: null pointer");
   int32_t rc = require_device();
   if (rc != BG_OK) return rc;
-  FusedCtx* c = nullptr;
+  SideCtx* c = nullptr;
   if ((rc = fused_ctx(&c)) != BG_OK) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
   MovegenArgs a{boards,  players,   rolls,       B,         item_cap,  pool_cap,   out_boards, nullptr,
                 nullptr, out_flags, out_offsets, out_count, out_total, out_status, workspace,  workspace_bytes, nullptr};
-  a.tier1_total = out_total + 1;
-  a.tier1_event = c->ev_t1;
   // big batches have enough tail work to be worth sharing every SM: 3 x 20.5 KB second-tier CTAs next to the evaluator's one 161 KB CTA
   a.tier2_ctas_per_sm = B >= (1ll << 22) ? 3 : 0;
-  if ((rc = movegen_launch(a, s)) != BG_OK) return rc;
-  // side stream: rows of the bulk tier, as soon as it is done (the tail tiers are still running on `stream`)
-  cudaError_t e = cudaStreamWaitEvent(c->side, c->ev_t1, 0);
-  if (e != cudaSuccess) return check_cuda(e, "bg_movegen_eval: wait tier 1");
-  EvalArgs e1{out_boards, out_flags, nullptr, nullptr, 0, out_total + 1, pool_cap, prepared, H, out_v};
-  if ((rc = eval_launch(e1, c->side)) != BG_OK) return rc;
-  e = cudaEventRecord(c->ev_side, c->side);
-  if (e != cudaSuccess) return check_cuda(e, "bg_movegen_eval: record");
-  // main stream: the rows the tail tiers added, then join
-  EvalArgs e2{out_boards, out_flags, nullptr, nullptr, 0, out_total, pool_cap, prepared, H, out_v, out_total + 1};
-  if ((rc = eval_launch(e2, s)) != BG_OK) return rc;
-  return check_cuda(cudaStreamWaitEvent(s, c->ev_side, 0), "bg_movegen_eval: join");
+  return movegen_eval_overlapped(a, out_total, prepared, H, out_v, c, (cudaStream_t)stream);
 }
 
 /* ---- arena ---- */

@@ -624,8 +624,8 @@ struct Arena {
   int64_t tp_ws_bytes = 0;
   int64_t tp_cands_alloc = 0;
   // side stream: the pool evaluation of the bulk move-generator tier and the evaluation of the current positions overlap the tail tiers
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_t1 = nullptr, ev_side = nullptr;
+  SideCtx side{};
+  cudaEvent_t ev_fork = nullptr, ev_cur = nullptr;
   std::vector<void*> allocs;
 };
 
@@ -746,11 +746,8 @@ int32_t arena_create(Arena** out, int32_t device, int64_t n_games, int32_t H, in
 int32_t arena_destroy(Arena* A) {
   if (!A) return BG_OK;
   cudaSetDevice(A->device);
-  if (A->side) {
-    cudaStreamSynchronize(A->side);
-    cudaStreamDestroy(A->side);
-  }
-  for (cudaEvent_t ev : {A->ev_fork, A->ev_t1, A->ev_side})
+  side_ctx_destroy(&A->side);
+  for (cudaEvent_t ev : {A->ev_fork, A->ev_cur})
     if (ev) cudaEventDestroy(ev);
   for (void* p : A->allocs) cudaFree(p);
   delete A;
@@ -873,31 +870,18 @@ int32_t arena_step(Arena* A, int32_t n_plies, int32_t lookahead, const int32_t* 
     // fork: the side stream evaluates the current positions (independent of move generation) and, as soon as the bulk tier
     // is done, the afterstates it produced; the main stream meanwhile runs the tail tiers (a few very wide doubles trees whose
     // latency used to sit on the ply's critical path) and then evaluates only the rows they added
-    if (!A->side) {
-      cudaError_t ce = cudaStreamCreateWithFlags(&A->side, cudaStreamNonBlocking);
-      if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&A->ev_fork, cudaEventDisableTiming);
-      if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&A->ev_t1, cudaEventDisableTiming);
-      if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&A->ev_side, cudaEventDisableTiming);
-      if (ce != cudaSuccess) return check_cuda(ce, "arena side stream");
+    if (!A->side.stream) {
+      TRY(side_ctx_create(&A->side, true));
+      cudaError_t ce = cudaEventCreateWithFlags(&A->ev_fork, cudaEventDisableTiming);
+      if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&A->ev_cur, cudaEventDisableTiming);
+      if (ce != cudaSuccess) return check_cuda(ce, "arena events");
     }
-    m.tier1_total = A->total + 1;
-    m.tier1_event = A->ev_t1;
     cudaError_t fe = cudaEventRecord(A->ev_fork, s);
-    if (fe == cudaSuccess) fe = cudaStreamWaitEvent(A->side, A->ev_fork, 0);
+    if (fe == cudaSuccess) fe = cudaStreamWaitEvent(A->side.stream, A->ev_fork, 0);
     if (fe != cudaSuccess) return check_cuda(fe, "arena fork");
     EvalArgs ec{reinterpret_cast<const int8_t*>(A->D.board), A->D.player, nullptr, nullptr, C.G, nullptr, C.G, A->prepared[A->cur_w], A->H, A->v_cur};
-    TRY(eval_launch(ec, A->side));
-    TRY(movegen_launch(m, s));
-    fe = cudaStreamWaitEvent(A->side, A->ev_t1, 0);
-    if (fe != cudaSuccess) return check_cuda(fe, "arena wait tier 1");
-    EvalArgs ev1{A->pool, A->pflags, nullptr, nullptr, 0, A->total + 1, A->pool_cap, A->prepared[A->cur_w], A->H, A->v_pool};
-    TRY(eval_launch(ev1, A->side));
-    fe = cudaEventRecord(A->ev_side, A->side);
-    if (fe != cudaSuccess) return check_cuda(fe, "arena record side");
-    EvalArgs ev2{A->pool, A->pflags, nullptr, nullptr, 0, A->total, A->pool_cap, A->prepared[A->cur_w], A->H, A->v_pool, A->total + 1};
-    TRY(eval_launch(ev2, s));
-    fe = cudaStreamWaitEvent(s, A->ev_side, 0);  // join
-    if (fe != cudaSuccess) return check_cuda(fe, "arena join");
+    TRY(eval_launch(ec, A->side.stream));
+    TRY(movegen_eval_overlapped(m, A->total, A->prepared[A->cur_w], A->H, A->v_pool, &A->side, s));  // joins the side stream
     const float* sel_score = nullptr;
     const int32_t* sel_idx = nullptr;
     const int32_t* sel_n = nullptr;
@@ -914,6 +898,7 @@ int32_t arena_step(Arena* A, int32_t n_plies, int32_t lookahead, const int32_t* 
       t.workspace = A->tp_ws;
       t.workspace_bytes = A->tp_ws_bytes;
       t.reply_counter = A->D.stats + BG_STAT_REPLIES;
+      t.side = &A->side;
       if (A->la_cands > 0) {  // reference setting: rescore the top-C candidates of each decision with >= C moves
         k_pick_candidates<<<grid_for(C.G), 256, 0, s>>>(A->D, A->C, reinterpret_cast<const uint32_t*>(A->pool), (const long long*)A->offsets,
                                                         A->counts, A->v_pool, A->la_cands, reinterpret_cast<uint32_t*>(A->cand_boards),

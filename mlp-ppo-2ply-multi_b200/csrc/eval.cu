@@ -399,4 +399,47 @@ int32_t encode_launch(const int8_t* boards, const uint8_t* flags, int64_t N, flo
   return BG_OK;
 }
 
+int32_t side_ctx_create(SideCtx* c, bool high_priority) {
+  if (c->stream) return BG_OK;
+  int lo = 0, hi = 0;
+  cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, high_priority ? hi : lo);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_t1, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming);
+  return check_cuda(e, "side stream");
+}
+
+void side_ctx_destroy(SideCtx* c) {
+  if (c->stream) {
+    cudaStreamSynchronize(c->stream);
+    cudaStreamDestroy(c->stream);
+  }
+  if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+  if (c->ev_side) cudaEventDestroy(c->ev_side);
+  *c = SideCtx{};
+}
+
+int32_t movegen_eval_overlapped(MovegenArgs m, int64_t* total2, const float* prepared, int32_t H, float* out_v, SideCtx* side,
+                                cudaStream_t stream) {
+  m.out_total = total2;
+  int32_t rc;
+  if (!side || !side->stream) {
+    if ((rc = movegen_launch(m, stream)) != BG_OK) return rc;
+    EvalArgs ev{m.out_boards, m.out_flags, nullptr, nullptr, 0, total2, m.pool_cap, prepared, H, out_v};
+    return eval_launch(ev, stream);
+  }
+  m.tier1_total = total2 + 1;
+  m.tier1_event = side->ev_t1;
+  if ((rc = movegen_launch(m, stream)) != BG_OK) return rc;
+  cudaError_t e = cudaStreamWaitEvent(side->stream, side->ev_t1, 0);
+  if (e != cudaSuccess) return check_cuda(e, "wait bulk tier");
+  EvalArgs e1{m.out_boards, m.out_flags, nullptr, nullptr, 0, total2 + 1, m.pool_cap, prepared, H, out_v};
+  if ((rc = eval_launch(e1, side->stream)) != BG_OK) return rc;
+  e = cudaEventRecord(side->ev_side, side->stream);
+  if (e != cudaSuccess) return check_cuda(e, "record side");
+  EvalArgs e2{m.out_boards, m.out_flags, nullptr, nullptr, 0, total2, m.pool_cap, prepared, H, out_v, total2 + 1};
+  if ((rc = eval_launch(e2, stream)) != BG_OK) return rc;
+  return check_cuda(cudaStreamWaitEvent(stream, side->ev_side, 0), "join side stream");
+}
+
 }  // namespace bg

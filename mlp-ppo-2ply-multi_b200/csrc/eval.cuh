@@ -1,6 +1,7 @@
 // eval.cuh -- host-side launch interface of the fused evaluator / encoder (see eval.cu)
 #pragma once
 #include "bg_common.cuh"
+#include "movegen.cuh"
 
 namespace bg {
 
@@ -30,6 +31,18 @@ int64_t eval_tc_image_bytes();
 int32_t eval_tc_prepare(const float* packed, uint8_t* img, cudaStream_t stream);
 int32_t eval_tc_launch(const EvalArgs& a, const uint8_t* img, int32_t* err_flag, cudaStream_t stream);
 int32_t eval_tc_status();  // synchronising: 0 ok, != 0 a bounded mbarrier wait timed out in k_eval_tc
+// Move generation + evaluation of the whole afterstate pool with the tail tiers overlapped: the rows written by the move generator's
+// bulk tier are evaluated on `side->stream` as soon as that tier is done, while `stream` runs the tail tiers (a few very wide doubles
+// trees) and then evaluates only the rows they added; `stream` joins before returning.  `total2` is a device int64[2]
+// ({rows used, rows of the bulk tier}); m.out_total / m.tier1_* are set here.  side == nullptr: plain sequential launch.
+struct SideCtx {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_t1 = nullptr, ev_side = nullptr;
+};
+int32_t side_ctx_create(SideCtx* c, bool high_priority);
+void side_ctx_destroy(SideCtx* c);
+int32_t movegen_eval_overlapped(MovegenArgs m, int64_t* total2, const float* prepared, int32_t H, float* out_v, SideCtx* side,
+                                cudaStream_t stream);
 int32_t encode_launch(const int8_t* boards, const uint8_t* flags, int64_t N, float* out, cudaStream_t stream);
 
 }  // namespace bg

@@ -198,18 +198,14 @@ int32_t two_ply_launch(const TwoPlyArgs& a, cudaStream_t s) {
     m.out_flags = (uint8_t*)(w + L.o_owner);
     m.out_offsets = (int64_t*)(w + L.o_off);
     m.out_count = (int32_t*)(w + L.o_cnt);
-    m.out_total = (int64_t*)(w + L.o_tot);
-    m.out_status = (int32_t*)(w + L.o_tot + 8);
+    m.out_status = (int32_t*)(w + L.o_tot + 16);
     m.workspace = w + L.o_ws;
     m.workspace_bytes = L.ws_bytes;
     m.active = (const uint8_t*)(w + L.o_act);
-    int32_t rc = movegen_launch(m, s);
-    if (rc != BG_OK) return rc;
-    EvalArgs ev{m.out_boards, m.out_flags, nullptr, nullptr, 0, m.out_total, L.rows, a.prepared, a.H, (float*)(w + L.o_val)};
-    rc = eval_launch(ev, s);
+    int32_t rc = movegen_eval_overlapped(m, (int64_t*)(w + L.o_tot), a.prepared, a.H, (float*)(w + L.o_val), a.side, s);
     if (rc != BG_OK) return rc;
     k_reduce<<<grid, 256, 0, s>>>((const float*)(w + L.o_val), (const long long*)(w + L.o_off), (const int32_t*)(w + L.o_cnt), a.S, c0, nc,
-                                  a.top_k, a.alpha, a.beta, a.out_score, (long long*)a.out_replies, (const int32_t*)(w + L.o_tot + 8),
+                                  a.top_k, a.alpha, a.beta, a.out_score, (long long*)a.out_replies, (const int32_t*)(w + L.o_tot + 16),
                                   a.out_status, a.reply_counter);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return check_cuda(e, "two_ply launch");

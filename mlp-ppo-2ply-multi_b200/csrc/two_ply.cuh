@@ -1,6 +1,7 @@
 // two_ply.cuh -- host-side interface of the 2-ply scorer (see two_ply.cu)
 #pragma once
 #include "bg_common.cuh"
+#include "eval.cuh"
 
 namespace bg {
 
@@ -20,6 +21,7 @@ struct TwoPlyArgs {
   int64_t workspace_bytes;
   const uint8_t* cand_active = nullptr;            // optional [N]: inactive candidates are skipped (score = alpha * S)
   unsigned long long* reply_counter = nullptr;     // optional device counter: += replies evaluated
+  SideCtx* side = nullptr;                         // optional: evaluate each chunk's bulk-tier replies while its tail tiers run
 };
 
 int64_t two_ply_workspace_bytes(int64_t N);
