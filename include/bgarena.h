@@ -15,6 +15,8 @@
  *   - every function returns a status: BG_OK, or < 0 (see below).  Nothing throws or aborts.
  *     bg_last_error() gives a thread-local description of the last failure.
  *   - there is NO CPU fallback: without a CUDA device every compute entry point returns BG_ERR_CUDA.
+ *   - bg_movegen_eval, bg_two_ply and bg_arena_step overlap independent kernels on library-owned non-blocking streams; these are
+ *     forked from and joined back into `stream` inside the call, so the caller sees ordinary stream ordering on `stream`.
  *
  * Data model (reference: src/backgammon/board/immutable_board.py:16-24, src/backgammon/types/moves.py:7-46)
  *   board  : int8[52]  = positions_0[24] | positions_1[24] | bar[2] | borne_off[2]   (absolute points)

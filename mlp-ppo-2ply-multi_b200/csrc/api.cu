@@ -49,11 +49,12 @@ namespace {
 std::mutex g_fused_mu;
 SideCtx g_fused[64];
 
+// Callers hold g_fused_mu from here until their launches are enqueued: the context's events are recorded and waited on in pairs,
+// and two host threads interleaving those pairs on one device would wait on each other's records.
 int32_t fused_ctx(SideCtx** out) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess || dev < 0 || dev >= 64) return check_cuda(e == cudaSuccess ? cudaErrorInvalidDevice : e, "cudaGetDevice");
-  std::lock_guard<std::mutex> lk(g_fused_mu);
   int32_t rc = side_ctx_create(&g_fused[dev], true);
   *out = &g_fused[dev];
   return rc;
@@ -159,6 +160,7 @@ int32_t bg_two_ply(const int8_t* cand_boards, const uint8_t* mover, const float*
   int32_t rc = require_device();
   if (rc != BG_OK) return rc;
   TwoPlyArgs a{cand_boards, mover, S, N, prepared, H, top_k, alpha, beta, out_score, out_replies, out_status, workspace, workspace_bytes, nullptr, nullptr};
+  std::lock_guard<std::mutex> lk(g_fused_mu);
   SideCtx* c = nullptr;
   if ((rc = fused_ctx(&c)) != BG_OK) return rc;
   a.side = c;
@@ -177,6 +179,7 @@ int32_t bg_movegen_eval(const int8_t* boards, const uint8_t* players, const uint
   BG_REQUIRE(out_boards && out_flags && out_total && out_v && prepared && workspace, "bg_movegen_eval: null pointer");
   int32_t rc = require_device();
   if (rc != BG_OK) return rc;
+  std::lock_guard<std::mutex> lk(g_fused_mu);
   SideCtx* c = nullptr;
   if ((rc = fused_ctx(&c)) != BG_OK) return rc;
   MovegenArgs a{boards,  players,   rolls,       B,         item_cap,  pool_cap,   out_boards, nullptr,
