@@ -238,6 +238,7 @@ def main():
         res, _ = bg.movegen_evaluate(ib, ip, ir, weights, pool, pflags, values, workspace=ws, item_cap=500)
         return res
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # nvidia-smi needs ~0.5 s to start: begin before the warm-up; idle samples are filtered by power
     for _ in range(max(args.warmup, 3)):
         res = step()
     torch.cuda.synchronize()
@@ -245,7 +246,6 @@ def main():
     res.raise_for_status()
 
     # ---- timed region: K steps, CUDA events, barrier + sync on both sides, max over ranks ---------------------------------
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     profiling = os.environ.get("BG_PROFILE") == "1"  # ncu --profile-from-start off: capture only the timed region
@@ -258,7 +258,6 @@ def main():
     barrier()
     if profiling:
         torch.cuda.profiler.stop()
-    clocks = sampler.stop() if sampler else None
     total_ms_fused = t_beg.elapsed_time(t_end)
     # per-kernel durations for the roofline: the same pass with the two operators issued back to back on one stream, so that CUDA
     # events on that stream bracket each of them
@@ -271,6 +270,7 @@ def main():
         ev[3 * k + 2].record()
         ev[3 * k + 3].record()
     barrier()
+    clocks = sampler.stop() if sampler else None
     total_ms = total_ms_fused
     unfused_ms_per_step = ev[0].elapsed_time(ev[3 * args.steps]) / args.steps
     t_movegen = sum(ev[3 * k].elapsed_time(ev[3 * k + 1]) for k in range(args.steps)) / args.steps

@@ -600,10 +600,10 @@ constexpr int RT = 128;  // rows per X tile; longer episodes take several tiles
 constexpr int UT = 16;   // hidden units per CTA
 
 struct SmemTC {
-  float P[NROW * UT], M[NROW * UT], V[NROW * UT];
+  alignas(16) float w2s[UT];   // value-head weights of this CTA's units (every other parameter lives in its owner's registers)
   float hs[TMAX * UT];         // sigmoid activations [t][unit]
   float ypart[MAXCL_TC * TMAX];
-  float Y[TMAX], dY[TMAX], rew[TMAX];
+  float Y[TMAX], rew[TMAX];
   float2 sc[NSC];
   int64_t offs[EC + 1];
   alignas(16) float pr[NT / 32][UT];  // per-warp partials of the w2 gradient
@@ -663,12 +663,25 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update_tc(const LearnerArgs a) {
   const int64_t iB2 = (int64_t)NROW * H;
   const float k15 = 1.0f / 15.0f;
 
-  for (int s = tid; s < NROW * UT; s += NT) {
-    const int64_t gi = (int64_t)(s / UT) * H + rank * UT + (s % UT);
-    S.P[s] = a.params[gi];
-    S.M[s] = a.m[gi];
-    S.V[s] = a.v[gi];
-  }
+  // Every parameter of the slice is owned by exactly one thread for the whole launch -- the thread whose mma accumulator fragment
+  // receives its gradient: slot (i, hh, nt, k) is feature row f = (warp + 8 i) * 16 + g + 8 hh, unit nt * 8 + 2 q + k.  Weight and
+  // both Adam moments stay in that thread's registers; shared memory only holds the bf16 operand image of W1/b1 and w2.
+  float pW[2][2][2][2], pM[2][2][2][2], pV[2][2][2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int f = (warp + 8 * i) * 16 + g + 8 * hh;
+          const int64_t gi = (int64_t)f * H + rank * UT + nt * 8 + 2 * q + k;
+          const bool own = f < NROW;
+          pW[i][hh][nt][k] = own ? a.params[gi] : 0.f;
+          pM[i][hh][nt][k] = own ? a.m[gi] : 0.f;
+          pV[i][hh][nt][k] = own ? a.v[gi] : 0.f;
+        }
   if (tid == 0) {
     S.b2[0] = a.params[iB2];
     S.b2[1] = a.m[iB2];
@@ -688,12 +701,23 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update_tc(const LearnerArgs a) {
   };
   fill_scalars();
   __syncthreads();
-  // operand image of the weights: rows 0..197 = W1^T (the two borne-off rows scaled by 1/15: X holds the count), row 198 = b1
-  for (int i = tid; i < (NF + 1) * (UT / 2); i += NT) {
-    const int f = i / (UT / 2), n = (i % (UT / 2)) * 2;
-    const float sc = (f == 193 || f == 195) ? k15 : 1.0f;
-    store_split2(S.Ws, f * WS + n, S.P[f * UT + n] * sc, S.P[f * UT + n + 1] * sc);
-  }
+  // operand image of the weights: rows 0..197 = W1^T (the two borne-off rows scaled by 1/15: X holds the count), row 198 = b1;
+  // row 199 (w2) is not a GEMM operand, it goes to w2s
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int f = (warp + 8 * i) * 16 + g + 8 * hh;
+        const int n = nt * 8 + 2 * q;
+        if (f <= NF) {
+          const float wsc = (f == 193 || f == 195) ? k15 : 1.0f;
+          store_split2(S.Ws, f * WS + n, pW[i][hh][nt][0] * wsc, pW[i][hh][nt][1] * wsc);
+        } else if (f == NF + 1) {
+          *reinterpret_cast<float2*>(&S.w2s[n]) = make_float2(pW[i][hh][nt][0], pW[i][hh][nt][1]);
+        }
+      }
   __syncthreads();
   cluster.sync();
 
@@ -794,8 +818,8 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update_tc(const LearnerArgs a) {
       };
 
       // ---- B: forward, tile by tile: Z = X W on the tensor cores (three bf16 pieces of W), sigmoid, value partials to every CTA ----
-      const float2 w2a = *reinterpret_cast<const float2*>(&S.P[(NF + 1) * UT + 2 * q]);      // units 2q, 2q+1
-      const float2 w2b = *reinterpret_cast<const float2*>(&S.P[(NF + 1) * UT + 8 + 2 * q]);  // units 8+2q, 9+2q
+      const float2 w2a = *reinterpret_cast<const float2*>(&S.w2s[2 * q]);      // units 2q, 2q+1
+      const float2 w2b = *reinterpret_cast<const float2*>(&S.w2s[8 + 2 * q]);  // units 8+2q, 9+2q
       for (int tb = 0; tb < T; tb += RT) {
         if (tb) __syncthreads();  // previous tile's X fully consumed
         const int rows = decode_tile(tb);
@@ -858,46 +882,14 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update_tc(const LearnerArgs a) {
       cluster.sync();
       PH(3);
 
-      // ---- C: values, TD(0) targets (trainer.py:110-115), dL/dY of the mse loss (:118), metric sums ----
+      // ---- C: values ----
       for (int t = tid; t < T; t += NT) {
         float y = S.b2[0];
         for (int c = 0; c < CL; ++c) y += S.ypart[c * TMAX + t];
         S.Y[t] = y;
       }
       __syncthreads();
-      {
-        float r5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int t = tid; t < T; t += NT) {
-          const float y = S.Y[t];
-          float tg = S.rew[t];
-          if (t + 1 < T) tg = __fadd_rn(tg, __fmul_rn(a.gamma, S.Y[t + 1]));
-          const float d = y - tg;
-          const float dy = 2.0f * d / (float)T;
-          S.dY[t] = dy;
-          r5[0] += d * d;
-          r5[1] += fabsf(d);
-          r5[2] += y;
-          r5[3] += S.rew[t];
-          r5[4] += dy;
-        }
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) r5[k] += __shfl_xor_sync(BG_FULL, r5[k], o);
-        }
-        if (lane == 0)
-          for (int k = 0; k < 5; ++k) S.red[warp][k] = r5[k];
-      }
-      __syncthreads();
       PH(4);
-      float msum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-      if (tid == 0) {
-        for (int k = 0; k < 5; ++k) {
-          float s = 0.f;
-          for (int w = 0; w < NT / 32; ++w) s += S.red[w][k];
-          msum[k] = s;
-        }
-      }
 
       // ---- D + E: per tile, dL/dz split into three bf16 pieces, then G += X^T dZ on the tensor cores.  Warp w owns the feature
       //             m-tiles w and w + 8 (16 features each) for both 8-unit halves; the result stays in registers for Adam ----
@@ -910,18 +902,31 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update_tc(const LearnerArgs a) {
           for (int nt = 0; nt < 2; ++nt) G3[s][i][nt][0] = G3[s][i][nt][1] = G3[s][i][nt][2] = G3[s][i][nt][3] = 0.f;
       float2 gw2 = make_float2(0.f, 0.f);  // this thread's unit pair (2 * (tid % 8)), summed over its rows
       const int np = (tid & 7) * 2;
-      const float2 w2p = *reinterpret_cast<const float2*>(&S.P[(NF + 1) * UT + np]);
+      const float2 w2p = *reinterpret_cast<const float2*>(&S.w2s[np]);
+      float r5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // loss, |td|, value, reward, dL/dY sums (counted by the np == 0 thread of each row)
       for (int tb = 0; tb < T; tb += RT) {
         int rows = min(RT, ((T - tb) + 15) & ~15);
         if (T > RT) {  // the forward pass left another tile in X
           __syncthreads();
           rows = decode_tile(tb);
         }
+        // TD(0) target (trainer.py:110-115), dL/dY of the mse loss (:118), dL/dz and its three bf16 pieces, one (row, unit pair) per thread
         for (int i = tid; i < rows * 8; i += NT) {
           const int tr = i >> 3, t = tb + tr;
           float2 dz = make_float2(0.f, 0.f);
           if (t < T) {
-            const float dy = S.dY[t];
+            const float y = S.Y[t], rw = S.rew[t];
+            float tg = rw;
+            if (t + 1 < T) tg = __fadd_rn(tg, __fmul_rn(a.gamma, S.Y[t + 1]));
+            const float d = y - tg;
+            const float dy = 2.0f * d / (float)T;
+            if (np == 0) {
+              r5[0] = fmaf(d, d, r5[0]);
+              r5[1] += fabsf(d);
+              r5[2] += y;
+              r5[3] += rw;
+              r5[4] += dy;
+            }
             const float2 h = *reinterpret_cast<const float2*>(&S.hs[t * UT + np]);
             gw2.x = fmaf(dy, h.x, gw2.x);
             gw2.y = fmaf(dy, h.y, gw2.y);
@@ -933,23 +938,24 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update_tc(const LearnerArgs a) {
         __syncthreads();
         PH(5);
         const int brow = ((lane >> 3) & 1) * 8 + (lane & 7), bcol = (lane >> 4) * 8;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int mt = warp + 8 * i;
-          if (mt < KP / 16) {
-            // A = X^T: stored [row t][feature]; sub-matrices (features 0-7 | 8-15) x (rows 0-7 | 8-15), loaded transposed
-            const __nv_bfloat16* xa = &S.X[((lane >> 4) * 8 + (lane & 7)) * XS + mt * 16 + ((lane >> 3) & 1) * 8];
+        // A = X^T: stored [row t][feature]; sub-matrices (features 0-7 | 8-15) x (rows 0-7 | 8-15), loaded transposed.  The dZ
+        // fragments of a k-step are shared by the warp's two m-tiles.
+        const __nv_bfloat16* xa0 = &S.X[((lane >> 4) * 8 + (lane & 7)) * XS + warp * 16 + ((lane >> 3) & 1) * 8];
+        const bool two = warp + 8 < KP / 16;
 #pragma unroll 2
-            for (int ks = 0; ks < rows / 16; ++ks) {
-              uint32_t af[4];
-              ldsm_x4_t(af, xa + ks * 16 * XS);
+        for (int ks = 0; ks < rows / 16; ++ks) {
+          uint32_t af0[4], af1[4] = {0u, 0u, 0u, 0u};
+          ldsm_x4_t(af0, xa0 + ks * 16 * XS);
+          if (two) ldsm_x4_t(af1, xa0 + ks * 16 * XS + 8 * 16);
 #pragma unroll
-              for (int s = 0; s < 3; ++s) {
-                uint32_t bfr[4];
-                ldsm_x4_t(bfr, &S.Ds[s][(ks * 16 + brow) * WS + bcol]);
-                mma_bf16(G3[s][i][0], af, bfr[0], bfr[1]);
-                mma_bf16(G3[s][i][1], af, bfr[2], bfr[3]);
-              }
+          for (int s = 0; s < 3; ++s) {
+            uint32_t bfr[4];
+            ldsm_x4_t(bfr, &S.Ds[s][(ks * 16 + brow) * WS + bcol]);
+            mma_bf16(G3[s][0][0], af0, bfr[0], bfr[1]);
+            mma_bf16(G3[s][0][1], af0, bfr[2], bfr[3]);
+            if (two) {
+              mma_bf16(G3[s][1][0], af1, bfr[0], bfr[1]);
+              mma_bf16(G3[s][1][1], af1, bfr[2], bfr[3]);
             }
           }
         }
@@ -960,7 +966,22 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update_tc(const LearnerArgs a) {
       gw2.x += __shfl_xor_sync(BG_FULL, gw2.x, 16);
       gw2.y += __shfl_xor_sync(BG_FULL, gw2.y, 16);
       if (lane < 8) *reinterpret_cast<float2*>(&S.pr[warp][np]) = gw2;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r5[k] += __shfl_xor_sync(BG_FULL, r5[k], o);
+      }
+      if (lane == 0)
+        for (int k = 0; k < 5; ++k) S.red[warp][k] = r5[k];
       __syncthreads();
+      float msum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      if (tid == 0) {
+        for (int k = 0; k < 5; ++k) {
+          float sres = 0.f;
+          for (int w = 0; w < NT / 32; ++w) sres += S.red[w][k];
+          msum[k] = sres;
+        }
+      }
       // fragment ownership: G[i][nt][2 * hh + k] is feature f = (warp + 8 i) * 16 + g + 8 hh, unit nt * 8 + 2 q + k
       float G[2][2][4];
 #pragma unroll
@@ -1019,16 +1040,15 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update_tc(const LearnerArgs a) {
           if (f < NROW) {
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
-              const int s = f * UT + nt * 8 + 2 * q;
-              float2 p = *reinterpret_cast<float2*>(&S.P[s]), m = *reinterpret_cast<float2*>(&S.M[s]), v = *reinterpret_cast<float2*>(&S.V[s]);
-              p.x = adam1(p.x, m.x, v.x, G[i][nt][2 * hh] * coef, sc.x, sc.y);
-              p.y = adam1(p.y, m.y, v.y, G[i][nt][2 * hh + 1] * coef, sc.x, sc.y);
-              *reinterpret_cast<float2*>(&S.P[s]) = p;
-              *reinterpret_cast<float2*>(&S.M[s]) = m;
-              *reinterpret_cast<float2*>(&S.V[s]) = v;
-              if (f <= NF) {
+              float(&w)[2] = pW[i][hh][nt];
+              w[0] = adam1(w[0], pM[i][hh][nt][0], pV[i][hh][nt][0], G[i][nt][2 * hh] * coef, sc.x, sc.y);
+              w[1] = adam1(w[1], pM[i][hh][nt][1], pV[i][hh][nt][1], G[i][nt][2 * hh + 1] * coef, sc.x, sc.y);
+              const int n = nt * 8 + 2 * q;
+              if (f <= NF) {  // the thread that owns a weight rewrites its three bf16 pieces
                 const float wsc = (f == 193 || f == 195) ? k15 : 1.0f;
-                store_split2(S.Ws, f * WS + nt * 8 + 2 * q, p.x * wsc, p.y * wsc);
+                store_split2(S.Ws, f * WS + n, w[0] * wsc, w[1] * wsc);
+              } else {
+                *reinterpret_cast<float2*>(&S.w2s[n]) = make_float2(w[0], w[1]);
               }
             }
           }
@@ -1063,12 +1083,22 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update_tc(const LearnerArgs a) {
            ph[8] / kstep, ph[9] / kstep);
 #endif
 
-  for (int s = tid; s < NROW * UT; s += NT) {
-    const int64_t gi = (int64_t)(s / UT) * H + rank * UT + (s % UT);
-    a.params[gi] = S.P[s];
-    a.m[gi] = S.M[s];
-    a.v[gi] = S.V[s];
-  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int f = (warp + 8 * i) * 16 + g + 8 * hh;
+          if (f < NROW) {
+            const int64_t gi = (int64_t)f * H + rank * UT + nt * 8 + 2 * q + k;
+            a.params[gi] = pW[i][hh][nt][k];
+            a.m[gi] = pM[i][hh][nt][k];
+            a.v[gi] = pV[i][hh][nt][k];
+          }
+        }
   if (rank == 0 && tid == 0) {
     a.params[iB2] = S.b2[0];
     a.m[iB2] = S.b2[1];
