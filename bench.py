@@ -426,18 +426,19 @@ def main():
             # ply u of every game (weights of update u-2) || learner update u-1 on its own stream; then publish update u-1,
             # hand 200 fresh episodes to the learner, drop the surplus (the sequential learner is the bottleneck)
             ar.step(1)
-            m = None
-            if rank == 0:
-                m = tr.finish()  # stream-ordered wait for update u-1, set_packed -> (broadcast) -> arena.set_weights
-            elif n_iter[0] > 0:  # rank 0 publishes update u-1 in iteration u: nothing to receive in the very first one
-                pm.sync_from_source()
             quota = 200 // world  # every rank's arena feeds the trainer, as every worker process feeds the reference's queue
             batch = ar.drain(max_episodes=quota)
             while batch.n_episodes < quota:  # not reached with tens of thousands of games in flight
                 ar.step(1)
                 batch = ar.drain(max_episodes=quota)
             if world > 1:
-                batch = bgd.all_gather_episodes(batch, quota, quota * 300)  # one all_gather of ~1.3 MB in total
+                batch = bgd.all_gather_episodes(batch, quota, quota * 300, compact=False)  # one all_gather (~4 MB padded), no host sync
+            # only now wait for update u-1 (it ran next to the ply, the drain and the gather) and publish it
+            m = None
+            if rank == 0:
+                m = tr.finish()  # stream-ordered wait, set_packed -> (broadcast) -> arena.set_weights
+            elif n_iter[0] > 0:  # rank 0 publishes update u-1 in iteration u: nothing to receive in the very first one
+                pm.sync_from_source()
             if rank == 0:
                 lstream.wait_stream(torch.cuda.current_stream(dev))
                 with torch.cuda.stream(lstream):

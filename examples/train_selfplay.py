@@ -47,16 +47,16 @@ def main():
     t0, metrics = time.time(), {}
     for u in range(args.updates):
         arena.step(1)                                           # next ply of every game || the previous update on learn_stream
-        if rank == 0:
-            metrics = trainer.finish() or metrics               # publish update u-1 (one broadcast when world > 1)
-        elif u > 0:
-            pm.sync_from_source()
         batch = arena.drain(max_episodes=quota)
         while batch.n_episodes < quota:
             arena.step(1)
             batch = arena.drain(max_episodes=quota)
         if world > 1:
-            batch = bgd.all_gather_episodes(batch, quota, quota * arena.max_plies)
+            batch = bgd.all_gather_episodes(batch, quota, quota * arena.max_plies, compact=False)
+        if rank == 0:
+            metrics = trainer.finish() or metrics               # publish update u-1 (one broadcast when world > 1)
+        elif u > 0:
+            pm.sync_from_source()
         if rank == 0:
             learn_stream.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(learn_stream):

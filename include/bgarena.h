@@ -273,6 +273,8 @@ int32_t bg_learner_get_parameters(bg_learner* l, float* packed_out, void* stream
 int32_t bg_learner_get_optimizer(bg_learner* l, float* exp_avg, float* exp_avg_sq, int64_t* step, void* stream);
 /*
  * One Trainer.update over n_episodes episodes in CSR form (ep_offsets[n_episodes+1], device).
+ *   ep_len      : optional device int32[n_episodes].  When given, episode e is the rows [ep_offsets[e], ep_offsets[e] + ep_len[e]) and only
+ *                 ep_offsets[0..n_episodes) is read, so the episodes need not be contiguous (padded per-rank segments of an all-gather).
  *   records == 0: boards[N,52] / flags[N] are the OBSERVATIONS (board the decision was made on, player to move).
  *   records == 1: boards / flags are bg_arena_drain_episodes' after_boards / meta exactly as drained: experience t's
  *                 observation board is record t-1's after_board (the initial board for t = 0), its flag is meta bit 0.
@@ -281,7 +283,7 @@ int32_t bg_learner_get_optimizer(bg_learner* l, float* exp_avg, float* exp_avg_s
  *                 (such episodes, and empty ones, are skipped without an optimiser step).
  */
 int32_t bg_learner_update(bg_learner* l, const int8_t* boards, const uint8_t* flags, const float* reward, const int64_t* ep_offsets,
-                          int64_t n_episodes, int32_t records, float* out_metrics, int32_t* out_status, void* stream);
+                          const int32_t* ep_len /*or NULL*/, int64_t n_episodes, int32_t records, float* out_metrics, int32_t* out_status, void* stream);
 
 #ifdef __cplusplus
 }

@@ -56,7 +56,7 @@ SIGNATURES = {
     "bg_learner_set_parameters": (_i32, [_vp, _vp, _i32, _vp]),
     "bg_learner_get_parameters": (_i32, [_vp, _vp, _vp]),
     "bg_learner_get_optimizer": (_i32, [_vp, _vp, _vp, _vp, _vp]),
-    "bg_learner_update": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "bg_learner_update": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
 }
 
 

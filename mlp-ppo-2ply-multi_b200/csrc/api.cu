@@ -278,10 +278,10 @@ int32_t bg_learner_get_optimizer(bg_learner* l, float* exp_avg, float* exp_avg_s
 }
 
 int32_t bg_learner_update(bg_learner* l, const int8_t* boards, const uint8_t* flags, const float* reward, const int64_t* ep_offsets,
-                          int64_t n_episodes, int32_t records, float* out_metrics, int32_t* out_status, void* stream) {
+                          const int32_t* ep_len, int64_t n_episodes, int32_t records, float* out_metrics, int32_t* out_status, void* stream) {
   BG_REQUIRE(l && n_episodes >= 0, "bg_learner_update: bad arguments");
   BG_REQUIRE(n_episodes == 0 || (boards && flags && reward && ep_offsets), "bg_learner_update: null pointer");
-  return learner_update(reinterpret_cast<Learner*>(l), boards, flags, reward, ep_offsets, n_episodes, records, out_metrics, out_status,
+  return learner_update(reinterpret_cast<Learner*>(l), boards, flags, reward, ep_offsets, ep_len, n_episodes, records, out_metrics, out_status,
                         (cudaStream_t)stream);
 }
 

@@ -49,6 +49,7 @@ struct LearnerArgs {
   const uint8_t* flags;  // records == 0: observation flag; records == 1: arena meta byte (bit0 = mover)
   const float* reward;
   const int64_t* ep_offsets;
+  const int32_t* ep_len;  // optional: explicit episode lengths (ep_offsets then only gives the first row of each episode)
   int64_t n_eps;
   int32_t records;
   float* params;  // packed [W1t(198,H) | b1 | w2 | b2]
@@ -74,7 +75,7 @@ struct Smem {
   float Y[TMAX], dY[TMAX], rew[TMAX];
   alignas(16) float pr[2][NT / 32][UPC];  // per-warp partials of the w2 / b1 gradients
   float2 sc[NSC];              // (lr / bias_correction1, 1 / sqrt(bias_correction2)) for the next NSC optimiser steps
-  int64_t offs[EC + 1];
+  int64_t offs[EC + 1], lens[EC];
   float npart[MAXCL];          // per-CTA sums of squared gradients, pushed by each CTA
   float red[8][8];
   float red2[8];
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update(const LearnerArgs a) {
   int64_t c0 = 0, c1 = 0;
   auto next_valid = [&](int64_t e) {
     for (; e < c1; ++e) {
-      const int64_t Tl = S.offs[e - c0 + 1] - S.offs[e - c0];
+      const int64_t Tl = S.lens[e - c0];
       if (Tl > 0 && Tl <= TMAX) break;
       if (rank == 0 && tid == 0) {
         if (Tl > TMAX && a.status) *a.status = BG_ERR_CAPACITY;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update(const LearnerArgs a) {
   float pf_rew[2] = {0.f, 0.f};
   auto prefetch = [&](int64_t e, int buf) {
     const int64_t lo = S.offs[e - c0];
-    const int T = (int)(S.offs[e - c0 + 1] - lo);
+    const int T = (int)S.lens[e - c0];
     for (int w = tid; w < T * 13; w += NT) {
       const int t = w / 13, k = w - t * 13;
       if (a.records && t == 0)
@@ -224,14 +225,17 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update(const LearnerArgs a) {
   for (c0 = 0; c0 < a.n_eps; c0 += EC) {
     c1 = c0 + EC < a.n_eps ? c0 + EC : a.n_eps;
     __syncthreads();
-    for (int i = tid; i <= (int)(c1 - c0); i += NT) S.offs[i] = a.ep_offsets[c0 + i];
+    for (int i = tid; i < (int)(c1 - c0); i += NT) {  // episode e: rows [offs[e], offs[e] + len); len from ep_len or the next CSR offset
+      S.offs[i] = a.ep_offsets[c0 + i];
+      S.lens[i] = a.ep_len ? (int64_t)a.ep_len[c0 + i] : a.ep_offsets[c0 + i + 1] - a.ep_offsets[c0 + i];
+    }
     __syncthreads();
     int buf = 0;
     int64_t e = next_valid(c0);
     if (e < c1) prefetch(e, buf);
     while (e < c1) {
       PH(9);
-      const int T = (int)(S.offs[e - c0 + 1] - S.offs[e - c0]);
+      const int T = (int)S.lens[e - c0];
       const int nch = (T + 31) >> 5;
       const uint32_t* brd32 = S.brd[buf];
       const uint8_t* brd8 = reinterpret_cast<const uint8_t*>(S.brd[buf]);
@@ -605,7 +609,7 @@ struct SmemTC {
   float ypart[MAXCL_TC * TMAX];
   float Y[TMAX], rew[TMAX];
   float2 sc[NSC];
-  int64_t offs[EC + 1];
+  int64_t offs[EC + 1], lens[EC];
   alignas(16) float pr[NT / 32][UT];  // per-warp partials of the w2 gradient
   uint2 xtab[16];              // the four bf16 thermometer features of a point holding c checkers
   float npart[MAXCL_TC];
@@ -725,7 +729,7 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update_tc(const LearnerArgs a) {
   int64_t c0 = 0, c1 = 0;
   auto next_valid = [&](int64_t e) {
     for (; e < c1; ++e) {
-      const int64_t Tl = S.offs[e - c0 + 1] - S.offs[e - c0];
+      const int64_t Tl = S.lens[e - c0];
       if (Tl > 0 && Tl <= TMAX) break;
       if (rank == 0 && tid == 0) {
         if (Tl > TMAX && a.status) *a.status = BG_ERR_CAPACITY;
@@ -739,7 +743,7 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update_tc(const LearnerArgs a) {
   float pf_rew[2] = {0.f, 0.f};
   auto prefetch = [&](int64_t e, int buf) {
     const int64_t lo = S.offs[e - c0];
-    const int T = (int)(S.offs[e - c0 + 1] - lo);
+    const int T = (int)S.lens[e - c0];
     for (int w = tid; w < T * 13; w += NT) {
       const int t = w / 13, k = w - t * 13;
       if (a.records && t == 0)
@@ -764,14 +768,17 @@ __global__ void __launch_bounds__(NT, 1) k_td0_update_tc(const LearnerArgs a) {
   for (c0 = 0; c0 < a.n_eps; c0 += EC) {
     c1 = c0 + EC < a.n_eps ? c0 + EC : a.n_eps;
     __syncthreads();
-    for (int i = tid; i <= (int)(c1 - c0); i += NT) S.offs[i] = a.ep_offsets[c0 + i];
+    for (int i = tid; i < (int)(c1 - c0); i += NT) {  // episode e: rows [offs[e], offs[e] + len); len from ep_len or the next CSR offset
+      S.offs[i] = a.ep_offsets[c0 + i];
+      S.lens[i] = a.ep_len ? (int64_t)a.ep_len[c0 + i] : a.ep_offsets[c0 + i + 1] - a.ep_offsets[c0 + i];
+    }
     __syncthreads();
     int buf = 0;
     int64_t e = next_valid(c0);
     if (e < c1) prefetch(e, buf);
     while (e < c1) {
       PH(9);
-      const int T = (int)(S.offs[e - c0 + 1] - S.offs[e - c0]);
+      const int T = (int)S.lens[e - c0];
       const uint8_t* brd8 = reinterpret_cast<const uint8_t*>(S.brd[buf]);
 
       // ---- A: land the staged episode; start fetching the next one ----
@@ -1249,7 +1256,7 @@ static int32_t choose_path(Learner* L) {
 }
 
 int32_t learner_update(Learner* L, const int8_t* boards, const uint8_t* flags_or_meta, const float* reward, const int64_t* ep_offsets,
-                       int64_t n_eps, int32_t records, float* out_metrics, int32_t* out_status, cudaStream_t s) {
+                       const int32_t* ep_len, int64_t n_eps, int32_t records, float* out_metrics, int32_t* out_status, cudaStream_t s) {
   cudaError_t e = cudaSetDevice(L->device);
   if (e != cudaSuccess) return check_cuda(e, "cudaSetDevice");
   if ((reinterpret_cast<uintptr_t>(boards) & 3) != 0) {
@@ -1261,7 +1268,7 @@ int32_t learner_update(Learner* L, const int8_t* boards, const uint8_t* flags_or
     if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(status)");
   }
   if (n_eps == 0) return BG_OK;
-  LearnerArgs a{boards, flags_or_meta, reward, ep_offsets, n_eps, records, L->params, L->m, L->v, &L->opt->step,
+  LearnerArgs a{boards, flags_or_meta, reward, ep_offsets, ep_len, n_eps, records, L->params, L->m, L->v, &L->opt->step,
                 L->lr, L->gamma, L->grad_clip, out_metrics, out_status, L->H};
   int32_t rc = choose_path(L);
   if (rc != BG_OK) return rc;

@@ -12,6 +12,6 @@ int32_t learner_set_parameters(Learner* L, const float* packed_dev, int32_t rese
 int32_t learner_get_parameters(Learner* L, float* packed_dev, cudaStream_t s);
 int32_t learner_get_optimizer(Learner* L, float* m_dev, float* v_dev, int64_t* step_dev, cudaStream_t s);
 int32_t learner_update(Learner* L, const int8_t* boards, const uint8_t* flags_or_meta, const float* reward, const int64_t* ep_offsets,
-                       int64_t n_eps, int32_t records, float* out_metrics, int32_t* out_status, cudaStream_t s);
+                       const int32_t* ep_len, int64_t n_eps, int32_t records, float* out_metrics, int32_t* out_status, cudaStream_t s);
 
 }  // namespace bg

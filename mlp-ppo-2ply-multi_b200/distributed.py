@@ -41,11 +41,16 @@ _EP_FIELDS = (("after_boards", torch.int8, 52), ("meta", torch.uint8, 1), ("rewa
               ("next_state_value", torch.float32, 1), ("n_moves", torch.int16, 1), ("action", torch.int16, 1), ("roll", torch.uint8, 2))
 
 
-def all_gather_episodes(batch, max_episodes: int, max_experiences: int, group=None):
+def all_gather_episodes(batch, max_episodes: int, max_experiences: int, group=None, compact: bool = True):
     """Config 5 (collective 3): every rank contributes its drained episodes (at most max_episodes /
-    max_experiences) and receives the concatenation in rank order as one EpisodeBatch -- what the trainer rank feeds to
-    Trainer.update.  ONE all_gather of a fixed-size byte buffer per rank (compact records: 72 B per experience, so 200 episodes
-    are ~1.3 MB in total); replaces the reference's ExperienceQueue.put from every worker process (src/multi/worker.py:60-64)."""
+    max_experiences) and receives all of them in rank order as one EpisodeBatch -- what the trainer rank feeds to Trainer.update.
+    ONE all_gather of a fixed-size byte buffer per rank (compact records: 72 B per experience, so 200 episodes are ~1.3 MB in
+    total); replaces the reference's ExperienceQueue.put from every worker process (src/multi/worker.py:60-64).
+
+    compact=True : the result is a dense CSR batch (one small host read-back for the per-rank sizes).
+    compact=False: no host synchronisation at all -- every rank's records stay in their padded segment and the batch carries explicit
+                   episode lengths (EpisodeBatch.ep_len; bg_learner_update's ep_len argument); n_episodes = world * max_episodes, ranks
+                   that supplied fewer episodes contribute zero-length ones, which the learner skips."""
     from .episode import EpisodeBatch
 
     E, N = int(batch.n_episodes), int(batch.n_experiences)
@@ -63,36 +68,49 @@ def all_gather_episodes(batch, max_episodes: int, max_experiences: int, group=No
     parts = [torch.tensor([E, N], dtype=torch.int64, device=dev).view(torch.uint8)]
     parts += [pad_bytes(getattr(batch, name), max_experiences, cols, dt, N) for name, dt, cols in _EP_FIELDS]
     parts.append(pad_bytes(batch.ep_offsets[: E + 1] if E else batch.ep_offsets[:1], max_episodes + 1, 1, torch.int64, E + 1))
-    parts.append(pad_bytes(batch.ep_info, max_episodes, batch.ep_info.shape[1], torch.int32, E))
+    cols_info = batch.ep_info.shape[1]
+    parts.append(pad_bytes(batch.ep_info, max_episodes, cols_info, torch.int32, E))
     mine = torch.cat(parts)
     if world > 1:
         allb = torch.empty((world, mine.numel()), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(allb, mine, group=group) if dev.type == "cuda" else dist.all_gather(list(allb.unbind(0)), mine, group=group)
     else:
         allb = mine.reshape(1, -1)
-    cols_info = batch.ep_info.shape[1]
-    out = {name: [] for name, _, _ in _EP_FIELDS}
-    offs, infos, tot_e, tot_n = [torch.zeros(1, dtype=torch.int64, device=dev)], [], 0, 0
-    hdr = allb[:, :16].clone().view(torch.int64).reshape(world, 2).tolist()  # the one host read-back
-    for r in range(world):
-        row = allb[r]
-        e_r, n_r = hdr[r]
-        pos = 16
-        for name, dt, cols in _EP_FIELDS:
-            nb = max_experiences * cols * torch.empty(0, dtype=dt).element_size()
-            t = row[pos:pos + nb].clone().view(dt).reshape(max_experiences, cols)[:n_r]  # clone: aligned storage for the wider view
-            out[name].append(t if cols > 1 else t.reshape(-1))
-            pos += nb
-        nb = (max_episodes + 1) * 8
-        o = row[pos:pos + nb].clone().view(torch.int64)[: e_r + 1]
-        pos += nb
-        nb = max_episodes * cols_info * 4
-        infos.append(row[pos:pos + nb].clone().view(torch.int32).reshape(max_episodes, cols_info)[:e_r])
+
+    def field(pos, rows, cols, dt):  # [world, rows, cols] view of one field of every rank (one strided copy, freshly aligned)
+        nb = rows * cols * torch.empty(0, dtype=dt).element_size()
+        return allb[:, pos:pos + nb].contiguous().view(dt).reshape(world, rows, cols), pos + nb
+
+    hdr, pos = allb[:, :16].contiguous().view(torch.int64).reshape(world, 2), 16
+    f = {}
+    for name, dt, cols in _EP_FIELDS:
+        f[name], pos = field(pos, max_experiences, cols, dt)
+    offs, pos = field(pos, max_episodes + 1, 1, torch.int64)
+    offs = offs.reshape(world, max_episodes + 1)
+    info, pos = field(pos, max_episodes, cols_info, torch.int32)
+
+    def flat(name, sel=None):
+        t = f[name] if sel is None else f[name][sel]
+        cols = t.shape[-1]
+        return t.reshape(-1, cols).contiguous() if cols > 1 else t.reshape(-1).contiguous()
+
+    if not compact:
+        j = torch.arange(max_episodes, device=dev).reshape(1, -1)
+        ep_len = torch.where(j < hdr[:, 0:1], offs[:, 1:] - offs[:, :-1], torch.zeros_like(offs[:, 1:])).clamp_(min=0)
+        begin = offs[:, :-1] + torch.arange(world, device=dev).reshape(-1, 1) * max_experiences
+        ep_offsets = torch.cat([begin.reshape(-1), torch.full((1,), world * max_experiences, dtype=torch.int64, device=dev)])
+        return EpisodeBatch(world * max_episodes, world * max_experiences, flat("after_boards"), flat("meta"), flat("reward"), flat("state_value"),
+                            flat("next_state_value"), flat("n_moves"), flat("action"), flat("roll"), ep_offsets.contiguous(),
+                            info.reshape(-1, cols_info).contiguous(), ep_len=ep_len.reshape(-1).to(torch.int32).contiguous())
+    sizes = hdr.tolist()  # the one host read-back
+    rows = torch.cat([torch.arange(n_r, device=dev) + r * max_experiences for r, (_, n_r) in enumerate(sizes)]) if sizes else None
+    o_parts, tot = [torch.zeros(1, dtype=torch.int64, device=dev)], 0
+    for r, (e_r, n_r) in enumerate(sizes):
         if e_r:
-            offs.append(o[1:] - o[0] + tot_n)
-        tot_e += e_r
-        tot_n += n_r
-    cat = {k: torch.cat(v) if v else None for k, v in out.items()}
-    return EpisodeBatch(tot_e, tot_n, cat["after_boards"].contiguous(), cat["meta"].contiguous(), cat["reward"].contiguous(),
-                        cat["state_value"].contiguous(), cat["next_state_value"].contiguous(), cat["n_moves"].contiguous(),
-                        cat["action"].contiguous(), cat["roll"].contiguous(), torch.cat(offs).contiguous(), torch.cat(infos).contiguous())
+            o_parts.append(offs[r, 1:e_r + 1] - offs[r, 0] + tot)
+        tot += n_r
+    eps = torch.cat([torch.arange(e_r, device=dev) + r * max_episodes for r, (e_r, _) in enumerate(sizes)])
+    pick = lambda name: flat(name)[rows]  # noqa: E731
+    return EpisodeBatch(sum(e for e, _ in sizes), tot, pick("after_boards"), pick("meta"), pick("reward"), pick("state_value"),
+                        pick("next_state_value"), pick("n_moves"), pick("action"), pick("roll"), torch.cat(o_parts).contiguous(),
+                        info.reshape(-1, cols_info)[eps].contiguous())

@@ -95,6 +95,11 @@ class EpisodeBatch:
     roll: torch.Tensor  # uint8 [N,2]
     ep_offsets: torch.Tensor  # int64 [E+1]
     ep_info: torch.Tensor  # int32 [E,12]
+    ep_len: Optional[torch.Tensor] = None  # int32 [E]: set when the episodes are NOT contiguous (ep_offsets[e] is then only the first row of e)
+
+    def episode_lengths(self) -> torch.Tensor:
+        E = self.n_episodes
+        return self.ep_len[:E].to(torch.int64) if self.ep_len is not None else self.ep_offsets[1:E + 1] - self.ep_offsets[:E]
 
     def observation_boards(self):
         """(obs_boards int8[N,52], obs_flags uint8[N]): the board each decision was made on and the player to move."""
@@ -131,6 +136,7 @@ class EpisodeBatch:
         obs = self.observations().unbind(0)
         nxt = self.next_observations().unbind(0) if with_next_observation else [None] * N
         off = self.ep_offsets[: E + 1].tolist()
+        lens = self.episode_lengths().tolist()
         info = self.ep_info[:E].tolist()
         # 0-dim tensor views, the dtypes Episode.to_tensor(device) produces in the reference (float -> fp32, bool -> int64)
         sv = self.state_value[:N].unbind(0)
@@ -146,7 +152,7 @@ class EpisodeBatch:
                 if (inf[8] >> p) & 1:
                     ep.close_out_counts[Player(p)] = inf[4 + p]
                     ep.prime_reward_counts[Player(p)] = inf[6 + p]
-            lo, hi = off[k], off[k + 1]
+            lo, hi = off[k], off[k] + lens[k]
             ep.experiences = [Experience(obs[t], sv[t], rew[t], done[t], nxt[t], nsv[t]) for t in range(lo, hi)]
             out.append(ep)
         return out

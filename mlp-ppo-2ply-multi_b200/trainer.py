@@ -96,7 +96,7 @@ class TD0Learner:
         return m, v, int(step.item())
 
     def update(self, boards: torch.Tensor, flags: torch.Tensor, reward: torch.Tensor, ep_offsets: torch.Tensor, n_episodes: Optional[int] = None,
-               records: bool = False, check_status: bool = True) -> torch.Tensor:
+               records: bool = False, check_status: bool = True, ep_len: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One sequential pass over the episodes (CSR).  records=False: boards/flags are the observations; records=True: they are the
         arena's after_boards/meta as drained.  -> per-episode metrics fp32 [E,6] (device): loss, mean |TD|, clipped grad norm, mean V,
         reward sum, length."""
@@ -105,9 +105,11 @@ class TD0Learner:
         reward = ops._req(reward, torch.float32, "reward")
         ep_offsets = ops._req(ep_offsets, torch.int64, "ep_offsets")
         E = ep_offsets.numel() - 1 if n_episodes is None else int(n_episodes)
+        if ep_len is not None:
+            ep_len = ops._req(ep_len, torch.int32, "ep_len")
         met = torch.zeros((max(E, 0), NMETRICS), dtype=torch.float32, device=self.device)
         status = torch.zeros(1, dtype=torch.int32, device=self.device)
-        check(lib().bg_learner_update(self._h, boards.data_ptr(), flags.data_ptr(), reward.data_ptr(), ep_offsets.data_ptr(), E, int(records),
+        check(lib().bg_learner_update(self._h, boards.data_ptr(), flags.data_ptr(), reward.data_ptr(), ep_offsets.data_ptr(), ops._ptr(ep_len), E, int(records),
                                       met.data_ptr(), status.data_ptr(), self._stream()))
         self.last_status = status  # device int32[1]; read lazily by callers that must not synchronise here
         if check_status and int(status.item()) != 0:
@@ -117,7 +119,7 @@ class TD0Learner:
     def update_batch(self, batch: EpisodeBatch, check_status: bool = True) -> torch.Tensor:
         """Consume drained arena episodes without materialising observations (zero-copy hand-off)."""
         return self.update(batch.after_boards, batch.meta, batch.reward, batch.ep_offsets, n_episodes=batch.n_episodes, records=True,
-                           check_status=check_status)
+                           check_status=check_status, ep_len=batch.ep_len)
 
 
 class Trainer:
@@ -161,7 +163,7 @@ class Trainer:
         if isinstance(episodes, EpisodeBatch):
             met = self.learner.update_batch(episodes, check_status=False)
             info = episodes.ep_info[:n].to(torch.float32)
-            lens = (episodes.ep_offsets[1:n + 1] - episodes.ep_offsets[:n]).to(torch.float32)
+            lens = episodes.episode_lengths().to(torch.float32)
             wins = torch.stack([(info[:, 0] == k).sum() for k in (1, 2, 3)]).to(torch.float32)
             seen = torch.stack([((episodes.ep_info[:n, 8] >> p) & 1).sum() for p in (0, 1)]).to(torch.float32)
             # the reference adds the episode's count dict once per EXPERIENCE (trainer.py:88-100)

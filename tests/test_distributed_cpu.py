@@ -48,6 +48,9 @@ def _worker(rank, world, port, out_dir):
                       torch.randint(1, 7, (N + 5, 2), generator=g, dtype=torch.uint8), torch.tensor([0] + list(np.cumsum(lens)) + [0, 0], dtype=torch.int64),
                       torch.full((E + 2, 12), 100 + rank, dtype=torch.int32))
     merged = bgd.all_gather_episodes(eb, max_episodes=4, max_experiences=12)
+    padded = bgd.all_gather_episodes(eb, max_episodes=4, max_experiences=12, compact=False)  # no host sync; explicit episode lengths
+    np.savez(os.path.join(out_dir, f"pad{rank}.npz"), n=np.array([padded.n_episodes, padded.n_experiences]), begin=padded.ep_offsets.numpy(),
+             len=padded.ep_len.numpy(), after=padded.after_boards.numpy(), reward=padded.reward.numpy(), info=padded.ep_info.numpy())
     np.savez(os.path.join(out_dir, f"ep{rank}.npz"), n=np.array([merged.n_episodes, merged.n_experiences]), off=merged.ep_offsets.numpy(),
              after=merged.after_boards.numpy(), reward=merged.reward.numpy(), info=merged.ep_info.numpy(), roll=merged.roll.numpy(),
              action=merged.action.numpy(), my_after=eb.after_boards[:N].numpy(), my_reward=eb.reward[:N].numpy())
@@ -73,6 +76,17 @@ def test_two_rank_weight_broadcast_sharding_and_stats(tmp_path):
     assert np.array_equal(e0["after"], np.concatenate([e0["my_after"], e1["my_after"]]))
     assert np.array_equal(e0["reward"], np.concatenate([e0["my_reward"], e1["my_reward"]]))
     assert e0["info"][:, 0].tolist() == [100, 100, 101, 101, 101]
+    p0 = np.load(tmp_path / "pad0.npz")
+    assert p0["n"].tolist() == [8, 24] and p0["len"].tolist() == [3, 1, 0, 0, 4, 1, 4, 0]  # world * max_episodes slots, missing ones empty
+    k = 0
+    for slot in range(8):  # the non-empty slots, in order, are exactly the compact batch's episodes
+        if p0["len"][slot]:
+            lo, n = int(p0["begin"][slot]), int(p0["len"][slot])
+            assert np.array_equal(p0["after"][lo:lo + n], e0["after"][e0["off"][k]:e0["off"][k + 1]])
+            assert np.array_equal(p0["reward"][lo:lo + n], e0["reward"][e0["off"][k]:e0["off"][k + 1]])
+            assert p0["info"][slot, 0] == e0["info"][k, 0]
+            k += 1
+    assert k == 5
 
 
 def test_shard_games_partition():

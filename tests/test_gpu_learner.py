@@ -86,6 +86,35 @@ def test_learner_other_hidden_sizes_vs_oracle(bg, golden, oracle, H):
     assert np.allclose(met, omet, rtol=2e-3, atol=2e-6)
 
 
+def test_learner_explicit_episode_lengths_equal_csr(bg, golden):
+    """ep_len: episodes given as (first row, length) in padded, non-contiguous segments (the sync-free all-gather layout) train exactly
+    like the same episodes in CSR form; zero-length slots take no optimiser step."""
+    g = golden("learner")
+    H = int(g["H"])
+    off = g["ep_offsets"]
+    N, half = int(off[-1]), int(off[100])
+    PAD = 12000  # rows per segment
+    boards = np.full((2 * PAD, 52), 9, np.int8)
+    flags = np.full(2 * PAD, 255, np.uint8)
+    rew = np.full(2 * PAD, 123.0, np.float32)
+    boards[:half], flags[:half], rew[:half] = g["obs_boards"][:half], g["obs_flags"][:half], g["reward"][:half]
+    boards[PAD:PAD + N - half], flags[PAD:PAD + N - half], rew[PAD:PAD + N - half] = g["obs_boards"][half:], g["obs_flags"][half:], g["reward"][half:]
+    begin = np.concatenate([off[:100], [half, half], off[100:200] - half + PAD, [0]]).astype(np.int64)  # two empty slots in the middle
+    lens = np.concatenate([np.diff(off)[:100], [0, 0], np.diff(off)[100:]]).astype(np.int32)
+    outs = []
+    for padded in (False, True):
+        L = bg.TD0Learner(H, DEV)
+        L.set_parameters(torch.from_numpy(g["packed0"]), reset_optimizer=True)
+        if padded:
+            met = L.update(*_dev(boards, flags, rew, begin), n_episodes=202, ep_len=torch.from_numpy(lens).to(DEV))
+            met = met[torch.from_numpy(lens != 0).to(DEV)]
+        else:
+            met = L.update(*_dev(g["obs_boards"], g["obs_flags"], g["reward"], off))
+        assert L.optimizer_state()[2] == 200
+        outs.append((L.packed().cpu().numpy(), met.cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
 def test_learner_cuda_core_fallback_kernel(bg, golden, oracle, monkeypatch):
     """H > 128 normally runs the tensor-core kernel in a 10-16 CTA cluster; the 32-units-per-CTA CUDA-core kernel is the fallback when
     the device refuses that cluster size.  Force it and check it against the oracle."""
