@@ -335,7 +335,8 @@ def main():
                 "traffic_source": "profiles/r01_ncu_fullsize_dram_traffic.txt (ncu --set full, same command; bytes per launch)" if full_cfg else None,
                 "algorithmic_bytes": kern[dom][1],
                 "peak_source": peak_src, "ms_per_launch": kern[dom][0],
-                "note": "integer-issue / shared-memory bound by design: algorithmic bytes are tiny (SURVEY.md 8(d))",
+                "note": "integer-issue bound, not bandwidth bound: algorithmic bytes are tiny (SURVEY.md 8(d)); ncu on the bulk tier: issue-active 76.6 %, "
+                        "ALU pipe 72 %, 2,021 warp instructions per item, DRAM 4 % of peak (profiles/r01_ncu_v2_movegen_tiers_and_eval_tc.txt)",
                 "kernels_ms": {k: v[0] for k, v in kern.items()},
                 "eval_fp32_tflops_dense_equiv": n_after * FLOP_PER_AFTERSTATE / (t_eval * 1e-3) / 1e12}
     # the evaluator is a tensor-core kernel: 3 bf16 splits x (2 * 208 * 128) FLOP per afterstate actually issued to tcgen05
