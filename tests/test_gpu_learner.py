@@ -115,6 +115,27 @@ def test_learner_explicit_episode_lengths_equal_csr(bg, golden):
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
 
 
+@pytest.mark.parametrize("H", [128, 256])
+def test_learner_long_episodes_all_tile_counts(bg, golden, oracle, H):
+    """episode lengths around the kernel's row-tile (128) and capacity (320) boundaries: 1, 2 and 3 tiles, the longest accepted episode"""
+    g = golden("learner")
+    lens = [300, 320, 257, 256, 129, 128, 127, 17, 16, 15, 1]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    N = int(off[-1])
+    rng = np.random.default_rng(5)
+    packed = (rng.standard_normal(200 * H + 1) * 0.1).astype(np.float32)
+    boards, flags, rew = g["obs_boards"][:N], g["obs_flags"][:N], g["reward"][:N]
+    L = bg.TD0Learner(H, DEV)
+    L.set_parameters(torch.from_numpy(packed), reset_optimizer=True)
+    met = L.update(*_dev(boards, flags, rew, off)).cpu().numpy()
+    O = oracle.Learner(packed, H)
+    omet = O.update(boards, flags, rew, off)
+    assert L.optimizer_state()[2] == len(lens) and met[:, 5].tolist() == [float(x) for x in lens]
+    d = np.abs(L.packed().cpu().numpy() - O.state()[0])
+    assert d.max() < 1e-4 and (d > W_TOL).sum() <= 8
+    assert np.allclose(met, omet, rtol=2e-3, atol=2e-6)
+
+
 def test_learner_cuda_core_fallback_kernel(bg, golden, oracle, monkeypatch):
     """H > 128 normally runs the tensor-core kernel in a 10-16 CTA cluster; the 32-units-per-CTA CUDA-core kernel is the fallback when
     the device refuses that cluster size.  Force it and check it against the oracle."""
