@@ -8,7 +8,7 @@ from .env import BackgammonEnv
 from .episode import Episode, EpisodeBatch, Experience
 from .moves import execute_full_move_on_board_copy, generate_all_board_features, get_all_possible_moves
 from .parameter_manager import ParameterManager
-from .match import play_match
+from .match import agent_play_step, play_match, select_highest_value_action
 from .policy_network import BackgammonPolicyNetwork
 from .trainer import TD0Learner, Trainer, features_to_boards
 from .types import BoardState, FullMove, Player, Position, SubMove
@@ -16,7 +16,7 @@ from ._lib import BgError, SO_PATH
 from .ops import (DICE_ROLLS, HostPipeline, MovegenResult, PreparedWeights, encode, evaluate, movegen, movegen_evaluate, pack_weights, prepare_weights, select,
                   two_ply, unpack_weights)
 
-__all__ = ["HostPipeline", "play_match", "Trainer", "TD0Learner", "features_to_boards", "ImmutableBoard", "BackgammonEnv", "ParameterManager", "BackgammonPolicyNetwork", "execute_full_move_on_board_copy",
+__all__ = ["HostPipeline", "agent_play_step", "select_highest_value_action", "play_match", "Trainer", "TD0Learner", "features_to_boards", "ImmutableBoard", "BackgammonEnv", "ParameterManager", "BackgammonPolicyNetwork", "execute_full_move_on_board_copy",
            "generate_all_board_features", "get_all_possible_moves", "Arena", "temperature_for_version", "Episode", "EpisodeBatch", "Experience", "BoardState", "FullMove", "Player",
            "Position", "SubMove", "ops", "BgError", "SO_PATH", "DICE_ROLLS", "MovegenResult", "PreparedWeights", "encode", "evaluate", "movegen", "movegen_evaluate",
            "pack_weights", "prepare_weights", "select", "two_ply", "unpack_weights"]

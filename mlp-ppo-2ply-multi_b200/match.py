@@ -83,3 +83,14 @@ def play_match(weights_a, weights_b, n_games: int = 4096, hidden_size: int = 128
     if return_batch:
         out["batch"] = batch
     return out
+
+
+def select_highest_value_action(policy_network, x: torch.Tensor) -> int:
+    """The reference agent's decision rule (src/play/play_versus_ai.py:188-195): argmax of the afterstate values, lowest index on ties."""
+    with torch.no_grad():
+        return int(torch.argmax(policy_network.forward(x)).item())
+
+
+def agent_play_step(policy_network, env) -> int:
+    """src/play/play_versus_ai.py:165-185 without the printing: the action index the agent picks in `env`'s current position."""
+    return select_highest_value_action(policy_network, env.legal_board_features[: env.num_moves])

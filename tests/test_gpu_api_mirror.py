@@ -121,3 +121,32 @@ def test_policy_network_values_match_forward(bg, golden):
     assert torch.allclose(got, torch.from_numpy(v["values"]), atol=1e-5, rtol=0)  # vs the reference's torch forward
     x = bg.encode(boards, flags).cpu()
     assert torch.allclose(net(x), got, atol=1e-5, rtol=0)
+
+
+def test_agent_play_step_plays_the_reference_greedy_game(bg, golden):
+    """agent_play_step / select_highest_value_action (play_versus_ai.py:165-195) driving BackgammonEnv reproduce the reference's own
+    greedy games (same dice): action for action, V(observation) and V(chosen afterstate) within 1e-5."""
+    g, v = golden("greedy_games"), golden("values")
+    H = int(v["H"])
+    net = bg.BackgammonPolicyNetwork(hidden_size=H)
+    net.load_state_dict(bg.unpack_weights(torch.from_numpy(v["packed"]), H))
+    for k in range(2):
+        tape = g["tape"][g["tape_off"][k]:g["tape_off"][k + 1]]
+        env = TapeEnv(bg, tape)
+        obs = env.reset()
+        lo, hi = g["dec_off"][k], g["dec_off"][k + 1]
+        d, done, steps = lo, False, 0
+        while not done and steps < 300:
+            if env.num_moves == 0:
+                obs, _, done, _ = env.step(None)
+            else:
+                a = bg.agent_play_step(net, env)
+                assert a == int(g["action"][d]) and env.num_moves == int(g["nmoves"][d])
+                with torch.no_grad():
+                    vals = net(torch.cat([obs.unsqueeze(0), env.legal_board_features[: env.num_moves]]))
+                assert abs(float(vals[0]) - float(g["v"][d])) < 1e-5 and abs(float(vals[1 + a]) - float(g["vnext"][d])) < 1e-5
+                obs, r, done, _ = env.step(a)
+                assert float(r) == pytest.approx(float(g["reward"][d]), abs=1e-7)
+                d += 1
+            steps += 1
+        assert d == hi and steps == int(g["n_steps"][k])
