@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--selfplay-games", type=int, default=65536)
     ap.add_argument("--selfplay-plies", type=int, default=200)
     ap.add_argument("--selfplay2-plies", type=int, default=20)
+    ap.add_argument("--e2e-chunks", type=int, default=0, help="chunks of the host-to-host pipeline (0 = default)")
     ap.add_argument("--td0-updates", type=int, default=50)
     ap.add_argument("--cpu-selfplay-games", type=int, default=16384)
     ap.add_argument("--no-selfplay", action="store_true")
@@ -294,7 +295,7 @@ def main():
     res = r = None
     del pool, values, pflags, ws
     torch.cuda.empty_cache()
-    n_chunks = 8 if B >= (1 << 20) else 2
+    n_chunks = args.e2e_chunks if args.e2e_chunks > 0 else (8 if B >= (1 << 20) else 2)
     pipe = bg.HostPipeline(weights, items_per_chunk=(B + n_chunks - 1) // n_chunks, device=dev, item_cap=500)
 
     def e2e_step():
