@@ -317,7 +317,7 @@ def main():
     e2e_value = n_after_all / (float(te[0]) / args.steps * 1e-3)
     h2d = h_b.numel() + h_p.numel() + h_r.numel()
     d2h = h_act.numel() * 4 + h_cnt.numel() * 4
-    n_e2e_kernels = 7 * n_chunks  # movegen tiers (4) + eval (2) + select per chunk
+    n_e2e_kernels = 8 * n_chunks  # movegen tiers (5) + eval (2) + select per chunk
     e2e_check = int((h_cnt.to(torch.int64).clamp(max=500)).sum().item())  # must reproduce the afterstate count of the resident path
     del pipe
 
@@ -325,13 +325,13 @@ def main():
     peak, peak_src = load_peaks()
     eval_bytes = n_after * (52 + 1 + 4)  # board in + flag in + value out
     movegen_bytes = B * (52 + 1 + 2 + 8 + 4) + n_after * (52 + 1)  # item in/out + board, flag out
-    kern = {"bg::k_eval_tc (tcgen05, H=128)": (t_eval, eval_bytes), "bg::k_movegen<128|512|2048|4096> (4 tiers)": (t_movegen, movegen_bytes)}
+    kern = {"bg::k_eval_tc (tcgen05, H=128)": (t_eval, eval_bytes), "bg::k_movegen<128|256|512|2048|4096> (5 tiers)": (t_movegen, movegen_bytes)}
     dom = max(kern, key=lambda k: kern[k][0])
     ach = kern[dom][1] / (kern[dom][0] * 1e-3) / 1e9
     # dram__bytes_read + dram__bytes_write per launch from one `ncu --set full` capture of this command at the full configuration
     # (profiles/r01_ncu_fullsize_dram_traffic.txt); only valid for that configuration
     full_cfg = int(boards.shape[0]) == 1048576
-    traffic = {"bg::k_eval_tc (tcgen05, H=128)": 27.62e9, "bg::k_movegen<128|512|2048|4096> (4 tiers)": 27.2e9} if full_cfg else {}
+    traffic = {"bg::k_eval_tc (tcgen05, H=128)": 27.62e9, "bg::k_movegen<128|256|512|2048|4096> (5 tiers)": 27.2e9} if full_cfg else {}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic.get(dom),
                 "traffic_source": "profiles/r01_ncu_fullsize_dram_traffic.txt (ncu --set full, same command; bytes per launch)" if full_cfg else None,
                 "algorithmic_bytes": kern[dom][1],
@@ -577,7 +577,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "afterstates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "what": f"bg.HostPipeline.run: pinned host boards/players/rolls -> {n_chunks} chunks on 2 streams (H2D, bg_movegen, bg_eval, bg_select(greedy), D2H) -> host actions + counts",
                     "afterstates_check": e2e_check},
-            "gpu_launches": 6 * args.steps, "gpu_launches_note": f"timed region, per step (bg_movegen_eval): k_movegen tiers 128 / 512 / 2048 / 4096 + k_eval_tc twice (bulk-tier rows on the side stream, tail-tier rows after); unfused ms_per_step {unfused_ms_per_step:.2f}; the e2e region launches {n_e2e_kernels} per step (the same six + k_select, per chunk)",
+            "gpu_launches": 7 * args.steps, "gpu_launches_note": f"timed region, per step (bg_movegen_eval): k_movegen tiers 128 / 256 / 512 / 2048 / 4096 + k_eval_tc twice (bulk-tier rows on the side stream, tail-tier rows after); unfused ms_per_step {unfused_ms_per_step:.2f}; the e2e region launches {n_e2e_kernels} per step (the same seven + k_select, per chunk)",
             "roofline": roofline, "roofline_eval": roofline_eval, "cpu_baseline": cpu, "clocks": clocks, "selfplay_1ply": selfplay, "selfplay_2ply": selfplay2,
             "selfplay_2ply_all_candidates": selfplay2b, "learner": learner, "td0_loop": td0}
     print(json.dumps(line), flush=True)

@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" boundary of libbgarena.so (include/bgarena.h).  No torch / C++ types cross it.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -184,8 +185,6 @@ int32_t bg_movegen_eval(const int8_t* boards, const uint8_t* players, const uint
   if ((rc = fused_ctx(&c)) != BG_OK) return rc;
   MovegenArgs a{boards,  players,   rolls,       B,         item_cap,  pool_cap,   out_boards, nullptr,
                 nullptr, out_flags, out_offsets, out_count, out_total, out_status, workspace,  workspace_bytes, nullptr};
-  // big batches have enough tail work to be worth sharing every SM: 3 x 20.5 KB second-tier CTAs next to the evaluator's one 161 KB CTA
-  a.tier2_ctas_per_sm = B >= (1ll << 22) ? 3 : 0;
   return movegen_eval_overlapped(a, out_total, prepared, H, out_v, c, (cudaStream_t)stream);
 }
 

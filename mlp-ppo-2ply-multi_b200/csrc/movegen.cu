@@ -18,7 +18,7 @@
 //     (parent, move) pairs are flattened over the warp so that every lane builds one child per round.
 //   * non-doubles keep the reference's literal control flow (both die orders, singles only when an order has
 //     no two-move play, quirk Q1 skip, shared seen-set, max-length filter).
-//   * four capacity tiers (128 / 512 / 2048 nodes per ply in shared memory, 4096 in L2-resident global scratch);
+//   * five capacity tiers (128 / 256 / 512 / 2048 nodes per ply in shared memory, 4096 in L2-resident global scratch);
 //     an item overflowing a tier is queued for the next one.  Overflowing the last tier is BG_ERR_CAPACITY.
 #include "movegen.cuh"
 
@@ -583,11 +583,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_movegen(MovegenParams P) {
   }
 }
 
-// capacity tiers: nodes per ply.  T1-T3 keep the frontiers in shared memory, T4 in L2-resident global scratch.
+// capacity tiers: nodes per ply.  T1-T4 keep the frontiers in shared memory, T5 in L2-resident global scratch.  The small tiers buy
+// occupancy (more resident warps for the many light items), the 2048 tier buys latency for the rare very wide doubles trees.
 constexpr int T1_CAP = 128, T1_WARPS = 4, T1_CTAS_PER_SM = 8;
-constexpr int T2_CAP = 512, T2_WARPS = 1, T2_CTAS_PER_SM = 10;
-constexpr int T3_CAP = 2048, T3_WARPS = 1, T3_CTAS_PER_SM = 2;   // still in shared memory: the rare very wide doubles trees
-constexpr int T4_CAP = 4096, T4_WARPS = 2, T4_CTAS_PER_SM = 3;
+constexpr int T2_CAP = 256, T2_WARPS = 1, T2_CTAS_PER_SM = 20;
+constexpr int T3_CAP = 512, T3_WARPS = 1, T3_CTAS_PER_SM = 10;
+constexpr int T4_CAP = 2048, T4_WARPS = 1, T4_CTAS_PER_SM = 2;
+constexpr int T5_CAP = 4096, T5_WARPS = 2, T5_CTAS_PER_SM = 3;
 constexpr int NUM_SMS = 148;
 
 constexpr size_t smem_bytes(int cap, bool global, bool moves, int warps) {
@@ -595,29 +597,42 @@ constexpr size_t smem_bytes(int cap, bool global, bool moves, int warps) {
 }
 
 constexpr int64_t HDR_BYTES = 256;
-constexpr int64_t GFRONT_BYTES = (int64_t)NUM_SMS * T4_CTAS_PER_SM * T4_WARPS * 2 * 6 * T4_CAP * 4;
+constexpr int64_t GFRONT_BYTES = (int64_t)NUM_SMS * T5_CTAS_PER_SM * T5_WARPS * 2 * 6 * T5_CAP * 4;
+constexpr int N_OVF = 4;  // overflow lists chaining the five tiers
+
+template <int CAP, bool GLOBAL, bool MOVES, int WARPS, int CTAS>
+int32_t prepare_tier() {
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(k_movegen<CAP, GLOBAL, MOVES, WARPS, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_bytes(CAP, GLOBAL, MOVES, WARPS));
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_movegen)");
+    done = true;
+  }
+  return BG_OK;
+}
+
+// a tail tier: consumes overflow list `in`, produces list `out` (out < 0: last tier), uses work counter `in + 1`
+template <int CAP, bool GLOBAL, bool MOVES, int WARPS, int CTAS>
+int32_t launch_tail_tier(MovegenParams P, int in, int out, int ctas, int32_t* ctr, int32_t* const (&ovf)[N_OVF], int32_t* const (&ovf_n)[N_OVF],
+                         cudaStream_t stream) {
+  int32_t rc = prepare_tier<CAP, GLOBAL, MOVES, WARPS, CTAS>();
+  if (rc != BG_OK) return rc;
+  P.item_counter = ctr + in + 1;
+  P.in_list = ovf[in];
+  P.in_count = ovf_n[in];
+  P.ovf_list = out >= 0 ? ovf[out] : nullptr;
+  P.ovf_count = out >= 0 ? ovf_n[out] : nullptr;
+  P.grab = 1;
+  k_movegen<CAP, GLOBAL, MOVES, WARPS, CTAS><<<NUM_SMS * ctas, WARPS * 32, smem_bytes(CAP, GLOBAL, MOVES, WARPS), stream>>>(P);
+  return BG_OK;
+}
 
 template <bool MOVES>
-int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* const (&ovf)[3], int32_t* const (&ovf_n)[3], int64_t* tier1_total,
-                     cudaEvent_t tier1_event, int32_t tier2_ctas, cudaStream_t stream) {
-  auto k1 = k_movegen<T1_CAP, false, MOVES, T1_WARPS, T1_CTAS_PER_SM>;
-  auto k2 = k_movegen<T2_CAP, false, MOVES, T2_WARPS, T2_CTAS_PER_SM>;
-  auto k3 = k_movegen<T3_CAP, false, MOVES, T3_WARPS, T3_CTAS_PER_SM>;
-  auto k4 = k_movegen<T4_CAP, true, MOVES, T4_WARPS, T4_CTAS_PER_SM>;
-  constexpr size_t s1 = smem_bytes(T1_CAP, false, MOVES, T1_WARPS), s2 = smem_bytes(T2_CAP, false, MOVES, T2_WARPS),
-                   s3 = smem_bytes(T3_CAP, false, MOVES, T3_WARPS), s4 = smem_bytes(T4_CAP, true, MOVES, T4_WARPS);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tier1)");
-    e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tier2)");
-    e = cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tier3)");
-    e = cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s4);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tier4)");
-    attr_done = true;
-  }
+int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* const (&ovf)[N_OVF], int32_t* const (&ovf_n)[N_OVF],
+                     int64_t* tier1_total, cudaEvent_t tier1_event, int32_t tier2_ctas, cudaStream_t stream) {
+  int32_t rc = prepare_tier<T1_CAP, false, MOVES, T1_WARPS, T1_CTAS_PER_SM>();
+  if (rc != BG_OK) return rc;
   // tier 1: every item
   P.item_counter = ctr + 0;
   P.in_list = nullptr;
@@ -627,7 +642,7 @@ int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* const (&
   P.grab = B > (1 << 20) ? 8 : 1;
   int64_t want = (B + T1_WARPS - 1) / T1_WARPS;
   int grid = (int)(want < (int64_t)NUM_SMS * T1_CTAS_PER_SM ? want : (int64_t)NUM_SMS * T1_CTAS_PER_SM);
-  k1<<<grid, T1_WARPS * 32, s1, stream>>>(P);
+  k_movegen<T1_CAP, false, MOVES, T1_WARPS, T1_CTAS_PER_SM><<<grid, T1_WARPS * 32, smem_bytes(T1_CAP, false, MOVES, T1_WARPS), stream>>>(P);
   if (tier1_total) {
     cudaError_t e = cudaMemcpyAsync(tier1_total, P.pool_cursor, 8, cudaMemcpyDeviceToDevice, stream);
     if (e != cudaSuccess) return check_cuda(e, "copy tier1_total");
@@ -636,28 +651,16 @@ int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* const (&
     cudaError_t e = cudaEventRecord(tier1_event, stream);
     if (e != cudaSuccess) return check_cuda(e, "record tier1_event");
   }
-  // tier 2: items that overflowed 128 nodes in some ply
-  P.item_counter = ctr + 1;
-  P.in_list = ovf[0];
-  P.in_count = ovf_n[0];
-  P.ovf_list = ovf[1];
-  P.ovf_count = ovf_n[1];
-  P.grab = 1;
-  k2<<<NUM_SMS * (tier2_ctas > 0 && tier2_ctas < T2_CTAS_PER_SM ? tier2_ctas : T2_CTAS_PER_SM), T2_WARPS * 32, s2, stream>>>(P);
-  // tier 3: items that overflowed 512 nodes (frontier still in shared memory, two warps per SM)
-  P.item_counter = ctr + 2;
-  P.in_list = ovf[1];
-  P.in_count = ovf_n[1];
-  P.ovf_list = ovf[2];
-  P.ovf_count = ovf_n[2];
-  k3<<<NUM_SMS * T3_CTAS_PER_SM, T3_WARPS * 32, s3, stream>>>(P);
-  // tier 4: items that overflowed 2048 nodes (frontier in L2-resident global scratch)
-  P.item_counter = ctr + 3;
-  P.in_list = ovf[2];
-  P.in_count = ovf_n[2];
-  P.ovf_list = nullptr;
-  P.ovf_count = nullptr;
-  k4<<<NUM_SMS * T4_CTAS_PER_SM, T4_WARPS * 32, s4, stream>>>(P);
+  // tail tiers: the items that overflowed 128 / 256 / 512 / 2048 nodes in some ply.  The 256 tier (twice the resident warps of the 512
+  // tier) pays when the overflow lists are long; for small batches (one self-play ply) every extra tier is one more kernel whose
+  // slowest item sits on the critical path, so the chain goes 128 -> 512 directly.
+  const bool use256 = B >= (1 << 20);
+  const int c2 = tier2_ctas > 0 && tier2_ctas < T2_CTAS_PER_SM ? tier2_ctas : T2_CTAS_PER_SM;
+  if (use256 && (rc = launch_tail_tier<T2_CAP, false, MOVES, T2_WARPS, T2_CTAS_PER_SM>(P, 0, 1, c2, ctr, ovf, ovf_n, stream)) != BG_OK) return rc;
+  if ((rc = launch_tail_tier<T3_CAP, false, MOVES, T3_WARPS, T3_CTAS_PER_SM>(P, use256 ? 1 : 0, 2, T3_CTAS_PER_SM, ctr, ovf, ovf_n, stream)) != BG_OK)
+    return rc;
+  if ((rc = launch_tail_tier<T4_CAP, false, MOVES, T4_WARPS, T4_CTAS_PER_SM>(P, 2, 3, T4_CTAS_PER_SM, ctr, ovf, ovf_n, stream)) != BG_OK) return rc;
+  if ((rc = launch_tail_tier<T5_CAP, true, MOVES, T5_WARPS, T5_CTAS_PER_SM>(P, 3, -1, T5_CTAS_PER_SM, ctr, ovf, ovf_n, stream)) != BG_OK) return rc;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return check_cuda(e, "k_movegen launch");
   return BG_OK;
@@ -666,12 +669,12 @@ int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* const (&
 }  // namespace
 
 int64_t movegen_workspace_bytes(int64_t B) {
-  int64_t lists = ((3 * B * 4 + 255) / 256) * 256;
+  int64_t lists = ((N_OVF * B * 4 + 255) / 256) * 256;
   return HDR_BYTES + lists + GFRONT_BYTES;
 }
 
 // workspace header layout (first HDR_BYTES): [0] u64 pool cursor, [8] i32 status, [12] i32 counter1,
-// [16] i32 counter2, [20] i32 counter3, [24] i32 counter4, [32] [36] [40] i32 overflow-list counts of tiers 1-3
+// [16] .. [28] i32 counters of tiers 2-5, [32] [36] [40] [44] i32 overflow-list counts of tiers 1-4
 int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream) {
   if (a.B < 0 || a.B >= (1ll << 31) || a.item_cap < 0 || a.pool_cap < 0) {
     set_error("bg_movegen: bad sizes (B=%lld item_cap=%d pool_cap=%lld)", (long long)a.B, a.item_cap, (long long)a.pool_cap);
@@ -685,7 +688,7 @@ int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream) {
   char* ws = (char*)a.workspace;
   cudaError_t e = cudaMemsetAsync(ws, 0, HDR_BYTES, stream);
   if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(workspace)");
-  int64_t lists = ((3 * a.B * 4 + 255) / 256) * 256;
+  int64_t lists = ((N_OVF * a.B * 4 + 255) / 256) * 256;
   MovegenParams P;
   P.boards = a.boards;
   P.players = a.players;
@@ -705,8 +708,8 @@ int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream) {
   P.active = a.active;
   int32_t* ctr = (int32_t*)(ws + 12);
   int32_t* const l0 = (int32_t*)(ws + HDR_BYTES);
-  int32_t* const ovf[3] = {l0, l0 + a.B, l0 + 2 * a.B};
-  int32_t* const ovf_n[3] = {(int32_t*)(ws + 32), (int32_t*)(ws + 36), (int32_t*)(ws + 40)};
+  int32_t* const ovf[N_OVF] = {l0, l0 + a.B, l0 + 2 * a.B, l0 + 3 * a.B};
+  int32_t* const ovf_n[N_OVF] = {(int32_t*)(ws + 32), (int32_t*)(ws + 36), (int32_t*)(ws + 40), (int32_t*)(ws + 44)};
   if (a.B > 0) {
     // the sub-move history (2 extra words per node) is only carried when the caller asks for the FullMove sequences
     int32_t rc = a.out_submoves ? launch_tiers<true>(P, a.B, ctr, ovf, ovf_n, a.tier1_total, a.tier1_event, a.tier2_ctas_per_sm, stream)
