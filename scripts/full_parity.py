@@ -3,7 +3,7 @@
 Every item's legal-afterstate list from bg_movegen is compared with the CPU oracle -- count, content and ORDER -- through a 64-bit
 order-sensitive checksum per item; features are checked bit-exactly through bg_encode on a strided sample of the afterstates and
 values through bg_eval to 1e-5.  Runs on the GPU box in chunks of 131,072 positions (the oracle side is the slow part).
-    python scripts/full_parity.py [n_positions] > profiles/r01_full_parity.txt"""
+    python scripts/full_parity.py [n_positions [positions_per_call]] > profiles/r01_full_parity.txt"""
 import os
 import sys
 import time
@@ -61,7 +61,7 @@ def main():
     w = bg.prepare_weights(torch.from_numpy(packed).to(DEV), H)
     t0 = time.time()
     boards, players = po.random_positions(n_pos, seed=2026)
-    CHUNK = 131072
+    CHUNK = int(sys.argv[2]) if len(sys.argv) > 2 else 262144  # 262,144 positions x 21 = 5.5 M items per call: every capacity tier is exercised
     items = afterstates = bad_items = 0
     feat_rows = feat_bad = 0
     max_dv = 0.0
