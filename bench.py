@@ -340,8 +340,8 @@ def main():
                         "ALU pipe 72 %, 2,021 warp instructions per item, DRAM 4 % of peak (profiles/r01_ncu_v2_movegen_tiers_and_eval_tc.txt)",
                 "kernels_ms": {k: v[0] for k, v in kern.items()},
                 "eval_fp32_tflops_dense_equiv": n_after * FLOP_PER_AFTERSTATE / (t_eval * 1e-3) / 1e12}
-    # the evaluator is a tensor-core kernel: 3 bf16 splits x (2 * 208 * 128) FLOP per afterstate actually issued to tcgen05
-    tc_flops = n_after * 3 * 2 * 208 * H
+    # the evaluator is a tensor-core kernel: 2 fp16 pieces x (2 * 208 * 128) FLOP per afterstate actually issued to tcgen05
+    tc_flops = n_after * 2 * 2 * 208 * H
     tpeak = None
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
@@ -350,7 +350,7 @@ def main():
     tach = tc_flops / (t_eval * 1e-3) / 1e12
     roofline_eval = {"bound": "tensor", "kernel": "bg::k_eval_tc (tcgen05, H=128)", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s",
                      "frac": tach / tpeak, "traffic": traffic.get("bg::k_eval_tc (tcgen05, H=128)"), "peak_source": tsrc, "ms_per_launch": t_eval,
-                     "note": "bf16 FLOPs issued: 3 weight splits x 2*208*128 per afterstate (fp32-exact layer 1); dense fp32-equivalent is 1/3.27 of this"}
+                     "note": "16-bit tensor FLOPs issued: 2 fp16 weight pieces x 2*208*128 per afterstate (fp32-exact layer 1); dense fp32-equivalent is 1/2.09 of this. The kernel is co-limited: issue slots ~55 %, MUFU (ex2/rcp of the 128 sigmoids per board) ~35 %, tensor pipe ~30 %"}
 
     del ib, ip, ir
     torch.cuda.empty_cache()

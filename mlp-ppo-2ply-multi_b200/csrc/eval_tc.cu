@@ -3,18 +3,20 @@
 // Same contract as eval.cu / eval128.cu (reference src/backgammon/board/immutable_board.py:86-128 +
 // src/agents/policy_network.py:53-70, |dV| <= 1e-5), for LARGE afterstate batches where layer 1 is a real GEMM:
 //   Z[128 boards, 128 hidden] = X[128, 208] * W^T[208, 128]
-// * fp32-equivalent on bf16 tensor cores: every feature value is EXACT in bf16 ({0, 1, k/2}); the two off/15 features are
-//   carried as three bf16 terms (hi + mid + lo) in spare K columns; the weights (and b1, as the column of a constant-1
-//   feature) are split into three bf16 terms W = hi + mid + lo (24 mantissa bits), so the 3 x 13 tcgen05.mma
-//   (kind::f16, M128 N128 K16, fp32 accumulate in TMEM) form every product exactly and only the accumulation rounds.
+// * fp32-equivalent on fp16 tensor cores: every feature value is EXACT in fp16 ({0, 1, k/2}); the two off/15 features are
+//   carried as three fp16 terms (hi + mid + lo) in spare K columns; the weights (and b1, as the column of a constant-1
+//   feature) are split into TWO fp16 pieces W = hi + lo: 11 + 11 significand bits, so the residual is <= 2^-24 |W|, the
+//   rounding error fp32 itself has (valid for |W| < 65504; fp16 subnormals keep the low piece of tiny weights to 3e-8 abs).
+//   The 2 x 13 tcgen05.mma (kind::f16, M128 N128 K16, fp32 accumulate in TMEM) form every product exactly and only the
+//   accumulation rounds.  (Round 1 first used three bf16 pieces: same accuracy, 1.5x the tensor work.)
 // * A never touches shared memory: each of 128 worker threads owns one TMEM lane (= one board), builds its 208-entry
-//   bf16 feature row in registers and tcgen05.st's it into TMEM (A-from-TMEM "TS" MMA); B (3 x 128 x 208 bf16 = 156 KB,
+//   fp16 feature row in registers and tcgen05.st's it into TMEM (A-from-TMEM "TS" MMA); B (2 x 128 x 208 fp16 = 104 KB,
 //   no-swizzle K-major core-matrix layout) stays resident in shared memory; D is read back with tcgen05.ld and the
 //   sigmoid / w2 dot product / +b2 epilogue runs one thread per board.
 // * two worker groups (2 x 4 warps) alternate tiles against one MMA-issuer warp, TMEM = [A0 | D0 | A1 | D1] (512 columns),
 //   so one group's epilogue + next feature build overlaps the other group's MMAs.  mbarriers: full[g] (128 arrivals) ->
 //   MMA thread; tcgen05.commit -> done[g] -> workers.  All waits are bounded (an error flag instead of a hang).
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "eval.cuh"
 
@@ -22,16 +24,17 @@ namespace bg {
 
 namespace {
 
-constexpr int H = 128, KP = 208, KSTEPS = KP / 16, NSPLIT = 3;
+constexpr int H = 128, KP = 208, KSTEPS = KP / 16, NSPLIT = 2;
 constexpr int KCHUNK_BYTES = 16 * 128;                      // one 8-wide K chunk of all 128 rows: 16 N-groups x 128 B
 constexpr int SPLIT_BYTES = (KP / 8) * KCHUNK_BYTES;        // 26 chunks = 53,248 B
 constexpr int B_BYTES = NSPLIT * SPLIT_BYTES;               // 159,744 B
 constexpr int THREADS = 288;                                // warps 0-3 group 0, 4-7 group 1, warp 8 MMA issuer
 constexpr int TMEM_COLS = 512, A_COLS = 128, D_COLS = 128;  // per group: A at +0 (104 used), D at +128
 constexpr int NUM_SMS = 148;
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// instruction descriptor, kind::f16: D = F32 (bit 4), A = B = F16 (format fields 0), N = 128, M = 128
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
-__constant__ uint32_t c_off15_split[16][2];  // n/15 = hi + mid + lo in bf16: [n][0] = hi | mid << 16, [n][1] = lo
+__constant__ uint32_t c_off15_split[16][2];  // n/15 = hi + mid + lo in fp16: [n][0] = hi | mid << 16, [n][1] = lo
 
 // feature index -> source row of the packed weights for the K-padded operand (198..201: off/15 mid/lo terms, 202: bias)
 __device__ __forceinline__ int krow_source(int k) {
@@ -42,20 +45,18 @@ __device__ __forceinline__ int krow_source(int k) {
   return -1;
 }
 
-// B operand image (bf16, 3 splits, canonical no-swizzle K-major layout), built once per weight set
+// B operand image (fp16, 2 pieces, canonical no-swizzle K-major layout), built once per weight set
 __global__ void k_prepare_tc(const float* __restrict__ packed, uint8_t* __restrict__ img) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < KP * H; i += gridDim.x * blockDim.x) {
     const int k = i / H, n = i - k * H;
     const int src = krow_source(k);
     const float w = src < 0 ? 0.f : packed[src * H + n];
-    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-    const float r1 = w - __bfloat162float(hi);
-    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    // two fp16 pieces carry 22+ mantissa bits: w - (hi + lo) <= 2^-24 |w|, the rounding error of fp32 itself (|w| < 65504)
+    const __half hi = __float2half_rn(w);
+    const __half lo = __float2half_rn(w - __half2float(hi));
     const int off = (k >> 3) * KCHUNK_BYTES + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(img + 0 * SPLIT_BYTES + off) = hi;
-    *reinterpret_cast<__nv_bfloat16*>(img + 1 * SPLIT_BYTES + off) = mid;
-    *reinterpret_cast<__nv_bfloat16*>(img + 2 * SPLIT_BYTES + off) = lo;
+    *reinterpret_cast<__half*>(img + 0 * SPLIT_BYTES + off) = hi;
+    *reinterpret_cast<__half*>(img + 1 * SPLIT_BYTES + off) = lo;
   }
   // trailer: w2[128], b2
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= H; i += gridDim.x * blockDim.x)
@@ -113,12 +114,12 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
-// thermometer code of one checker count as two packed bf16x2 words: (c>=1, c>=2), (c>=3, (c-3)/2)
+// thermometer code of one checker count as two packed fp16x2 words: (c>=1, c>=2), (c>=3, (c-3)/2)
 __device__ __forceinline__ void point_words(uint32_t c, uint32_t& w0, uint32_t& w1) {
-  const uint32_t ONE = 0x3f80u;  // bf16 1.0
+  const uint32_t ONE = 0x3c00u;  // fp16 1.0
   w0 = (c >= 1 ? ONE : 0u) | (c >= 2 ? ONE << 16 : 0u);
   uint32_t ex = 0;
-  if (c > 3) ex = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn((float)(c - 3) * 0.5f));  // 0.5 .. 6.0: exact in bf16
+  if (c > 3) ex = (uint32_t)__half_as_ushort(__float2half_rn((float)(c - 3) * 0.5f));  // 0.5 .. 6.0: exact in fp16
   w1 = (c >= 3 ? ONE : 0u) | (ex << 16);
 }
 
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     for (int64_t t = (int64_t)blockIdx.x * 2 + g; t < n_tiles; t += tstride, ++it) {
       const int64_t i = t * 128 + row;
       const bool valid = i < N;
-      // ---- build this board's bf16 feature row, 8 TMEM columns (= one K16 step = four points) at a time ----
+      // ---- build this board's fp16 feature row, 8 TMEM columns (= one K16 step = four points) at a time ----
 #pragma unroll
       for (int wd = 0; wd < 12; ++wd) {  // board word wd: 4 points -> 16 features -> 8 columns
         uint32_t r[8];
@@ -205,11 +206,11 @@ __global__ void __launch_bounds__(THREADS, 1)
         tmem_st8(tA + wd * 8, r);
       }
       {
-        const uint32_t ONE = 0x3f80u;
+        const uint32_t ONE = 0x3c00u;
         const uint32_t w12 = bw[12];
         const uint32_t bar0 = w12 & 0xffu, bar1 = (w12 >> 8) & 0xffu, off0 = (w12 >> 16) & 15u, off1 = (w12 >> 24) & 15u;
-        const uint32_t hb0 = __bfloat16_as_ushort(__float2bfloat16_rn((float)bar0 * 0.5f));
-        const uint32_t hb1 = __bfloat16_as_ushort(__float2bfloat16_rn((float)bar1 * 0.5f));
+        const uint32_t hb0 = __half_as_ushort(__float2half_rn((float)bar0 * 0.5f));
+        const uint32_t hb1 = __half_as_ushort(__float2half_rn((float)bar1 * 0.5f));
         const uint32_t s0a = c_off15_split[off0][0], s0b = c_off15_split[off0][1];
         const uint32_t s1a = c_off15_split[off1][0], s1b = c_off15_split[off1][1];
         uint32_t r[8];
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(full);
       fetch(t + tstride);  // overlaps the MMAs
-      // ---- wait for the 39 MMAs of this tile, then the epilogue straight out of TMEM ----
+      // ---- wait for the 26 MMAs of this tile, then the epilogue straight out of TMEM ----
       if (!mbar_wait(done, it & 1u)) {
         if (lane == 0) atomicExch(err, 1);
         break;
@@ -240,14 +241,21 @@ __global__ void __launch_bounds__(THREADS, 1)
         tmem_ld32(tD + c0, z);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          // two sigmoids per reciprocal: 1/(1+a) = (1+b) * r, 1/(1+b) = (1+a) * r with r = 1/((1+a)(1+b));
-          // z is clamped at -40 (sigmoid < 5e-18) so the product stays finite
-          const float a1 = 1.0f + ex2_approx(fmaxf(__uint_as_float(z[c]), -40.f) * -1.4426950408889634f);
-          const float b1 = 1.0f + ex2_approx(fmaxf(__uint_as_float(z[c + 1]), -40.f) * -1.4426950408889634f);
-          const float r = rcp_approx(a1 * b1);
-          v = fmaf(sW2[c0 + c], b1 * r, v);
-          v = fmaf(sW2[c0 + c + 1], a1 * r, v);
+        for (int c = 0; c < 32; c += 4) {
+          // the epilogue is SFU-bound (ex2 and rcp share the 16-lane MUFU pipe), so FOUR sigmoids share one reciprocal:
+          // with p = (1+a)(1+b), q = (1+c)(1+d), r = 1/(pq):  1/(1+a) = (1+b) q r, ...  z is clamped at -20 (sigmoid < 2.1e-9, far
+          // below the 1e-5 contract) so that the product of four terms stays below 5.5e34
+          const float a1 = 1.0f + ex2_approx(fmaxf(__uint_as_float(z[c]), -20.f) * -1.4426950408889634f);
+          const float b1 = 1.0f + ex2_approx(fmaxf(__uint_as_float(z[c + 1]), -20.f) * -1.4426950408889634f);
+          const float c1 = 1.0f + ex2_approx(fmaxf(__uint_as_float(z[c + 2]), -20.f) * -1.4426950408889634f);
+          const float d1 = 1.0f + ex2_approx(fmaxf(__uint_as_float(z[c + 3]), -20.f) * -1.4426950408889634f);
+          const float p = a1 * b1, q = c1 * d1;
+          const float r = rcp_approx(p * q);
+          const float rp = r * q, rq = r * p;  // 1/p, 1/q
+          v = fmaf(sW2[c0 + c], b1 * rp, v);
+          v = fmaf(sW2[c0 + c + 1], a1 * rp, v);
+          v = fmaf(sW2[c0 + c + 2], d1 * rq, v);
+          v = fmaf(sW2[c0 + c + 3], c1 * rq, v);
         }
       }
       if (valid) out_v[i] = v + sW2[H];
@@ -314,10 +322,10 @@ int32_t eval_tc_launch(const EvalArgs& a, const uint8_t* img, int32_t* err_flag,
     uint32_t h[16][2];
     for (int n = 0; n < 16; ++n) {
       const float x = (float)((double)n / 15.0);
-      const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-      const float r1 = x - __bfloat162float(hi);
-      const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
-      const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+      const __half hi = __float2half_rn(x);
+      const float r1 = x - __half2float(hi);
+      const __half mid = __float2half_rn(r1);
+      const __half lo = __float2half_rn(r1 - __half2float(mid));
       unsigned short uh, um, ul;
       memcpy(&uh, &hi, 2);
       memcpy(&um, &mid, 2);
