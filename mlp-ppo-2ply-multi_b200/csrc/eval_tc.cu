@@ -268,10 +268,11 @@ __global__ void __launch_bounds__(THREADS, 1)
           const float p = a1 * b1, q = c1 * d1;
           const float r = rcp_approx(p * q);
           const float rp = r * q, rq = r * p;  // 1/p, 1/q
-          v = fmaf(sW2[c0 + c], b1 * rp, v);
-          v = fmaf(sW2[c0 + c + 1], a1 * rp, v);
-          v = fmaf(sW2[c0 + c + 2], d1 * rq, v);
-          v = fmaf(sW2[c0 + c + 3], c1 * rq, v);
+          const float4 w4 = *reinterpret_cast<const float4*>(&sW2[c0 + c]);  // one broadcast 16-byte read per four units
+          v = fmaf(w4.x, b1 * rp, v);
+          v = fmaf(w4.y, a1 * rp, v);
+          v = fmaf(w4.z, d1 * rq, v);
+          v = fmaf(w4.w, c1 * rq, v);
         }
       }
       if (valid) out_v[i] = v + sW2[H];
