@@ -274,8 +274,10 @@ def main():
     clocks = sampler.stop() if sampler else None
     total_ms = total_ms_fused
     unfused_ms_per_step = ev[0].elapsed_time(ev[3 * args.steps]) / args.steps
-    t_movegen = sum(ev[3 * k].elapsed_time(ev[3 * k + 1]) for k in range(args.steps)) / args.steps
-    t_eval = sum(ev[3 * k + 1].elapsed_time(ev[3 * k + 2]) for k in range(args.steps)) / args.steps
+    # median over the steps: robust against a single perturbed launch (the value itself is the mean over the fused timed region)
+    t_movegen = statistics.median(ev[3 * k].elapsed_time(ev[3 * k + 1]) for k in range(args.steps))
+    t_eval = statistics.median(ev[3 * k + 1].elapsed_time(ev[3 * k + 2]) for k in range(args.steps))
+    t_movegen_all = [round(ev[3 * k].elapsed_time(ev[3 * k + 1]), 2) for k in range(args.steps)]
     t = torch.tensor([total_ms, float(n_after)], dtype=torch.float64, device=dev)
     if dist is not None:
         tmax = t.clone()
@@ -338,7 +340,7 @@ def main():
                 "peak_source": peak_src, "ms_per_launch": kern[dom][0],
                 "note": "integer-issue bound, not bandwidth bound: algorithmic bytes are tiny (SURVEY.md 8(d)); ncu on the bulk tier: issue-active 76.6 %, "
                         "ALU pipe 72 %, 2,021 warp instructions per item, DRAM 4 % of peak (profiles/r01_ncu_v2_movegen_tiers_and_eval_tc.txt)",
-                "kernels_ms": {k: v[0] for k, v in kern.items()},
+                "kernels_ms": {k: v[0] for k, v in kern.items()}, "movegen_ms_per_step": t_movegen_all,
                 "eval_fp32_tflops_dense_equiv": n_after * FLOP_PER_AFTERSTATE / (t_eval * 1e-3) / 1e12}
     # the evaluator is a tensor-core kernel: 2 fp16 pieces x (2 * 208 * 128) FLOP per afterstate actually issued to tcgen05
     tc_flops = n_after * 2 * 2 * 208 * H
