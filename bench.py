@@ -352,7 +352,7 @@ def main():
     tach = tc_flops / (t_eval * 1e-3) / 1e12
     roofline_eval = {"bound": "tensor", "kernel": "bg::k_eval_tc (tcgen05, H=128)", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s",
                      "frac": tach / tpeak, "traffic": traffic.get("bg::k_eval_tc (tcgen05, H=128)"), "peak_source": tsrc, "ms_per_launch": t_eval,
-                     "note": "16-bit tensor FLOPs issued: 2 fp16 weight pieces x 2*208*128 per afterstate (fp32-exact layer 1); dense fp32-equivalent is 1/2.09 of this. The kernel is co-limited: issue slots ~55 %, MUFU (ex2/rcp of the 128 sigmoids per board) ~35 %, tensor pipe ~30 %"}
+                     "note": "16-bit tensor FLOPs issued: 2 fp16 weight pieces x 2*208*128 per afterstate (fp32-exact layer 1); dense fp32-equivalent is 1/2.09 of this. ncu (profiles/r01_ncu_eval_tc_final_fp16x2.txt): tensor pipe 60 %, MUFU (ex2/rcp of the 128 sigmoids per board) 47 %, issue slots 53 % -- latency/co-limited with two worker warps per scheduler"}
 
     del ib, ip, ir
     torch.cuda.empty_cache()
