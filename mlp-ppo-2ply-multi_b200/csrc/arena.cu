@@ -194,23 +194,44 @@ __device__ __forceinline__ bool finalize_episode(const ArenaDev& D, const ArenaC
   }
   const int64_t src = g * C.P;
   const int64_t d0 = (int64_t)(x0 % (unsigned long long)C.E);
-  for (int t = lane; t < n * 13; t += 32) {
-    const int e = t / 13, w = t - e * 13;
-    int64_t dst = d0 + e;
-    if (dst >= C.E) dst -= C.E;
-    D.fp_after[dst * 13 + w] = D.xb_after[(src + e) * 13 + w];
+  // The copy sits on the critical path of the ply (a finishing game's warp is the slowest of its CTA): the loads of several
+  // records are issued before the first store, so their latencies overlap instead of adding up (source and destination never
+  // alias, which the compiler cannot know).
+  for (int t0 = lane; t0 < n * 13; t0 += 32 * 4) {
+    uint32_t v[4];
+    int64_t di[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int t = t0 + 32 * k;
+      const int e = t / 13, w = t - e * 13;
+      int64_t dst = d0 + e;
+      if (dst >= C.E) dst -= C.E;
+      di[k] = dst * 13 + w;
+      v[k] = t < n * 13 ? D.xb_after[(src + e) * 13 + w] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (t0 + 32 * k < n * 13) D.fp_after[di[k]] = v[k];
   }
   for (int e = lane; e < n; e += 32) {
     int64_t dst = d0 + e;
     if (dst >= C.E) dst -= C.E;
-    D.fp_v[dst] = D.xb_v[src + e];
-    D.fp_vnext[dst] = D.xb_vnext[src + e];
-    D.fp_reward[dst] = D.xb_reward[src + e];
-    D.fp_meta[dst] = D.xb_meta[src + e];
-    D.fp_nmoves[dst] = D.xb_nmoves[src + e];
-    D.fp_action[dst] = D.xb_action[src + e];
-    D.fp_roll[2 * dst] = D.xb_roll[2 * (src + e)];
-    D.fp_roll[2 * dst + 1] = D.xb_roll[2 * (src + e) + 1];
+    const auto x_v = D.xb_v[src + e];
+    const auto x_vn = D.xb_vnext[src + e];
+    const auto x_r = D.xb_reward[src + e];
+    const auto x_m = D.xb_meta[src + e];
+    const auto x_nm = D.xb_nmoves[src + e];
+    const auto x_a = D.xb_action[src + e];
+    const auto x_r0 = D.xb_roll[2 * (src + e)];
+    const auto x_r1 = D.xb_roll[2 * (src + e) + 1];
+    D.fp_v[dst] = x_v;
+    D.fp_vnext[dst] = x_vn;
+    D.fp_reward[dst] = x_r;
+    D.fp_meta[dst] = x_m;
+    D.fp_nmoves[dst] = x_nm;
+    D.fp_action[dst] = x_a;
+    D.fp_roll[2 * dst] = x_r0;
+    D.fp_roll[2 * dst + 1] = x_r1;
   }
   __threadfence();
   return true;
