@@ -258,6 +258,8 @@ __global__ void __launch_bounds__(256) k_apply(ArenaDev D, ArenaCfg C, const uin
       win_type = (D.gflags[g] >> 6) & 3;
       winner = D.player[g];
     } else {
+      // every per-game scalar the ply needs is loaded here, before the first store of the iteration: the compiler cannot move a
+      // load above a store through another pointer, and each late load would cost a full memory latency on the critical path
       const int n_true = counts[g];
       const int n = n_true < C.move_cap ? n_true : C.move_cap;
       const long long off = offsets[g];
@@ -265,6 +267,10 @@ __global__ void __launch_bounds__(256) k_apply(ArenaDev D, ArenaCfg C, const uin
       int step = D.step[g];
       const int64_t serial = D.serial[g];
       int32_t dctr = D.dice_ctr[g];
+      const uint32_t gf_in = D.gflags[g];
+      const int e_in = D.nexp[g];
+      const uint8_t roll_in0 = D.roll[2 * g], roll_in1 = D.roll[2 * g + 1];
+      const float vcur_in = v_cur[g];
       if (n_true < 0 || (n > 0 && off < 0)) {  // generator overflow for this item: surface, stop the game
         if (lane == 0) {
           atomicAdd(&D.stats[BG_STAT_ERRORS], 1ull);
@@ -330,7 +336,7 @@ __global__ void __launch_bounds__(256) k_apply(ArenaDev D, ArenaCfg C, const uin
           done = true;
           meta |= 4u;
         } else {  // shaping rewards, once per player per game (backgammon_env.py:195-218, env_helper.py:167-242)
-          uint32_t gf = D.gflags[g];
+          uint32_t gf = gf_in;
           const bool closed = opp_bar > 0 && (made & home) == home;
           const uint32_t m5 = made & (made >> 1) & (made >> 2) & (made >> 3) & (made >> 4);
           bool prime = false;
@@ -372,26 +378,26 @@ __global__ void __launch_bounds__(256) k_apply(ArenaDev D, ArenaCfg C, const uin
           meta |= (uint32_t)d0 << 8 | (uint32_t)d1 << 12;
         }
         meta |= (uint32_t)next_flag << 1;
-        const int e = D.nexp[g];
+        const int e = e_in;
         const int64_t xi = g * C.P + e;
         if (lane < 13) {
           D.xb_after[xi * 13 + lane] = bw[lane];
           D.board[g * 13 + lane] = bw[lane];
         }
         if (lane == 0) {
-          D.xb_v[xi] = v_cur[g];
+          D.xb_v[xi] = vcur_in;
           D.xb_vnext[xi] = v_pool[off + a];
           D.xb_reward[xi] = reward;
           D.xb_meta[xi] = (uint8_t)(meta & 0xffu);
           D.xb_nmoves[xi] = (int16_t)n;
           D.xb_action[xi] = (int16_t)a;
-          D.xb_roll[2 * xi] = D.roll[2 * g];
-          D.xb_roll[2 * xi + 1] = D.roll[2 * g + 1];
+          D.xb_roll[2 * xi] = roll_in0;
+          D.xb_roll[2 * xi + 1] = roll_in1;
           D.nexp[g] = e + 1;
           step += 1;
           D.step[g] = step;
           if (done) {
-            D.gflags[g] = (uint8_t)((D.gflags[g] & 0x3fu) | ((uint32_t)win_type << 6) | (1u << (4 + mover)));
+            D.gflags[g] = (uint8_t)((gf_in & 0x3fu) | ((uint32_t)win_type << 6) | (1u << (4 + mover)));
           } else {
             D.roll[2 * g] = (uint8_t)((meta >> 8) & 15u);
             D.roll[2 * g + 1] = (uint8_t)((meta >> 12) & 15u);
