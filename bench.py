@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--selfplay-plies", type=int, default=200)
     ap.add_argument("--selfplay2-plies", type=int, default=20)
     ap.add_argument("--e2e-chunks", type=int, default=0, help="chunks of the host-to-host pipeline (0 = default)")
+    ap.add_argument("--e2e-streams", type=int, default=3)
     ap.add_argument("--td0-updates", type=int, default=50)
     ap.add_argument("--cpu-selfplay-games", type=int, default=16384)
     ap.add_argument("--no-selfplay", action="store_true")
@@ -297,8 +298,8 @@ def main():
     res = r = None
     del pool, values, pflags, ws
     torch.cuda.empty_cache()
-    n_chunks = args.e2e_chunks if args.e2e_chunks > 0 else (8 if B >= (1 << 20) else 2)
-    pipe = bg.HostPipeline(weights, items_per_chunk=(B + n_chunks - 1) // n_chunks, device=dev, item_cap=500)
+    n_chunks = args.e2e_chunks if args.e2e_chunks > 0 else (12 if B >= (1 << 20) else 3)
+    pipe = bg.HostPipeline(weights, items_per_chunk=(B + n_chunks - 1) // n_chunks, device=dev, item_cap=500, n_streams=args.e2e_streams)
 
     def e2e_step():
         pipe.run(h_b, h_p, h_r, h_act, h_cnt, temperature=0.0)  # chunked: copies of neighbouring chunks overlap the kernels
@@ -577,7 +578,7 @@ def main():
                        "positions_per_gpu": int(boards.shape[0]), "items_per_gpu": int(B), "afterstates_per_gpu_step": int(n_after), "hidden": H,
                        "l2": "inputs+outputs per step (>25 GB) far exceed the 126 MB L2", "parallelism": f"{world} x independent shards"},
             "e2e": {"value": e2e_value, "unit": "afterstates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "what": f"bg.HostPipeline.run: pinned host boards/players/rolls -> {n_chunks} chunks on 2 streams (H2D, bg_movegen, bg_eval, bg_select(greedy), D2H) -> host actions + counts",
+                    "what": f"bg.HostPipeline.run: pinned host boards/players/rolls -> {n_chunks} chunks on {args.e2e_streams} streams (H2D, bg_movegen_eval, bg_select(greedy), D2H) -> host actions + counts",
                     "afterstates_check": e2e_check},
             "gpu_launches": 7 * args.steps, "gpu_launches_note": f"timed region, per step (bg_movegen_eval): k_movegen tiers 128 / 256 / 512 / 2048 / 4096 + k_eval_tc twice (bulk-tier rows on the side stream, tail-tier rows after); unfused ms_per_step {unfused_ms_per_step:.2f}; the e2e region launches {n_e2e_kernels} per step (the same seven + k_select, per chunk)",
             "roofline": roofline, "roofline_eval": roofline_eval, "cpu_baseline": cpu, "clocks": clocks, "selfplay_1ply": selfplay, "selfplay_2ply": selfplay2,

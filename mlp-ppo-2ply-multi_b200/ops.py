@@ -246,18 +246,20 @@ def two_ply(cand_boards: torch.Tensor, mover: torch.Tensor, S: torch.Tensor, wei
 class HostPipeline:
     """The per-decision hot path for HOST-resident batches: pinned (boards, players, rolls) in, (action, count) per item out.
 
-    The batch is cut into chunks that alternate between two CUDA streams, so chunk k+1's host->device copy and chunk k-1's
-    device->host copy overlap chunk k's kernels (bg_movegen -> bg_eval -> bg_select); all device buffers are allocated once.
+    The batch is cut into chunks that rotate over n_streams CUDA streams (three measured best: two cover the copies, the third lets one
+    chunk's tail tiers and selection overlap the next chunk's bulk tier), so chunk k+1's host->device copy and chunk k-1's device->host
+    copy overlap chunk k's kernels (bg_movegen_eval -> bg_select); all device buffers are allocated once.
     This is the call a CPU-side caller of get_all_possible_moves + generate_all_board_features + policy_network.forward +
     argmax/sample (reference worker.py:101-143) makes when its positions live in host memory."""
 
-    def __init__(self, weights: PreparedWeights, items_per_chunk: int = 1 << 21, device=None, item_cap: int = 500, rows_per_item: int = 26):
+    def __init__(self, weights: PreparedWeights, items_per_chunk: int = 1 << 21, device=None, item_cap: int = 500, rows_per_item: int = 26,
+                 n_streams: int = 3):
         self.dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.weights, self.item_cap, self.Bc = weights, int(item_cap), int(items_per_chunk)
-        self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(2)]
+        self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(max(2, int(n_streams)))]
         cap = self.Bc * rows_per_item + (1 << 18)
         self.buf = []
-        for _ in range(2):
+        for _ in self.streams:
             self.buf.append(dict(
                 b=torch.empty((self.Bc, BOARD_BYTES), dtype=torch.int8, device=self.dev), p=torch.empty(self.Bc, dtype=torch.uint8, device=self.dev),
                 r=torch.empty((self.Bc, 2), dtype=torch.uint8, device=self.dev), pool=torch.empty((cap, BOARD_BYTES), dtype=torch.int8, device=self.dev),
@@ -275,7 +277,7 @@ class HostPipeline:
         for k, lo in enumerate(range(0, B, self.Bc)):
             hi = min(B, lo + self.Bc)
             n = hi - lo
-            d, s = self.buf[k & 1], self.streams[k & 1]
+            d, s = self.buf[k % len(self.streams)], self.streams[k % len(self.streams)]
             with torch.cuda.stream(s):
                 d["b"][:n].copy_(h_boards[lo:hi], non_blocking=True)
                 d["p"][:n].copy_(h_players[lo:hi], non_blocking=True)
