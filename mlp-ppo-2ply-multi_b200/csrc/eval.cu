@@ -305,10 +305,10 @@ static int64_t generic_table_bytes(int32_t H) { return ((int64_t)(200 * H + 1) *
 static int64_t table128_bytes() { return (eval128_table_floats() * 4 + 255) / 256 * 256; }
 
 int64_t prepared_weights_bytes(int32_t H) {
-  return generic_table_bytes(H) + (H == 128 ? table128_bytes() + eval_tc_image_bytes() : 0);
+  return generic_table_bytes(H) + (H == 128 ? table128_bytes() : 0) + (H <= 128 ? eval_tc_image_bytes() : 0);
 }
 
-// which H == 128 evaluator: BG_EVAL_PATH = "tc" (tcgen05 for batches >= 32768 rows, default), "ffma" (always eval128)
+// which evaluator for H <= 128: BG_EVAL_PATH = "tc" (tcgen05 for batches >= 32768 rows, default), "ffma" (always the CUDA-core kernels)
 static int tc_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -338,8 +338,9 @@ int32_t prepare_weights_launch(const float* packed, int32_t H, float* prepared, 
   if (H == 128) {
     int32_t rc = eval128_prepare(packed, prepared + generic_table_bytes(H) / 4, stream);
     if (rc != BG_OK) return rc;
-    return eval_tc_prepare(packed, reinterpret_cast<uint8_t*>(prepared) + generic_table_bytes(H) + table128_bytes(), stream);
+    return eval_tc_prepare(packed, H, reinterpret_cast<uint8_t*>(prepared) + generic_table_bytes(H) + table128_bytes(), stream);
   }
+  if (H < 128) return eval_tc_prepare(packed, H, reinterpret_cast<uint8_t*>(prepared) + generic_table_bytes(H), stream);
   return BG_OK;
 }
 
@@ -353,7 +354,8 @@ int32_t eval_launch(const EvalArgs& a, cudaStream_t stream) {
     return BG_ERR_ARG;
   }
   if ((a.N_dev ? a.max_N : a.N) <= 0) return BG_OK;
-  if (a.H == 128) {
+  if (a.H <= 128) {
+    // large batches of any net with <= 128 hidden units go to the tensor-core kernel (smaller nets zero-padded to 128 units)
     const int64_t bound = a.N_dev ? a.max_N : a.N;
     if (tc_mode() == 1 && a.flags && bound >= 32768) {
       if (!g_tc_err) {
@@ -361,9 +363,10 @@ int32_t eval_launch(const EvalArgs& a, cudaStream_t stream) {
         if (e == cudaSuccess) e = cudaMemset(g_tc_err, 0, 4);
         if (e != cudaSuccess) return check_cuda(e, "cudaMalloc(tc status)");
       }
-      return eval_tc_launch(a, reinterpret_cast<const uint8_t*>(a.prepared) + generic_table_bytes(128) + table128_bytes(), g_tc_err, stream);
+      const int64_t img_off = generic_table_bytes(a.H) + (a.H == 128 ? table128_bytes() : 0);
+      return eval_tc_launch(a, reinterpret_cast<const uint8_t*>(a.prepared) + img_off, g_tc_err, stream);
     }
-    return eval128_launch(a, a.prepared + generic_table_bytes(128) / 4, stream);
+    if (a.H == 128) return eval128_launch(a, a.prepared + generic_table_bytes(128) / 4, stream);
   }
   int32_t rc = init_constants();
   if (rc != BG_OK) return rc;

@@ -46,13 +46,14 @@ __device__ __forceinline__ int krow_source(int k) {
 }
 
 // B operand image (fp16, 2 pieces, canonical no-swizzle K-major layout), built once per weight set
-__global__ void k_prepare_tc(const float* __restrict__ packed, uint8_t* __restrict__ img) {
+// Hs: hidden size of the packed source weights (<= 128); units Hs..127 are zero padding (zero weights and zero w2: they add nothing)
+__global__ void k_prepare_tc(const float* __restrict__ packed, int Hs, uint8_t* __restrict__ img) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < KP * H; i += gridDim.x * blockDim.x) {
     const int k = i / H, n = i - k * H;
     const int src = krow_source(k);
     // the operand is W scaled by -log2(e): the accumulator then holds y = -z log2(e) and the epilogue's sigmoid is 1 / (1 + 2^y) with no
     // multiply per unit
-    const float w = src < 0 ? 0.f : packed[src * H + n] * -1.4426950408889634f;
+    const float w = (src < 0 || n >= Hs) ? 0.f : packed[src * Hs + n] * -1.4426950408889634f;
     // two fp16 pieces carry 22+ mantissa bits: w - (hi + lo) <= 2^-24 |w|, the rounding error of fp32 itself (|w| < 65504)
     const __half hi = __float2half_rn(w);
     const __half lo = __float2half_rn(w - __half2float(hi));
@@ -60,9 +61,9 @@ __global__ void k_prepare_tc(const float* __restrict__ packed, uint8_t* __restri
     *reinterpret_cast<__half*>(img + 0 * SPLIT_BYTES + off) = hi;
     *reinterpret_cast<__half*>(img + 1 * SPLIT_BYTES + off) = lo;
   }
-  // trailer: w2[128], b2
+  // trailer: w2[128] (zero for the padding units), b2
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= H; i += gridDim.x * blockDim.x)
-    reinterpret_cast<float*>(img + B_BYTES)[i] = packed[199 * H + i];
+    reinterpret_cast<float*>(img + B_BYTES)[i] = i == H ? packed[200 * Hs] : i < Hs ? packed[199 * Hs + i] : 0.f;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -325,8 +326,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 
 int64_t eval_tc_image_bytes() { return ((int64_t)B_BYTES + (H + 1) * 4 + 255) / 256 * 256; }
 
-int32_t eval_tc_prepare(const float* packed, uint8_t* img, cudaStream_t stream) {
-  k_prepare_tc<<<104, 256, 0, stream>>>(packed, img);
+int32_t eval_tc_prepare(const float* packed, int32_t H_src, uint8_t* img, cudaStream_t stream) {
+  k_prepare_tc<<<104, 256, 0, stream>>>(packed, H_src, img);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return check_cuda(e, "k_prepare_tc launch");
   return BG_OK;

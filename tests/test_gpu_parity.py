@@ -298,7 +298,7 @@ def test_two_ply_reference_setting_and_best_reply(bg, oracle, golden):
 
 @pytest.mark.parametrize("which", ["packed", "packed_init0"])
 def test_eval_tensor_core_and_ffma_kernels_agree_with_oracle(bg, oracle, golden, which):
-    """H = 128 has two evaluators: tcgen05/TMEM (3x bf16-split weights, batches >= 32768 rows) and FFMA gather (smaller
+    """H = 128 has two evaluators: tcgen05/TMEM (two fp16 weight pieces, batches >= 32768 rows) and FFMA gather (smaller
     batches).  Both must meet the 1e-5 contract against the double-accumulated oracle, including ragged tails and stacks > 6."""
     g = golden("values")
     w = bg.prepare_weights(dev(g[which]), 128)
@@ -324,6 +324,21 @@ def test_eval_tensor_core_and_ffma_kernels_agree_with_oracle(bg, oracle, golden,
     v_ff = np.concatenate([bg.evaluate(dev(o_b[i:i + 20000]), dev(flags[i:i + 20000]), w).cpu().numpy() for i in range(0, n, 20000)])
     assert np.abs(v_ff - ref).max() < 1e-5
     assert np.abs(v_ff - v_tc).max() < 2e-6
+
+
+@pytest.mark.parametrize("H", [32, 64, 96])
+def test_eval_small_nets_on_the_tensor_core_path(bg, oracle, H):
+    """nets with fewer than 128 hidden units run on the same tcgen05 kernel, zero-padded to 128 units, for batches >= 32768 rows; the
+    CUDA-core kernel serves smaller batches.  Both against the oracle (1e-5) and against each other."""
+    rng = np.random.default_rng(1000 + H)
+    packed = (rng.standard_normal(200 * H + 1) * 0.5).astype(np.float32)
+    boards, players = oracle.random_positions(40000, seed=H)
+    w = bg.prepare_weights(dev(packed), H)
+    ref = oracle.value(packed, H, boards, players)
+    v_tc = bg.evaluate(dev(boards), dev(players), w).cpu().numpy()  # 40,000 rows: tensor-core path
+    assert bg._lib.lib().bg_eval_tc_status() == 0
+    v_ff = np.concatenate([bg.evaluate(dev(boards[i:i + 20000]), dev(players[i:i + 20000]), w).cpu().numpy() for i in (0, 20000)])
+    assert np.abs(v_tc - ref).max() < 1e-5 and np.abs(v_ff - ref).max() < 1e-5 and np.abs(v_tc - v_ff).max() < 4e-6
 
 
 def test_host_pipeline_equals_resident_path(bg, oracle):
