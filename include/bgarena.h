@@ -125,8 +125,8 @@ int32_t bg_movegen_eval(const int8_t* boards /*[B,52]*/, const uint8_t* players 
                         void* workspace, int64_t workspace_bytes, const float* prepared, int32_t H, float* out_v /*[pool_cap]*/,
                         void* stream);
 
-/* Diagnostic for the tcgen05 evaluator (H = 128, batches >= 32768 rows with per-row flags; set BG_EVAL_PATH=ffma to force the
- * FFMA kernel): synchronises and returns 0, or non-zero if one of its bounded mbarrier waits ever timed out. */
+/* Diagnostic for the tcgen05 evaluator (batches >= 32768 rows with per-row flags, any H: 128 hidden units per pass, smaller nets
+ * zero-padded, wider nets in two passes; set BG_EVAL_PATH=ffma to force the CUDA-core kernels): synchronises and returns 0, or non-zero if one of its bounded mbarrier waits ever timed out. */
 int32_t bg_eval_tc_status(void);
 
 /*

@@ -305,7 +305,7 @@ static int64_t generic_table_bytes(int32_t H) { return ((int64_t)(200 * H + 1) *
 static int64_t table128_bytes() { return (eval128_table_floats() * 4 + 255) / 256 * 256; }
 
 int64_t prepared_weights_bytes(int32_t H) {
-  return generic_table_bytes(H) + (H == 128 ? table128_bytes() : 0) + (H <= 128 ? eval_tc_image_bytes() : 0);
+  return generic_table_bytes(H) + (H == 128 ? table128_bytes() : 0) + (H <= 128 ? 1 : 2) * eval_tc_image_bytes();
 }
 
 // which evaluator for H <= 128: BG_EVAL_PATH = "tc" (tcgen05 for batches >= 32768 rows, default), "ffma" (always the CUDA-core kernels)
@@ -338,10 +338,12 @@ int32_t prepare_weights_launch(const float* packed, int32_t H, float* prepared, 
   if (H == 128) {
     int32_t rc = eval128_prepare(packed, prepared + generic_table_bytes(H) / 4, stream);
     if (rc != BG_OK) return rc;
-    return eval_tc_prepare(packed, H, reinterpret_cast<uint8_t*>(prepared) + generic_table_bytes(H) + table128_bytes(), stream);
+    return eval_tc_prepare(packed, H, 0, reinterpret_cast<uint8_t*>(prepared) + generic_table_bytes(H) + table128_bytes(), stream);
   }
-  if (H < 128) return eval_tc_prepare(packed, H, reinterpret_cast<uint8_t*>(prepared) + generic_table_bytes(H), stream);
-  return BG_OK;
+  uint8_t* img = reinterpret_cast<uint8_t*>(prepared) + generic_table_bytes(H);
+  int32_t rc = eval_tc_prepare(packed, H, 0, img, stream);
+  if (rc == BG_OK && H > 128) rc = eval_tc_prepare(packed, H, 128, img + eval_tc_image_bytes(), stream);
+  return rc;
 }
 
 int32_t eval_launch(const EvalArgs& a, cudaStream_t stream) {
@@ -354,8 +356,8 @@ int32_t eval_launch(const EvalArgs& a, cudaStream_t stream) {
     return BG_ERR_ARG;
   }
   if ((a.N_dev ? a.max_N : a.N) <= 0) return BG_OK;
-  if (a.H <= 128) {
-    // large batches of any net with <= 128 hidden units go to the tensor-core kernel (smaller nets zero-padded to 128 units)
+  {
+    // large batches go to the tensor-core kernel, 128 hidden units per pass: smaller nets zero-padded, wider nets in two passes
     const int64_t bound = a.N_dev ? a.max_N : a.N;
     if (tc_mode() == 1 && a.flags && bound >= 32768) {
       if (!g_tc_err) {
@@ -363,8 +365,10 @@ int32_t eval_launch(const EvalArgs& a, cudaStream_t stream) {
         if (e == cudaSuccess) e = cudaMemset(g_tc_err, 0, 4);
         if (e != cudaSuccess) return check_cuda(e, "cudaMalloc(tc status)");
       }
-      const int64_t img_off = generic_table_bytes(a.H) + (a.H == 128 ? table128_bytes() : 0);
-      return eval_tc_launch(a, reinterpret_cast<const uint8_t*>(a.prepared) + img_off, g_tc_err, stream);
+      const uint8_t* img = reinterpret_cast<const uint8_t*>(a.prepared) + generic_table_bytes(a.H) + (a.H == 128 ? table128_bytes() : 0);
+      int32_t rc = eval_tc_launch(a, img, g_tc_err, stream, 0);
+      if (rc == BG_OK && a.H > 128) rc = eval_tc_launch(a, img + eval_tc_image_bytes(), g_tc_err, stream, 1);
+      return rc;
     }
     if (a.H == 128) return eval128_launch(a, a.prepared + generic_table_bytes(128) / 4, stream);
   }

@@ -26,11 +26,12 @@ int32_t eval_launch(const EvalArgs& a, cudaStream_t stream);
 int64_t eval128_table_floats();
 int32_t eval128_prepare(const float* packed, float* t128, cudaStream_t stream);
 int32_t eval128_launch(const EvalArgs& a, const float* t128, cudaStream_t stream);
-// H <= 128 tensor-core (tcgen05 / TMEM) kernel (eval_tc.cu; smaller nets are zero-padded to 128 hidden units); its operand image follows the
-// generic (and, for H == 128, the eval128) table
+// tensor-core (tcgen05 / TMEM) kernel (eval_tc.cu): 128 hidden units per pass.  Smaller nets are zero-padded to 128 units; wider nets
+// (H <= 256) take two passes over the boards, the second one accumulating the other half of the units into out_v.  The operand
+// image(s) follow the generic (and, for H == 128, the eval128) table
 int64_t eval_tc_image_bytes();
-int32_t eval_tc_prepare(const float* packed, int32_t H_src, uint8_t* img, cudaStream_t stream);
-int32_t eval_tc_launch(const EvalArgs& a, const uint8_t* img, int32_t* err_flag, cudaStream_t stream);
+int32_t eval_tc_prepare(const float* packed, int32_t H_src, int32_t unit0, uint8_t* img, cudaStream_t stream);
+int32_t eval_tc_launch(const EvalArgs& a, const uint8_t* img, int32_t* err_flag, cudaStream_t stream, int accumulate = 0);
 int32_t eval_tc_status();  // synchronising: 0 ok, != 0 a bounded mbarrier wait timed out in k_eval_tc
 // Move generation + evaluation of the whole afterstate pool with the tail tiers overlapped: the rows written by the move generator's
 // bulk tier are evaluated on `side->stream` as soon as that tier is done, while `stream` runs the tail tiers (a few very wide doubles

@@ -46,14 +46,15 @@ __device__ __forceinline__ int krow_source(int k) {
 }
 
 // B operand image (fp16, 2 pieces, canonical no-swizzle K-major layout), built once per weight set
-// Hs: hidden size of the packed source weights (<= 128); units Hs..127 are zero padding (zero weights and zero w2: they add nothing)
-__global__ void k_prepare_tc(const float* __restrict__ packed, int Hs, uint8_t* __restrict__ img) {
+// Hs: hidden size of the packed source weights; the image holds its units [u0, u0 + 128), units >= Hs are zero padding (zero weights and
+// zero w2: they add nothing).  b2 goes into the image of the first 128 units only.
+__global__ void k_prepare_tc(const float* __restrict__ packed, int Hs, int u0, uint8_t* __restrict__ img) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < KP * H; i += gridDim.x * blockDim.x) {
     const int k = i / H, n = i - k * H;
     const int src = krow_source(k);
     // the operand is W scaled by -log2(e): the accumulator then holds y = -z log2(e) and the epilogue's sigmoid is 1 / (1 + 2^y) with no
     // multiply per unit
-    const float w = (src < 0 || n >= Hs) ? 0.f : packed[src * Hs + n] * -1.4426950408889634f;
+    const float w = (src < 0 || u0 + n >= Hs) ? 0.f : packed[src * Hs + u0 + n] * -1.4426950408889634f;
     // two fp16 pieces carry 22+ mantissa bits: w - (hi + lo) <= 2^-24 |w|, the rounding error of fp32 itself (|w| < 65504)
     const __half hi = __float2half_rn(w);
     const __half lo = __float2half_rn(w - __half2float(hi));
@@ -63,7 +64,7 @@ __global__ void k_prepare_tc(const float* __restrict__ packed, int Hs, uint8_t* 
   }
   // trailer: w2[128] (zero for the padding units), b2
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= H; i += gridDim.x * blockDim.x)
-    reinterpret_cast<float*>(img + B_BYTES)[i] = i == H ? packed[200 * Hs] : i < Hs ? packed[199 * Hs + i] : 0.f;
+    reinterpret_cast<float*>(img + B_BYTES)[i] = i == H ? (u0 == 0 ? packed[200 * Hs] : 0.f) : u0 + i < Hs ? packed[199 * Hs + u0 + i] : 0.f;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,7 +130,7 @@ __device__ __forceinline__ void point_words(uint32_t c, uint32_t& w0, uint32_t& 
 __global__ void __launch_bounds__(THREADS, 1)
     k_eval_tc(const int8_t* __restrict__ boards, const uint8_t* __restrict__ flags, int64_t N_host, const int64_t* __restrict__ N_dev,
               int64_t max_N, const uint8_t* __restrict__ img, float* __restrict__ out_v, int32_t* __restrict__ err,
-              const int64_t* __restrict__ start_dev) {
+              const int64_t* __restrict__ start_dev, int accumulate) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sB = smem;                                             // B operand image
   float* sW2 = reinterpret_cast<float*>(smem + B_BYTES);          // w2[128], b2
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(THREADS, 1)
           v = fmaf(w4.w, c1 * rq, v);
         }
       }
-      if (valid) out_v[i] = v + sW2[H];
+      if (valid) out_v[i] = (accumulate ? out_v[i] : 0.f) + (v + sW2[H]);  // accumulate: second half of the units of a wider net
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // D / A of this group are free again after our loads
     }
   } else if (lane == 0) {
@@ -326,14 +327,14 @@ __global__ void __launch_bounds__(THREADS, 1)
 
 int64_t eval_tc_image_bytes() { return ((int64_t)B_BYTES + (H + 1) * 4 + 255) / 256 * 256; }
 
-int32_t eval_tc_prepare(const float* packed, int32_t H_src, uint8_t* img, cudaStream_t stream) {
-  k_prepare_tc<<<104, 256, 0, stream>>>(packed, H_src, img);
+int32_t eval_tc_prepare(const float* packed, int32_t H_src, int32_t unit0, uint8_t* img, cudaStream_t stream) {
+  k_prepare_tc<<<104, 256, 0, stream>>>(packed, H_src, unit0, img);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return check_cuda(e, "k_prepare_tc launch");
   return BG_OK;
 }
 
-int32_t eval_tc_launch(const EvalArgs& a, const uint8_t* img, int32_t* err_flag, cudaStream_t stream) {
+int32_t eval_tc_launch(const EvalArgs& a, const uint8_t* img, int32_t* err_flag, cudaStream_t stream, int accumulate) {
   static bool init = false;
   constexpr size_t smem = (size_t)B_BYTES + 1024 + 128;
   if (!init) {
@@ -361,7 +362,7 @@ int32_t eval_tc_launch(const EvalArgs& a, const uint8_t* img, int32_t* err_flag,
   int64_t want = (bound + 255) / 256;
   if (want < 1) want = 1;
   const int grid = (int)(want < NUM_SMS ? want : NUM_SMS);
-  k_eval_tc<<<grid, THREADS, smem, stream>>>(a.boards, a.flags, a.N, a.N_dev, a.max_N, img, a.out_v, err_flag, a.start_dev);
+  k_eval_tc<<<grid, THREADS, smem, stream>>>(a.boards, a.flags, a.N, a.N_dev, a.max_N, img, a.out_v, err_flag, a.start_dev, accumulate);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return check_cuda(e, "k_eval_tc launch");
   return BG_OK;
