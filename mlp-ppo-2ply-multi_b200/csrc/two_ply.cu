@@ -61,10 +61,12 @@ __global__ void __launch_bounds__(256) k_reduce(const float* __restrict__ v, con
     double W = 0.0;
     long long nrep = 0;
     bool bad = false;
+    // the 21 (count, offset) pairs of this candidate are fetched by 21 lanes at once: one memory latency instead of 21 dependent ones
+    const int my_n = lane < 21 ? counts[c * 21 + lane] : 0;
+    const long long my_off = lane < 21 ? offsets[c * 21 + lane] : 0;
     for (int r = 0; r < 21; ++r) {
-      const int64_t t = c * 21 + r;
-      const int n = counts[t];
-      const long long off = offsets[t];
+      const int n = __shfl_sync(BG_FULL, my_n, r);
+      const long long off = __shfl_sync(BG_FULL, my_off, r);
       if (n < 0 || (n > 0 && off < 0)) {
         bad = true;
         continue;
