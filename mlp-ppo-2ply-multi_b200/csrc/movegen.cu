@@ -23,6 +23,7 @@
 #include "movegen.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace bg {
 
@@ -654,7 +655,7 @@ int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* const (&
   // tail tiers: the items that overflowed 128 / 256 / 512 / 2048 nodes in some ply.  The 256 tier (twice the resident warps of the 512
   // tier) pays when the overflow lists are long; for small batches (one self-play ply) every extra tier is one more kernel whose
   // slowest item sits on the critical path, so the chain goes 128 -> 512 directly.
-  const bool use256 = B >= (1 << 22);
+  const bool use256 = B >= (1 << 20);
   const int c2 = tier2_ctas > 0 && tier2_ctas < T2_CTAS_PER_SM ? tier2_ctas : T2_CTAS_PER_SM;
   if (use256 && (rc = launch_tail_tier<T2_CAP, false, MOVES, T2_WARPS, T2_CTAS_PER_SM>(P, 0, 1, c2, ctr, ovf, ovf_n, stream)) != BG_OK) return rc;
   if ((rc = launch_tail_tier<T3_CAP, false, MOVES, T3_WARPS, T3_CTAS_PER_SM>(P, use256 ? 1 : 0, 2, T3_CTAS_PER_SM, ctr, ovf, ovf_n, stream)) != BG_OK)
