@@ -79,9 +79,9 @@ def all_gather_episodes(batch, max_episodes: int, max_experiences: int, group=No
 
     def field(pos, rows, cols, dt):  # [world, rows, cols] view of one field of every rank (one strided copy, freshly aligned)
         nb = rows * cols * torch.empty(0, dtype=dt).element_size()
-        return allb[:, pos:pos + nb].contiguous().view(dt).reshape(world, rows, cols), pos + nb
+        return allb[:, pos:pos + nb].clone(memory_format=torch.contiguous_format).view(dt).reshape(world, rows, cols), pos + nb  # clone: fresh, aligned, dense storage
 
-    hdr, pos = allb[:, :16].contiguous().view(torch.int64).reshape(world, 2), 16
+    hdr, pos = allb[:, :16].clone(memory_format=torch.contiguous_format).view(torch.int64).reshape(world, 2), 16
     f = {}
     for name, dt, cols in _EP_FIELDS:
         f[name], pos = field(pos, max_experiences, cols, dt)

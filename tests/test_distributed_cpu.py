@@ -188,3 +188,24 @@ def test_reference_checkpoints_load_unchanged(golden):
         assert bg.pack_weights(net.state_dict()).numel() == 200 * net.hidden_size + 1
     sd = torch.load([f for f in files if f.endswith("backgammon_256_standard_episode_2100000.pth")][0], map_location="cpu")
     assert np.array_equal(bg.pack_weights(sd).numpy(), golden("values")["packed"])
+
+
+def test_all_gather_episodes_single_process():
+    """world size 1 (no process group): both layouts return the local batch unchanged"""
+    from mlp_ppo_2ply_multi_b200 import distributed as bgd
+    from mlp_ppo_2ply_multi_b200.episode import EpisodeBatch
+
+    lens = [3, 1, 4]
+    E, N = len(lens), sum(lens)
+    g = torch.Generator().manual_seed(1)
+    eb = EpisodeBatch(E, N, torch.randint(0, 6, (N + 5, 52), generator=g, dtype=torch.int8), torch.randint(0, 32, (N + 5,), generator=g, dtype=torch.uint8),
+                      torch.rand(N + 5, generator=g), torch.rand(N + 5, generator=g), torch.rand(N + 5, generator=g),
+                      torch.randint(1, 50, (N + 5,), generator=g, dtype=torch.int16), torch.randint(0, 50, (N + 5,), generator=g, dtype=torch.int16),
+                      torch.randint(1, 7, (N + 5, 2), generator=g, dtype=torch.uint8), torch.tensor([0] + list(np.cumsum(lens)) + [0, 0], dtype=torch.int64),
+                      torch.full((E + 2, 12), 7, dtype=torch.int32))
+    m = bgd.all_gather_episodes(eb, 4, 12)
+    assert (m.n_episodes, m.n_experiences, m.ep_offsets.tolist()) == (3, 8, [0, 3, 4, 8])
+    assert torch.equal(m.after_boards, eb.after_boards[:N]) and torch.equal(m.reward, eb.reward[:N]) and torch.equal(m.roll, eb.roll[:N])
+    p = bgd.all_gather_episodes(eb, 4, 12, compact=False)
+    assert p.n_episodes == 4 and p.ep_len.tolist() == [3, 1, 4, 0] and p.ep_offsets[:4].tolist() == [0, 3, 4, 8]
+    assert torch.equal(p.after_boards[:N], eb.after_boards[:N]) and p.episode_lengths().tolist() == [3, 1, 4, 0]
