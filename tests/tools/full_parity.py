@@ -3,7 +3,7 @@
 Every item's legal-afterstate list from bg_movegen is compared with the CPU oracle -- count, content and ORDER -- through a 64-bit
 order-sensitive checksum per item; features are checked bit-exactly through bg_encode on a strided sample of the afterstates and
 values through bg_eval to 1e-5.  Runs on the GPU box in chunks of 131,072 positions (the oracle side is the slow part).
-    python scripts/full_parity.py [n_positions [positions_per_call]] > profiles/r01_full_parity.txt"""
+    python tests/tools/full_parity.py [n_positions [positions_per_call]] > profiles/r01_full_parity.txt"""
 import os
 import sys
 import time
@@ -11,7 +11,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import mlp_ppo_2ply_multi_b200 as bg  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402

@@ -5,11 +5,11 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import mlp_ppo_2ply_multi_b200 as bg
 from oracle import pyoracle as po
 
-g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "learner.npz"))
+g = np.load(os.path.join(os.path.dirname(__file__), "..", "golden", "learner.npz"))
 dev = "cuda:0"
 n_ep = 24
 off = g["ep_offsets"][:n_ep + 1]

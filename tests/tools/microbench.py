@@ -1,6 +1,6 @@
 """Developer micro-benchmark (NOT bench.py): times bg_movegen / bg_eval on oracle-generated positions."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import mlp_ppo_2ply_multi_b200 as bg
 from oracle import pyoracle as po

@@ -1,6 +1,6 @@
 """Developer check of the tcgen05 evaluator: values vs the double-accumulated oracle and vs the FFMA kernel, timing."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import mlp_ppo_2ply_multi_b200 as bg
 from oracle import pyoracle as po
