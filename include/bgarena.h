@@ -125,6 +125,26 @@ int32_t bg_movegen_eval(const int8_t* boards /*[B,52]*/, const uint8_t* players 
                         void* workspace, int64_t workspace_bytes, const float* prepared, int32_t H, float* out_v /*[pool_cap]*/,
                         void* stream);
 
+/*
+ * Position-major forms of bg_movegen / bg_movegen_eval: EVERY one of the 21 unordered rolls of each of P positions, i.e. the batch
+ * shape of BASELINE config 2 (positions x 21 rolls) and of the 2-ply lookahead (compute_weighted_opponent_response iterates
+ * DICE_ROLLS for each candidate board, src/multi/two_ply.py:93-150).  Item index = position * 21 + r with r indexing DICE_ROLLS
+ * (src/multi/two_ply.py:10-32: (1,1), (1,2), ... (1,6), (2,2), ... (6,6)); out_offsets / out_count have 21 * P entries; results,
+ * order and pool layout rules are those of bg_movegen (get_all_possible_moves per item).  One warp expands a whole position
+ * (csrc/movegen21.cu): the inputs are 1/21 of the replicated item form and the first two plies are shared by all rolls.
+ * Workspace: bg_movegen_workspace_bytes(21 * P).  out_submoves != NULL or item_cap < 320 routes through the per-item kernels.
+ */
+int32_t bg_movegen_all_rolls(const int8_t* boards /*[P,52]*/, const uint8_t* players /*[P]*/, int64_t P, int32_t item_cap,
+                             int64_t pool_cap, int8_t* out_boards /*[pool_cap,52]*/, uint8_t* out_submoves /*[pool_cap,4,3] or NULL*/,
+                             int32_t* out_owner /*[pool_cap] or NULL*/, uint8_t* out_flags /*[pool_cap] or NULL*/,
+                             int64_t* out_offsets /*[21*P]*/, int32_t* out_count /*[21*P]*/, int64_t* out_total /*[1]*/,
+                             int32_t* out_status /*[1]*/, void* workspace, int64_t workspace_bytes, void* stream);
+int32_t bg_movegen_eval_all_rolls(const int8_t* boards /*[P,52]*/, const uint8_t* players /*[P]*/, int64_t P, int32_t item_cap,
+                                  int64_t pool_cap, int8_t* out_boards /*[pool_cap,52]*/, uint8_t* out_flags /*[pool_cap]*/,
+                                  int64_t* out_offsets /*[21*P]*/, int32_t* out_count /*[21*P]*/, int64_t* out_total /*[2]*/,
+                                  int32_t* out_status /*[1]*/, void* workspace, int64_t workspace_bytes, const float* prepared, int32_t H,
+                                  float* out_v /*[pool_cap]*/, void* stream);
+
 /* Diagnostic for the tcgen05 evaluator (batches >= 32768 rows with per-row flags, any H: 128 hidden units per pass, smaller nets
  * zero-padded, wider nets in two passes; set BG_EVAL_PATH=ffma to force the CUDA-core kernels): synchronises and returns 0, or non-zero if one of its bounded mbarrier waits ever timed out. */
 int32_t bg_eval_tc_status(void);

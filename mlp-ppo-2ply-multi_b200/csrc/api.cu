@@ -188,6 +188,38 @@ int32_t bg_movegen_eval(const int8_t* boards, const uint8_t* players, const uint
   return movegen_eval_overlapped(a, out_total, prepared, H, out_v, c, (cudaStream_t)stream);
 }
 
+int32_t bg_movegen_all_rolls(const int8_t* boards, const uint8_t* players, int64_t P, int32_t item_cap, int64_t pool_cap, int8_t* out_boards,
+                             uint8_t* out_submoves, int32_t* out_owner, uint8_t* out_flags, int64_t* out_offsets, int32_t* out_count,
+                             int64_t* out_total, int32_t* out_status, void* workspace, int64_t workspace_bytes, void* stream) {
+  BG_REQUIRE(P >= 0, "bg_movegen_all_rolls: P < 0");
+  BG_REQUIRE(P == 0 || (boards && players && out_offsets && out_count), "bg_movegen_all_rolls: null input/output pointer");
+  BG_REQUIRE(pool_cap == 0 || out_boards, "bg_movegen_all_rolls: out_boards is null");
+  BG_REQUIRE(workspace, "bg_movegen_all_rolls: workspace is null");
+  int32_t rc = require_device();
+  if (rc != BG_OK) return rc;
+  MovegenArgs a{boards,    players,   nullptr,     P,         item_cap,  pool_cap,   out_boards, out_submoves,
+                out_owner, out_flags, out_offsets, out_count, out_total, out_status, workspace,  workspace_bytes, nullptr};
+  a.all_rolls = 1;
+  return movegen_launch(a, (cudaStream_t)stream);
+}
+
+int32_t bg_movegen_eval_all_rolls(const int8_t* boards, const uint8_t* players, int64_t P, int32_t item_cap, int64_t pool_cap, int8_t* out_boards,
+                                  uint8_t* out_flags, int64_t* out_offsets, int32_t* out_count, int64_t* out_total /*[2]*/, int32_t* out_status,
+                                  void* workspace, int64_t workspace_bytes, const float* prepared, int32_t H, float* out_v, void* stream) {
+  BG_REQUIRE(P >= 0, "bg_movegen_eval_all_rolls: P < 0");
+  BG_REQUIRE(P == 0 || (boards && players && out_offsets && out_count), "bg_movegen_eval_all_rolls: null input/output pointer");
+  BG_REQUIRE(out_boards && out_flags && out_total && out_v && prepared && workspace, "bg_movegen_eval_all_rolls: null pointer");
+  int32_t rc = require_device();
+  if (rc != BG_OK) return rc;
+  std::lock_guard<std::mutex> lk(g_fused_mu);
+  SideCtx* c = nullptr;
+  if ((rc = fused_ctx(&c)) != BG_OK) return rc;
+  MovegenArgs a{boards,  players,   nullptr,     P,         item_cap,  pool_cap,   out_boards, nullptr,
+                nullptr, out_flags, out_offsets, out_count, out_total, out_status, workspace,  workspace_bytes, nullptr};
+  a.all_rolls = 1;
+  return movegen_eval_overlapped(a, out_total, prepared, H, out_v, c, (cudaStream_t)stream);
+}
+
 /* ---- arena ---- */
 
 int32_t bg_arena_create(bg_arena** out, int32_t device, int64_t n_games, int32_t H, int32_t max_plies, int32_t move_cap, uint64_t seed,

@@ -21,6 +21,7 @@
 //   * five capacity tiers (128 / 256 / 512 / 2048 nodes per ply in shared memory, 4096 in L2-resident global scratch);
 //     an item overflowing a tier is queued for the next one.  Overflowing the last tier is BG_ERR_CAPACITY.
 #include "movegen.cuh"
+#include "movegen_dev.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -56,113 +57,6 @@ struct Frontier {
   }
   __device__ __forceinline__ uint32_t* table() const { return dyn_smem() + toff; }
 };
-
-struct Root {
-  int player;
-  int dirsign;       // +1 / -1
-  uint32_t blocked;  // opponent >= 2 (24 bits)
-  uint32_t blot;     // opponent == 1 (24 bits)
-  uint32_t home;     // mover's home mask
-  bool valid15;      // mover has exactly 15 checkers (conditions.py:191-194)
-};
-
-struct Node {
-  uint32_t k0, k1, k2, k3, m0, m1;
-};
-
-// 24 nibbles (3 words) -> 24-bit occupancy mask (bit p set iff nibble p != 0)
-__device__ __forceinline__ uint32_t nib_occupancy(uint32_t w) {  // 8 nibbles -> 8 bits
-  uint32_t t = w | (w >> 1);
-  t |= t >> 2;
-  t &= 0x11111111u;                    // bit 4i = nibble i non-zero
-  t = (t | (t >> 3)) & 0x03030303u;    // byte b: bits 0,1 = nibbles 2b, 2b+1
-  t = (t | (t >> 6)) & 0x000f000fu;    // half h: bits 0..3 = nibbles 4h..4h+3
-  return (t | (t >> 12)) & 0xffu;
-}
-
-// One-die move set of node `p` as a slot mask, in the reference's get_moves_with_one_die order (slot order):
-//   bits 0..23 in-board move from that point, 24 bar entry, 25 bear-off of the farthest checker, 26 exact bear-off;
-//   bits 27..31 carry `last` (the farthest checker's point) for slot 25.
-__device__ __forceinline__ uint32_t move_mask(const Node& p, const Root& r, int die) {
-  const uint32_t occ = nib_occupancy(p.k0) | (nib_occupancy(p.k1) << 8) | (nib_occupancy(p.k2) << 16);
-  const uint32_t bar = (p.k3 >> 24) & 15u, off = p.k3 >> 28;
-  if (off == 15u) return 0u;  // GAME_OVER (conditions.py:16-17)
-  if (bar > 0) {              // ON_BAR (get_moves_one_die.py:86-130)
-    const int e = r.player == 0 ? die - 1 : 24 - die;
-    return ((r.blocked >> e) & 1u) ? 0u : (1u << 24);
-  }
-  // NORMAL (:40-83) / in-home moves of BEAR_OFF (:164-189): destination on the board and not blocked
-  uint32_t vm = r.player == 0 ? (occ & ~(r.blocked >> die) & ((1u << (24 - die)) - 1u))
-                              : (occ & ~(r.blocked << die) & (0xffffffu & ~((1u << die) - 1u)));
-  uint32_t last = 0;
-  if (r.valid15 && (occ & ~r.home) == 0) {  // BEAR_OFF (:192-249)
-    last = r.player == 0 ? (occ ? __ffs(occ) - 1 : 18) : (occ ? 31 - __clz(occ) : 5);
-    const bool far_off = r.player == 0 ? ((int)last + die >= 24) : ((int)last - die < 0);
-    const uint32_t ps = r.player == 0 ? 24 - die : die - 1;
-    if (far_off) vm |= 1u << 25;
-    if (ps != last && ((occ >> ps) & 1u)) vm |= 1u << 26;
-  }
-  return vm | (last << 27);
-}
-
-// n-th (0-based) set bit of m
-__device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
-  int pos = 0;
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) {
-    const int c = __popc((m >> pos) & ((1u << s) - 1u));
-    if (c <= n) {
-      n -= c;
-      pos += s;
-    }
-  }
-  return pos;
-}
-
-// apply the move in `slot` of parent p (immutable_board.py:183-258 on the packed key)
-__device__ __forceinline__ void make_child(const Node& p, const Root& r, int slot, uint32_t last, int die, int depth, Node& c) {
-  int s, e;
-  if (slot < 24) {
-    s = slot;
-    e = slot + r.dirsign * die;
-  } else if (slot == 24) {
-    s = 24;
-    e = r.player == 0 ? die - 1 : 24 - die;
-  } else {
-    s = slot == 25 ? (int)last : (r.player == 0 ? 24 - die : die - 1);
-    e = 25;
-  }
-  uint32_t k[3] = {p.k0, p.k1, p.k2};
-  uint32_t k3 = p.k3;
-  uint32_t hit = 0;
-  if (s == 24) {
-    k3 -= 1u << 24;
-  } else {
-    const uint32_t ds = 1u << ((s & 7) * 4);
-    const int ws = s >> 3;
-    k[0] -= ws == 0 ? ds : 0u;
-    k[1] -= ws == 1 ? ds : 0u;
-    k[2] -= ws == 2 ? ds : 0u;
-  }
-  if (e == 25) {
-    k3 += 1u << 28;
-  } else {
-    const uint32_t de = 1u << ((e & 7) * 4);
-    const int we = e >> 3;
-    k[0] += we == 0 ? de : 0u;
-    k[1] += we == 1 ? de : 0u;
-    k[2] += we == 2 ? de : 0u;
-    hit = ((r.blot & ~p.k3) >> e) & 1u;
-    k3 |= hit << e;
-  }
-  const uint32_t sm = (uint32_t)s | ((uint32_t)e << 5) | (hit << 10) | (1u << 11);
-  c.k0 = k[0];
-  c.k1 = k[1];
-  c.k2 = k[2];
-  c.k3 = k3;
-  c.m0 = depth < 2 ? (p.m0 | (sm << (16 * depth))) : p.m0;
-  c.m1 = depth < 2 ? p.m1 : (p.m1 | (sm << (16 * (depth - 2))));
-}
 
 template <int CAP, bool GLOBAL, bool MOVES>
 __device__ __forceinline__ Node load_node(const Frontier<CAP, GLOBAL, MOVES>& F, int lvl, int pos) {
@@ -475,7 +369,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_movegen(MovegenParams P) {
       const int64_t t = (int64_t)t0 + g;
       if (t >= n_items) break;
       const int item = P.in_list ? P.in_list[t] : (int)t;
-      if (P.active && !P.active[item]) {
+      const int src = P.all_rolls ? item / 21 : item;  // position-major: 21 items share one board
+      if (P.active && !P.active[src]) {
         if (lane == 0) {
           P.out_count[item] = 0;
           P.out_offsets[item] = 0;
@@ -483,10 +378,22 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_movegen(MovegenParams P) {
         continue;
       }
       __syncwarp();
-      if (lane < 13) rootw[lane] = reinterpret_cast<const uint32_t*>(P.boards)[(int64_t)item * 13 + lane];
+      if (lane < 13) rootw[lane] = reinterpret_cast<const uint32_t*>(P.boards)[(int64_t)src * 13 + lane];
       __syncwarp();
-      const int player = P.players[item] & 1;
-      const int d0 = P.rolls[2 * (int64_t)item], d1 = P.rolls[2 * (int64_t)item + 1];
+      const int player = P.players[src] & 1;
+      int d0, d1;
+      if (P.all_rolls) {  // roll index -> (d0 <= d1), lexicographic (src/multi/two_ply.py:10-32)
+        int ri = item - src * 21;
+        d0 = 1;
+        while (ri >= 7 - d0) {
+          ri -= 7 - d0;
+          ++d0;
+        }
+        d1 = d0 + ri;
+      } else {
+        d0 = P.rolls[2 * (int64_t)item];
+        d1 = P.rolls[2 * (int64_t)item + 1];
+      }
       ItemOut io;
       const int rc = generate<CAP, GLOBAL, MOVES>(F, rootw, player, d0, d1, lane, io);
       if (rc == ITEM_OVERFLOW) {
@@ -632,18 +539,29 @@ int32_t launch_tail_tier(MovegenParams P, int in, int out, int ctas, int32_t* ct
 template <bool MOVES>
 int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* const (&ovf)[N_OVF], int32_t* const (&ovf_n)[N_OVF],
                      int64_t* tier1_total, cudaEvent_t tier1_event, int32_t tier2_ctas, cudaStream_t stream) {
-  int32_t rc = prepare_tier<T1_CAP, false, MOVES, T1_WARPS, T1_CTAS_PER_SM>();
-  if (rc != BG_OK) return rc;
+  int32_t rc = BG_OK;
   // tier 1: every item
   P.item_counter = ctr + 0;
   P.in_list = nullptr;
   P.in_count = nullptr;
   P.ovf_list = ovf[0];
   P.ovf_count = ovf_n[0];
-  P.grab = B > (1 << 20) ? 8 : 1;
-  int64_t want = (B + T1_WARPS - 1) / T1_WARPS;
-  int grid = (int)(want < (int64_t)NUM_SMS * T1_CTAS_PER_SM ? want : (int64_t)NUM_SMS * T1_CTAS_PER_SM);
-  k_movegen<T1_CAP, false, MOVES, T1_WARPS, T1_CTAS_PER_SM><<<grid, T1_WARPS * 32, smem_bytes(T1_CAP, false, MOVES, T1_WARPS), stream>>>(P);
+  // position-major bulk tier (movegen21.cu): one warp per position, all 21 rolls.  It never truncates an item (its items have fewer
+  // results than its buffer holds), so it needs item_cap >= that buffer
+  const bool fast21 = P.all_rolls && !MOVES && P.item_cap >= MOVEGEN21_MIN_ITEM_CAP;
+  if (fast21) {
+    P.grab = 1;
+    P.B = B / 21;
+    rc = movegen21_launch_kernel(P, stream);
+    P.B = B;
+    if (rc != BG_OK) return rc;
+  } else {
+    if ((rc = prepare_tier<T1_CAP, false, MOVES, T1_WARPS, T1_CTAS_PER_SM>()) != BG_OK) return rc;
+    P.grab = B > (1 << 20) ? 8 : 1;
+    int64_t want = (B + T1_WARPS - 1) / T1_WARPS;
+    int grid = (int)(want < (int64_t)NUM_SMS * T1_CTAS_PER_SM ? want : (int64_t)NUM_SMS * T1_CTAS_PER_SM);
+    k_movegen<T1_CAP, false, MOVES, T1_WARPS, T1_CTAS_PER_SM><<<grid, T1_WARPS * 32, smem_bytes(T1_CAP, false, MOVES, T1_WARPS), stream>>>(P);
+  }
   if (tier1_total) {
     cudaError_t e = cudaMemcpyAsync(tier1_total, P.pool_cursor, 8, cudaMemcpyDeviceToDevice, stream);
     if (e != cudaSuccess) return check_cuda(e, "copy tier1_total");
@@ -655,7 +573,7 @@ int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* const (&
   // tail tiers: the items that overflowed 128 / 256 / 512 / 2048 nodes in some ply.  The 256 tier (twice the resident warps of the 512
   // tier) pays when the overflow lists are long; for small batches (one self-play ply) every extra tier is one more kernel whose
   // slowest item sits on the critical path, so the chain goes 128 -> 512 directly.
-  const bool use256 = B >= (1 << 20);
+  const bool use256 = B >= (1 << 20) && !fast21;  // what the position-major tier hands over is wider than 224 nodes per ply
   const int c2 = tier2_ctas > 0 && tier2_ctas < T2_CTAS_PER_SM ? tier2_ctas : T2_CTAS_PER_SM;
   if (use256 && (rc = launch_tail_tier<T2_CAP, false, MOVES, T2_WARPS, T2_CTAS_PER_SM>(P, 0, 1, c2, ctr, ovf, ovf_n, stream)) != BG_OK) return rc;
   if ((rc = launch_tail_tier<T3_CAP, false, MOVES, T3_WARPS, T3_CTAS_PER_SM>(P, use256 ? 1 : 0, 2, T3_CTAS_PER_SM, ctr, ovf, ovf_n, stream)) != BG_OK)
@@ -681,20 +599,25 @@ int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream) {
     set_error("bg_movegen: bad sizes (B=%lld item_cap=%d pool_cap=%lld)", (long long)a.B, a.item_cap, (long long)a.pool_cap);
     return BG_ERR_ARG;
   }
-  if (a.workspace_bytes < movegen_workspace_bytes(a.B)) {
+  const int64_t n_items = a.all_rolls ? a.B * 21 : a.B;
+  if (n_items >= (1ll << 31)) {
+    set_error("bg_movegen: too many items (%lld)", (long long)n_items);
+    return BG_ERR_ARG;
+  }
+  if (a.workspace_bytes < movegen_workspace_bytes(n_items)) {
     set_error("bg_movegen: workspace too small (%lld < %lld)", (long long)a.workspace_bytes,
-              (long long)movegen_workspace_bytes(a.B));
+              (long long)movegen_workspace_bytes(n_items));
     return BG_ERR_ARG;
   }
   char* ws = (char*)a.workspace;
   cudaError_t e = cudaMemsetAsync(ws, 0, HDR_BYTES, stream);
   if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(workspace)");
-  int64_t lists = ((N_OVF * a.B * 4 + 255) / 256) * 256;
+  int64_t lists = ((N_OVF * n_items * 4 + 255) / 256) * 256;
   MovegenParams P;
   P.boards = a.boards;
   P.players = a.players;
   P.rolls = a.rolls;
-  P.B = a.B;
+  P.B = n_items;
   P.item_cap = a.item_cap;
   P.pool_cap = a.pool_cap;
   P.out_boards = a.out_boards;
@@ -707,14 +630,15 @@ int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream) {
   P.status = (int32_t*)(ws + 8);
   P.gfront = (uint32_t*)(ws + HDR_BYTES + lists);
   P.active = a.active;
+  P.all_rolls = a.all_rolls;
   int32_t* ctr = (int32_t*)(ws + 12);
   int32_t* const l0 = (int32_t*)(ws + HDR_BYTES);
-  int32_t* const ovf[N_OVF] = {l0, l0 + a.B, l0 + 2 * a.B, l0 + 3 * a.B};
+  int32_t* const ovf[N_OVF] = {l0, l0 + n_items, l0 + 2 * n_items, l0 + 3 * n_items};
   int32_t* const ovf_n[N_OVF] = {(int32_t*)(ws + 32), (int32_t*)(ws + 36), (int32_t*)(ws + 40), (int32_t*)(ws + 44)};
   if (a.B > 0) {
     // the sub-move history (2 extra words per node) is only carried when the caller asks for the FullMove sequences
-    int32_t rc = a.out_submoves ? launch_tiers<true>(P, a.B, ctr, ovf, ovf_n, a.tier1_total, a.tier1_event, a.tier2_ctas_per_sm, stream)
-                                : launch_tiers<false>(P, a.B, ctr, ovf, ovf_n, a.tier1_total, a.tier1_event, a.tier2_ctas_per_sm, stream);
+    int32_t rc = a.out_submoves ? launch_tiers<true>(P, n_items, ctr, ovf, ovf_n, a.tier1_total, a.tier1_event, a.tier2_ctas_per_sm, stream)
+                                : launch_tiers<false>(P, n_items, ctr, ovf, ovf_n, a.tier1_total, a.tier1_event, a.tier2_ctas_per_sm, stream);
     if (rc != BG_OK) return rc;
   }
   if (a.out_total) {

@@ -29,6 +29,9 @@ struct MovegenArgs {
   // optional: resident CTAs per SM of the second tier (0 = default).  A consumer that overlaps the tail tiers with another kernel
   // lowers this so that both fit on an SM at the same time
   int32_t tier2_ctas_per_sm = 0;
+  // position-major mode (movegen21.cu): boards / players / active are per POSITION (B of them), `rolls` is ignored, and the items are
+  // position * 21 + roll index in the roll order of src/multi/two_ply.py:10-32; out_offsets / out_count have 21 * B entries
+  int32_t all_rolls = 0;
 };
 
 // kernel parameter block
@@ -55,9 +58,13 @@ struct MovegenParams {
   uint32_t* gfront;
   int32_t grab;
   const uint8_t* active;
+  int32_t all_rolls;  // items are position * 21 + roll index; boards / players / active are indexed by position
 };
 
-int64_t movegen_workspace_bytes(int64_t B);
+int64_t movegen_workspace_bytes(int64_t B);  // B = number of ITEMS (21 per position in position-major mode)
+// movegen21.cu: the position-major bulk tier (one warp per position, all 21 rolls); overflowing items go to P.ovf_list
+constexpr int MOVEGEN21_MIN_ITEM_CAP = 320;
+int32_t movegen21_launch_kernel(const MovegenParams& P, cudaStream_t stream);
 int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream);
 
 }  // namespace bg

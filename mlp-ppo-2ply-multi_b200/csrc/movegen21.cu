@@ -1,0 +1,790 @@
+// movegen21.cu -- position-major legal-move generation on sm_100a: ONE WARP PER POSITION, ALL 21 ROLLS.
+//
+// Same contract as movegen.cu (get_all_possible_moves for every roll, reference src/backgammon/moves/generate_all_moves.py:7-90,
+// handle_move_types.py:7-221, + execute_full_move_on_board_copy, src/environments/env_helper.py:27-91; output order == the
+// reference's action order), for the workloads that ask for every roll of a position: BASELINE config 2 (positions x 21 rolls) and
+// the 2-ply lookahead (src/multi/two_ply.py:93-150: 21 opponent rolls per candidate).  Item index = position * 21 + roll index
+// (roll order of src/multi/two_ply.py:10-32: (1,1), (1,2), ... (6,6)).
+//
+// What the position-major formulation buys over one warp per (board, roll) item:
+//   * the root is decoded once, the one-die move sets of the six dice are computed once, and each of the <= 64 first-move
+//     children gets its six second-die move sets in one lane-per-child pass: every non-double (hi, lo) reads its two die orders
+//     out of that table, every double d-d its first two plies;
+//   * a result is a 30-bit CODE, not a board: for a non-double the sorted sources / sorted destinations of the two sub-moves
+//     after cancelling a point that is both, plus the one intermediate point whose blot was hit; for a double the sorted
+//     multiset of (up to four) source points.  Equal codes <=> equal boards (the mover's configuration is root - sources +
+//     destinations and every landing point that holds a blot is hit), so first-occurrence dedup is an exact one-word hash set,
+//     and boards are only materialised for the survivors, at emit time;
+//   * candidates that provably duplicate an EARLIER candidate are never generated (tests/tools/proto_movegen21.py checks both rules
+//     against the oracle): in a non-double's reverse order, the second sub-move from a point that could already move first
+//     (the commuting pair was produced by the forward order); in a doubles tree, a slot below the parent's last slot whose move
+//     was already legal one ply earlier (the same multiset is reached through an earlier parent).  What is left is ~1.1x the
+//     unique results instead of ~2x / ~4x;
+//   * candidates of all rolls are flattened over the warp (parent batches of 32, one lane per candidate in canonical order), so
+//     lanes stay busy even though a single (position, roll) item has ~14 results;
+//   * results are buffered per warp and emitted in bulk: one pool reservation per flush (~2 per position instead of 21),
+//     rows rebuilt from the root bytes + code in shared memory and copied out with coalesced word stores.
+// Anything that does not fit the fast path's per-warp capacities (a doubles tree wider than RCAP / FCAP nodes per ply, more than
+// C1CAP first moves) is queued, per item, for the generic capacity tiers of movegen.cu.
+#include "movegen.cuh"
+#include "movegen_dev.cuh"
+
+namespace bg {
+
+namespace {
+
+constexpr int C1CAP = 64;    // first-move children over the six dice (observed max 70 in 20,000 positions, p99 44)
+constexpr int DCAP = 128;    // candidate descriptors per sub-batch
+constexpr int TCAP = 512;    // hash-set slots (>= 2 x the live keys)
+constexpr int RCAP = 320;    // buffered result codes
+constexpr int FCAP = 224;    // doubles frontier nodes per ply
+constexpr uint32_t NONE5 = 31u;
+
+// per-warp shared memory (words)
+constexpr int O_ROOT = 0;                       // 16: the 13 root words
+constexpr int O_C1INFO = O_ROOT + 16;           // C1CAP: slot | src << 5 | dst << 10 | die0 << 15 | lone << 18
+constexpr int O_C1MASK = O_C1INFO + C1CAP;      // 6 x C1CAP: second-die move sets of each child, [die0][child]
+constexpr int O_DESC = O_C1MASK + 6 * C1CAP;    // DCAP u16: parent lane | slot << 5
+constexpr int O_TAB = O_DESC + DCAP / 2;        // TCAP: hash set; doubles as the emit staging area (32 rows x 13 words)
+constexpr int O_RES = O_TAB + TCAP;             // RCAP result codes
+constexpr int O_FA = O_RES + RCAP;              // FCAP frontier (ply 2)
+constexpr int O_FB = O_FA + FCAP;               // FCAP frontier (ply 3)
+constexpr int O_ISTART = O_FB + FCAP;           // 24 + 24: per-item result ranges of a flush
+constexpr int WARP_WORDS = O_ISTART + 48;
+static_assert(TCAP >= 32 * 13, "staging area");
+static_assert(RCAP <= MOVEGEN21_MIN_ITEM_CAP, "the fast tier never truncates an item");
+
+constexpr int WARPS21 = 4;
+constexpr int CTAS21 = 6;
+
+// the 15 non-double rolls in roll-index order: 0-based (lo, hi) dice, 3 bits each
+constexpr uint64_t pack15(const int (&v)[15]) {
+  uint64_t r = 0;
+  for (int i = 0; i < 15; ++i) r |= (uint64_t)v[i] << (3 * i);
+  return r;
+}
+constexpr int ND_LO_V[15] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 3, 3, 4};
+constexpr int ND_HI_V[15] = {1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
+constexpr uint64_t ND_LO = pack15(ND_LO_V), ND_HI = pack15(ND_HI_V);
+constexpr uint32_t DBL_IDS = (1u << 0) | (1u << 6) | (1u << 11) | (1u << 15) | (1u << 18) | (1u << 20);  // roll indices of d-d
+
+__device__ __forceinline__ uint32_t* wsm() {
+  extern __shared__ uint32_t bg_dyn_smem21[];
+  return bg_dyn_smem21 + (threadIdx.x >> 5) * WARP_WORDS;
+}
+
+// occupancy / state summary of a node, from which the move set of any die is a few bit operations (same rules as move_mask)
+struct View {
+  uint32_t occ, bar, off, last;
+  bool bear;
+};
+
+__device__ __forceinline__ View make_view(uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3, const Root& r) {
+  View v;
+  v.occ = nib_occupancy(k0) | (nib_occupancy(k1) << 8) | (nib_occupancy(k2) << 16);
+  v.bar = (k3 >> 24) & 15u;
+  v.off = k3 >> 28;
+  v.bear = r.valid15 && (v.occ & ~r.home) == 0;
+  v.last = r.player == 0 ? (v.occ ? __ffs(v.occ) - 1 : 18) : (v.occ ? 31 - __clz(v.occ) : 5);
+  return v;
+}
+
+// slot mask of one die (bits 0..23 point moves, 24 bar entry, 25 farthest bear-off, 26 exact bear-off; bits 27..31 `last`)
+__device__ __forceinline__ uint32_t view_mask(const View& v, const Root& r, int die) {
+  if (v.off == 15u) return 0u;
+  if (v.bar > 0) {
+    const int e = r.player == 0 ? die - 1 : 24 - die;
+    return ((r.blocked >> e) & 1u) ? 0u : (1u << 24);
+  }
+  uint32_t vm = r.player == 0 ? (v.occ & ~(r.blocked >> die) & ((1u << (24 - die)) - 1u))
+                              : (v.occ & ~(r.blocked << die) & (0xffffffu & ~((1u << die) - 1u)));
+  uint32_t last = 0;
+  if (v.bear) {
+    last = v.last;
+    const bool far_off = r.player == 0 ? ((int)last + die >= 24) : ((int)last - die < 0);
+    const uint32_t ps = r.player == 0 ? 24 - die : die - 1;
+    if (far_off) vm |= 1u << 25;
+    if (ps != last && ((v.occ >> ps) & 1u)) vm |= 1u << 26;
+  }
+  return vm | (last << 27);
+}
+
+// (source, destination) of a slot: points 0..23, BAR = 24 as a source, BEAR_OFF = 25 as a destination
+__device__ __forceinline__ void slot_se(const Root& r, uint32_t slot, uint32_t last, int die, uint32_t& s, uint32_t& e) {
+  if (slot < 24u) {
+    s = slot;
+    e = slot + r.dirsign * die;
+  } else if (slot == 24u) {
+    s = 24u;
+    e = r.player == 0 ? die - 1 : 24 - die;
+  } else {
+    s = slot == 25u ? last : (r.player == 0 ? 24 - die : die - 1);
+    e = 25u;
+  }
+}
+
+// move one checker s -> e on the packed key (immutable_board.py:183-258)
+__device__ __forceinline__ void key_move(uint32_t& k0, uint32_t& k1, uint32_t& k2, uint32_t& k3, const Root& r, uint32_t s, uint32_t e) {
+  if (s == 24u) {
+    k3 -= 1u << 24;
+  } else {
+    const uint32_t ds = 1u << ((s & 7u) * 4u);
+    const uint32_t ws = s >> 3;
+    k0 -= ws == 0u ? ds : 0u;
+    k1 -= ws == 1u ? ds : 0u;
+    k2 -= ws == 2u ? ds : 0u;
+  }
+  if (e == 25u) {
+    k3 += 1u << 28;
+  } else {
+    const uint32_t de = 1u << ((e & 7u) * 4u);
+    const uint32_t we = e >> 3;
+    k0 += we == 0u ? de : 0u;
+    k1 += we == 1u ? de : 0u;
+    k2 += we == 2u ? de : 0u;
+    k3 |= ((r.blot >> e) & 1u) << e;
+  }
+}
+
+__device__ __forceinline__ uint32_t key_count(uint32_t k0, uint32_t k1, uint32_t k2, uint32_t p) {
+  const uint32_t w = p < 8u ? k0 : (p < 16u ? k1 : k2);
+  return (w >> ((p & 7u) * 4u)) & 15u;
+}
+
+// destination of a doubles source point for die (0-based point or BAR)
+__device__ __forceinline__ uint32_t dbl_dest(const Root& r, uint32_t s, int die) {
+  if (s == 24u) return r.player == 0 ? die - 1 : 24 - die;
+  const int e = (int)s + r.dirsign * die;
+  return (e < 0 || e > 23) ? 25u : (uint32_t)e;
+}
+
+__device__ __forceinline__ uint32_t hash_key(uint32_t k) { return (k * 0x9E3779B1u) >> (32 - 9); }
+static_assert(TCAP == 512, "hash_key shift");
+
+__device__ __forceinline__ void clear_tab(uint32_t* tab, int lane) {
+#pragma unroll
+  for (int i = 0; i < TCAP / 32; ++i) tab[i * 32 + lane] = 0u;
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// flush: emit the complete items res[0 .. n_emit) -- reserve pool rows, write each item's offset / count, rebuild the boards from
+// the root bytes + codes in the staging area and copy them out -- then move the partial tail res[n_emit .. n_res) to the front and
+// rebuild the hash set from it (the staging area IS the hash set's memory).  Returns the new emitted-items mask.
+// ---------------------------------------------------------------------------------------------------------------------------
+__device__ __noinline__ uint32_t flush21(const MovegenParams* __restrict__ Pp, int64_t pos, int player, uint32_t blot, int n_emit, int n_res,
+                                         uint32_t emitted, bool rehash) {
+  const MovegenParams& P = *Pp;
+  uint32_t* const W = wsm();
+  uint32_t* const res = W + O_RES;
+  uint32_t* const stage = W + O_TAB;
+  const int lane = threadIdx.x & 31;
+  if (n_emit > 0) {
+    long long base = 0;
+    if (lane == 0) {
+      base = (long long)atomicAdd(P.pool_cursor, (unsigned long long)n_emit);
+      if (base + n_emit > P.pool_cap) {
+        base = -1;
+        atomicMin(P.status, BG_ERR_CAPACITY);
+      }
+    }
+    base = __shfl_sync(BG_FULL, base, 0);
+    // per-item ranges: the results of an item are contiguous
+    if (lane < 24) {
+      W[O_ISTART + lane] = 0u;
+      W[O_ISTART + 24 + lane] = 0u;
+    }
+    __syncwarp();
+    for (int i0 = 0; i0 < n_emit; i0 += 32) {
+      const int i = i0 + lane;
+      if (i < n_emit) {
+        const uint32_t id = res[i] >> 25;
+        const uint32_t pid = i > 0 ? res[i - 1] >> 25 : 0u;
+        const uint32_t nid = i + 1 < n_emit ? res[i + 1] >> 25 : 0u;
+        if (id != pid) W[O_ISTART + id] = (uint32_t)i;
+        if (id != nid) W[O_ISTART + 24 + id] = (uint32_t)(i + 1);
+      }
+    }
+    __syncwarp();
+    if (lane >= 1 && lane <= 21) {
+      const uint32_t s = W[O_ISTART + lane], e = W[O_ISTART + 24 + lane];
+      if (e > s) {
+        const int64_t item = pos * 21 + (lane - 1);
+        P.out_count[item] = (int32_t)(e - s);
+        P.out_offsets[item] = base < 0 ? -1ll : base + (long long)s;
+      }
+    }
+    emitted |= __ballot_sync(BG_FULL, lane >= 1 && lane <= 21 && W[O_ISTART + 24 + lane] > W[O_ISTART + lane]) >> 1;
+    if (base >= 0) {
+      uint32_t* const ob = reinterpret_cast<uint32_t*>(P.out_boards) + base * 13;
+      const int own = player * 24, opp = (1 - player) * 24;
+      const int dirsign = player == 0 ? 1 : -1;
+      for (int i0 = 0; i0 < n_emit; i0 += 32) {
+        const int i = i0 + lane;
+        __syncwarp();
+        if (i < n_emit) {
+          uint32_t* const row = stage + lane * 13;
+#pragma unroll
+          for (int q = 0; q < 13; ++q) row[q] = W[O_ROOT + q];
+          uint8_t* const rb = reinterpret_cast<uint8_t*>(row);
+          const uint32_t w = res[i];
+          const uint32_t rid = (w >> 25) - 1u;
+          uint32_t hit = 0;
+          if ((DBL_IDS >> rid) & 1u) {
+            const int die = __popc(DBL_IDS & ((1u << rid) - 1u)) + 1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t s = (w >> (5 * q)) & 31u;
+              if (s != NONE5) {
+                uint32_t e;
+                if (s == 24u) {
+                  rb[48 + player] -= 1;
+                  e = player == 0 ? die - 1 : 24 - die;
+                } else {
+                  rb[own + s] -= 1;
+                  const int ee = (int)s + dirsign * die;
+                  e = (ee < 0 || ee > 23) ? 25u : (uint32_t)ee;
+                }
+                if (e == 25u) {
+                  rb[50 + player] += 1;
+                } else {
+                  rb[own + e] += 1;
+                  hit |= blot & (1u << e);
+                }
+              }
+            }
+          } else {
+            const uint32_t sa = w & 31u, sb = (w >> 5) & 31u, da = (w >> 10) & 31u, db = (w >> 15) & 31u, in = (w >> 20) & 31u;
+            if (sa == 24u) rb[48 + player] -= 1; else rb[own + sa] -= 1;
+            if (sb != NONE5) {
+              if (sb == 24u) rb[48 + player] -= 1; else rb[own + sb] -= 1;
+            }
+            if (da == 25u) rb[50 + player] += 1; else { rb[own + da] += 1; hit |= blot & (1u << da); }
+            if (db != NONE5) {
+              if (db == 25u) rb[50 + player] += 1; else { rb[own + db] += 1; hit |= blot & (1u << db); }
+            }
+            if (in != NONE5) hit |= 1u << in;
+          }
+          rb[48 + 1 - player] += (uint8_t)__popc(hit);
+          while (hit) {
+            const int p = __ffs(hit) - 1;
+            hit &= hit - 1u;
+            rb[opp + p] -= 1;
+          }
+        }
+        __syncwarp();
+        const int nw = (n_emit - i0 < 32 ? n_emit - i0 : 32) * 13;
+        for (int t = lane; t < nw; t += 32) ob[i0 * 13 + t] = stage[t];
+        if (i < n_emit) {
+          if (P.out_flags) P.out_flags[base + i] = (uint8_t)player;
+          if (P.out_owner) P.out_owner[base + i] = (int32_t)(pos * 21 + (res[i] >> 25) - 1);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // keep the partial tail and rebuild the hash set from it
+  const int keep = n_res - n_emit;
+  if (n_emit > 0 && keep > 0) {
+    for (int i0 = 0; i0 < keep; i0 += 32) {
+      const int i = i0 + lane;
+      const uint32_t w = i < keep ? res[n_emit + i] : 0u;
+      __syncwarp();
+      if (i < keep) res[i] = w;
+    }
+  }
+  if (rehash) {
+    clear_tab(W + O_TAB, lane);
+    for (int i = lane; i < keep; i += 32) {
+      const uint32_t w = res[i];
+      const bool dbl = (DBL_IDS >> ((w >> 25) - 1u)) & 1u;
+      const uint32_t key = dbl ? (w & ~(31u << 20)) : w;
+      uint32_t idx = hash_key(key);
+      while (atomicCAS(&W[O_TAB + idx], 0u, key) != 0u) idx = (idx + 1) & (TCAP - 1);
+    }
+  }
+  __syncwarp();
+  return emitted;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// One batch of <= 32 parents (one per lane: `pinfo` describes the parent, the low 27 bits of `m` are its candidate slots) -> its
+// candidates in canonical order (parent order, then slot order), first-occurrence dedup through the hash set, survivors appended
+// to dst[n ..).  mode 0: non-doubles (pinfo = src1 | dst1 << 5 | die0 of the second sub-move << 10 | single << 13 | last << 14 |
+// id << 25); mode 1: doubles (pinfo = the parent's sorted sources (20 bits) | last << 20 | id << 25; the child records its slot).
+// Sub-batches of <= DCAP candidates; returns n | (resume + 1) << 16 when the next sub-batch would not fit below `cap` (the caller
+// makes room and calls again with start = resume), or n with the high half 0 when the batch is done.
+// ---------------------------------------------------------------------------------------------------------------------------
+__device__ __noinline__ uint32_t expand21(int mode, uint32_t pinfo, uint32_t m, int start, int dst_off, int n, int cap, int player, uint32_t blot,
+                                          int die) {
+  uint32_t* const W = wsm();
+  uint16_t* const desc = reinterpret_cast<uint16_t*>(W + O_DESC);
+  uint32_t* const tab = W + O_TAB;
+  uint32_t* const dst = W + dst_off;
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  Root r;
+  r.player = player;
+  r.dirsign = player == 0 ? 1 : -1;
+  const uint32_t mm0 = m & 0x7ffffffu;
+  const int cnt = __popc(mm0);
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(BG_FULL, inc, o);
+    if (lane >= o) inc += t;
+  }
+  const int total = __shfl_sync(BG_FULL, inc, 31);
+  const int exc = inc - cnt;
+  while (start < total) {
+    const int limit = start + DCAP;
+    const uint32_t nofit = __ballot_sync(BG_FULL, inc > limit);
+    const int next_start = nofit ? __shfl_sync(BG_FULL, exc, __ffs(nofit) - 1) : total;
+    const int ncand = next_start - start;
+    if (n + ncand > cap) return (uint32_t)n | ((uint32_t)(start + 1) << 16);
+    if (exc >= start && inc <= limit) {
+      uint32_t mm = mm0;
+      int o = exc - start;
+      while (mm) {
+        const int slot = __ffs(mm) - 1;
+        mm &= mm - 1u;
+        desc[o++] = (uint16_t)(lane | (slot << 5));
+      }
+    }
+    __syncwarp();
+    for (int t0 = 0; t0 < ncand; t0 += 32) {
+      const int t = t0 + lane;
+      const bool cv = t < ncand;
+      const uint32_t dsc = cv ? desc[t] : 0u;
+      const uint32_t pi = __shfl_sync(BG_FULL, pinfo, dsc & 31u);
+      const uint32_t slot = dsc >> 5;
+      uint32_t word, key;
+      if (mode == 0) {
+        const uint32_t s1 = pi & 31u, e1 = (pi >> 5) & 31u;
+        uint32_t code;
+        if ((pi >> 13) & 1u) {  // single sub-move result (handle_move_types.py:70-81)
+          code = s1 | (NONE5 << 5) | (e1 << 10) | (NONE5 << 15) | (NONE5 << 20);
+        } else {
+          uint32_t s2, e2;
+          slot_se(r, slot, (pi >> 14) & 31u, (int)((pi >> 10) & 7u) + 1, s2, e2);
+          if (s2 == e1) {  // a checker lands on e1 and a checker leaves it
+            const uint32_t in = ((blot >> e1) & 1u) ? e1 : NONE5;
+            code = s1 | (NONE5 << 5) | (e2 << 10) | (NONE5 << 15) | (in << 20);
+          } else if (s1 == e2) {  // the second sub-move lands on the point the first one left
+            code = s2 | (NONE5 << 5) | (e1 << 10) | (NONE5 << 15) | (NONE5 << 20);
+          } else {
+            code = min(s1, s2) | (max(s1, s2) << 5) | (min(e1, e2) << 10) | (max(e1, e2) << 15) | (NONE5 << 20);
+          }
+        }
+        word = code | (pi & (31u << 25));
+        key = word;
+      } else {
+        uint32_t s, e;
+        slot_se(r, slot, (pi >> 20) & 31u, die, s, e);
+        // sorted insert of s into the parent's (at most three) sources
+        const uint32_t a0 = pi & 31u, a1 = (pi >> 5) & 31u, a2 = (pi >> 10) & 31u;
+        const uint32_t l0 = min(a0, s), t1 = max(a0, s);
+        const uint32_t l1 = min(a1, t1), t2 = max(a1, t1);
+        const uint32_t l2 = min(a2, t2), l3 = max(a2, t2);
+        key = l0 | (l1 << 5) | (l2 << 10) | (l3 << 15) | (pi & (31u << 25));
+        word = key | (slot << 20);
+      }
+      // first occurrence wins: equal keys inside the round elect their lowest lane, earlier rounds are in the hash set
+      const uint32_t grp = __match_any_sync(BG_FULL, cv ? key : (0x80000000u | (uint32_t)lane));
+      bool isnew = false;
+      if (cv && (__ffs(grp) - 1) == lane) {
+        uint32_t idx = hash_key(key);
+        while (true) {
+          const uint32_t old = atomicCAS(&tab[idx], 0u, key);
+          if (old == 0u) {
+            isnew = true;
+            break;
+          }
+          if (old == key) break;
+          idx = (idx + 1) & (TCAP - 1);
+        }
+      }
+      const uint32_t bal = __ballot_sync(BG_FULL, isnew);
+      if (isnew) dst[n + __popc(bal & lt)] = word;
+      n += __popc(bal);
+    }
+    __syncwarp();
+    start = next_start;
+  }
+  return (uint32_t)n;
+}
+
+__device__ __forceinline__ void push_overflow(const MovegenParams& P, int64_t item) {
+  const int q = atomicAdd(P.ovf_count, 1);
+  P.ovf_list[q] = (int32_t)item;
+}
+
+__global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid_constant__ MovegenParams P) {
+  uint32_t* const W = wsm();
+  const int lane = threadIdx.x & 31;
+  const uint32_t* const boards32 = reinterpret_cast<const uint32_t*>(P.boards);
+  while (true) {
+    long long pos = 0;
+    if (lane == 0) pos = atomicAdd(P.item_counter, 1);
+    pos = __shfl_sync(BG_FULL, pos, 0);
+    if (pos >= P.B) break;
+    __syncwarp();
+    if (P.active && !P.active[pos]) {
+      if (lane < 21) {
+        P.out_count[pos * 21 + lane] = 0;
+        P.out_offsets[pos * 21 + lane] = 0;
+      }
+      continue;
+    }
+    if (lane < 13) W[O_ROOT + lane] = boards32[pos * 13 + lane];
+    __syncwarp();
+    const int player = P.players[pos] & 1;
+    // ---- root (as movegen.cu generate()) ------------------------------------------------------------------------------
+    const int ob = player * 6, pb = (1 - player) * 6;
+    uint32_t bad = 0;
+#pragma unroll
+    for (int i = 0; i < 13; ++i) bad |= W[O_ROOT + i] & 0xf0f0f0f0u;
+    if (bad) {
+      if (lane < 21) {
+        P.out_count[pos * 21 + lane] = 0;
+        P.out_offsets[pos * 21 + lane] = -1;
+      }
+      if (lane == 0) atomicMin(P.status, BG_ERR_INVARIANT);
+      continue;
+    }
+    const uint32_t w12 = W[O_ROOT + 12];
+    const uint32_t rk0 = bytes_to_nib4(W[O_ROOT + ob + 0]) | (bytes_to_nib4(W[O_ROOT + ob + 1]) << 16);
+    const uint32_t rk1 = bytes_to_nib4(W[O_ROOT + ob + 2]) | (bytes_to_nib4(W[O_ROOT + ob + 3]) << 16);
+    const uint32_t rk2 = bytes_to_nib4(W[O_ROOT + ob + 4]) | (bytes_to_nib4(W[O_ROOT + ob + 5]) << 16);
+    const uint32_t own_bar = (w12 >> (8 * player)) & 15u, own_off = (w12 >> (16 + 8 * player)) & 15u;
+    const uint32_t rk3 = (own_bar << 24) | (own_off << 28);
+    Root r;
+    r.player = player;
+    r.dirsign = player == 0 ? 1 : -1;
+    r.home = player == 0 ? 0xfc0000u : 0x00003fu;
+    {
+      uint32_t oc = 0;
+      if (lane < 24) oc = (W[O_ROOT + pb + (lane >> 2)] >> ((lane & 3) * 8)) & 0xffu;
+      r.blocked = __ballot_sync(BG_FULL, oc >= 2) & 0xffffffu;
+      r.blot = __ballot_sync(BG_FULL, oc == 1) & 0xffffffu;
+      uint32_t total = own_bar + own_off;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const uint32_t w = W[O_ROOT + ob + i];
+        total += (w & 0xff) + ((w >> 8) & 0xff) + ((w >> 16) & 0xff) + (w >> 24);
+      }
+      r.valid15 = total == 15u;
+    }
+    // ---- ply 1: the six dice (lane = die - 1) ------------------------------------------------------------------------------
+    const View rv = make_view(rk0, rk1, rk2, rk3, r);
+    const uint32_t m1 = lane < 6 ? view_mask(rv, r, lane + 1) : 0u;
+    const int n1 = __popc(m1 & 0x7ffffffu);
+    int inc1 = n1;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const int t = __shfl_up_sync(BG_FULL, inc1, o);
+      if (lane >= o) inc1 += t;
+    }
+    const int exc1 = inc1 - n1;
+    const int N1 = __shfl_sync(BG_FULL, inc1, 5);
+    if (N1 > C1CAP) {  // too many first moves for the table: every roll of this position goes to the generic tiers
+      if (lane < 21) push_overflow(P, pos * 21 + lane);
+      continue;
+    }
+    // ---- children of the root and their six second-die move sets (lane = child) ------------------------------------------------
+    uint32_t has2a = 0, has2b = 0;  // bit 6a+b (a < 5) / bit b (a == 5): some child of die a has a move with die b
+    for (int c0 = 0; c0 < N1; c0 += 32) {
+      const int c = c0 + lane;
+      const bool valid = c < N1;
+      int d = 0;
+#pragma unroll
+      for (int q = 0; q < 5; ++q) d += __shfl_sync(BG_FULL, inc1, q) <= c ? 1 : 0;
+      const uint32_t md = __shfl_sync(BG_FULL, m1, d);
+      const int bd = __shfl_sync(BG_FULL, exc1, d);
+      uint32_t nz = 0;
+      if (valid) {
+        const uint32_t slot = nth_set_bit(md & 0x7ffffffu, c - bd);
+        uint32_t s, e;
+        slot_se(r, slot, md >> 27, d + 1, s, e);
+        uint32_t k0 = rk0, k1 = rk1, k2 = rk2, k3 = rk3;
+        key_move(k0, k1, k2, k3, r, s, e);
+        const View v = make_view(k0, k1, k2, k3, r);
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+          const uint32_t m = view_mask(v, r, b + 1);
+          W[O_C1MASK + b * C1CAP + c] = m;
+          nz |= ((m & 0x7ffffffu) != 0u ? 1u : 0u) << b;
+        }
+        const uint32_t lone = (e < 24u && key_count(k0, k1, k2, e) == 1u) ? 1u : 0u;
+        W[O_C1INFO + c] = slot | (s << 5) | (e << 10) | ((uint32_t)d << 15) | (lone << 18);
+      }
+      has2a |= __reduce_or_sync(BG_FULL, (valid && d < 5) ? nz << (6 * d) : 0u);
+      has2b |= __reduce_or_sync(BG_FULL, (valid && d == 5) ? nz : 0u);
+    }
+    __syncwarp();
+
+    uint32_t emitted = 0;  // bit i: item i (roll index) has been written
+    int n_res = 0;
+    // ---- non-doubles (generate_all_moves.py:25-53, handle_move_types.py:7-81) ------------------------------------------------
+    // lane < 15 = roll; which die orders contribute which kind of entries:
+    //   forward order has two-move plays: they are results; the reverse order's two-move plays too (its singles would be filtered);
+    //   otherwise the forward order's singles are results, unless exactly one (quirk Q1: reverse order skipped), none (reverse
+    //   order alone), or the reverse order has two-move plays (the singles are filtered by the max-length rule).
+    {
+      int cnt0 = 0, cnt1 = 0;
+      uint32_t sg0 = 0, sg1 = 0;
+      const int lo = (int)((ND_LO >> (3 * (lane < 15 ? lane : 0))) & 7u), hi = (int)((ND_HI >> (3 * (lane < 15 ? lane : 0))) & 7u);
+      const int nh = __shfl_sync(BG_FULL, n1, hi), nl = __shfl_sync(BG_FULL, n1, lo);
+      if (lane < 15) {
+        const bool H0 = hi < 5 ? (has2a >> (6 * hi + lo)) & 1u : (has2b >> lo) & 1u;
+        const bool H1 = (has2a >> (6 * lo + hi)) & 1u;  // lo < 5 always
+        if (H0) {
+          cnt0 = nh;
+          cnt1 = H1 ? nl : 0;
+        } else if (nh == 1) {
+          cnt0 = 1;
+          sg0 = 1;
+        } else if (nh == 0) {
+          cnt1 = nl;
+          sg1 = H1 ? 0u : 1u;
+        } else if (H1) {
+          cnt1 = nl;
+        } else {
+          cnt0 = nh;
+          cnt1 = nl;
+          sg0 = sg1 = 1;
+        }
+      }
+      const int pe = cnt0 + cnt1;
+      int pinc = pe;
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+        const int t = __shfl_up_sync(BG_FULL, pinc, o);
+        if (lane >= o) pinc += t;
+      }
+      const int PE = __shfl_sync(BG_FULL, pinc, 14);
+      if (lane >= 15) pinc = 0x7fffffff;
+      const int pexc = pinc - pe;
+      const uint32_t rinfo = (uint32_t)cnt0 | (sg0 << 6) | (sg1 << 7);
+      if (PE > 0) clear_tab(W + O_TAB, lane);
+      bool nd_abort = false;
+      for (int e0 = 0; e0 < PE && !nd_abort; e0 += 32) {
+        const int e = e0 + lane;
+        const bool valid = e < PE;
+        int q = 0;  // roll of entry e: number of rolls whose inclusive end <= e
+#pragma unroll
+        for (int sft = 8; sft > 0; sft >>= 1) {
+          const int v = __shfl_sync(BG_FULL, pinc, q + sft - 1);
+          if (v <= e) q += sft;
+        }
+        q = q > 14 ? 14 : q;
+        const int j = e - __shfl_sync(BG_FULL, pexc, q);
+        const uint32_t ri = __shfl_sync(BG_FULL, rinfo, q);
+        const int c0n = (int)(ri & 63u);
+        const int order = j >= c0n ? 1 : 0;
+        const int qlo = (int)((ND_LO >> (3 * q)) & 7u), qhi = (int)((ND_HI >> (3 * q)) & 7u);
+        const int fa = order ? qlo : qhi, fb = order ? qhi : qlo;
+        const int c = __shfl_sync(BG_FULL, exc1, fa) + (order ? j - c0n : j);
+        const uint32_t single = (ri >> (6 + order)) & 1u;
+        const uint32_t mhi = __shfl_sync(BG_FULL, m1, qhi);
+        uint32_t pinfo = 0, m = 0;
+        if (valid) {
+          const uint32_t info = W[O_C1INFO + c];
+          m = single ? 1u : W[O_C1MASK + fb * C1CAP + c];
+          // reverse order: a second sub-move from a point that could move first with the high die commutes with an earlier pair
+          if (!single && order == 1 && own_bar == 0u && (info & 31u) < 24u) m &= ~(mhi & 0xffffffu);
+          pinfo = ((info >> 5) & 1023u) | ((uint32_t)fb << 10) | (single << 13) | ((m >> 27) << 14) | ((uint32_t)(q + 1 + qlo + 1) << 25);
+        }
+        int st = 0;
+        while (!nd_abort) {
+          const uint32_t rc = expand21(0, pinfo, m, st, O_RES, n_res, RCAP, player, r.blot, 0);
+          n_res = (int)(rc & 0xffffu);
+          if ((rc >> 16) == 0u) break;
+          st = (int)(rc >> 16) - 1;
+          // make room: candidate `st` belongs to the first parent whose inclusive candidate count exceeds st; every result before
+          // the first one of that parent's roll is a complete item (entries, hence results, are in roll order)
+          int inl = __popc(m & 0x7ffffffu);
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(BG_FULL, inl, o);
+            if (lane >= o) inl += t;
+          }
+          const uint32_t id0 = __shfl_sync(BG_FULL, pinfo >> 25, __ffs(__ballot_sync(BG_FULL, inl > st)) - 1);
+          int keep_from = n_res;
+          for (int i0 = 0; i0 < n_res; i0 += 32) {
+            const int i = i0 + lane;
+            const uint32_t b = __ballot_sync(BG_FULL, i < n_res && (W[O_RES + i] >> 25) == id0);
+            if (b) {
+              keep_from = i0 + __ffs(b) - 1;
+              break;
+            }
+          }
+          if (keep_from == 0) {  // one roll alone exceeds the buffer (not observed: a non-double has <= ~120 results)
+            nd_abort = true;
+            break;
+          }
+          emitted = flush21(&P, pos, player, r.blot, keep_from, n_res, emitted, true);
+          n_res -= keep_from;
+        }
+      }
+      if (nd_abort) {  // hand every non-double that has not been written to the generic tiers
+        n_res = 0;
+        if (lane < 21 && !((DBL_IDS >> lane) & 1u) && !((emitted >> lane) & 1u)) push_overflow(P, pos * 21 + lane);
+        emitted |= ~DBL_IDS & 0x1fffffu;
+      }
+    }
+    // ---- doubles (handle_move_types.py:84-193): breadth-first by ply, one die at a time -----------------------------------
+    for (int d0 = 0; d0 < 6; ++d0) {
+      const int die = d0 + 1;
+      const int nd1 = __shfl_sync(BG_FULL, n1, d0), bd1 = __shfl_sync(BG_FULL, exc1, d0);
+      if (nd1 == 0) continue;
+      const uint32_t id = (uint32_t)(d0 * 6 - d0 * (d0 - 1) / 2) + 1u;
+      bool overflow = false;
+      // ply 1 -> 2: parents are the children of die d0 (their move sets are in the table)
+      int n2 = 0, n3 = 0;
+      clear_tab(W + O_TAB, lane);
+      {
+        uint32_t pinfo = 0, m = 0;
+        if (lane < nd1) {
+          const uint32_t info = W[O_C1INFO + bd1 + lane];
+          m = W[O_C1MASK + d0 * C1CAP + bd1 + lane];
+          const uint32_t t = info & 31u, e = (info >> 10) & 31u;
+          if (t < 24u) {
+            uint32_t keep = ~((1u << t) - 1u);
+            if (e < t && ((info >> 18) & 1u)) keep |= 1u << e;
+            m &= keep | 0xff000000u;
+          }
+          pinfo = ((info >> 5) & 31u) | (NONE5 << 5) | (NONE5 << 10) | (NONE5 << 15) | ((m >> 27) << 20) | (id << 25);
+        }
+        const uint32_t rc = expand21(1, pinfo, m, 0, O_FA, 0, FCAP, player, r.blot, die);
+        n2 = (int)(rc & 0xffffu);
+        overflow = (rc >> 16) != 0u;
+      }
+      // plies 2 -> 3 and 3 -> 4
+      int n_last = nd1, last_ply = 1;  // the deepest non-empty ply and its size
+      if (!overflow && n2 > 0) {
+        n_last = n2;
+        last_ply = 2;
+        for (int ply = 2; ply <= 3 && !overflow; ++ply) {
+          const int src_off = ply == 2 ? O_FA : O_FB;
+          const int n_src = ply == 2 ? n2 : n3;
+          const bool to_res = ply == 3;
+          int n_dst = to_res ? n_res : 0;
+          const int dst_off = to_res ? O_RES : O_FB;
+          const int cap = to_res ? RCAP : FCAP;
+          const int res_mark = n_res;  // results of this die start here (ply 4 is written straight into the result buffer)
+          int mark = res_mark;
+          clear_tab(W + O_TAB, lane);
+          for (int p0 = 0; p0 < n_src && !overflow; p0 += 32) {
+            uint32_t pinfo = 0, m = 0;
+            if (p0 + lane < n_src) {
+              const uint32_t w = W[src_off + p0 + lane];
+              uint32_t k0 = rk0, k1 = rk1, k2 = rk2, k3 = rk3;
+#pragma unroll
+              for (int q = 0; q < 3; ++q) {
+                const uint32_t s = (w >> (5 * q)) & 31u;
+                if (s != NONE5) key_move(k0, k1, k2, k3, r, s, dbl_dest(r, s, die));
+              }
+              const View v = make_view(k0, k1, k2, k3, r);
+              m = view_mask(v, r, die);
+              const uint32_t t = (w >> 20) & 31u;
+              if (t < 24u) {
+                uint32_t keep = ~((1u << t) - 1u);
+                const int lt = (int)t + r.dirsign * die;
+                if (lt >= 0 && lt < (int)t && key_count(k0, k1, k2, (uint32_t)lt) == 1u) keep |= 1u << lt;
+                m &= keep | 0xff000000u;
+              }
+              pinfo = (w & 0xfffffu) | ((m >> 27) << 20) | (id << 25);
+            }
+            int st = 0;
+            while (true) {
+              const uint32_t rc = expand21(1, pinfo, m, st, dst_off, n_dst, cap, player, r.blot, die);
+              n_dst = (int)(rc & 0xffffu);
+              if ((rc >> 16) == 0u) break;
+              st = (int)(rc >> 16) - 1;
+              if (!to_res || mark == 0) {  // a frontier, or this die's fourth ply alone, exceeds the fast path's capacity
+                overflow = true;
+                break;
+              }
+              // make room: everything before this die's results is complete
+              emitted = flush21(&P, pos, player, r.blot, mark, n_dst, emitted, true);
+              n_dst -= mark;
+              mark = 0;
+            }
+          }
+          if (overflow) {
+            if (to_res) n_res = mark;  // drop this die's partial fourth ply
+            break;
+          }
+          if (to_res) {
+            if (n_dst > mark) {
+              n_res = n_dst;
+              last_ply = 4;
+            } else {
+              n_res = mark;
+            }
+          } else {
+            n3 = n_dst;
+            if (n3 > 0) {
+              n_last = n3;
+              last_ply = 3;
+            } else {
+              break;
+            }
+          }
+        }
+      }
+      if (overflow) {
+        if (lane == 0) push_overflow(P, pos * 21 + (id - 1));
+        emitted |= 1u << (id - 1);
+        continue;
+      }
+      if (last_ply < 4) {  // the deepest ply is a frontier (or the children table): its nodes are the results
+        if (n_res + n_last > RCAP) {
+          emitted = flush21(&P, pos, player, r.blot, n_res, n_res, emitted, false);
+          n_res = 0;
+        }
+        for (int i = lane; i < n_last; i += 32) {
+          uint32_t w;
+          if (last_ply == 1)
+            w = ((W[O_C1INFO + bd1 + i] >> 5) & 31u) | (NONE5 << 5) | (NONE5 << 10) | (NONE5 << 15) | (id << 25);
+          else
+            w = W[(last_ply == 2 ? O_FA : O_FB) + i];
+          W[O_RES + n_res + i] = w;
+        }
+        n_res += n_last;
+        __syncwarp();
+      }
+    }
+    emitted = flush21(&P, pos, player, r.blot, n_res, n_res, emitted, false);
+    if (lane < 21 && !((emitted >> lane) & 1u)) {
+      P.out_count[pos * 21 + lane] = 0;
+      P.out_offsets[pos * 21 + lane] = 0;
+    }
+  }
+}
+
+}  // namespace
+
+size_t movegen21_smem_bytes() { return (size_t)WARPS21 * WARP_WORDS * 4; }
+
+int32_t movegen21_launch_kernel(const MovegenParams& P, cudaStream_t stream) {
+  static bool done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return check_cuda(e, "cudaGetDevice");
+  if (dev < 0 || dev >= 64 || !done[dev]) {
+    e = cudaFuncSetAttribute(k_movegen21, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)movegen21_smem_bytes());
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_movegen21)");
+    if (dev >= 0 && dev < 64) done[dev] = true;
+  }
+  int64_t want = (P.B + WARPS21 - 1) / WARPS21;
+  const int64_t full = (int64_t)148 * CTAS21;
+  const int grid = (int)(want < full ? want : full);
+  k_movegen21<<<grid, WARPS21 * 32, movegen21_smem_bytes(), stream>>>(P);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return check_cuda(e, "k_movegen21 launch");
+  return BG_OK;
+}
+
+}  // namespace bg

@@ -207,6 +207,63 @@ def movegen_evaluate(boards: torch.Tensor, players: torch.Tensor, rolls: torch.T
     return res, out_values
 
 
+def movegen_all_rolls(boards: torch.Tensor, players: torch.Tensor, item_cap: int = 500, pool_cap: Optional[int] = None,
+                      want_submoves: bool = False, want_owner: bool = False, check_status: bool = True, out_boards: Optional[torch.Tensor] = None,
+                      workspace: Optional[torch.Tensor] = None, want_flags: bool = True, out_flags: Optional[torch.Tensor] = None) -> MovegenResult:
+    """get_all_possible_moves for EVERY roll of DICE_ROLLS (reference src/multi/two_ply.py:10-32) of each position: item
+    p * 21 + r.  One warp expands a whole position (bg_movegen_all_rolls); same results as movegen() on the replicated items."""
+    boards = _req(boards, torch.int8, "boards").reshape(-1, BOARD_BYTES)
+    P = boards.shape[0]
+    B = 21 * P
+    players = _req(players, torch.uint8, "players").reshape(P)
+    dev = boards.device
+    if pool_cap is None:
+        pool_cap = out_boards.shape[0] if out_boards is not None else max(1024, B * 64)
+    if out_boards is None:
+        out_boards = torch.empty((pool_cap, BOARD_BYTES), dtype=torch.int8, device=dev)
+    sub = torch.empty((pool_cap, 4, 3), dtype=torch.uint8, device=dev) if want_submoves else None
+    owner = torch.empty(pool_cap, dtype=torch.int32, device=dev) if want_owner else None
+    flags = out_flags if out_flags is not None else (torch.empty(pool_cap, dtype=torch.uint8, device=dev) if want_flags else None)
+    offsets = torch.empty(B, dtype=torch.int64, device=dev)
+    counts = torch.empty(B, dtype=torch.int32, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = workspace if workspace is not None else _workspace(B, dev)
+    check(lib().bg_movegen_all_rolls(boards.data_ptr(), players.data_ptr(), P, item_cap, pool_cap, out_boards.data_ptr(), _ptr(sub), _ptr(owner),
+                                     _ptr(flags), offsets.data_ptr(), counts.data_ptr(), total.data_ptr(), status.data_ptr(), ws.data_ptr(),
+                                     ws.numel(), _stream()))
+    res = MovegenResult(out_boards, sub, owner, flags, offsets, counts, total, status, item_cap)
+    if check_status:
+        res.raise_for_status()
+    return res
+
+
+def movegen_evaluate_all_rolls(boards: torch.Tensor, players: torch.Tensor, weights: PreparedWeights, out_boards: torch.Tensor,
+                               out_flags: torch.Tensor, out_values: torch.Tensor, workspace: Optional[torch.Tensor] = None, item_cap: int = 500,
+                               check_status: bool = False):
+    """bg_movegen_eval_all_rolls: every roll of every position generated (one warp per position) and every afterstate evaluated."""
+    boards = _req(boards, torch.int8, "boards").reshape(-1, BOARD_BYTES)
+    P = boards.shape[0]
+    B = 21 * P
+    players = _req(players, torch.uint8, "players").reshape(P)
+    dev = boards.device
+    pool_cap = out_boards.shape[0]
+    if out_flags.numel() < pool_cap or out_values.numel() < pool_cap:
+        raise ValueError("out_flags / out_values must have pool_cap entries")
+    offsets = torch.empty(B, dtype=torch.int64, device=dev)
+    counts = torch.empty(B, dtype=torch.int32, device=dev)
+    total = torch.zeros(2, dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = workspace if workspace is not None else _workspace(B, dev)
+    check(lib().bg_movegen_eval_all_rolls(boards.data_ptr(), players.data_ptr(), P, item_cap, pool_cap, out_boards.data_ptr(),
+                                          out_flags.data_ptr(), offsets.data_ptr(), counts.data_ptr(), total.data_ptr(), status.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), weights.table.data_ptr(), weights.H, out_values.data_ptr(), _stream()))
+    res = MovegenResult(out_boards, None, None, out_flags, offsets, counts, total[:1], status, item_cap)
+    if check_status:
+        res.raise_for_status()
+    return res, out_values
+
+
 def select(values: torch.Tensor, offsets: torch.Tensor, counts: torch.Tensor, temperature: float, seed: int = 0, ctr: int = 0,
            item_cap: int = 500, item_id_base: int = 0) -> torch.Tensor:
     """softmax(V/T) sampling (reference worker.py:136-143) or, temperature <= 0, first-index argmax (play_versus_ai.py:188-195)."""
