@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libbgarena.so")
+SO_PATH = os.environ.get("BG_LIBBGARENA") or os.path.join(_HERE, "libbgarena.so")  # the override is for A/B builds during development
 
 BG_OK = 0
 BG_ERR_ARG, BG_ERR_CUDA, BG_ERR_CAPACITY, BG_ERR_INVARIANT = -1, -2, -3, -4

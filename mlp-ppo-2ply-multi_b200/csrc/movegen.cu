@@ -546,11 +546,11 @@ int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* const (&
   P.in_count = nullptr;
   P.ovf_list = ovf[0];
   P.ovf_count = ovf_n[0];
-  // position-major bulk tier (movegen21.cu): one warp per position, all 21 rolls.  It never truncates an item (its items have fewer
-  // results than its buffer holds), so it needs item_cap >= that buffer
+  // position-major bulk tier (movegen21.cu): one warp per position, all 21 rolls
   const bool fast21 = P.all_rolls && !MOVES && P.item_cap >= MOVEGEN21_MIN_ITEM_CAP;
   if (fast21) {
     P.grab = 1;
+    if (const char* dbg = getenv("BG_MG21_DEBUG")) P.grab = atoi(dbg) | 1;  // development: bit 1 skip non-doubles, bit 2 skip doubles, bit 3 skip board stores
     P.B = B / 21;
     rc = movegen21_launch_kernel(P, stream);
     P.B = B;

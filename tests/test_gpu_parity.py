@@ -141,6 +141,109 @@ def test_movegen_capacity_tiers(bg, oracle):
     assert np.array_equal(off, o_off) and np.array_equal(ob, o_b) and np.array_equal(om, o_m)
 
 
+def test_truncation_at_500_matches_reference_golden(bg, golden):
+    """positions with more than 500 legal moves: the reference env keeps the first 500 (backgammon_env.py:35,262-272); out_count is the true count"""
+    g = golden("env_truncate")
+    res = bg.movegen(dev(g["boards"]), dev(g["players"]), dev(g["rolls"]), item_cap=500)
+    assert np.array_equal(res.counts.cpu().numpy(), g["true_count"])
+    off, ob, _ = res.canonical()
+    assert np.array_equal(off.cpu().numpy(), g["kept_off"]) and np.array_equal(ob.cpu().numpy(), g["kept"])
+    # the env mirror on the same positions
+    for i in range(len(g["boards"])):
+        env = bg.BackgammonEnv()
+        env.reset()
+        env.set_board(bg.ImmutableBoard.from_array(g["boards"][i]))
+        env.set_current_player(bg.Player(int(g["players"][i])))
+        env.roll_result = [int(x) for x in g["rolls"][i]]
+        env.update_legal_moves()
+        assert env.num_moves == 500 and len(env.legal_moves) == 500 and int(env.action_mask.sum().item()) == 500
+        kept = g["kept"][g["kept_off"][i]:g["kept_off"][i + 1]]
+        assert np.array_equal(np.asarray(env._legal_boards[:500]), kept)
+
+
+def all_rolls_reference(oracle, boards, players, item_cap):
+    ib, ip, ir = oracle.all_rolls_items(boards, players)
+    off, ob, _ = oracle.movegen_batch(ib, ip, ir, want_moves=False)
+    cnt = np.diff(off)
+    if (cnt > item_cap).any():  # keep the first item_cap rows of every item
+        keep = np.concatenate([np.arange(off[i], off[i] + min(cnt[i], item_cap)) for i in range(len(cnt))])
+        ob = ob[keep]
+        off = np.concatenate([[0], np.cumsum(np.minimum(cnt, item_cap))])
+    return cnt, off, ob
+
+
+def test_movegen_all_rolls_vs_oracle(bg, oracle, golden):
+    """bg_movegen_all_rolls (one warp per position, all 21 rolls; csrc/movegen21.cu) == get_all_possible_moves per (position, roll):
+    the reference's own golden positions, 6,000 random positions, the capacity-tier boards (doubles trees too wide for the fast path are
+    handed to the per-item tiers), truncation at item_cap, inactive / invalid positions"""
+    g = golden("movegen")
+    # the golden file holds 21 consecutive items per position, in DICE_ROLLS order
+    gb, gp = g["boards"][::21], g["players"][::21]
+    assert np.array_equal(np.repeat(gb, 21, 0), g["boards"]) and np.array_equal(g["rolls"][:21], np.array(bg.DICE_ROLLS, np.uint8))
+    res = bg.movegen_all_rolls(dev(gb), dev(gp), item_cap=4096)
+    off, ob, _ = res.canonical()
+    assert np.array_equal(off.cpu().numpy(), g["offsets"]) and np.array_equal(ob.cpu().numpy(), g["out_boards"])  # vs the reference itself
+    res = bg.movegen_all_rolls(dev(gb), dev(gp), item_cap=4096, want_submoves=True)  # sub-moves route through the per-item kernels
+    off, ob, om = res.canonical()
+    assert np.array_equal(ob.cpu().numpy(), g["out_boards"]) and np.array_equal(om.cpu().numpy(), g["out_submoves"])
+    boards, players = oracle.random_positions(6000, seed=77)
+    # wide doubles trees (> the fast path's arena), bar / bear-off specials
+    rng = np.random.default_rng(3)
+    wide = []
+    for k in range(48):
+        npts = [8, 10, 12, 13, 15, 15][k % 6]
+        b = np.zeros(52, np.int8)
+        pts = rng.choice(np.arange(0, 20), size=npts, replace=False)
+        for p in pts:
+            b[p] += 1
+        b[int(pts[0])] += 15 - b[:24].sum()
+        b[24 + 23] = 15
+        wide.append(b)
+    boards = np.concatenate([boards, np.array(wide, np.int8)])
+    players = np.concatenate([players, np.zeros(len(wide), np.uint8)])
+    for cap in (4096, 500, 40):
+        cnt, off, ob = all_rolls_reference(oracle, boards, players, cap)
+        res = bg.movegen_all_rolls(dev(boards), dev(players), item_cap=cap, pool_cap=int(off[-1]) + 64, want_owner=True)
+        assert np.array_equal(res.counts.cpu().numpy(), cnt)
+        assert res.total == int(off[-1])
+        o2, b2, _ = res.canonical()
+        assert np.array_equal(o2.cpu().numpy(), off) and np.array_equal(b2.cpu().numpy(), ob)
+        T = res.total
+        own = res.owner[:T].to(torch.int64)
+        assert bool((res.flags[:T] == dev(players)[own // 21]).all())
+    assert cnt.max() > 1024
+    # an invalid board poisons only its own position
+    bad = boards[:64].copy()
+    bad[5, 3] = 17
+    res = bg.movegen_all_rolls(dev(bad), dev(players[:64]), item_cap=4096, check_status=False)
+    assert int(res.status_dev.item()) == -4
+    c = res.counts.cpu().numpy().reshape(64, 21)
+    cnt64 = cnt[:64 * 21].reshape(64, 21)
+    assert (c[5] == 0).all() and np.array_equal(np.delete(c, 5, 0), np.delete(cnt64, 5, 0))
+
+
+def test_movegen_eval_all_rolls_equals_item_form(bg, oracle, golden):
+    """bg_movegen_eval_all_rolls == bg_movegen_eval on the replicated items: counts, boards, values (<= 1e-5 vs the double oracle)"""
+    v = golden("values")
+    H = int(v["H"])
+    w = bg.prepare_weights(dev(v["packed"]), H)
+    boards, players = oracle.random_positions(3000, seed=5)
+    cnt, off, ob = all_rolls_reference(oracle, boards, players, 500)
+    cap = int(off[-1]) + 4096
+    pool = torch.empty((cap, 52), dtype=torch.int8, device="cuda")
+    flags = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    vals = torch.empty(cap, dtype=torch.float32, device="cuda")
+    res, vals = bg.movegen_evaluate_all_rolls(dev(boards), dev(players), w, pool, flags, vals, item_cap=500, check_status=True)
+    assert np.array_equal(res.counts.cpu().numpy(), cnt) and res.total == int(off[-1])
+    o2, b2, _ = res.canonical()
+    assert np.array_equal(b2.cpu().numpy(), ob)
+    kept = torch.clamp(res.counts.to(torch.int64), max=500)
+    item = torch.repeat_interleave(torch.arange(kept.numel(), device="cuda"), kept)
+    rows = res.offsets[item] + (torch.arange(item.numel(), device="cuda") - o2[item])
+    want = oracle.value(v["packed"], H, ob, np.repeat(np.repeat(players, 21), cnt.clip(max=500)))
+    assert np.abs(vals[rows].cpu().numpy() - want).max() < 1e-5
+
+
 def test_encode_bit_exact(bg, oracle, golden):
     g = golden("features")
     f = bg.encode(dev(g["boards"]), dev(g["flags"])).cpu().numpy()

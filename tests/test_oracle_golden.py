@@ -84,8 +84,14 @@ def test_predicates_golden(oracle, golden):
     assert np.array_equal(got, g["pred"])
 
 
-def test_env_random_games_golden(oracle, golden):
-    g = golden("env_random")
+@pytest.mark.parametrize("which", ["env_random", "env_shaping"])
+def test_env_games_golden(oracle, golden, which):
+    """the reference env's own games (random actions; a point-making policy that collects the +0.30 close-out and +0.20 prime
+    rewards, backgammon_env.py:195-218) replayed through the oracle on the recorded dice"""
+    g = golden(which)
+    if which == "env_shaping":
+        assert ((g["info"] & 4) != 0).sum() >= 1 and ((g["info"] & 8) != 0).sum() >= 5
+        assert {20, 30} <= set(np.round(g["reward"] * 100).astype(int).tolist())
     n_games = len(g["tape_off"]) - 1
     for k in range(n_games):
         tape = g["tape"][g["tape_off"][k]:g["tape_off"][k + 1]]
@@ -108,6 +114,43 @@ def test_env_random_games_golden(oracle, golden):
             else:
                 assert env.win_type == (int(g["info"][s]) >> 8)
         assert env.tape_pos == len(tape)  # consumed exactly the reference's dice, rejected doubles included
+
+
+def test_env_truncate_golden(oracle, golden):
+    """positions with more than 500 legal moves: the reference env keeps the first 500 (backgammon_env.py:262-272)"""
+    g = golden("env_truncate")
+    assert (g["true_count"] > 500).all()
+    for i in range(len(g["boards"])):
+        ob, _ = oracle.legal_moves(g["boards"][i], int(g["players"][i]), tuple(g["rolls"][i]))
+        assert len(ob) == g["true_count"][i]
+        assert np.array_equal(ob[:500], g["kept"][g["kept_off"][i]:g["kept_off"][i + 1]])
+
+
+def test_worker_cap_golden(oracle, golden):
+    """a game the unmodified Worker.play_episode cut at MAX_TIMESTEPS = 300 (worker.py:101): the reference's sampled actions replayed
+    on its dice; 300 env steps, 295 experiences, no winner; values of the observation and of the chosen afterstate"""
+    g = golden("worker_cap")
+    packed, H = g["packed"], int(g["H"])
+    env = oracle.Env(tape=g["tape"])
+    env.reset()
+    e = 0
+    for t in range(int(g["n_steps"])):
+        a = int(g["action"][t])
+        if a < 0:
+            assert env.num_moves == 0
+            r, done, info = env.step(None)
+            assert r == 0.0 and not done
+            continue
+        obs, mover = env.board, env.player
+        after = env.afterstates[a]
+        v = oracle.value(packed, H, np.stack([obs, after]), np.array([mover, mover], np.uint8))
+        assert abs(v[0] - g["state_value"][e]) < 1e-5 and abs(v[1] - g["next_state_value"][e]) < 1e-5
+        r, done, info = env.step(a)
+        assert abs(r - float(g["reward"][e])) < 1e-7 and int(done) == int(g["done"][e]) == 0
+        e += 1
+    assert e == int(g["n_experiences"]) == 295 and int(g["n_steps"]) == 300 and int(g["win_type"]) == 0
+    assert np.array_equal(env.board, g["final_board"]) and env.player == int(g["final_player"])
+    assert env.tape_pos == len(g["tape"])
 
 
 def test_greedy_games_golden(oracle, golden):
