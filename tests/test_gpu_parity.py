@@ -144,7 +144,7 @@ def test_movegen_capacity_tiers(bg, oracle):
 def test_truncation_at_500_matches_reference_golden(bg, golden):
     """positions with more than 500 legal moves: the reference env keeps the first 500 (backgammon_env.py:35,262-272); out_count is the true count"""
     g = golden("env_truncate")
-    res = bg.movegen(dev(g["boards"]), dev(g["players"]), dev(g["rolls"]), item_cap=500)
+    res = bg.movegen(dev(g["boards"]), dev(g["players"]), dev(g["rolls"]), item_cap=500, pool_cap=4096)
     assert np.array_equal(res.counts.cpu().numpy(), g["true_count"])
     off, ob, _ = res.canonical()
     assert np.array_equal(off.cpu().numpy(), g["kept_off"]) and np.array_equal(ob.cpu().numpy(), g["kept"])
