@@ -5,10 +5,13 @@
 
 Workload (BASELINE.json configs[1]): P = 1,048,576 random-but-legal positions x the 21 unordered rolls
 (22,020,096 (position, roll) items, ~4.8e8 afterstates) per GPU.  One "step" = one pass of the hot path over that batch:
-legal-move generation (bg_movegen) + fused 198-feature encode + sigmoid-MLP value of every afterstate (bg_eval).
+legal-move generation (bg_movegen_all_rolls: one warp per position, all 21 rolls) + fused 198-feature encode + sigmoid-MLP value of every
+afterstate (bg_eval), one C-ABI call (bg_movegen_eval_all_rolls).
 Metric: afterstates evaluated per second (whole job, all GPUs).  Positions are synthetic: produced by the arena itself
 playing uniformly random legal moves from the start position (temperature -> infinity), snapshotted at spread-out plies.
-Also reported: `e2e` (host buffers in, greedy action + count per item out, copies inside the timed region),
+The first 65,536 positions are the committed fixture tests/golden/bench_positions.npz (made by this generator, scripts/make_bench_positions.py),
+which is also what `--impl reference` and the cpu_baseline leg run on.
+Also reported: `e2e` (bg_hostpipe_run: host positions in, greedy action + count per item out, copies inside the timed region),
 `roofline` for the dominant kernel, `cpu_baseline` (the C oracle port on the host cores, bounded sample),
 `selfplay_1ply` (BASELINE configs[2]: 65,536 concurrent games, games/s).
 Under torchrun each rank owns an independent shard (weak scaling, no data-path collective); rank 0 prints ONE JSON line.
@@ -128,6 +131,34 @@ def make_positions(bg, n_pos, device, seed):
     return boards, players
 
 
+FIXTURE = os.path.join(ROOT, "tests", "golden", "bench_positions.npz")
+
+
+def fixture_positions():
+    """the committed head of the benchmark's position set (numpy), or None"""
+    if not os.path.exists(FIXTURE):
+        return None
+    import numpy as np
+
+    g = np.load(FIXTURE)
+    return g["boards"], g["players"]
+
+
+def bench_positions(bg, n_pos, device, seed, rank):
+    """n_pos positions: the fixture first (rank 0 only: the other ranks' shards are disjoint arena draws), then fresh arena draws"""
+    import torch
+
+    fx = fixture_positions() if rank == 0 else None
+    if fx is None:
+        b, p = make_positions(bg, n_pos, device, seed)
+        return b, p, 0
+    fb, fp = torch.from_numpy(fx[0]).to(device), torch.from_numpy(fx[1]).to(device)
+    if n_pos <= fb.shape[0]:
+        return fb[:n_pos].contiguous(), fp[:n_pos].contiguous(), n_pos
+    b, p = make_positions(bg, n_pos - fb.shape[0], device, seed)
+    return torch.cat([fb, b]).contiguous(), torch.cat([fp, p]).contiguous(), int(fb.shape[0])
+
+
 def expand_rolls(bg, boards, players):
     import torch
 
@@ -137,6 +168,30 @@ def expand_rolls(bg, boards, players):
     ip = players.repeat_interleave(21)
     ir = rolls.repeat(n, 1)
     return ib.contiguous(), ip.contiguous(), ir.contiguous()
+
+
+def run_python_reference(mode, cores):
+    """oracle/reference_bench.py legs as subprocesses (the reference needs its own sys.path and `spawn`); each prints one JSON line"""
+    if mode == "off":
+        return {"unavailable": "--pyref off"}
+    games, secs = (100, 60) if mode == "full" else (30, 20)
+    script = os.path.join(ROOT, "oracle", "reference_bench.py")
+    legs = {"single_xavier_T1.5": ["single", "--games", str(games), "--policy", "xavier"],
+            "single_ckpt2.1M_greedy": ["single", "--games", str(games), "--policy", "ckpt"],
+            "workers_1thread": ["workers", "--procs", str(cores), "--seconds", str(secs), "--threads", "1"],
+            "workers_default_threads": ["workers", "--procs", str(cores), "--seconds", str(secs), "--threads", "default"]}
+    out = {"protocol": f"BASELINE.md 3.1-3.2 ({mode}: {games} games per single-process leg, {secs} s per all-cores leg from the first episode's arrival)",
+           "host_cores": cores}
+    for name, argv in legs.items():
+        try:
+            r = subprocess.run([sys.executable, script] + argv, capture_output=True, text=True, timeout=secs * 6 + 600)
+            lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            out[name] = json.loads(lines[-1]) if lines else {"unavailable": (r.stderr or "no output")[-300:]}
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"unavailable": repr(e)[:300]}
+        if "unavailable" in out[name] and "no copy of the reference" in str(out[name]["unavailable"]):
+            return {"python_reference": None, "reason": out[name]["unavailable"]}
+    return out
 
 
 def run_reference(args, rank, world):
@@ -151,7 +206,13 @@ def run_reference(args, rank, world):
     po.build()
     cores = os.cpu_count() or 1
     n_pos = args.ref_positions
-    boards, players = po.random_positions(n_pos, seed=2026)
+    fx = fixture_positions()
+    if fx is not None and n_pos <= len(fx[0]):  # the head of the position set the GPU arm runs on
+        boards, players = fx[0][:n_pos], fx[1][:n_pos]
+        pos_src = "the first %d positions of the benchmark's set (tests/golden/bench_positions.npz)" % n_pos
+    else:
+        boards, players = po.random_positions(n_pos, seed=2026)
+        pos_src = "%d oracle-generated random-playout positions" % n_pos
     ib, ip, ir = po.all_rolls_items(boards, players)
     packed = packed_random_weights(0).numpy()
     for _ in range(args.warmup):
@@ -163,7 +224,7 @@ def run_reference(args, rank, world):
         total += n
     dt = time.perf_counter() - t0
     val = total / dt
-    sample = f"{n_pos} positions x 21 rolls ({len(ib)} items, {total // max(args.steps, 1)} afterstates) per step"
+    sample = f"{pos_src} x 21 rolls ({len(ib)} items, {total // max(args.steps, 1)} afterstates) per step"
     line = {"impl": "reference", "metric": "afterstates_evaluated_per_sec", "value": val, "unit": "afterstates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int8 boards / fp32 values", "data": "synthetic",
@@ -192,6 +253,9 @@ def main():
     ap.add_argument("--cpu-selfplay-games", type=int, default=16384)
     ap.add_argument("--no-selfplay", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pyref", default="short", choices=["off", "short", "full"],
+                    help="time the UNMODIFIED Python reference when a copy is on the host (baseline/_ref): short = 30 games / 20 s per leg, "
+                         "full = BASELINE.md 3.1-3.2 (100 games, 60 s per leg)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -225,9 +289,9 @@ def main():
     # ---- inputs (resident in HBM before the timed region) --------------------------------------------------------
     packed = packed_random_weights(0).to(dev)
     weights = bg.prepare_weights(packed, H)
-    boards, players = make_positions(bg, args.positions, dev, seed=2026 + 7919 * rank)
-    ib, ip, ir = expand_rolls(bg, boards, players)
-    B = ib.shape[0]
+    boards, players, n_fixture = bench_positions(bg, args.positions, dev, seed=2026 + 7919 * rank, rank=rank)
+    P = boards.shape[0]
+    B = 21 * P  # items: (position, roll), roll order of src/multi/two_ply.py:10-32
     pool_cap = int(B * 26) + (1 << 20)
     pool = torch.empty((pool_cap, 52), dtype=torch.int8, device=dev)
     values = torch.empty(pool_cap, dtype=torch.float32, device=dev)
@@ -235,9 +299,9 @@ def main():
     ws = torch.empty(bg._lib.lib().bg_movegen_workspace_bytes(B), dtype=torch.uint8, device=dev)
 
     def step():
-        # one pass of the hot path over the batch: bg_movegen_eval = bg_movegen + bg_eval over the pool, the evaluation of the bulk
-        # tier's afterstates overlapping the generation of the tail tiers
-        res, _ = bg.movegen_evaluate(ib, ip, ir, weights, pool, pflags, values, workspace=ws, item_cap=500)
+        # one pass of the hot path over the batch: bg_movegen_eval_all_rolls = position-major move generation + bg_eval over the pool, the
+        # evaluation of the bulk tier's afterstates overlapping the generation of the tail tiers (the few doubles trees too wide for it)
+        res, _ = bg.movegen_evaluate_all_rolls(boards, players, weights, pool, pflags, values, workspace=ws, item_cap=500)
         return res
 
     sampler = ClockSampler(local_rank) if rank == 0 else None  # nvidia-smi needs ~0.5 s to start: begin before the warm-up; idle samples are filtered by power
@@ -266,7 +330,7 @@ def main():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     ev[0].record()
     for k in range(args.steps):
-        r = bg.movegen(ib, ip, ir, item_cap=500, out_boards=pool, check_status=False, workspace=ws, want_owner=False, out_flags=pflags)
+        r = bg.movegen_all_rolls(boards, players, item_cap=500, out_boards=pool, check_status=False, workspace=ws, out_flags=pflags)
         ev[3 * k + 1].record()
         bg.evaluate(pool, r.flags, weights, n_dev=r.total_dev, out=values)
         ev[3 * k + 2].record()
@@ -292,17 +356,33 @@ def main():
     value = n_after_all / (ms_per_step * 1e-3)
 
     # ---- e2e: public API from HOST buffers (pinned), H2D of the step's inputs and D2H of its result inside the timed region ----
-    h_b, h_p, h_r = ib.cpu().pin_memory(), ip.cpu().pin_memory(), ir.cpu().pin_memory()
+    h_b, h_p = boards.cpu().pin_memory(), players.cpu().pin_memory()
     h_act = torch.empty(B, dtype=torch.int32).pin_memory()
     h_cnt = torch.empty(B, dtype=torch.int32).pin_memory()
     res = r = None
+    # ---- the materialising encoder alone (bg_encode: 52 + 1 bytes in, 198 fp32 out per row): the one purely bandwidth-bound kernel ----
+    n_enc = int(min(n_after, 1 << 22))
+    feat = torch.empty((n_enc, 198), dtype=torch.float32, device=dev)
+    enc_lib = bg._lib.lib()
+    def enc():
+        bg._lib.check(enc_lib.bg_encode(pool.data_ptr(), pflags.data_ptr(), n_enc, feat.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    for _ in range(3):
+        enc()
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    q0.record()
+    for _ in range(10):
+        enc()
+    q1.record()
+    torch.cuda.synchronize()
+    t_enc = q0.elapsed_time(q1) / 10
+    del feat
     del pool, values, pflags, ws
     torch.cuda.empty_cache()
-    n_chunks = args.e2e_chunks if args.e2e_chunks > 0 else (12 if B >= (1 << 20) else 3)
-    pipe = bg.HostPipeline(weights, items_per_chunk=(B + n_chunks - 1) // n_chunks, device=dev, item_cap=500, n_streams=args.e2e_streams)
+    n_chunks = args.e2e_chunks if args.e2e_chunks > 0 else (12 if P >= (1 << 19) else 3)
+    pipe = bg.HostPipeline(weights, items_per_chunk=(P + n_chunks - 1) // n_chunks, device=dev, item_cap=500, n_streams=args.e2e_streams, all_rolls=True)
 
     def e2e_step():
-        pipe.run(h_b, h_p, h_r, h_act, h_cnt, temperature=0.0)  # chunked: copies of neighbouring chunks overlap the kernels
+        pipe.run(h_b, h_p, None, h_act, h_cnt, temperature=0.0)  # bg_hostpipe_run: chunked inside the library, copies overlap the kernels
 
     e2e_step()
     barrier()
@@ -318,44 +398,57 @@ def main():
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = n_after_all / (float(te[0]) / args.steps * 1e-3)
-    h2d = h_b.numel() + h_p.numel() + h_r.numel()
+    h2d = h_b.numel() + h_p.numel()
     d2h = h_act.numel() * 4 + h_cnt.numel() * 4
-    n_e2e_kernels = 8 * n_chunks  # movegen tiers (5) + eval (2) + select per chunk
+    n_step_kernels = 6  # k_movegen21 + the 512 / 2048 / 4096 per-item tail tiers + k_eval_tc twice (bulk-tier rows on the side stream, tail rows after)
+    n_e2e_kernels = (n_step_kernels + 2) * n_chunks  # + status fold + k_select, per chunk
     e2e_check = int((h_cnt.to(torch.int64).clamp(max=500)).sum().item())  # must reproduce the afterstate count of the resident path
+    pipe.close()
     del pipe
 
     # ---- roofline of the dominant kernel (algorithmic bytes / measured kernel time) -----------------------------------------
     peak, peak_src = load_peaks()
     eval_bytes = n_after * (52 + 1 + 4)  # board in + flag in + value out
-    movegen_bytes = B * (52 + 1 + 2 + 8 + 4) + n_after * (52 + 1)  # item in/out + board, flag out
-    kern = {"bg::k_eval_tc (tcgen05, H=128)": (t_eval, eval_bytes), "bg::k_movegen<128|256|512|2048|4096> (5 tiers)": (t_movegen, movegen_bytes)}
+    movegen_bytes = P * (52 + 1) + B * (8 + 4) + n_after * (52 + 1)  # position in, item offset / count out, board + flag out
+    k_mg, k_ev = "bg::k_movegen21 (+ 512 / 2048 / 4096 tail tiers)", "bg::k_eval_tc (tcgen05, H=128)"
+    kern = {k_ev: (t_eval, eval_bytes), k_mg: (t_movegen, movegen_bytes)}
     dom = max(kern, key=lambda k: kern[k][0])
     ach = kern[dom][1] / (kern[dom][0] * 1e-3) / 1e9
-    # dram__bytes_read + dram__bytes_write per launch from one `ncu --set full` capture of this command at the full configuration
-    # (profiles/r01_ncu_fullsize_dram_traffic.txt); only valid for that configuration
-    full_cfg = int(boards.shape[0]) == 1048576
-    traffic = {"bg::k_eval_tc (tcgen05, H=128)": 27.62e9, "bg::k_movegen<128|256|512|2048|4096> (5 tiers)": 27.2e9} if full_cfg else {}
+    # dram__bytes_read + dram__bytes_write per launch, from the `ncu --set full` capture of this command that scripts/ncu_traffic.py
+    # summarised into profiles/r02_traffic.json (valid for the configuration named in that file only)
+    traffic, traffic_src = {}, None
+    tj = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tj):
+        td = json.load(open(tj))
+        if int(td.get("positions", -1)) == P:
+            traffic = {k_mg: td.get("movegen_bytes"), k_ev: td.get("eval_bytes")}
+            traffic_src = "profiles/r02_traffic.json <- " + str(td.get("source"))
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic.get(dom),
-                "traffic_source": "profiles/r01_ncu_fullsize_dram_traffic.txt (ncu --set full, same command; bytes per launch)" if full_cfg else None,
-                "algorithmic_bytes": kern[dom][1],
+                "traffic_source": traffic_src, "algorithmic_bytes": kern[dom][1],
                 "peak_source": peak_src, "ms_per_launch": kern[dom][0],
-                "note": "integer-issue bound, not bandwidth bound: algorithmic bytes are tiny (SURVEY.md 8(d)); ncu on the bulk tier: issue-active 76.6 %, "
-                        "ALU pipe 72 %, 2,021 warp instructions per item, DRAM 4 % of peak (profiles/r01_ncu_v2_movegen_tiers_and_eval_tc.txt)",
+                "note": "both kernels are issue / tensor bound, not bandwidth bound: algorithmic bytes are tiny (SURVEY.md 8(d)); see roofline_movegen and roofline_eval",
                 "kernels_ms": {k: v[0] for k, v in kern.items()}, "movegen_ms_per_step": t_movegen_all,
                 "eval_fp32_tflops_dense_equiv": n_after * FLOP_PER_AFTERSTATE / (t_eval * 1e-3) / 1e12}
+    roofline_movegen = {"bound": "hbm", "kernel": k_mg, "achieved": movegen_bytes / (t_movegen * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": movegen_bytes / (t_movegen * 1e-3) / 1e9 / peak, "traffic": traffic.get(k_mg), "algorithmic_bytes": movegen_bytes,
+                        "ms_per_launch": t_movegen, "items_per_sec": B / (t_movegen * 1e-3)}
+    enc_bytes = n_enc * (52 + 1 + 198 * 4)
+    roofline_encode = {"bound": "hbm", "kernel": "bg::k_encode (materialised 198 fp32 features, parity / hand-off path)", "achieved": enc_bytes / (t_enc * 1e-3) / 1e9,
+                       "peak": peak, "unit": "GB/s", "frac": enc_bytes / (t_enc * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes": enc_bytes,
+                       "ms_per_launch": t_enc, "rows": n_enc}
     # the evaluator is a tensor-core kernel: 2 fp16 pieces x (2 * 208 * 128) FLOP per afterstate actually issued to tcgen05
     tc_flops = n_after * 2 * 2 * 208 * H
     tpeak = None
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
-        tpeak = float(json.load(open(pk)).get("bf16_tflops", 0.0)) or None
-    tpeak, tsrc = (tpeak, "measured (MEASURED_PEAKS.json bf16_tflops, burst)") if tpeak else (1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)")
+        pkd = json.load(open(pk))
+        tpeak = float(pkd.get("bf16_tflops_sustained", 0.0) or pkd.get("bf16_tflops", 0.0)) or None
+    tpeak, tsrc = (tpeak, "measured (MEASURED_PEAKS.json bf16_tflops_sustained: the kernel is timed inside a long step)") if tpeak else (1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)")
     tach = tc_flops / (t_eval * 1e-3) / 1e12
     roofline_eval = {"bound": "tensor", "kernel": "bg::k_eval_tc (tcgen05, H=128)", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s",
                      "frac": tach / tpeak, "traffic": traffic.get("bg::k_eval_tc (tcgen05, H=128)"), "peak_source": tsrc, "ms_per_launch": t_eval,
                      "note": "16-bit tensor FLOPs issued: 2 fp16 weight pieces x 2*208*128 per afterstate (fp32-exact layer 1); dense fp32-equivalent is 1/2.09 of this. ncu (profiles/r01_ncu_eval_tc_final_fp16x2.txt): tensor pipe 60 %, MUFU (ex2/rcp of the 128 sigmoids per board) 47 %, issue slots 53 % -- latency/co-limited with two worker warps per scheduler"}
 
-    del ib, ip, ir
     torch.cuda.empty_cache()
 
     # ---- secondary: BASELINE configs[2] / configs[3], self-play with 65,536 concurrent games per GPU (all ranks, sharded by game id) ----
@@ -549,7 +642,7 @@ def main():
         po.build()
         cores = os.cpu_count() or 1
         ns = min(args.cpu_positions, boards.shape[0])
-        sb, sp, sr = (x.cpu().numpy() for x in expand_rolls(bg, boards[:ns], players[:ns]))
+        sb, sp, sr = po.all_rolls_items(boards[:ns].cpu().numpy(), players[:ns].cpu().numpy())
         pk = packed.cpu().numpy()
         po.movegen_eval_bench(sb[:4096], sp[:4096], sr[:4096], pk, H, nthreads=cores)
         t0 = time.perf_counter()
@@ -560,11 +653,14 @@ def main():
         if selfplay is not None:  # BASELINE configs[0]: the reference's CPU self-play loop (1-ply, T = 1.5), one game per thread at a time
             ng = args.cpu_selfplay_games
             t0 = time.perf_counter()
-            n_after, n_steps, n_dec = po.selfplay_bench(pk, H, 1.5, ng, seed=0, nthreads=cores)
+            n_after_sp, n_steps, n_dec = po.selfplay_bench(pk, H, 1.5, ng, seed=0, nthreads=cores)
             dt = time.perf_counter() - t0
-            selfplay["cpu_baseline"] = {"value": ng / dt, "unit": "games/s", "cores": cores, "kind": "port", "afterstates_per_sec": n_after / dt,
+            selfplay["cpu_baseline"] = {"value": ng / dt, "unit": "games/s", "cores": cores, "kind": "port", "afterstates_per_sec": n_after_sp / dt,
                                         "sample": f"{ng} complete 1-ply self-play games (T=1.5) through the C restatement of Worker.play_episode, "
                                                   f"{n_steps / ng:.1f} plies/game, {dt:.1f} s, OpenMP over games"}
+
+        # ---- the UNMODIFIED Python reference on the same host cores (BASELINE.md 3.1-3.2, configs[0]), when a copy is on the host ----
+        cpu["python_reference"] = run_python_reference(args.pyref, cores)
 
     if rank != 0:
         if dist is not None:
@@ -576,12 +672,14 @@ def main():
             "dtype": "int8 boards / fp32 values", "data": "synthetic",
             "config": {"workload": "config2: random-legal positions x 21 rolls -> legal-move generation + fused 198-feature encode + 198x128x1 sigmoid-MLP value",
                        "positions_per_gpu": int(boards.shape[0]), "items_per_gpu": int(B), "afterstates_per_gpu_step": int(n_after), "hidden": H,
+                       "positions_from_fixture": int(n_fixture),
                        "l2": "inputs+outputs per step (>25 GB) far exceed the 126 MB L2", "parallelism": f"{world} x independent shards"},
             "e2e": {"value": e2e_value, "unit": "afterstates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "what": f"bg.HostPipeline.run: pinned host boards/players/rolls -> {n_chunks} chunks on {args.e2e_streams} streams (H2D, bg_movegen_eval, bg_select(greedy), D2H) -> host actions + counts",
+                    "what": f"bg_hostpipe_run (C ABI; bg.HostPipeline): pinned host positions + players -> {n_chunks} chunks on {args.e2e_streams} library streams (H2D, bg_movegen_eval_all_rolls, bg_select(greedy), D2H) -> 21 host (action, count) pairs per position",
                     "afterstates_check": e2e_check},
-            "gpu_launches": 7 * args.steps, "gpu_launches_note": f"timed region, per step (bg_movegen_eval): k_movegen tiers 128 / 256 / 512 / 2048 / 4096 + k_eval_tc twice (bulk-tier rows on the side stream, tail-tier rows after); unfused ms_per_step {unfused_ms_per_step:.2f}; the e2e region launches {n_e2e_kernels} per step (the same seven + k_select, per chunk)",
-            "roofline": roofline, "roofline_eval": roofline_eval, "cpu_baseline": cpu, "clocks": clocks, "selfplay_1ply": selfplay, "selfplay_2ply": selfplay2,
+            "gpu_launches": n_step_kernels * args.steps,
+            "gpu_launches_note": f"timed region, per step (bg_movegen_eval_all_rolls): k_movegen21 + per-item tail tiers k_movegen<512|2048|4096> + k_eval_tc twice (bulk-tier rows on the side stream, tail-tier rows after); unfused ms_per_step {unfused_ms_per_step:.2f}; the e2e region launches {n_e2e_kernels} per step (the same six + status fold + k_select, per chunk)",
+            "roofline": roofline, "roofline_movegen": roofline_movegen, "roofline_eval": roofline_eval, "roofline_encode": roofline_encode, "cpu_baseline": cpu, "clocks": clocks, "selfplay_1ply": selfplay, "selfplay_2ply": selfplay2,
             "selfplay_2ply_all_candidates": selfplay2b, "learner": learner, "td0_loop": td0}
     print(json.dumps(line), flush=True)
     if dist is not None:

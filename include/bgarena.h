@@ -179,6 +179,30 @@ int32_t bg_two_ply(const int8_t* cand_boards /*[N,52]*/, const uint8_t* mover /*
                    int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Host-resident batches: the same hot path with HOST pointers in and out (what a CPU-side caller of get_all_possible_moves +
+ * generate_all_board_features + policy_network.forward + argmax / Categorical.sample makes, src/multi/worker.py:101-143).
+ * The batch is cut into chunks of chunk_units that rotate over n_streams library-owned streams, so that the host->device copy of
+ * chunk k+1 and the device->host copy of chunk k-1 overlap the kernels of chunk k (bg_movegen_eval[_all_rolls] + bg_select); all
+ * device buffers are allocated once, here.  Pinned host memory makes the copies asynchronous; pageable memory works, serialised.
+ *   all_rolls != 0 : units are POSITIONS, every one expanded to the 21 rolls of DICE_ROLLS (bg_movegen_all_rolls); h_rolls is
+ *                    ignored and h_actions / h_counts have 21 * n_units entries (item = position * 21 + roll index);
+ *   all_rolls == 0 : units are (board, player, roll) items (bg_movegen).
+ *   rows_per_item  : pool rows provisioned per item of a chunk (the mean is ~22; 26 + a fixed slack is what bench.py uses).
+ * bg_hostpipe_run enqueues and returns; `stream` is ordered after every chunk (synchronise it before reading the outputs).
+ * h_actions[i] = selected action (argmax for temperature <= 0, else softmax(V/T) sample keyed by (seed, i)), -1 without a legal move;
+ * h_counts[i] = true legal-move count.  bg_hostpipe_status synchronises the pipe's streams and returns the worst status of every chunk
+ * since the previous call (BG_OK, BG_ERR_CAPACITY, BG_ERR_INVARIANT) in *out_status.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct bg_hostpipe bg_hostpipe;
+int32_t bg_hostpipe_create(bg_hostpipe** out, int32_t device, int32_t H, int64_t chunk_units, int32_t all_rolls, int32_t item_cap,
+                           int32_t rows_per_item, int32_t n_streams);
+int32_t bg_hostpipe_destroy(bg_hostpipe* p);
+int32_t bg_hostpipe_run(bg_hostpipe* p, const int8_t* h_boards /*host [n,52]*/, const uint8_t* h_players /*host [n]*/,
+                        const uint8_t* h_rolls /*host [n,2] or NULL*/, int64_t n_units, const float* prepared /*device*/, float temperature,
+                        uint64_t seed, int32_t* h_actions /*host*/, int32_t* h_counts /*host*/, void* stream);
+int32_t bg_hostpipe_status(bg_hostpipe* p, int32_t* out_status /*host*/);
+
+/* ------------------------------------------------------------------------------------------------
  * Stateful self-play arena: n_games concurrent games resident on one GPU.
  * Replaces the reference's worker processes: Worker.play_episode (src/multi/worker.py:78-174) over
  * BackgammonEnv.reset/step (src/environments/backgammon_env.py:92-329), Experience/Episode recording

@@ -11,6 +11,7 @@
 #include "movegen.cuh"
 #include "select.cuh"
 #include "two_ply.cuh"
+#include "hostpath.cuh"
 
 namespace bg {
 
@@ -218,6 +219,33 @@ int32_t bg_movegen_eval_all_rolls(const int8_t* boards, const uint8_t* players, 
                 nullptr, out_flags, out_offsets, out_count, out_total, out_status, workspace,  workspace_bytes, nullptr};
   a.all_rolls = 1;
   return movegen_eval_overlapped(a, out_total, prepared, H, out_v, c, (cudaStream_t)stream);
+}
+
+/* ---- host-resident batches ---- */
+
+int32_t bg_hostpipe_create(bg_hostpipe** out, int32_t device, int32_t H, int64_t chunk_units, int32_t all_rolls, int32_t item_cap,
+                           int32_t rows_per_item, int32_t n_streams) {
+  BG_REQUIRE(out, "bg_hostpipe_create: out is null");
+  int32_t rc = require_device();
+  if (rc != BG_OK) return rc;
+  HostPipe* p = nullptr;
+  rc = hostpipe_create(&p, device, H, chunk_units, all_rolls, item_cap, rows_per_item, n_streams);
+  *out = reinterpret_cast<bg_hostpipe*>(p);
+  return rc;
+}
+
+int32_t bg_hostpipe_destroy(bg_hostpipe* p) { return hostpipe_destroy(reinterpret_cast<HostPipe*>(p)); }
+
+int32_t bg_hostpipe_run(bg_hostpipe* p, const int8_t* h_boards, const uint8_t* h_players, const uint8_t* h_rolls, int64_t n_units,
+                        const float* prepared, float temperature, uint64_t seed, int32_t* h_actions, int32_t* h_counts, void* stream) {
+  BG_REQUIRE(p, "bg_hostpipe_run: null pipe");
+  return hostpipe_run(reinterpret_cast<HostPipe*>(p), h_boards, h_players, h_rolls, n_units, prepared, temperature, seed, h_actions, h_counts,
+                      (cudaStream_t)stream);
+}
+
+int32_t bg_hostpipe_status(bg_hostpipe* p, int32_t* out_status) {
+  BG_REQUIRE(p, "bg_hostpipe_status: null pipe");
+  return hostpipe_status(reinterpret_cast<HostPipe*>(p), out_status);
 }
 
 /* ---- arena ---- */

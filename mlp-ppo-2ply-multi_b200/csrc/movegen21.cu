@@ -172,11 +172,13 @@ __device__ __forceinline__ uint32_t dbl_dest(const Root& r, uint32_t s, int die)
   return (e < 0 || e > 23) ? 25u : (uint32_t)e;
 }
 
+#if BG_EMIT_NIBBLE
 // 4 nibbles (low 16 bits) -> 4 bytes
 __device__ __forceinline__ uint32_t nib4_spread(uint32_t x) {
   const uint32_t y = (x | (x << 8)) & 0x00ff00ffu;
   return (y | (y << 4)) & 0x0f0f0f0fu;
 }
+#endif
 
 __device__ __forceinline__ uint32_t hash_key(uint32_t k) { return (k * 0x9E3779B1u) >> (32 - 10); }
 static_assert(TCAP == 1024, "hash_key shift");

@@ -8,7 +8,7 @@
 // top_k = 5, alpha = 1, beta = 0.9 is the reference's setting; top_k = 1 is north_star's "best reply" expectimax.
 // The reference's random.sample(replies, 50) on 1-1/2-2/3-3 (two_ply.py:119-121) is NOT reproduced: it is
 // nondeterministic there; every reply is evaluated here.
-// Composition: k_expand (candidate x roll -> items) -> movegen tiers -> k_eval -> k_reduce (warp per candidate, top-k
+// Composition: position-major movegen (one warp per candidate, all 21 rolls; overflow -> per-item tiers) -> k_eval -> k_reduce (warp per candidate, top-k
 // selection and the 21-term expectation entirely in registers).  Candidates are processed in workspace-sized chunks.
 #include "two_ply.cuh"
 
@@ -19,34 +19,17 @@ namespace bg {
 
 namespace {
 
-__constant__ uint8_t c_roll_d0[21] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 5, 5, 6};
-__constant__ uint8_t c_roll_d1[21] = {1, 2, 3, 4, 5, 6, 2, 3, 4, 5, 6, 3, 4, 5, 6, 4, 5, 6, 5, 6, 6};
-
 constexpr int ROWS_PER_ITEM = 48;  // pool rows provisioned per (candidate, roll) item (mean is ~22)
 constexpr int MAX_TOPK = 8;
 
-__global__ void __launch_bounds__(256) k_expand(const int8_t* __restrict__ cand, const uint8_t* __restrict__ mover, const uint8_t* __restrict__ cand_active,
-                                                int64_t c0, int64_t nc, int8_t* __restrict__ ib, uint8_t* __restrict__ ip, uint8_t* __restrict__ ir,
-                                                uint8_t* __restrict__ iactive) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
-  const uint32_t* c32 = reinterpret_cast<const uint32_t*>(cand);
-  uint32_t* o32 = reinterpret_cast<uint32_t*>(ib);
-  for (int64_t c = warp; c < nc; c += nwarps) {
-    const uint32_t w = lane < 13 ? c32[(c0 + c) * 13 + lane] : 0u;
-    const uint8_t opp = 1 - (mover[c0 + c] & 1);
-    for (int r = 0; r < 21; ++r) {
-      const int64_t t = c * 21 + r;
-      if (lane < 13) o32[t * 13 + lane] = w;
-    }
-    if (lane < 21) {
-      const int64_t t = c * 21 + lane;
-      ip[t] = opp;
-      iactive[t] = cand_active ? cand_active[c0 + c] : (uint8_t)1;
-      ir[2 * t] = c_roll_d0[lane];
-      ir[2 * t + 1] = c_roll_d1[lane];
-    }
-  }
+// the opponent (the player who replies) and the active flag of each candidate; the 21 rolls of a candidate are expanded by the
+// position-major move generator itself (movegen21.cu), so the candidate boards are read in place instead of being replicated 21 times
+__global__ void __launch_bounds__(256) k_repliers(const uint8_t* __restrict__ mover, const uint8_t* __restrict__ cand_active, int64_t c0, int64_t nc,
+                                                  uint8_t* __restrict__ ip, uint8_t* __restrict__ iactive) {
+  const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (c >= nc) return;
+  ip[c] = 1 - (mover[c0 + c] & 1);
+  iactive[c] = cand_active ? cand_active[c0 + c] : (uint8_t)1;
 }
 
 __global__ void __launch_bounds__(256) k_reduce(const float* __restrict__ v, const long long* __restrict__ offsets, const int32_t* __restrict__ counts,
@@ -114,7 +97,7 @@ __global__ void __launch_bounds__(256) k_reduce(const float* __restrict__ v, con
 struct Layout {
   int64_t C;  // candidates per chunk
   int64_t items, rows;
-  int64_t o_ib, o_ip, o_ir, o_act, o_off, o_cnt, o_tot, o_pool, o_owner, o_val, o_ws, ws_bytes, total;
+  int64_t o_ip, o_act, o_off, o_cnt, o_tot, o_pool, o_owner, o_val, o_ws, ws_bytes, total;
 };
 
 int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
@@ -125,14 +108,10 @@ Layout make_layout(int64_t C) {
   L.items = C * 21;
   L.rows = L.items * ROWS_PER_ITEM;
   int64_t o = 0;
-  L.o_ib = o;
-  o += align256(L.items * 52);
   L.o_ip = o;
-  o += align256(L.items);
-  L.o_ir = o;
-  o += align256(L.items * 2);
+  o += align256(L.C);
   L.o_act = o;
-  o += align256(L.items);
+  o += align256(L.C);
   L.o_off = o;
   o += align256(L.items * 8);
   L.o_cnt = o;
@@ -182,16 +161,15 @@ int32_t two_ply_launch(const TwoPlyArgs& a, cudaStream_t s) {
   }
   for (int64_t c0 = 0; c0 < a.N; c0 += C) {
     const int64_t nc = a.N - c0 < C ? a.N - c0 : C;
-    const int64_t items = nc * 21;
     int64_t blocks = (nc + 7) / 8;
     const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
-    k_expand<<<grid, 256, 0, s>>>(a.cand_boards, a.mover, a.cand_active, c0, nc, (int8_t*)(w + L.o_ib), (uint8_t*)(w + L.o_ip),
-                                  (uint8_t*)(w + L.o_ir), (uint8_t*)(w + L.o_act));
+    k_repliers<<<(int)((nc + 255) / 256), 256, 0, s>>>(a.mover, a.cand_active, c0, nc, (uint8_t*)(w + L.o_ip), (uint8_t*)(w + L.o_act));
     MovegenArgs m{};
-    m.boards = (const int8_t*)(w + L.o_ib);
+    m.boards = a.cand_boards + c0 * 52;
     m.players = (const uint8_t*)(w + L.o_ip);
-    m.rolls = (const uint8_t*)(w + L.o_ir);
-    m.B = items;
+    m.rolls = nullptr;
+    m.all_rolls = 1;  // items = candidate * 21 + roll index
+    m.B = nc;
     m.item_cap = BG_MAX_ITEM_MOVES;
     m.pool_cap = L.rows;
     m.out_boards = (int8_t*)(w + L.o_pool);

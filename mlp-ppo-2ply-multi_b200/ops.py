@@ -301,55 +301,60 @@ def two_ply(cand_boards: torch.Tensor, mover: torch.Tensor, S: torch.Tensor, wei
 
 
 class HostPipeline:
-    """The per-decision hot path for HOST-resident batches: pinned (boards, players, rolls) in, (action, count) per item out.
-
-    The batch is cut into chunks that rotate over n_streams CUDA streams (three measured best: two cover the copies, the third lets one
-    chunk's tail tiers and selection overlap the next chunk's bulk tier), so chunk k+1's host->device copy and chunk k-1's device->host
-    copy overlap chunk k's kernels (bg_movegen_eval -> bg_select); all device buffers are allocated once.
+    """The per-decision hot path for HOST-resident batches (bg_hostpipe_*): pinned (boards, players[, rolls]) in, (action, count) per
+    item out.  Chunking, the copy / kernel overlap over n_streams streams and every device buffer live inside libbgarena.so; this class
+    only holds the handle.  all_rolls=True: the inputs are POSITIONS, each expanded to the 21 rolls of DICE_ROLLS (items_per_chunk is
+    then positions per chunk and the outputs have 21 entries per position).
     This is the call a CPU-side caller of get_all_possible_moves + generate_all_board_features + policy_network.forward +
     argmax/sample (reference worker.py:101-143) makes when its positions live in host memory."""
 
     def __init__(self, weights: PreparedWeights, items_per_chunk: int = 1 << 21, device=None, item_cap: int = 500, rows_per_item: int = 26,
-                 n_streams: int = 3):
-        self.dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-        self.weights, self.item_cap, self.Bc = weights, int(item_cap), int(items_per_chunk)
-        self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(max(2, int(n_streams)))]
-        cap = self.Bc * rows_per_item + (1 << 18)
-        self.buf = []
-        for _ in self.streams:
-            self.buf.append(dict(
-                b=torch.empty((self.Bc, BOARD_BYTES), dtype=torch.int8, device=self.dev), p=torch.empty(self.Bc, dtype=torch.uint8, device=self.dev),
-                r=torch.empty((self.Bc, 2), dtype=torch.uint8, device=self.dev), pool=torch.empty((cap, BOARD_BYTES), dtype=torch.int8, device=self.dev),
-                flags=torch.empty(cap, dtype=torch.uint8, device=self.dev), v=torch.empty(cap, dtype=torch.float32, device=self.dev),
-                ws=torch.empty(lib().bg_movegen_workspace_bytes(self.Bc), dtype=torch.uint8, device=self.dev), status=[]))
+                 n_streams: int = 3, all_rolls: bool = False):
+        import ctypes as C
 
-    def run(self, h_boards: torch.Tensor, h_players: torch.Tensor, h_rolls: torch.Tensor, h_actions: torch.Tensor, h_counts: torch.Tensor,
+        self.dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.weights, self.all_rolls = weights, bool(all_rolls)
+        self._h = C.c_void_p()
+        check(lib().bg_hostpipe_create(C.byref(self._h), self.dev.index or 0, weights.H, int(items_per_chunk), int(self.all_rolls), int(item_cap),
+                                       int(rows_per_item), max(1, int(n_streams))))
+
+    def run(self, h_boards: torch.Tensor, h_players: torch.Tensor, h_rolls: Optional[torch.Tensor], h_actions: torch.Tensor, h_counts: torch.Tensor,
             temperature: float = 0.0, seed: int = 0) -> None:
-        """All five tensors are pinned host tensors ([B,52] int8, [B] uint8, [B,2] uint8, [B] int32, [B] int32).  Returns after
-        enqueueing; the calling stream waits for both worker streams (synchronise it to read the results)."""
-        B = h_boards.shape[0]
-        cur = torch.cuda.current_stream(self.dev)
-        for s in self.streams:
-            s.wait_stream(cur)
-        for k, lo in enumerate(range(0, B, self.Bc)):
-            hi = min(B, lo + self.Bc)
-            n = hi - lo
-            d, s = self.buf[k % len(self.streams)], self.streams[k % len(self.streams)]
-            with torch.cuda.stream(s):
-                d["b"][:n].copy_(h_boards[lo:hi], non_blocking=True)
-                d["p"][:n].copy_(h_players[lo:hi], non_blocking=True)
-                d["r"][:n].copy_(h_rolls[lo:hi], non_blocking=True)
-                res, _ = movegen_evaluate(d["b"][:n], d["p"][:n], d["r"][:n], self.weights, d["pool"], d["flags"], d["v"], workspace=d["ws"],
-                                          item_cap=self.item_cap)
-                act = select(d["v"], res.offsets, res.counts, temperature=temperature, seed=seed, item_cap=self.item_cap, item_id_base=lo)
-                h_actions[lo:hi].copy_(act, non_blocking=True)
-                h_counts[lo:hi].copy_(res.counts, non_blocking=True)
-                d["status"] = [res.status_dev]
-        for s in self.streams:
-            cur.wait_stream(s)
+        """Host tensors (pinned for asynchronous copies): [n,52] int8, [n] uint8, [n,2] uint8 (None with all_rolls), int32 outputs with
+        one entry per item (21 per position with all_rolls).  Returns after enqueueing; the current stream is ordered after every
+        chunk (synchronise it to read the results)."""
+        n = h_boards.shape[0]
+        per = 21 if self.all_rolls else 1
+        for t, name in ((h_boards, "h_boards"), (h_players, "h_players"), (h_actions, "h_actions"), (h_counts, "h_counts")):
+            if t.is_cuda or not t.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous host tensor")
+        if h_actions.numel() < n * per or h_counts.numel() < n * per or h_actions.dtype != torch.int32 or h_counts.dtype != torch.int32:
+            raise ValueError("h_actions / h_counts must be int32 with one entry per item")
+        if h_boards.dtype != torch.int8 or h_players.dtype != torch.uint8 or h_players.numel() != n:
+            raise ValueError("h_boards must be int8 [n,52] and h_players uint8 [n]")
+        if not self.all_rolls and (h_rolls is None or h_rolls.is_cuda or h_rolls.dtype != torch.uint8 or h_rolls.numel() != 2 * n):
+            raise ValueError("h_rolls must be a host uint8 [n,2] tensor")
+        with torch.cuda.device(self.dev):
+            check(lib().bg_hostpipe_run(self._h, h_boards.data_ptr(), h_players.data_ptr(), None if self.all_rolls else h_rolls.data_ptr(), n,
+                                        self.weights.table.data_ptr(), float(temperature), seed & (2**64 - 1), h_actions.data_ptr(),
+                                        h_counts.data_ptr(), torch.cuda.current_stream(self.dev).cuda_stream))
 
     def raise_for_status(self):
-        for d in self.buf:
-            for st in d["status"]:
-                if int(st.item()) != 0:
-                    raise _lib.BgError(int(st.item()), "HostPipeline: bg_movegen reported a capacity/invariant problem")
+        """synchronises the pipe; raises if ANY chunk since the last call reported a capacity / invariant problem"""
+        import ctypes as C
+
+        st = C.c_int32(0)
+        check(lib().bg_hostpipe_status(self._h, C.byref(st)))
+        if st.value != 0:
+            raise _lib.BgError(st.value, "HostPipeline: bg_movegen reported a capacity/invariant problem")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().bg_hostpipe_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -465,6 +465,24 @@ def test_host_pipeline_equals_resident_path(bg, oracle):
         torch.cuda.synchronize()
         pipe.raise_for_status()
         assert torch.equal(hc, res.counts.cpu()) and torch.equal(ha, act.cpu())
+    pipe.close()
+    # position-major form: host positions in, 21 (action, count) pairs per position out
+    hb1, hp1 = torch.from_numpy(boards).pin_memory(), torch.from_numpy(players).pin_memory()
+    ha.fill_(-7)
+    hc.fill_(-7)
+    pipe = bg.HostPipeline(w, items_per_chunk=len(boards) // 4 + 1, device=DEV, all_rolls=True)
+    pipe.run(hb1, hp1, None, ha, hc, temperature=0.0)
+    torch.cuda.synchronize()
+    pipe.raise_for_status()
+    assert torch.equal(hc, res.counts.cpu()) and torch.equal(ha, act.cpu())
+    # every chunk's status is kept: an invalid board in the FIRST chunk is still reported after the last one
+    bad = boards.copy()
+    bad[3, 7] = 19
+    pipe.run(torch.from_numpy(bad).pin_memory(), hp1, None, ha, hc, temperature=0.0)
+    with pytest.raises(bg.BgError):
+        pipe.raise_for_status()
+    pipe.raise_for_status()  # the status word is reset by the read
+    pipe.close()
 
 
 def test_fused_movegen_eval_equals_separate_calls(bg, oracle):
