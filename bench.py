@@ -530,11 +530,12 @@ def main():
                 ar.step(1)
                 batch = ar.drain(max_episodes=quota)
             if world > 1:
-                batch = bgd.all_gather_episodes(batch, quota, quota * 300, compact=False)  # one all_gather (~4 MB padded), no host sync
+                # each field the trainer reads gathered straight into its final padded array: no host sync, no unpacking copies
+                batch = bgd.all_gather_episodes(batch, quota, quota * 300, compact=False, fields=bgd.LEARNER_FIELDS)
             # only now wait for update u-1 (it ran next to the ply, the drain and the gather) and publish it
             m = None
             if rank == 0:
-                m = tr.finish()  # stream-ordered wait, set_packed -> (broadcast) -> arena.set_weights
+                m = tr.finish(metrics=False)  # stream-ordered wait, set_packed -> (broadcast) -> arena.set_weights; no host read-back
             elif n_iter[0] > 0:  # rank 0 publishes update u-1 in iteration u: nothing to receive in the very first one
                 pm.sync_from_source()
             if rank == 0:

@@ -38,7 +38,8 @@ def main():
     torch.manual_seed(args.seed)
     pm = bg.ParameterManager(hidden_size=args.hidden)           # reference: Manager().dict() + lock + version
     arena = bg.Arena(args.games, hidden_size=args.hidden, device=dev, seed=args.seed, game_id_base=rank * args.games)
-    pm.subscribe(arena)                                         # collective when world > 1: rank 0's initial weights everywhere
+    pm.subscribe(arena)                                         # local: this rank's current weights
+    pm.publish()                                                # collective when world > 1: rank 0's initial weights everywhere
     trainer = bg.Trainer(pm, device=dev) if rank == 0 else None
     initial = bg.pack_weights(pm.get_parameters()).to(dev)
     learn_stream = torch.cuda.Stream(device=dev)
@@ -63,13 +64,15 @@ def main():
                 trainer.update_async(batch)                     # 200 sequential TD(0)/Adam steps, one kernel launch, no host sync
         arena.drain(max_episodes=args.games, max_experiences=args.games * 48)  # the sequential learner is the bottleneck: drop the surplus
         if rank == 0 and args.eval_every and (u + 1) % args.eval_every == 0:
-            trainer.finish()
+            # evaluate the weights that ARE published (update u-1).  Publication is a collective: calling trainer.finish() here would
+            # issue a broadcast the other ranks do not take part in
+            if world == 1:
+                trainer.finish()
             now = bg.pack_weights(pm.get_parameters()).to(dev)
             m = bg.play_match(now, initial, n_games=4096, hidden_size=args.hidden, device=dev, seed=u)
             print(f"update {u + 1:6d}  version {pm.get_version()}  T {pm.get_temperature():.3f}  loss {metrics.get('Loss/Training Loss', 0):.5f}  "
                   f"len {metrics.get('Episode/Average Episode Length', 0):.1f}  vs initial: win {m['a_win_rate']:.3f}  ppg {m['a_points_per_game']:+.3f}  "
                   f"[{(u + 1) * 200 / (time.time() - t0):,.0f} episodes/s]", flush=True)
-            pm.publish() if world == 1 else None
     if rank == 0:
         trainer.finish()
         if args.save:

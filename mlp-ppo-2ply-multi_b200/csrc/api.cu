@@ -256,35 +256,44 @@ int32_t bg_arena_create(bg_arena** out, int32_t device, int64_t n_games, int32_t
   int32_t rc = require_device();
   if (rc != BG_OK) return rc;
   Arena* A = nullptr;
+  DeviceGuard guard(device);  // the caller's current device is restored on return
   rc = arena_create(&A, device, n_games, H, max_plies, move_cap, seed, game_id_base, ring_experiences, ring_episodes, auto_reset);
   *out = reinterpret_cast<bg_arena*>(A);
   return rc;
 }
 
-int32_t bg_arena_destroy(bg_arena* a) { return arena_destroy(reinterpret_cast<Arena*>(a)); }
+int32_t bg_arena_destroy(bg_arena* a) {
+  DeviceGuard guard(arena_device(reinterpret_cast<Arena*>(a)));
+  return arena_destroy(reinterpret_cast<Arena*>(a));
+}
 
 int32_t bg_arena_set_weights(bg_arena* a, const float* packed, int64_t version, float temperature, void* stream) {
   BG_REQUIRE(a && packed, "bg_arena_set_weights: null pointer");
+  DeviceGuard guard(arena_device(reinterpret_cast<Arena*>(a)));
   return arena_set_weights(reinterpret_cast<Arena*>(a), packed, version, temperature, (cudaStream_t)stream);
 }
 
 int32_t bg_arena_set_dice_tape(bg_arena* a, const uint8_t* tape, int64_t L, void* stream) {
   BG_REQUIRE(a, "bg_arena_set_dice_tape: null arena");
+  DeviceGuard guard(arena_device(reinterpret_cast<Arena*>(a)));
   return arena_set_dice_tape(reinterpret_cast<Arena*>(a), tape, L, (cudaStream_t)stream);
 }
 
 int32_t bg_arena_reset(bg_arena* a, void* stream) {
   BG_REQUIRE(a, "bg_arena_reset: null arena");
+  DeviceGuard guard(arena_device(reinterpret_cast<Arena*>(a)));
   return arena_reset(reinterpret_cast<Arena*>(a), (cudaStream_t)stream);
 }
 
 int32_t bg_arena_set_lookahead(bg_arena* a, int32_t n_candidates, int32_t top_k, float alpha, float beta) {
   BG_REQUIRE(a, "bg_arena_set_lookahead: null arena");
+  DeviceGuard guard(arena_device(reinterpret_cast<Arena*>(a)));
   return arena_set_lookahead(reinterpret_cast<Arena*>(a), n_candidates, top_k, alpha, beta);
 }
 
 int32_t bg_arena_step(bg_arena* a, int32_t n_plies, int32_t lookahead, const int32_t* forced_action, void* stream) {
   BG_REQUIRE(a && n_plies >= 0, "bg_arena_step: bad arguments");
+  DeviceGuard guard(arena_device(reinterpret_cast<Arena*>(a)));
   return arena_step(reinterpret_cast<Arena*>(a), n_plies, lookahead, forced_action, (cudaStream_t)stream);
 }
 
@@ -292,17 +301,20 @@ int32_t bg_arena_drain_episodes(bg_arena* a, int64_t max_episodes, int64_t max_e
                                 float* reward, float* v, float* v_next, int16_t* n_moves, int16_t* action, uint8_t* roll,
                                 int64_t* ep_offsets, int32_t* ep_info, int64_t* out_n, void* stream) {
   BG_REQUIRE(a, "bg_arena_drain_episodes: null arena");
+  DeviceGuard guard(arena_device(reinterpret_cast<Arena*>(a)));
   return arena_drain(reinterpret_cast<Arena*>(a), max_episodes, max_experiences, after_boards, meta, reward, v, v_next, n_moves, action,
                      roll, ep_offsets, ep_info, out_n, (cudaStream_t)stream);
 }
 
 int32_t bg_arena_stats(bg_arena* a, int64_t* out, void* stream) {
   BG_REQUIRE(a && out, "bg_arena_stats: null pointer");
+  DeviceGuard guard(arena_device(reinterpret_cast<Arena*>(a)));
   return arena_stats(reinterpret_cast<Arena*>(a), out, (cudaStream_t)stream);
 }
 
 int32_t bg_arena_export_state(bg_arena* a, int8_t* boards, uint8_t* players, uint8_t* rolls, uint8_t* game_state, void* stream) {
   BG_REQUIRE(a, "bg_arena_export_state: null arena");
+  DeviceGuard guard(arena_device(reinterpret_cast<Arena*>(a)));
   return arena_export_state(reinterpret_cast<Arena*>(a), boards, players, rolls, game_state, (cudaStream_t)stream);
 }
 
@@ -314,25 +326,32 @@ int32_t bg_learner_create(bg_learner** out, int32_t device, int32_t H, float lr,
   int32_t rc = require_device();
   if (rc != BG_OK) return rc;
   Learner* L = nullptr;
+  DeviceGuard guard(device);
   rc = learner_create(&L, device, H, lr, gamma, grad_clip);
   *out = reinterpret_cast<bg_learner*>(L);
   return rc;
 }
 
-int32_t bg_learner_destroy(bg_learner* l) { return learner_destroy(reinterpret_cast<Learner*>(l)); }
+int32_t bg_learner_destroy(bg_learner* l) {
+  DeviceGuard guard(learner_device(reinterpret_cast<Learner*>(l)));
+  return learner_destroy(reinterpret_cast<Learner*>(l));
+}
 
 int32_t bg_learner_set_parameters(bg_learner* l, const float* packed, int32_t reset_optimizer, void* stream) {
   BG_REQUIRE(l && packed, "bg_learner_set_parameters: null pointer");
+  DeviceGuard guard(learner_device(reinterpret_cast<Learner*>(l)));
   return learner_set_parameters(reinterpret_cast<Learner*>(l), packed, reset_optimizer, (cudaStream_t)stream);
 }
 
 int32_t bg_learner_get_parameters(bg_learner* l, float* packed_out, void* stream) {
   BG_REQUIRE(l && packed_out, "bg_learner_get_parameters: null pointer");
+  DeviceGuard guard(learner_device(reinterpret_cast<Learner*>(l)));
   return learner_get_parameters(reinterpret_cast<Learner*>(l), packed_out, (cudaStream_t)stream);
 }
 
 int32_t bg_learner_get_optimizer(bg_learner* l, float* exp_avg, float* exp_avg_sq, int64_t* step, void* stream) {
   BG_REQUIRE(l, "bg_learner_get_optimizer: null learner");
+  DeviceGuard guard(learner_device(reinterpret_cast<Learner*>(l)));
   return learner_get_optimizer(reinterpret_cast<Learner*>(l), exp_avg, exp_avg_sq, step, (cudaStream_t)stream);
 }
 
@@ -340,6 +359,7 @@ int32_t bg_learner_update(bg_learner* l, const int8_t* boards, const uint8_t* fl
                           const int32_t* ep_len, int64_t n_episodes, int32_t records, float* out_metrics, int32_t* out_status, void* stream) {
   BG_REQUIRE(l && n_episodes >= 0, "bg_learner_update: bad arguments");
   BG_REQUIRE(n_episodes == 0 || (boards && flags && reward && ep_offsets), "bg_learner_update: null pointer");
+  DeviceGuard guard(learner_device(reinterpret_cast<Learner*>(l)));
   return learner_update(reinterpret_cast<Learner*>(l), boards, flags, reward, ep_offsets, ep_len, n_episodes, records, out_metrics, out_status,
                         (cudaStream_t)stream);
 }

@@ -770,6 +770,8 @@ int32_t arena_create(Arena** out, int32_t device, int64_t n_games, int32_t H, in
   return BG_OK;
 }
 
+int arena_device(const Arena* A) { return A ? A->device : 0; }
+
 int32_t arena_destroy(Arena* A) {
   if (!A) return BG_OK;
   cudaSetDevice(A->device);

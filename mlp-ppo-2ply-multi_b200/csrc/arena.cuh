@@ -7,6 +7,7 @@
 namespace bg {
 
 struct Arena;
+int arena_device(const Arena* A);  // the device the handle lives on
 
 int32_t arena_create(Arena** out, int32_t device, int64_t n_games, int32_t H, int32_t max_plies, int32_t move_cap, uint64_t seed,
                      int64_t game_id_base, int64_t ring_exps, int64_t ring_eps, int32_t auto_reset);

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "../../include/bgarena.h"
 
 #define BG_WARP 32
@@ -13,6 +15,40 @@ namespace bg {
 // thread-local error string (host side)
 void set_error(const char* fmt, ...);
 int32_t check_cuda(cudaError_t e, const char* what);
+
+// One-time initialisation of PER-DEVICE state (cudaFuncSetAttribute opt-ins, __constant__ tables): runs `init` once for every device the
+// library is used on, thread safe.  (A process-global flag would leave a second device without its shared-memory opt-in / constant table.)
+struct DeviceOnce {
+  std::mutex mu;
+  uint64_t done = 0;  // bit d: initialised on device d
+  template <class F>
+  int32_t run(F&& init) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return check_cuda(e, "cudaGetDevice");
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64 && ((done >> dev) & 1ull)) return BG_OK;
+    const int32_t rc = init();
+    if (rc == BG_OK && dev >= 0 && dev < 64) done |= 1ull << dev;
+    return rc;
+  }
+};
+
+// Makes `dev` current for the lifetime of the guard and restores the caller's device afterwards (handle-based entry points must not
+// leave the calling thread on another device).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched && prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 

@@ -230,61 +230,90 @@ __global__ void __launch_bounds__(EVAL_THREADS, (HPL <= 4 ? 2 : 1))
   }
 }
 
+// Materialised 198-feature rows (immutable_board.py:86-128), bit-exact fp32.  Purely bandwidth-bound (52 + 1 bytes in, 792 out per row), so
+// it is written around 16-byte stores: a warp encodes TWO consecutive rows (2 x 792 B = 99 float4, 16-byte aligned for an even first row);
+// a float4 of the first row is one point's thermometer code (a 16-entry table read), of the second row the tail of one point and the
+// head of the next.
+__device__ __forceinline__ float4 thermo4(int c) {
+  return make_float4(c >= 1 ? 1.f : 0.f, c >= 2 ? 1.f : 0.f, c >= 3 ? 1.f : 0.f, c > 3 ? (float)(c - 3) * 0.5f : 0.f);
+}
+
 __global__ void __launch_bounds__(256) k_encode(const int8_t* __restrict__ boards, const uint8_t* __restrict__ flags, int64_t N,
                                                 float* __restrict__ out) {
-  __shared__ uint32_t sb[8][16];
+  __shared__ uint32_t sb[8][32];
+  __shared__ float4 s_t4[16];
+  if (threadIdx.x < 16) s_t4[threadIdx.x] = thermo4((int)threadIdx.x);
+  __syncthreads();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = (int64_t)blockIdx.x * 8 + wib, nwarps = (int64_t)gridDim.x * 8;
   const uint32_t* b32 = reinterpret_cast<const uint32_t*>(boards);
-  for (int64_t i = warp; i < N; i += nwarps) {
+  const int64_t n_pairs = (N + 1) / 2;
+  for (int64_t pr = warp; pr < n_pairs; pr += nwarps) {
+    const int64_t i0 = pr * 2;
+    const bool two = i0 + 1 < N;
     __syncwarp();
-    if (lane < 13) sb[wib][lane] = __ldg(b32 + i * 13 + lane);
+    if (lane < (two ? 26 : 13)) sb[wib][lane] = __ldg(b32 + i0 * 13 + lane);  // the two boards are 26 consecutive words
     __syncwarp();
-    const uint8_t* bb = reinterpret_cast<const uint8_t*>(sb[wib]);
-    const int flag = flags[i] & 1;
-    float* o = out + i * 198;
-    for (int f = lane; f < 198; f += 32) {
-      float x;
-      if (f < 192) {
-        const int c = (int8_t)bb[f >> 2], k = f & 3;
-        x = k == 0 ? (c >= 1 ? 1.f : 0.f) : k == 1 ? (c >= 2 ? 1.f : 0.f) : k == 2 ? (c >= 3 ? 1.f : 0.f) : (c > 3 ? (float)(c - 3) * 0.5f : 0.f);
-      } else if (f == 192) {
-        x = (float)(int8_t)bb[48] * 0.5f;
-      } else if (f == 193) {
-        x = c_off15[bb[50] & 15u];
-      } else if (f == 194) {
-        x = (float)(int8_t)bb[49] * 0.5f;
-      } else if (f == 195) {
-        x = c_off15[bb[51] & 15u];
-      } else {
-        x = (f - 196) == flag ? 1.f : 0.f;
+    const uint8_t* b0 = reinterpret_cast<const uint8_t*>(sb[wib]);
+    const uint8_t* b1 = b0 + 52;
+    const int flag0 = flags[i0] & 1, flag1 = two ? flags[i0 + 1] & 1 : 0;
+    float4* o4 = reinterpret_cast<float4*>(out + i0 * 198);  // i0 even: 16-byte aligned
+    if (two) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int j = lane + 32 * it;
+        if (j >= 99) break;
+        float4 x;
+        if (j < 48) {
+          x = s_t4[b0[j] & 15u];
+        } else if (j == 48) {
+          x = make_float4((float)(int8_t)b0[48] * 0.5f, c_off15[b0[50] & 15u], (float)(int8_t)b0[49] * 0.5f, c_off15[b0[51] & 15u]);
+        } else if (j == 49) {
+          const float4 n = s_t4[b1[0] & 15u];
+          x = make_float4(flag0 == 0 ? 1.f : 0.f, flag0 == 1 ? 1.f : 0.f, n.x, n.y);
+        } else if (j < 97) {
+          const float4 a = s_t4[b1[j - 50] & 15u], n = s_t4[b1[j - 49] & 15u];
+          x = make_float4(a.z, a.w, n.x, n.y);
+        } else if (j == 97) {
+          const float4 a = s_t4[b1[47] & 15u];
+          x = make_float4(a.z, a.w, (float)(int8_t)b1[48] * 0.5f, c_off15[b1[50] & 15u]);
+        } else {
+          x = make_float4((float)(int8_t)b1[49] * 0.5f, c_off15[b1[51] & 15u], flag1 == 0 ? 1.f : 0.f, flag1 == 1 ? 1.f : 0.f);
+        }
+        o4[j] = x;
       }
-      o[f] = x;
+    } else {  // the last row of an odd batch: 49 float4 + one float2
+      for (int j = lane; j < 50; j += 32) {
+        if (j < 48) {
+          o4[j] = s_t4[b0[j] & 15u];
+        } else if (j == 48) {
+          o4[j] = make_float4((float)(int8_t)b0[48] * 0.5f, c_off15[b0[50] & 15u], (float)(int8_t)b0[49] * 0.5f, c_off15[b0[51] & 15u]);
+        } else {
+          reinterpret_cast<float2*>(o4)[98] = make_float2(flag0 == 0 ? 1.f : 0.f, flag0 == 1 ? 1.f : 0.f);
+        }
+      }
     }
   }
 }
 
 int32_t init_constants() {
-  static bool done = false;
-  if (done) return BG_OK;
-  float h[16];
-  for (int n = 0; n < 16; ++n) h[n] = (float)((double)n / 15.0);
-  cudaError_t e = cudaMemcpyToSymbol(c_off15, h, sizeof(h));
-  if (e != cudaSuccess) return check_cuda(e, "cudaMemcpyToSymbol(c_off15)");
-  done = true;
-  return BG_OK;
+  static DeviceOnce once;
+  return once.run([]() -> int32_t {
+    float h[16];
+    for (int n = 0; n < 16; ++n) h[n] = (float)((double)n / 15.0);
+    return check_cuda(cudaMemcpyToSymbol(c_off15, h, sizeof(h)), "cudaMemcpyToSymbol(c_off15)");
+  });
 }
 
 template <int HPL>
 int32_t launch_eval_t(const EvalArgs& a, cudaStream_t stream) {
   constexpr int H = HPL * 32;
   const size_t smem = (size_t)(202 * H) * 4 + (EVAL_THREADS / 32) * 56 * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_eval<HPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_eval)");
-    attr_done = true;
-  }
+  static DeviceOnce once;
+  int32_t rc0 = once.run([&]() -> int32_t {
+    return check_cuda(cudaFuncSetAttribute(k_eval<HPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(k_eval)");
+  });
+  if (rc0 != BG_OK) return rc0;
   const int ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;
   const int64_t bound = a.N_dev ? a.max_N : a.N;
   int64_t want = (bound + (EVAL_THREADS / 32) - 1) / (EVAL_THREADS / 32);
@@ -398,7 +427,11 @@ int32_t encode_launch(const int8_t* boards, const uint8_t* flags, int64_t N, flo
   if (N <= 0) return BG_OK;
   int32_t rc = init_constants();
   if (rc != BG_OK) return rc;
-  int64_t want = (N + 7) / 8;
+  if ((reinterpret_cast<uintptr_t>(out) & 15u) || (reinterpret_cast<uintptr_t>(boards) & 3u)) {
+    set_error("bg_encode: out must be 16-byte aligned and boards 4-byte aligned");
+    return BG_ERR_ARG;
+  }
+  int64_t want = ((N + 1) / 2 + 7) / 8;
   const int grid = (int)(want < (int64_t)NUM_SMS * 8 ? want : (int64_t)NUM_SMS * 8);
   k_encode<<<grid, 256, 0, stream>>>(boards, flags, N, out);
   cudaError_t e = cudaGetLastError();

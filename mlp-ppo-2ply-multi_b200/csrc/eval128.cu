@@ -241,17 +241,16 @@ int32_t eval128_prepare(const float* packed, float* t128, cudaStream_t stream) {
 }
 
 int32_t eval128_launch(const EvalArgs& a, const float* t128, cudaStream_t stream) {
-  static bool init = false;
+  static DeviceOnce once;
   constexpr size_t smem = (size_t)TABLE_ROWS * H * 4 + (size_t)WARPS * 2 * (LIST_WORDS + ELIST_WORDS) * 4;
-  if (!init) {
+  int32_t rc0 = once.run([&]() -> int32_t {
     float h[16];
     for (int n = 0; n < 16; ++n) h[n] = (float)((double)n / 15.0);
     cudaError_t e = cudaMemcpyToSymbol(c_off15b, h, sizeof(h));
     if (e != cudaSuccess) return check_cuda(e, "cudaMemcpyToSymbol(c_off15b)");
-    e = cudaFuncSetAttribute(k_eval128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_eval128)");
-    init = true;
-  }
+    return check_cuda(cudaFuncSetAttribute(k_eval128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(k_eval128)");
+  });
+  if (rc0 != BG_OK) return rc0;
   const int64_t bound = a.N_dev ? a.max_N : a.N;
   int64_t want = (bound + WARPS * 2 - 1) / (WARPS * 2);
   if (want < 1) want = 1;

@@ -27,7 +27,7 @@ namespace {
 constexpr int H = 128, KP = 208, KSTEPS = KP / 16, NSPLIT = 2;
 constexpr int KCHUNK_BYTES = 16 * 128;                      // one 8-wide K chunk of all 128 rows: 16 N-groups x 128 B
 constexpr int SPLIT_BYTES = (KP / 8) * KCHUNK_BYTES;        // 26 chunks = 53,248 B
-constexpr int B_BYTES = NSPLIT * SPLIT_BYTES;               // 159,744 B
+constexpr int B_BYTES = NSPLIT * SPLIT_BYTES;               // 106,496 B
 constexpr int THREADS = 288;                                // warps 0-3 group 0, 4-7 group 1, warp 8 MMA issuer
 constexpr int TMEM_COLS = 512, A_COLS = 128, D_COLS = 128;  // per group: A at +0 (104 used), D at +128
 constexpr int NUM_SMS = 148;
@@ -335,9 +335,9 @@ int32_t eval_tc_prepare(const float* packed, int32_t H_src, int32_t unit0, uint8
 }
 
 int32_t eval_tc_launch(const EvalArgs& a, const uint8_t* img, int32_t* err_flag, cudaStream_t stream, int accumulate) {
-  static bool init = false;
+  static DeviceOnce once;
   constexpr size_t smem = (size_t)B_BYTES + 1024 + 128;
-  if (!init) {
+  int32_t rc0 = once.run([&]() -> int32_t {
     uint32_t h[16][2];
     for (int n = 0; n < 16; ++n) {
       const float x = (float)((double)n / 15.0);
@@ -354,10 +354,9 @@ int32_t eval_tc_launch(const EvalArgs& a, const uint8_t* img, int32_t* err_flag,
     }
     cudaError_t e = cudaMemcpyToSymbol(c_off15_split, h, sizeof(h));
     if (e != cudaSuccess) return check_cuda(e, "cudaMemcpyToSymbol(c_off15_split)");
-    e = cudaFuncSetAttribute(k_eval_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_eval_tc)");
-    init = true;
-  }
+    return check_cuda(cudaFuncSetAttribute(k_eval_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(k_eval_tc)");
+  });
+  if (rc0 != BG_OK) return rc0;
   const int64_t bound = a.N_dev ? a.max_N : a.N;
   int64_t want = (bound + 255) / 256;
   if (want < 1) want = 1;

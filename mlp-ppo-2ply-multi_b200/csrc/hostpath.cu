@@ -57,17 +57,6 @@ struct HostPipe {
     if (e__ != cudaSuccess) return check_cuda(e__, what); \
   } while (0)
 
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    if (prev != dev) cudaSetDevice(dev);
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
-
 int32_t hostpipe_destroy(HostPipe* p) {
   if (!p) return BG_OK;
   DeviceGuard g(p->device);

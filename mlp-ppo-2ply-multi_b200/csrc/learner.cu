@@ -1169,6 +1169,8 @@ int32_t learner_create(Learner** out, int32_t device, int32_t H, float lr, float
   return BG_OK;
 }
 
+int learner_device(const Learner* L) { return L ? L->device : 0; }
+
 int32_t learner_destroy(Learner* L) {
   if (!L) return BG_OK;
   cudaSetDevice(L->device);

@@ -5,6 +5,7 @@
 namespace bg {
 
 struct Learner;
+int learner_device(const Learner* L);  // the device the handle lives on
 
 int32_t learner_create(Learner** out, int32_t device, int32_t H, float lr, float gamma, float grad_clip);
 int32_t learner_destroy(Learner* L);

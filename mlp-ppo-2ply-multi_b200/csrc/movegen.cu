@@ -510,14 +510,12 @@ constexpr int N_OVF = 4;  // overflow lists chaining the five tiers
 
 template <int CAP, bool GLOBAL, bool MOVES, int WARPS, int CTAS>
 int32_t prepare_tier() {
-  static bool done = false;
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(k_movegen<CAP, GLOBAL, MOVES, WARPS, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem_bytes(CAP, GLOBAL, MOVES, WARPS));
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_movegen)");
-    done = true;
-  }
-  return BG_OK;
+  static DeviceOnce once;
+  return once.run([]() -> int32_t {
+    return check_cuda(cudaFuncSetAttribute(k_movegen<CAP, GLOBAL, MOVES, WARPS, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem_bytes(CAP, GLOBAL, MOVES, WARPS)),
+                      "cudaFuncSetAttribute(k_movegen)");
+  });
 }
 
 // a tail tier: consumes overflow list `in`, produces list `out` (out < 0: last tier), uses work counter `in + 1`

@@ -31,6 +31,8 @@
 #include "movegen.cuh"
 #include "movegen_dev.cuh"
 
+#include <stdlib.h>
+
 namespace bg {
 
 namespace {
@@ -965,17 +967,20 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
 size_t movegen21_smem_bytes() { return (size_t)WARPS21 * WARP_WORDS * 4; }
 
 int32_t movegen21_launch_kernel(const MovegenParams& P, cudaStream_t stream) {
-  static bool done[64] = {};
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return check_cuda(e, "cudaGetDevice");
-  if (dev < 0 || dev >= 64 || !done[dev]) {
-    e = cudaFuncSetAttribute(k_movegen21, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)movegen21_smem_bytes());
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_movegen21)");
-    if (dev >= 0 && dev < 64) done[dev] = true;
-  }
+  static DeviceOnce once;
+  int32_t rc0 = once.run([]() -> int32_t {
+    return check_cuda(cudaFuncSetAttribute(k_movegen21, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)movegen21_smem_bytes()),
+                      "cudaFuncSetAttribute(k_movegen21)");
+  });
+  if (rc0 != BG_OK) return rc0;
+  cudaError_t e;
   int64_t want = (P.B + WARPS21 - 1) / WARPS21;
-  const int64_t full = (int64_t)148 * CTAS21;
+  int ctas_per_sm = CTAS21;
+  if (const char* lim = getenv("BG_MG21_CTAS")) {  // development: fewer resident CTAs per SM (co-residency experiments)
+    const int v = atoi(lim);
+    if (v >= 1 && v < CTAS21) ctas_per_sm = v;
+  }
+  const int64_t full = (int64_t)148 * ctas_per_sm;
   const int grid = (int)(want < full ? want : full);
   k_movegen21<<<grid, WARPS21 * 32, movegen21_smem_bytes(), stream>>>(P);
   e = cudaGetLastError();

@@ -22,11 +22,13 @@ def shard_games(n_games_total: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def broadcast_weights(packed: torch.Tensor, version: int, temperature: float, src: int = 0, group=None):
-    """One collective: the packed fp32 blob with (version, temperature) appended.  Returns (packed, version, temperature)."""
+    """One collective: the packed fp32 blob with (version, temperature) appended.  Returns (packed, version, temperature); reads the two
+    scalars back on the host (one synchronisation) -- ParameterManager.publish avoids that by deriving them on every rank."""
     blob = torch.cat([packed.reshape(-1).to(torch.float32), torch.tensor([float(version), float(temperature)], device=packed.device)])
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.broadcast(blob, src=src, group=group)
-    return blob[:-2], int(blob[-2].item()), float(blob[-1].item())
+    tail = blob[-2:].tolist()
+    return blob[:-2], int(tail[0]), float(tail[1])
 
 
 def all_reduce_stats(stats: Dict[str, int], device=None, group=None) -> Dict[str, int]:
@@ -41,21 +43,94 @@ _EP_FIELDS = (("after_boards", torch.int8, 52), ("meta", torch.uint8, 1), ("rewa
               ("next_state_value", torch.float32, 1), ("n_moves", torch.int16, 1), ("action", torch.int16, 1), ("roll", torch.uint8, 2))
 
 
-def all_gather_episodes(batch, max_episodes: int, max_experiences: int, group=None, compact: bool = True):
+class _GatherWorkspace:
+    """per-(device, quota, world) send / receive buffers of all_gather_episodes(compact=False), allocated once"""
+
+    cache: dict = {}
+
+    @classmethod
+    def get(cls, dev, world, max_episodes, max_experiences, cols_info):
+        key = (str(dev), world, max_episodes, max_experiences, cols_info)
+        w = cls.cache.get(key)
+        if w is None:
+            w = {"send": {}, "recv": {}}
+            for name, dt, cols in _EP_FIELDS:
+                shape = (max_experiences, cols) if cols > 1 else (max_experiences,)
+                w["send"][name] = torch.zeros(shape, dtype=dt, device=dev)
+                w["recv"][name] = torch.zeros((world * max_experiences,) + shape[1:], dtype=dt, device=dev)
+            w["send"]["hdr"] = torch.zeros(max_episodes + 3, dtype=torch.int64, device=dev)  # E, N, offsets[max_episodes + 1]
+            w["recv"]["hdr"] = torch.zeros((world, max_episodes + 3), dtype=torch.int64, device=dev)
+            w["send"]["info"] = torch.zeros((max_episodes, cols_info), dtype=torch.int32, device=dev)
+            w["recv"]["info"] = torch.zeros((world * max_episodes, cols_info), dtype=torch.int32, device=dev)
+            cls.cache[key] = w
+        return w
+
+
+def _all_gather_padded(batch, max_episodes, max_experiences, group, fields):
+    """compact=False path: every field is gathered straight into its final [world * quota, ...] array (the layout bg_learner_update reads with
+    explicit episode lengths): no host synchronisation, no unpacking copies, buffers reused across calls."""
+    from .episode import EpisodeBatch
+
+    E, N = int(batch.n_episodes), int(batch.n_experiences)
+    dev = batch.after_boards.device
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    cols_info = batch.ep_info.shape[1]
+    w = _GatherWorkspace.get(dev, world, max_episodes, max_experiences, cols_info)
+    names = [n for n, _, _ in _EP_FIELDS if fields is None or n in fields]
+    for name in names:
+        if N:
+            w["send"][name][:N].copy_(getattr(batch, name)[:N])
+    hdr = w["send"]["hdr"]
+    hdr[0], hdr[1] = E, N
+    hdr[2:3 + E].copy_(batch.ep_offsets[: E + 1])
+    if E:
+        w["send"]["info"][:E].copy_(batch.ep_info[:E])
+    pairs = [(w["recv"][n], w["send"][n]) for n in names] + [(w["recv"]["hdr"], hdr), (w["recv"]["info"], w["send"]["info"])]
+    if world > 1:
+        for out, inp in pairs:  # as bytes: int16 is not a collective dtype
+            ob, ib = out.reshape(-1).view(torch.uint8), inp.reshape(-1).view(torch.uint8)
+            if dev.type == "cuda":
+                dist.all_gather_into_tensor(ob, ib, group=group)
+            else:  # gloo (CPU tests): list form
+                dist.all_gather(list(ob.reshape(world, -1).unbind(0)), ib, group=group)
+    else:
+        for out, inp in pairs:
+            out.reshape(inp.shape).copy_(inp)
+    H = w["recv"]["hdr"]
+    offs = H[:, 2:]
+    j = torch.arange(max_episodes, device=dev).reshape(1, -1)
+    ep_len = torch.where(j < H[:, 0:1], offs[:, 1:] - offs[:, :-1], torch.zeros_like(offs[:, 1:])).clamp_(min=0)
+    begin = offs[:, :-1] + torch.arange(world, device=dev).reshape(-1, 1) * max_experiences
+    ep_offsets = torch.cat([begin.reshape(-1), torch.full((1,), world * max_experiences, dtype=torch.int64, device=dev)])
+    g = lambda n: w["recv"][n] if n in names else None  # noqa: E731
+    return EpisodeBatch(world * max_episodes, world * max_experiences, g("after_boards"), g("meta"), g("reward"), g("state_value"),
+                        g("next_state_value"), g("n_moves"), g("action"), g("roll"), ep_offsets.contiguous(), w["recv"]["info"],
+                        ep_len=ep_len.reshape(-1).to(torch.int32).contiguous())
+
+
+LEARNER_FIELDS = ("after_boards", "meta", "reward")  # what Trainer.update / bg_learner_update(records=1) reads
+
+
+def all_gather_episodes(batch, max_episodes: int, max_experiences: int, group=None, compact: bool = True, fields=None):
     """Config 5 (collective 3): every rank contributes its drained episodes (at most max_episodes /
     max_experiences) and receives all of them in rank order as one EpisodeBatch -- what the trainer rank feeds to Trainer.update.
-    ONE all_gather of a fixed-size byte buffer per rank (compact records: 72 B per experience, so 200 episodes are ~1.3 MB in
-    total); replaces the reference's ExperienceQueue.put from every worker process (src/multi/worker.py:60-64).
+    Compact records (72 B per experience, so 200 episodes are ~1.3 MB in total); replaces the reference's ExperienceQueue.put from every
+    worker process (src/multi/worker.py:60-64).
 
-    compact=True : the result is a dense CSR batch (one small host read-back for the per-rank sizes).
-    compact=False: no host synchronisation at all -- every rank's records stay in their padded segment and the batch carries explicit
-                   episode lengths (EpisodeBatch.ep_len; bg_learner_update's ep_len argument); n_episodes = world * max_episodes, ranks
-                   that supplied fewer episodes contribute zero-length ones, which the learner skips."""
+    compact=True : ONE all_gather of a fixed-size byte buffer per rank; the result is a dense CSR batch (one small host read-back for the
+                   per-rank sizes).
+    compact=False: no host synchronisation and no unpacking copies -- each field is gathered straight into its final padded array (buffers
+                   are cached: the returned batch is valid until the next call with the same quota) and the batch carries explicit episode
+                   lengths (EpisodeBatch.ep_len; bg_learner_update's ep_len argument); n_episodes = world * max_episodes, ranks that supplied
+                   fewer episodes contribute zero-length ones, which the learner skips.  fields=LEARNER_FIELDS gathers only what the trainer
+                   reads (the other record fields are None)."""
     from .episode import EpisodeBatch
 
     E, N = int(batch.n_episodes), int(batch.n_experiences)
     if E > max_episodes or N > max_experiences:
         raise ValueError(f"batch ({E} episodes, {N} experiences) exceeds the gather quota ({max_episodes}, {max_experiences})")
+    if not compact:
+        return _all_gather_padded(batch, max_episodes, max_experiences, group, fields)
     dev = batch.after_boards.device
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
@@ -94,14 +169,6 @@ def all_gather_episodes(batch, max_episodes: int, max_experiences: int, group=No
         cols = t.shape[-1]
         return t.reshape(-1, cols).contiguous() if cols > 1 else t.reshape(-1).contiguous()
 
-    if not compact:
-        j = torch.arange(max_episodes, device=dev).reshape(1, -1)
-        ep_len = torch.where(j < hdr[:, 0:1], offs[:, 1:] - offs[:, :-1], torch.zeros_like(offs[:, 1:])).clamp_(min=0)
-        begin = offs[:, :-1] + torch.arange(world, device=dev).reshape(-1, 1) * max_experiences
-        ep_offsets = torch.cat([begin.reshape(-1), torch.full((1,), world * max_experiences, dtype=torch.int64, device=dev)])
-        return EpisodeBatch(world * max_episodes, world * max_experiences, flat("after_boards"), flat("meta"), flat("reward"), flat("state_value"),
-                            flat("next_state_value"), flat("n_moves"), flat("action"), flat("roll"), ep_offsets.contiguous(),
-                            info.reshape(-1, cols_info).contiguous(), ep_len=ep_len.reshape(-1).to(torch.int32).contiguous())
     sizes = hdr.tolist()  # the one host read-back
     rows = torch.cat([torch.arange(n_r, device=dev) + r * max_experiences for r, (_, n_r) in enumerate(sizes)]) if sizes else None
     o_parts, tot = [torch.zeros(1, dtype=torch.int64, device=dev)], 0

@@ -111,6 +111,7 @@ class EpisodeBatch:
         if N:
             obs[1:] = self.after_boards[: N - 1]
             first = self.ep_offsets[: self.n_episodes]
+            first = first[self.episode_lengths() > 0]  # padded batches carry zero-length filler episodes whose offset may be out of range
             obs[first] = torch.from_numpy(initial_board_array()).to(dev)
         return obs, (self.meta[:N] & 1)
 

@@ -2,8 +2,9 @@
 get_parameters / set_parameters / get_version / get_temperature, plus .pth save/load in the reference's checkpoint format.
 
 What changes: instead of a multiprocessing.Manager dict polled by worker processes, set_parameters() publishes the packed
-fp32 weight blob to every subscribed GPU arena -- directly on one GPU, and with ONE NCCL broadcast of the ~104 KB blob
-(+ version, temperature) from the trainer rank when torch.distributed is initialised."""
+fp32 weight blob to every subscribed GPU arena -- directly on one GPU, and with ONE NCCL broadcast of the ~104 KB blob from the
+trainer rank when torch.distributed is initialised; version and temperature are derived on every rank, so
+publication never synchronises with the host."""
 from __future__ import annotations
 
 import os
@@ -22,7 +23,14 @@ class ParameterManager:
     FINAL_TEMPERATURE = FINAL_TEMPERATURE
     MAX_UPDATES = MAX_UPDATES
 
-    def __init__(self, hidden_size: int = 128, src_rank: int = 0, process_group=None):
+    def __init__(self, *reference_args, hidden_size: int = 128, src_rank: int = 0, process_group=None):
+        """ParameterManager() or, as the reference constructs it (src/main.py:65-73), ParameterManager(lock, version, parameters): the
+        three multiprocessing.Manager proxies are accepted and ignored (there are no worker processes to share them with).  A single int
+        positional argument is taken as hidden_size."""
+        if len(reference_args) == 1 and isinstance(reference_args[0], int):
+            hidden_size = reference_args[0]
+        elif len(reference_args) not in (0, 3):
+            raise TypeError("ParameterManager() takes no positional arguments, or the reference's (lock, version, parameters)")
         self._lock = threading.Lock()
         self._version = 1
         self._hidden = hidden_size
@@ -31,6 +39,7 @@ class ParameterManager:
         self._arenas: List = []
         self.src_rank = src_rank
         self.process_group = process_group
+        self._bcast = None  # preallocated broadcast buffer (device)
 
     # ---- reference surface -----------------------------------------------------------------------------------------
     def get_parameters(self, device=None):
@@ -44,7 +53,8 @@ class ParameterManager:
         self.set_packed(ops.pack_weights(new_state_dict), new_state_dict["fc1.weight"].shape[0])
 
     def set_packed(self, packed: torch.Tensor, hidden_size: Optional[int] = None):
-        """set_parameters for an already packed (device) blob: what the CUDA learner hands over, no host round trip."""
+        """set_parameters for an already packed (device) blob: what the CUDA learner hands over, no host round trip.
+        COLLECTIVE when torch.distributed is initialised: every other rank calls sync_from_source() at the same point."""
         with self._lock:
             if hidden_size is not None:
                 self._hidden = int(hidden_size)
@@ -57,28 +67,55 @@ class ParameterManager:
 
     # ---- arena subscription / multi-GPU publication -------------------------------------------------------------------
     def subscribe(self, arena):
+        """LOCAL: the arena gets this rank's current weights now and every later publication.  (Ranks other than the source hold
+        freshly initialised weights until the first set_packed() / sync_from_source() pair.)"""
         self._arenas.append(arena)
-        self.publish()
+        arena.set_weights(self._packed.to(arena.device), version=self._version, temperature=self.get_temperature())
 
     def _distributed(self) -> bool:
         return torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size(self.process_group) > 1
 
+    def _comm_device(self):
+        if self._arenas:
+            return self._arenas[0].device
+        if self._packed.is_cuda:
+            return self._packed.device
+        backend = torch.distributed.get_backend(self.process_group)
+        return torch.device("cuda", torch.cuda.current_device()) if "nccl" in str(backend) else torch.device("cpu")
+
     def publish(self):
-        """Send the current weights (+version, temperature) to every subscribed arena; across ranks with one broadcast."""
-        if not self._arenas and not self._distributed():
-            return
+        """Send the current weights to every subscribed arena; across ranks with ONE broadcast of the packed blob into a preallocated
+        device buffer.  Version and temperature do not travel and nothing is read back on the host: the source bumps its version in
+        set_packed(), every other rank bumps it in the matching sync_from_source(), and the temperature is a function of the version
+        (parameter_manager.py:93-111 of the reference)."""
         if self._distributed():
-            dev = self._arenas[0].device if self._arenas else self._packed.device
-            blob = torch.cat([self._packed.to(dev), torch.tensor([float(self._version), self.get_temperature()], device=dev)])
-            torch.distributed.broadcast(blob, src=self.src_rank, group=self.process_group)
-            self._version = int(blob[-2].item())
-            self._packed = blob[:-2].clone()
+            dev = self._comm_device()
+            if self._bcast is None or self._bcast.numel() != self._packed.numel() or self._bcast.device != dev:
+                self._bcast = torch.empty(self._packed.numel(), dtype=torch.float32, device=dev)
+            if torch.distributed.get_rank(self.process_group) == self.src_rank:
+                self._bcast.copy_(self._packed, non_blocking=True)
+            torch.distributed.broadcast(self._bcast, src=self.src_rank, group=self.process_group)
+            self._packed = self._bcast.clone()
         for a in self._arenas:
             a.set_weights(self._packed.to(a.device), version=self._version, temperature=self.get_temperature())
 
     def sync_from_source(self):
-        """Non-source ranks call this where the source rank calls set_parameters()/publish() (collective)."""
+        """Ranks other than the source call this where the source rank calls set_packed() / set_parameters() (collective): receives the
+        blob and advances the local version the same way."""
+        if self._distributed() and torch.distributed.get_rank(self.process_group) != self.src_rank:
+            with self._lock:
+                self._version += 1
         self.publish()
+
+    def check_version_sync(self) -> bool:
+        """Debug aid (one host synchronisation): do all ranks agree on the version?"""
+        if not self._distributed():
+            return True
+        dev = self._comm_device()
+        v = torch.tensor([self._version, -self._version], dtype=torch.int64, device=dev)
+        torch.distributed.all_reduce(v, op=torch.distributed.ReduceOp.MAX, group=self.process_group)
+        lo_hi = v.tolist()
+        return lo_hi[0] == -lo_hi[1]
 
     # ---- checkpoints (reference :115-230, S3 dropped) ------------------------------------------------------------------
     def save_model(self, filename: Optional[str] = None, to_s3: bool = False):

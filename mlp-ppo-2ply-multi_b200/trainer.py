@@ -122,6 +122,28 @@ class TD0Learner:
                            check_status=check_status, ep_len=batch.ep_len)
 
 
+class _LearnerNetworkView:
+    """trainer.policy_network: state_dict() / load_state_dict() of the weights held by the CUDA learner (reference trainer.py:21-24)."""
+
+    def __init__(self, trainer):
+        self._t = trainer
+
+    def state_dict(self):
+        return ops.unpack_weights(self._t.learner.packed(), self._t.learner.H)
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        self._t.learner.set_parameters(state_dict, reset_optimizer=False)
+
+    def __call__(self, x):
+        from .policy_network import BackgammonPolicyNetwork
+
+        net = BackgammonPolicyNetwork(hidden_size=self._t.learner.H)
+        net.load_state_dict({k: v.cpu() for k, v in self.state_dict().items()})
+        return net(x.cpu())
+
+    forward = __call__
+
+
 class Trainer:
     """Drop-in for the reference Trainer (src/agents/trainer.py).  `episodes` may be a list of Episode objects in the reference's
     format (observations = [198] tensors) or an EpisodeBatch drained from the Arena."""
@@ -143,6 +165,12 @@ class Trainer:
         self.last_metrics: dict = {}
         self._pending = None
 
+    @property
+    def policy_network(self):
+        """The reference exposes the network being trained (main.py:101 calls trainer.policy_network.load_state_dict(state_dict)); here the
+        weights live in the CUDA learner, so this is a view with the same two methods."""
+        return _LearnerNetworkView(self)
+
     def update(self, episodes):
         """Reference semantics (trainer.py:48-228): train on exactly 200 episodes, hand the new weights to the parameter manager,
         return (and log) the batch metrics.  Blocks until the update has run."""
@@ -155,6 +183,8 @@ class Trainer:
         n = episodes.n_episodes if isinstance(episodes, EpisodeBatch) else len(episodes)
         if n != self.batch_episode_size:
             raise ValueError(f"Expected {self.batch_episode_size} episodes, but got {n}.")
+        if not isinstance(episodes, EpisodeBatch) and any(len(ep.experiences) > MAX_T for ep in episodes):
+            raise ValueError(f"an episode has more than {MAX_T} experiences (the learner's limit; the reference caps episodes at 300 steps)")
         if self._pending is not None:
             self.finish()
         start = time.time()
@@ -164,12 +194,14 @@ class Trainer:
             met = self.learner.update_batch(episodes, check_status=False)
             info = episodes.ep_info[:n].to(torch.float32)
             lens = episodes.episode_lengths().to(torch.float32)
+            # padded batches (all_gather_episodes(compact=False)) carry zero-length filler episodes: averages are over the real ones
+            n_real = (lens > 0).sum().clamp(min=1).to(torch.float32)
             wins = torch.stack([(info[:, 0] == k).sum() for k in (1, 2, 3)]).to(torch.float32)
             seen = torch.stack([((episodes.ep_info[:n, 8] >> p) & 1).sum() for p in (0, 1)]).to(torch.float32)
             # the reference adds the episode's count dict once per EXPERIENCE (trainer.py:88-100)
             close = torch.stack([(info[:, 4 + p] * lens).sum() for p in (0, 1)])
             prime = torch.stack([(info[:, 6 + p] * lens).sum() for p in (0, 1)])
-            summary = torch.cat([met.mean(dim=0), wins, seen, close, prime, self.learner.last_status.to(torch.float32)])  # read back once, in finish()
+            summary = torch.cat([met.sum(dim=0) / n_real, wins, seen, close, prime, self.learner.last_status.to(torch.float32)])  # read back once, in finish()
             host = None
         else:
             obs = torch.stack([x.observation for ep in episodes for x in ep.experiences]).to(dev)
@@ -193,21 +225,26 @@ class Trainer:
         done.record(torch.cuda.current_stream(dev))
         self._pending = (summary, host, packed, done, start, episodes)  # `episodes` kept alive until the kernel has consumed it
 
-    def finish(self):
+    def finish(self, metrics: bool = True):
         """Wait (stream-ordered) for the pending update, hand its weights to the parameter manager (trainer.py:166) and return the
-        metrics the reference logs (trainer.py:195-228)."""
+        metrics the reference logs (trainer.py:195-228).  metrics=False skips the read-back of the metrics (no host synchronisation:
+        publication is stream-ordered); the learner's status is then checked by the next finish() that reads."""
         if self._pending is None:
             return self.last_metrics
         summary, host, packed, done, start, _ = self._pending
         self._pending = None
         torch.cuda.current_stream(self.device).wait_event(done)
+        vals = None
+        if metrics:
+            vals = summary.tolist()
+            if vals[-1] != 0:  # checked BEFORE the weights are published: a partial update never reaches the arenas
+                raise RuntimeError(f"bg_learner_update: an episode exceeded {MAX_T} experiences and was skipped")
         if hasattr(self.parameter_manager, "set_packed"):
             self.parameter_manager.set_packed(packed, self.learner.H)  # device blob: no host round trip, one broadcast when distributed
         else:
             self.parameter_manager.set_parameters(ops.unpack_weights(packed, self.learner.H))
-        vals = summary.tolist()
-        if vals[-1] != 0:
-            raise RuntimeError(f"bg_learner_update: an episode exceeded {MAX_T} experiences and was skipped")
+        if vals is None:
+            return self.last_metrics
         avg = vals[:6]  # trainer.py:157-163: totals / batch_size
         if host is None:
             wins = dict(zip(("regular", "gammon", "backgammon"), (int(x) for x in vals[6:9])))

@@ -25,6 +25,19 @@ def _worker(rank, world, port, out_dir):
 
     torch.manual_seed(100 + rank)  # ranks start from DIFFERENT weights
     pm = bg.ParameterManager(hidden_size=128)
+
+    class FakeArena:  # records what a subscribed arena would receive
+        device = torch.device("cpu")
+
+        def __init__(self):
+            self.got = []
+
+        def set_weights(self, packed, version, temperature):
+            self.got.append((packed.clone(), version, temperature))
+
+    fa = FakeArena()
+    pm.subscribe(fa)  # LOCAL (no hidden collective): this rank's own initial weights
+    assert len(fa.got) == 1 and fa.got[0][1] == 1
     if rank == 0:
         net = bg.BackgammonPolicyNetwork()
         pm.set_parameters(net.state_dict())  # trainer rank publishes -> one broadcast
@@ -33,6 +46,27 @@ def _worker(rank, world, port, out_dir):
         pm.sync_from_source()
         pm.sync_from_source()
     packed = bg.pack_weights(pm.get_parameters())
+    assert len(fa.got) == 3 and fa.got[-1][1] == 3 and torch.equal(fa.got[-1][0], packed) and pm.check_version_sync()
+    # the training loop of examples/train_selfplay.py with evaluation enabled: rank 0 publishes update u-1 in iteration u, the other ranks
+    # receive it at the same point, and the evaluation branch issues NO collective (it reads the already published weights)
+    for u in range(5):
+        torch.distributed.all_reduce(torch.zeros(1))  # stands for the episode gather
+        if rank == 0:
+            if u > 0:
+                pm.set_packed(packed + u)
+        elif u > 0:
+            pm.sync_from_source()
+        if rank == 0 and (u + 1) % 2 == 0:
+            _ = bg.pack_weights(pm.get_parameters())  # evaluation: no publish, no finish
+    if rank == 0:
+        pm.set_packed(packed + 5)
+    else:
+        pm.sync_from_source()
+    assert pm.get_version() == 8 and pm.check_version_sync() and torch.equal(bg.pack_weights(pm.get_parameters()), packed + 5)
+    assert fa.got[-1][1] == 8 and fa.got[-1][2] == pm.get_temperature()
+    pm.set_packed(packed) if rank == 0 else pm.sync_from_source()
+    # the reference's constructor arguments (lock, version, parameters) are accepted
+    assert bg.ParameterManager(object(), object(), {}).get_version() == 1
     n_local, base = bgd.shard_games(65536 + 1, rank, world)
     stats = bgd.all_reduce_stats({"games": 10 + rank, "steps": 1000 * (rank + 1), "afterstates": 7})
     w, ver, temp = bgd.broadcast_weights(packed * (rank + 1), 5 + rank, 1.25 - rank, src=0)
@@ -49,6 +83,10 @@ def _worker(rank, world, port, out_dir):
                       torch.full((E + 2, 12), 100 + rank, dtype=torch.int32))
     merged = bgd.all_gather_episodes(eb, max_episodes=4, max_experiences=12)
     padded = bgd.all_gather_episodes(eb, max_episodes=4, max_experiences=12, compact=False)  # no host sync; explicit episode lengths
+    slim = bgd.all_gather_episodes(eb, max_episodes=4, max_experiences=12, compact=False, fields=bgd.LEARNER_FIELDS)  # what the trainer reads
+    assert slim.roll is None and slim.action is None and torch.equal(slim.after_boards, padded.after_boards) and torch.equal(slim.ep_len, padded.ep_len)
+    ob, of = padded.observation_boards()  # zero-length filler episodes must not index out of range
+    assert ob.shape == (24, 52)
     np.savez(os.path.join(out_dir, f"pad{rank}.npz"), n=np.array([padded.n_episodes, padded.n_experiences]), begin=padded.ep_offsets.numpy(),
              len=padded.ep_len.numpy(), after=padded.after_boards.numpy(), reward=padded.reward.numpy(), info=padded.ep_info.numpy())
     np.savez(os.path.join(out_dir, f"ep{rank}.npz"), n=np.array([merged.n_episodes, merged.n_experiences]), off=merged.ep_offsets.numpy(),
@@ -64,8 +102,8 @@ def test_two_rank_weight_broadcast_sharding_and_stats(tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     r0, r1 = (np.load(tmp_path / f"r{r}.npz") for r in range(world))
     assert np.array_equal(r0["packed"], r1["packed"])  # both ranks hold the trainer rank's weights
-    assert int(r0["version"]) == int(r1["version"]) == 3
-    assert float(r0["temperature"]) == float(r1["temperature"]) == pytest.approx(1.5 - 1.0 * 2 / 4000)
+    assert int(r0["version"]) == int(r1["version"]) == 9
+    assert float(r0["temperature"]) == float(r1["temperature"]) == pytest.approx(1.5 - 1.0 * 8 / 4000)
     assert int(r0["n_local"]) + int(r1["n_local"]) == 65537 and int(r0["base"]) == 0 and int(r1["base"]) == int(r0["n_local"])
     assert int(r0["games"]) == int(r1["games"]) == 21 and int(r0["steps"]) == 3000 and int(r1["after"]) == 14
     assert np.array_equal(r0["w"], r1["w"]) and int(r1["ver"]) == 5 and float(r1["temp"]) == 1.25
