@@ -544,8 +544,13 @@ int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* const (&
   P.in_count = nullptr;
   P.ovf_list = ovf[0];
   P.ovf_count = ovf_n[0];
-  // position-major bulk tier (movegen21.cu): one warp per position, all 21 rolls
-  const bool fast21 = P.all_rolls && !MOVES && P.item_cap >= MOVEGEN21_MIN_ITEM_CAP;
+  // Position-major batches: the bulk tier is the code-based generator of movegen21.cu, one warp per position expanding all 21 rolls.
+  // Per-item batches: the 128-node frontier kernel stays the bulk tier (a warp per item amortises nothing of the code-based kernel's set-up),
+  // but what overflows it -- the wide doubles trees -- goes to the code-based generator in single-roll mode, which prunes their
+  // duplicate candidates and holds ~670 results per item, instead of the 512- and 2048-node frontier tiers.  Only the FullMove sub-move
+  // histories (MOVES) still use the frontier tiers throughout.
+  const bool code_tiers = !MOVES && P.item_cap >= MOVEGEN21_MIN_ITEM_CAP && !getenv("BG_MOVEGEN_LEGACY");
+  const bool fast21 = code_tiers && P.all_rolls;
   if (fast21) {
     P.grab = 1;
     if (const char* dbg = getenv("BG_MG21_DEBUG")) P.grab = atoi(dbg) | 1;  // development: bit 1 skip non-doubles, bit 2 skip doubles, bit 3 skip board stores
@@ -574,8 +579,19 @@ int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* const (&
   const bool use256 = B >= (1 << 20) && !fast21;  // what the position-major tier hands over is wider than 224 nodes per ply
   const int c2 = tier2_ctas > 0 && tier2_ctas < T2_CTAS_PER_SM ? tier2_ctas : T2_CTAS_PER_SM;
   if (use256 && (rc = launch_tail_tier<T2_CAP, false, MOVES, T2_WARPS, T2_CTAS_PER_SM>(P, 0, 1, c2, ctr, ovf, ovf_n, stream)) != BG_OK) return rc;
-  if ((rc = launch_tail_tier<T3_CAP, false, MOVES, T3_WARPS, T3_CTAS_PER_SM>(P, use256 ? 1 : 0, 2, T3_CTAS_PER_SM, ctr, ovf, ovf_n, stream)) != BG_OK)
+  if (code_tiers && !P.all_rolls) {  // the code-based generator as the middle tier: consumes list (use256 ? 1 : 0), hands over to list 2
+    MovegenParams Q = P;
+    const int in = use256 ? 1 : 0;
+    Q.item_counter = ctr + in + 1;
+    Q.in_list = ovf[in];
+    Q.in_count = ovf_n[in];
+    Q.ovf_list = ovf[2];
+    Q.ovf_count = ovf_n[2];
+    Q.grab = 1;
+    if ((rc = movegen21_launch_kernel(Q, stream)) != BG_OK) return rc;
+  } else if ((rc = launch_tail_tier<T3_CAP, false, MOVES, T3_WARPS, T3_CTAS_PER_SM>(P, use256 ? 1 : 0, 2, T3_CTAS_PER_SM, ctr, ovf, ovf_n, stream)) != BG_OK) {
     return rc;
+  }
   if ((rc = launch_tail_tier<T4_CAP, false, MOVES, T4_WARPS, T4_CTAS_PER_SM>(P, 2, 3, T4_CTAS_PER_SM, ctr, ovf, ovf_n, stream)) != BG_OK) return rc;
   if ((rc = launch_tail_tier<T5_CAP, true, MOVES, T5_WARPS, T5_CTAS_PER_SM>(P, 3, -1, T5_CTAS_PER_SM, ctr, ovf, ovf_n, stream)) != BG_OK) return rc;
   cudaError_t e = cudaGetLastError();

@@ -285,7 +285,7 @@ __device__ __noinline__ uint32_t flush21(const MovegenParams* __restrict__ Pp, l
   }
   base = __shfl_sync(BG_FULL, base, 0);
   if (true_count > 0) {
-    const long long item = pos * 21 + (lane - 1);
+    const long long item = P.all_rolls ? pos * 21 + (lane - 1) : pos;  // single-roll mode: the position IS the item
     P.out_count[item] = (int32_t)true_count;
     P.out_offsets[item] = base < 0 ? -1ll : base + (long long)rs;
   }
@@ -372,7 +372,7 @@ __device__ __noinline__ uint32_t flush21(const MovegenParams* __restrict__ Pp, l
         }
 #endif
         if (P.out_flags) P.out_flags[base + i] = (uint8_t)player;
-        if (P.out_owner) P.out_owner[base + i] = (int32_t)(pos * 21 + (w >> 25) - 1);
+        if (P.out_owner) P.out_owner[base + i] = (int32_t)(P.all_rolls ? pos * 21 + (w >> 25) - 1 : pos);
       }
       __syncwarp();
       const int nw = (n_rows - i0 < 32 ? n_rows - i0 : 32) * 13;
@@ -581,20 +581,25 @@ __device__ __forceinline__ uint32_t node_mask(uint32_t w, const Root& r, uint32_
   return m;
 }
 
+template <bool ALL>
 __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid_constant__ MovegenParams P) {
   uint32_t* const W = wsm();
   const int lane = threadIdx.x & 31;
   const uint32_t* const boards32 = reinterpret_cast<const uint32_t*>(P.boards);
+  const long long n_work = (!ALL && P.in_list) ? (long long)(*P.in_count) : P.B;
   while (true) {
     long long pos = 0;
     if (lane == 0) pos = atomicAdd(P.item_counter, 1);
     pos = __shfl_sync(BG_FULL, pos, 0);
-    if (pos >= P.B) break;
+    if (pos >= n_work) break;
+    if constexpr (!ALL) {
+      if (P.in_list) pos = P.in_list[pos];  // single-roll mode as a tail tier: the items another tier handed over
+    }
     __syncwarp();
     if (P.active && !P.active[pos]) {
-      if (lane < 21) {
-        P.out_count[pos * 21 + lane] = 0;
-        P.out_offsets[pos * 21 + lane] = 0;
+      if (lane < (ALL ? 21 : 1)) {
+        P.out_count[ALL ? pos * 21 + lane : pos] = 0;
+        P.out_offsets[ALL ? pos * 21 + lane : pos] = 0;
       }
       continue;
     }
@@ -606,10 +611,21 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
     uint32_t bad = 0;
 #pragma unroll
     for (int i = 0; i < 13; ++i) bad |= W[O_ROOT + i] & 0xf0f0f0f0u;
+    // single-roll mode: the item's own roll; its roll index selects the one active lane of the non-doubles section / the one die
+    int my_rid = -1, need = 0x3f;
+    bool dbl_item = true;
+    if constexpr (!ALL) {
+      const int d0 = P.rolls[2 * pos], d1 = P.rolls[2 * pos + 1];
+      if (d0 < 1 || d0 > 6 || d1 < 1 || d1 > 6) bad = 1u;
+      const int lo0 = (d0 < d1 ? d0 : d1) - 1, hi0 = (d0 < d1 ? d1 : d0) - 1;
+      my_rid = lo0 * 6 - lo0 * (lo0 - 1) / 2 + (hi0 - lo0);  // index in the (1,1), (1,2), ... (6,6) order
+      need = (1 << lo0) | (1 << hi0);
+      dbl_item = lo0 == hi0;
+    }
     if (bad) {
-      if (lane < 21) {
-        P.out_count[pos * 21 + lane] = 0;
-        P.out_offsets[pos * 21 + lane] = -1;
+      if (lane < (ALL ? 21 : 1)) {
+        P.out_count[ALL ? pos * 21 + lane : pos] = 0;
+        P.out_offsets[ALL ? pos * 21 + lane : pos] = -1;
       }
       if (lane == 0) atomicMin(P.status, BG_ERR_INVARIANT);
       continue;
@@ -640,7 +656,7 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
     }
     // ---- ply 1: the six dice (lane = die - 1) ------------------------------------------------------------------------------
     const View rv = make_view(rk0, rk1, rk2, rk3, r);
-    const uint32_t m1 = lane < 6 ? view_mask(rv, r, lane + 1) : 0u;
+    const uint32_t m1 = (lane < 6 && ((need >> lane) & 1)) ? view_mask(rv, r, lane + 1) : 0u;
     const int n1 = __popc(m1 & 0x7ffffffu);
     int inc1 = n1;
 #pragma unroll
@@ -651,7 +667,7 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
     const int exc1 = inc1 - n1;
     const int N1 = __shfl_sync(BG_FULL, inc1, 5);
     if (N1 > C1CAP) {  // too many first moves for the table: every roll of this position goes to the generic tiers
-      if (lane < 21) push_overflow(P, pos * 21 + lane);
+      if (lane < (ALL ? 21 : 1)) push_overflow(P, ALL ? pos * 21 + lane : pos);
       continue;
     }
     // ---- children of the root and their six second-die move sets (lane = child) ------------------------------------------------
@@ -698,7 +714,7 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
       uint32_t sg0 = 0, sg1 = 0;
       const int lo = (int)((ND_LO >> (3 * (lane < 15 ? lane : 0))) & 7u), hi = (int)((ND_HI >> (3 * (lane < 15 ? lane : 0))) & 7u);
       const int nh = __shfl_sync(BG_FULL, n1, hi), nl = __shfl_sync(BG_FULL, n1, lo);
-      if (lane < 15) {
+      if (lane < 15 && (ALL || lane + 1 + lo == my_rid)) {  // roll index of non-double lane = lane + 1 + lo
         const bool H0 = hi < 5 ? (has2a >> (6 * hi + lo)) & 1u : (has2b >> lo) & 1u;
         const bool H1 = (has2a >> (6 * lo + hi)) & 1u;  // lo < 5 always
         if (H0) {
@@ -775,7 +791,11 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
       }
       if (nd_abort) {  // hand every non-double that has not been written to the generic tiers
         n_res = 0;
-        if (lane < 21 && !((DBL_IDS >> lane) & 1u) && !((emitted >> lane) & 1u)) push_overflow(P, pos * 21 + lane);
+        if constexpr (ALL) {
+          if (lane < 21 && !((DBL_IDS >> lane) & 1u) && !((emitted >> lane) & 1u)) push_overflow(P, pos * 21 + lane);
+        } else {
+          if (lane == 0) push_overflow(P, pos);
+        }
         emitted |= ~DBL_IDS & 0x1fffffu;
       }
     }
@@ -783,7 +803,7 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
     n_res = 0;
 
     // ---- doubles (handle_move_types.py:84-193): breadth-first by ply, the six trees together ------------------------------------
-    if (N1 > 0 && !(P.grab & 4)) {
+    if (N1 > 0 && !(P.grab & 4) && dbl_item) {
       // ply 1 -> 2 for every die: parents are the children table (their move sets are in it), nodes go to the bottom of the arena
       int n2 = 0;
       bool fail = false;
@@ -808,7 +828,7 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
         fail = (rc >> 16) != 0u;
       }
       if (fail) {  // the second plies alone overflow the arena: all doubles to the generic tiers
-        if (lane < 6 && n1 > 0) push_overflow(P, pos * 21 + (id_of_die0(lane) - 1));
+        if (lane < 6 && n1 > 0) push_overflow(P, ALL ? pos * 21 + (id_of_die0(lane) - 1) : pos);
         emitted |= DBL_IDS;
       } else {
         // per-die ranges of the ply-2 frontier (lane = die - 1; lane 6 = end)
@@ -947,7 +967,7 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
             if (g - d > 1) {
               singles = true;  // retry this group one die at a time
             } else {
-              if (lane == 0 && !((emitted >> (id_of_die0(d) - 1)) & 1u)) push_overflow(P, pos * 21 + (id_of_die0(d) - 1));
+              if (lane == 0 && !((emitted >> (id_of_die0(d) - 1)) & 1u)) push_overflow(P, ALL ? pos * 21 + (id_of_die0(d) - 1) : pos);
               emitted |= 1u << (id_of_die0(d) - 1);
               d = g;
             }
@@ -955,9 +975,16 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
         }
       }
     }
-    if (lane < 21 && !((emitted >> lane) & 1u)) {
-      P.out_count[pos * 21 + lane] = 0;
-      P.out_offsets[pos * 21 + lane] = 0;
+    if constexpr (ALL) {
+      if (lane < 21 && !((emitted >> lane) & 1u)) {
+        P.out_count[pos * 21 + lane] = 0;
+        P.out_offsets[pos * 21 + lane] = 0;
+      }
+    } else {
+      if (lane == 0 && !((emitted >> my_rid) & 1u)) {
+        P.out_count[pos] = 0;
+        P.out_offsets[pos] = 0;
+      }
     }
   }
 }
@@ -969,12 +996,13 @@ size_t movegen21_smem_bytes() { return (size_t)WARPS21 * WARP_WORDS * 4; }
 int32_t movegen21_launch_kernel(const MovegenParams& P, cudaStream_t stream) {
   static DeviceOnce once;
   int32_t rc0 = once.run([]() -> int32_t {
-    return check_cuda(cudaFuncSetAttribute(k_movegen21, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)movegen21_smem_bytes()),
-                      "cudaFuncSetAttribute(k_movegen21)");
+    cudaError_t e1 = cudaFuncSetAttribute(k_movegen21<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)movegen21_smem_bytes());
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_movegen21<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)movegen21_smem_bytes());
+    return check_cuda(e1, "cudaFuncSetAttribute(k_movegen21)");
   });
   if (rc0 != BG_OK) return rc0;
   cudaError_t e;
-  int64_t want = (P.B + WARPS21 - 1) / WARPS21;
+  int64_t want = P.in_list ? (int64_t)148 * CTAS21 : (P.B + WARPS21 - 1) / WARPS21;
   int ctas_per_sm = CTAS21;
   if (const char* lim = getenv("BG_MG21_CTAS")) {  // development: fewer resident CTAs per SM (co-residency experiments)
     const int v = atoi(lim);
@@ -982,7 +1010,10 @@ int32_t movegen21_launch_kernel(const MovegenParams& P, cudaStream_t stream) {
   }
   const int64_t full = (int64_t)148 * ctas_per_sm;
   const int grid = (int)(want < full ? want : full);
-  k_movegen21<<<grid, WARPS21 * 32, movegen21_smem_bytes(), stream>>>(P);
+  if (P.all_rolls)
+    k_movegen21<true><<<grid, WARPS21 * 32, movegen21_smem_bytes(), stream>>>(P);
+  else
+    k_movegen21<false><<<grid, WARPS21 * 32, movegen21_smem_bytes(), stream>>>(P);
   e = cudaGetLastError();
   if (e != cudaSuccess) return check_cuda(e, "k_movegen21 launch");
   return BG_OK;
