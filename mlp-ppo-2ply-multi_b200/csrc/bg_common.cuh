@@ -34,6 +34,16 @@ struct DeviceOnce {
   }
 };
 
+// Opt a kernel in to `bytes` of dynamic shared memory and ask for the maximum shared-memory carve-out.  Every large-shared-memory kernel of
+// the library uses the same carve-out: kernels that prefer different L1 / shared splits cannot be resident on an SM at the same time, so a
+// tail-tier CTA (2 x 82 KB) used to wait for the whole persistent evaluator (1 x 107 KB per SM, on the side stream) to drain.
+template <class K>
+inline cudaError_t opt_in_shared(K kernel, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  return e;
+}
+
 // Makes `dev` current for the lifetime of the guard and restores the caller's device afterwards (handle-based entry points must not
 // leave the calling thread on another device).
 struct DeviceGuard {

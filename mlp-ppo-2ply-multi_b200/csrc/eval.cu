@@ -311,7 +311,7 @@ int32_t launch_eval_t(const EvalArgs& a, cudaStream_t stream) {
   const size_t smem = (size_t)(202 * H) * 4 + (EVAL_THREADS / 32) * 56 * 4;
   static DeviceOnce once;
   int32_t rc0 = once.run([&]() -> int32_t {
-    return check_cuda(cudaFuncSetAttribute(k_eval<HPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(k_eval)");
+    return check_cuda(opt_in_shared(k_eval<HPL>, smem), "cudaFuncSetAttribute(k_eval)");
   });
   if (rc0 != BG_OK) return rc0;
   const int ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;

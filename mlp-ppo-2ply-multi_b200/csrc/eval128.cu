@@ -248,7 +248,7 @@ int32_t eval128_launch(const EvalArgs& a, const float* t128, cudaStream_t stream
     for (int n = 0; n < 16; ++n) h[n] = (float)((double)n / 15.0);
     cudaError_t e = cudaMemcpyToSymbol(c_off15b, h, sizeof(h));
     if (e != cudaSuccess) return check_cuda(e, "cudaMemcpyToSymbol(c_off15b)");
-    return check_cuda(cudaFuncSetAttribute(k_eval128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(k_eval128)");
+    return check_cuda(opt_in_shared(k_eval128, smem), "cudaFuncSetAttribute(k_eval128)");
   });
   if (rc0 != BG_OK) return rc0;
   const int64_t bound = a.N_dev ? a.max_N : a.N;

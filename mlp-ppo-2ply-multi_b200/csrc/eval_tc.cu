@@ -354,7 +354,7 @@ int32_t eval_tc_launch(const EvalArgs& a, const uint8_t* img, int32_t* err_flag,
     }
     cudaError_t e = cudaMemcpyToSymbol(c_off15_split, h, sizeof(h));
     if (e != cudaSuccess) return check_cuda(e, "cudaMemcpyToSymbol(c_off15_split)");
-    return check_cuda(cudaFuncSetAttribute(k_eval_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(k_eval_tc)");
+    return check_cuda(opt_in_shared(k_eval_tc, smem), "cudaFuncSetAttribute(k_eval_tc)");
   });
   if (rc0 != BG_OK) return rc0;
   const int64_t bound = a.N_dev ? a.max_N : a.N;

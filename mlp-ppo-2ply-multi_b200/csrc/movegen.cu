@@ -512,9 +512,7 @@ template <int CAP, bool GLOBAL, bool MOVES, int WARPS, int CTAS>
 int32_t prepare_tier() {
   static DeviceOnce once;
   return once.run([]() -> int32_t {
-    return check_cuda(cudaFuncSetAttribute(k_movegen<CAP, GLOBAL, MOVES, WARPS, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem_bytes(CAP, GLOBAL, MOVES, WARPS)),
-                      "cudaFuncSetAttribute(k_movegen)");
+    return check_cuda(opt_in_shared(k_movegen<CAP, GLOBAL, MOVES, WARPS, CTAS>, smem_bytes(CAP, GLOBAL, MOVES, WARPS)), "cudaFuncSetAttribute(k_movegen)");
   });
 }
 
@@ -579,20 +577,26 @@ int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* const (&
   const bool use256 = B >= (1 << 20) && !fast21;  // what the position-major tier hands over is wider than 224 nodes per ply
   const int c2 = tier2_ctas > 0 && tier2_ctas < T2_CTAS_PER_SM ? tier2_ctas : T2_CTAS_PER_SM;
   if (use256 && (rc = launch_tail_tier<T2_CAP, false, MOVES, T2_WARPS, T2_CTAS_PER_SM>(P, 0, 1, c2, ctr, ovf, ovf_n, stream)) != BG_OK) return rc;
-  if (code_tiers && !P.all_rolls) {  // the code-based generator as the middle tier: consumes list (use256 ? 1 : 0), hands over to list 2
+  auto code_tier = [&](int in, int out, int big) -> int32_t {  // the code-based generator (movegen21.cu) consuming overflow list `in`
     MovegenParams Q = P;
-    const int in = use256 ? 1 : 0;
     Q.item_counter = ctr + in + 1;
     Q.in_list = ovf[in];
     Q.in_count = ovf_n[in];
-    Q.ovf_list = ovf[2];
-    Q.ovf_count = ovf_n[2];
+    Q.ovf_list = ovf[out];
+    Q.ovf_count = ovf_n[out];
     Q.grab = 1;
-    if ((rc = movegen21_launch_kernel(Q, stream)) != BG_OK) return rc;
-  } else if ((rc = launch_tail_tier<T3_CAP, false, MOVES, T3_WARPS, T3_CTAS_PER_SM>(P, use256 ? 1 : 0, 2, T3_CTAS_PER_SM, ctr, ovf, ovf_n, stream)) != BG_OK) {
-    return rc;
+    return movegen21_launch_kernel(Q, stream, big);
+  };
+  if (code_tiers) {
+    // per-item batches: the standard configuration as the middle tier (many resident warps for the long overflow list of the 128-node tier);
+    // then, for both batch shapes, the big configuration (one warp per CTA, ~6,000 results per item) for the few trees that are wider still
+    if (!P.all_rolls && (rc = code_tier(use256 ? 1 : 0, 2, 0)) != BG_OK) return rc;
+    if ((rc = code_tier(P.all_rolls ? 0 : 2, 3, 1)) != BG_OK) return rc;
+  } else {
+    if ((rc = launch_tail_tier<T3_CAP, false, MOVES, T3_WARPS, T3_CTAS_PER_SM>(P, use256 ? 1 : 0, 2, T3_CTAS_PER_SM, ctr, ovf, ovf_n, stream)) != BG_OK)
+      return rc;
+    if ((rc = launch_tail_tier<T4_CAP, false, MOVES, T4_WARPS, T4_CTAS_PER_SM>(P, 2, 3, T4_CTAS_PER_SM, ctr, ovf, ovf_n, stream)) != BG_OK) return rc;
   }
-  if ((rc = launch_tail_tier<T4_CAP, false, MOVES, T4_WARPS, T4_CTAS_PER_SM>(P, 2, 3, T4_CTAS_PER_SM, ctr, ovf, ovf_n, stream)) != BG_OK) return rc;
   if ((rc = launch_tail_tier<T5_CAP, true, MOVES, T5_WARPS, T5_CTAS_PER_SM>(P, 3, -1, T5_CTAS_PER_SM, ctr, ovf, ovf_n, stream)) != BG_OK) return rc;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return check_cuda(e, "k_movegen launch");

@@ -64,7 +64,7 @@ struct MovegenParams {
 int64_t movegen_workspace_bytes(int64_t B);  // B = number of ITEMS (21 per position in position-major mode)
 // movegen21.cu: the position-major bulk tier (one warp per position, all 21 rolls); overflowing items go to P.ovf_list
 constexpr int MOVEGEN21_MIN_ITEM_CAP = 1;  // the position-major tier truncates an item to item_cap rows at flush time
-int32_t movegen21_launch_kernel(const MovegenParams& P, cudaStream_t stream);
+int32_t movegen21_launch_kernel(const MovegenParams& P, cudaStream_t stream, int big = 0);
 int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream);
 
 }  // namespace bg

@@ -39,39 +39,45 @@ namespace {
 
 constexpr int C1CAP = 64;      // first-move children over the six dice (observed max 70 in 20,000 positions, p99 44)
 constexpr int DCAP = 128;      // candidate descriptors per sub-batch
-constexpr int TCAP = 1024;     // hash-set slots
-constexpr int TLIVE = 640;     // most live keys the hash set is allowed to hold
-constexpr int BCAP = 1024;     // arena: buffered result codes (non-doubles) / ply-2 frontier + ply-3 frontier + results (doubles)
-constexpr int F2CAP = 512;     // most ply-2 nodes of the six doubles trees together
-constexpr int RES_RESERVE = 352;  // arena words kept for results behind the frontiers
 constexpr uint32_t NONE5 = 31u;
 #ifndef BG_EMIT_NIBBLE
 #define BG_EMIT_NIBBLE 0
 #endif
-#ifndef BG_COPY_UNROLL
-#define BG_COPY_UNROLL 0
-#endif
+
+// per-warp shared memory (words), common part
+constexpr int O_ROOT = 0;                       // 16: the 13 root words
+constexpr int O_C1INFO = O_ROOT + 16;           // C1CAP: slot | src << 5 | dst << 10 | die0 << 15 | lone << 18
+constexpr int O_C1MASK = O_C1INFO + C1CAP;      // 6 x C1CAP: second-die move sets of each child, [die0][child]
+constexpr int O_DESC = O_C1MASK + 6 * C1CAP;    // DCAP u16: parent lane | slot << 5
+constexpr int O_TAB = O_DESC + DCAP / 2;        // TCAP: hash set; doubles as the emit staging area (32 rows x 13 words + 3)
+
+// Capacity configuration of one instantiation of the kernel.  `Std` is the bulk tier (many resident warps, ~10 KB each); `Big` is the tail
+// tier for the few items whose doubles tree does not fit it (one warp per CTA, 68 KB): up to ~6,000 results per item, i.e. everything
+// below BG_MAX_ITEM_MOVES that the 512- / 2048-node frontier tiers of movegen.cu used to take, at a third of their candidates.
+template <int TLOG2, int BCAP_, int F2CAP_, int RESERVE_, int WARPS_, int CTAS_>
+struct Cfg21 {
+  static constexpr int TCAP_LOG2 = TLOG2;
+  static constexpr int TCAP = 1 << TLOG2;          // hash-set slots
+  static constexpr int TLIVE = TCAP * 5 / 8;       // most live keys the hash set is allowed to hold
+  static constexpr int BCAP = BCAP_;               // arena: buffered result codes (non-doubles) / ply-2 frontier + ply-3 frontier + results (doubles)
+  static constexpr int F2CAP = F2CAP_;             // most ply-2 nodes of the doubles trees together
+  static constexpr int RES_RESERVE = RESERVE_;     // arena words kept for results behind the frontiers
+  static constexpr int WARPS = WARPS_, CTAS = CTAS_;
+  static constexpr int O_BUF = O_TAB + TCAP;       // BCAP: the arena
+  static constexpr int O_ISTART = O_BUF + BCAP;    // 24 + 24: per-item result ranges of a flush
+  static constexpr int WARP_WORDS = O_ISTART + 48;
+  static_assert(TCAP >= 32 * 13 + 4, "staging area");
+  static_assert(O_TAB % 4 == 0 && WARP_WORDS % 4 == 0, "16-byte alignment of the staging area");
+  static constexpr size_t SMEM_BYTES = (size_t)WARPS * WARP_WORDS * 4;
+};
 #ifndef BG21_WARPS
 #define BG21_WARPS 4
 #endif
 #ifndef BG21_CTAS
 #define BG21_CTAS 5
 #endif
-
-// per-warp shared memory (words)
-constexpr int O_ROOT = 0;                       // 16: the 13 root words
-constexpr int O_C1INFO = O_ROOT + 16;           // C1CAP: slot | src << 5 | dst << 10 | die0 << 15 | lone << 18
-constexpr int O_C1MASK = O_C1INFO + C1CAP;      // 6 x C1CAP: second-die move sets of each child, [die0][child]
-constexpr int O_DESC = O_C1MASK + 6 * C1CAP;    // DCAP u16: parent lane | slot << 5
-constexpr int O_TAB = O_DESC + DCAP / 2;        // TCAP: hash set; doubles as the emit staging area (32 rows x 13 words + 3)
-constexpr int O_BUF = O_TAB + TCAP;             // BCAP: the arena
-constexpr int O_ISTART = O_BUF + BCAP;          // 24 + 24: per-item result ranges of a flush
-constexpr int WARP_WORDS = O_ISTART + 48;
-static_assert(TCAP >= 32 * 13 + 4, "staging area");
-static_assert(O_TAB % 4 == 0 && WARP_WORDS % 4 == 0, "16-byte alignment of the staging area");
-
-constexpr int WARPS21 = BG21_WARPS;
-constexpr int CTAS21 = BG21_CTAS;
+using Std21 = Cfg21<10, 1024, 512, 352, BG21_WARPS, BG21_CTAS>;
+using Big21 = Cfg21<13, 8192, 2048, 2560, 1, 3>;
 
 // the 15 non-double rolls in roll-index order: 0-based (lo, hi) dice, 3 bits each
 constexpr uint64_t pack15(const int (&v)[15]) {
@@ -84,9 +90,10 @@ constexpr int ND_HI_V[15] = {1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
 constexpr uint64_t ND_LO = pack15(ND_LO_V), ND_HI = pack15(ND_HI_V);
 constexpr uint32_t DBL_IDS = (1u << 0) | (1u << 6) | (1u << 11) | (1u << 15) | (1u << 18) | (1u << 20);  // roll indices of d-d
 
+template <class C>
 __device__ __forceinline__ uint32_t* wsm() {
   extern __shared__ uint32_t bg_dyn_smem21[];
-  return bg_dyn_smem21 + (threadIdx.x >> 5) * WARP_WORDS;
+  return bg_dyn_smem21 + (threadIdx.x >> 5) * C::WARP_WORDS;
 }
 
 // occupancy / state summary of a node, from which the move set of any die is a few bit operations (same rules as move_mask)
@@ -182,16 +189,19 @@ __device__ __forceinline__ uint32_t nib4_spread(uint32_t x) {
 }
 #endif
 
-__device__ __forceinline__ uint32_t hash_key(uint32_t k) { return (k * 0x9E3779B1u) >> (32 - 10); }
-static_assert(TCAP == 1024, "hash_key shift");
+template <class C>
+__device__ __forceinline__ uint32_t hash_key(uint32_t k) {
+  return (k * 0x9E3779B1u) >> (32 - C::TCAP_LOG2);
+}
 
 __device__ __forceinline__ bool is_double_id(uint32_t id) { return (DBL_IDS >> (id - 1u)) & 1u; }
 __device__ __forceinline__ int die_of_id(uint32_t id) { return __popc(DBL_IDS & ((1u << (id - 1u)) - 1u)) + 1; }
 __device__ __forceinline__ uint32_t id_of_die0(int d0) { return (uint32_t)(d0 * 6 - d0 * (d0 - 1) / 2) + 1u; }
 
+template <class C>
 __device__ __forceinline__ void clear_tab(uint32_t* tab, int lane) {
 #pragma unroll 4
-  for (int i = 0; i < TCAP / 32; ++i) tab[i * 32 + lane] = 0u;
+  for (int i = 0; i < C::TCAP / 32; ++i) tab[i * 32 + lane] = 0u;
   __syncwarp();
 }
 
@@ -206,15 +216,16 @@ __device__ __forceinline__ int lower_bound_id(const uint32_t* buf, int n, uint32
 }
 
 // rebuild the hash set from the results buf[from .. n)
+template <class C>
 __device__ __noinline__ void rehash21(int buf_off, int from, int n) {
-  uint32_t* const W = wsm();
+  uint32_t* const W = wsm<C>();
   const int lane = threadIdx.x & 31;
-  clear_tab(W + O_TAB, lane);
+  clear_tab<C>(W + O_TAB, lane);
   for (int i = from + lane; i < n; i += 32) {
     const uint32_t w = W[buf_off + i];
     const uint32_t key = is_double_id(w >> 25) ? (w & ~(31u << 20)) : w;
-    uint32_t idx = hash_key(key);
-    while (atomicCAS(&W[O_TAB + idx], 0u, key) != 0u) idx = (idx + 1) & (TCAP - 1);
+    uint32_t idx = hash_key<C>(key);
+    while (atomicCAS(&W[O_TAB + idx], 0u, key) != 0u) idx = (idx + 1) & (C::TCAP - 1);
   }
   __syncwarp();
 }
@@ -224,17 +235,18 @@ __device__ __noinline__ void rehash21(int buf_off, int from, int n) {
 // the root bytes + codes in the staging area (the hash set's memory: the caller rehashes afterwards if it still needs the set) and
 // copy them out -- then move the tail buf[n_emit .. n_res) to the front.  Returns the new emitted-items mask.
 // ---------------------------------------------------------------------------------------------------------------------------
+template <class C>
 __device__ __noinline__ uint32_t flush21(const MovegenParams* __restrict__ Pp, long long pos, int player, uint32_t blot, uint4 rk, int buf_off,
-                                         int n_emit, int n_res, uint32_t emitted) {
+                                         int n_emit, int n_res, uint32_t emitted, bool single) {
   const MovegenParams& P = *Pp;
-  uint32_t* const W = wsm();
+  uint32_t* const W = wsm<C>();
   uint32_t* const res = W + buf_off;
   const int lane = threadIdx.x & 31;
   if (n_emit <= 0) return emitted;
   // per-item ranges: the results of an item are contiguous
   if (lane < 24) {
-    W[O_ISTART + lane] = 0u;
-    W[O_ISTART + 24 + lane] = 0u;
+    W[C::O_ISTART + lane] = 0u;
+    W[C::O_ISTART + 24 + lane] = 0u;
   }
   __syncwarp();
   for (int i0 = 0; i0 < n_emit; i0 += 32) {
@@ -243,15 +255,15 @@ __device__ __noinline__ uint32_t flush21(const MovegenParams* __restrict__ Pp, l
       const uint32_t id = res[i] >> 25;
       const uint32_t pid = i > 0 ? res[i - 1] >> 25 : 0u;
       const uint32_t nid = i + 1 < n_emit ? res[i + 1] >> 25 : 0u;
-      if (id != pid) W[O_ISTART + id] = (uint32_t)i;
-      if (id != nid) W[O_ISTART + 24 + id] = (uint32_t)(i + 1);
+      if (id != pid) W[C::O_ISTART + id] = (uint32_t)i;
+      if (id != nid) W[C::O_ISTART + 24 + id] = (uint32_t)(i + 1);
     }
   }
   __syncwarp();
   int rs = 0, re = 0;  // lane = roll id (1..21): its range
   if (lane >= 1 && lane <= 21) {
-    rs = (int)W[O_ISTART + lane];
-    re = (int)W[O_ISTART + 24 + lane];
+    rs = (int)W[C::O_ISTART + lane];
+    re = (int)W[C::O_ISTART + 24 + lane];
   }
   const int true_count = re - rs;
   int n_rows = n_emit;
@@ -285,7 +297,7 @@ __device__ __noinline__ uint32_t flush21(const MovegenParams* __restrict__ Pp, l
   }
   base = __shfl_sync(BG_FULL, base, 0);
   if (true_count > 0) {
-    const long long item = P.all_rolls ? pos * 21 + (lane - 1) : pos;  // single-roll mode: the position IS the item
+    const long long item = single ? pos : pos * 21 + (lane - 1);  // single-roll mode: `pos` IS the item
     P.out_count[item] = (int32_t)true_count;
     P.out_offsets[item] = base < 0 ? -1ll : base + (long long)rs;
   }
@@ -372,7 +384,7 @@ __device__ __noinline__ uint32_t flush21(const MovegenParams* __restrict__ Pp, l
         }
 #endif
         if (P.out_flags) P.out_flags[base + i] = (uint8_t)player;
-        if (P.out_owner) P.out_owner[base + i] = (int32_t)(P.all_rolls ? pos * 21 + (w >> 25) - 1 : pos);
+        if (P.out_owner) P.out_owner[base + i] = (int32_t)(single ? pos : pos * 21 + (w >> 25) - 1);
       }
       __syncwarp();
       const int nw = (n_rows - i0 < 32 ? n_rows - i0 : 32) * 13;
@@ -413,9 +425,10 @@ __device__ __noinline__ uint32_t flush21(const MovegenParams* __restrict__ Pp, l
 // make room in the result buffer: every result before the first one with roll id `id0` (the item the pending candidates belong
 // to) is a complete item -- emit those, keep the rest, rebuild the hash set from it.  Returns emitted | n_res << 32, or bit 63 set
 // if the pending item alone fills the buffer.
+template <class C>
 __device__ __noinline__ unsigned long long make_room21(const MovegenParams* __restrict__ Pp, long long pos, int player, uint32_t blot, uint4 rk,
-                                                       int buf_off, int n_res, uint32_t id0, uint32_t emitted) {
-  uint32_t* const W = wsm();
+                                                       int buf_off, int n_res, uint32_t id0, uint32_t emitted, bool single) {
+  uint32_t* const W = wsm<C>();
   const int lane = threadIdx.x & 31;
   int keep_from = n_res;
   for (int i0 = 0; i0 < n_res; i0 += 32) {
@@ -427,9 +440,9 @@ __device__ __noinline__ unsigned long long make_room21(const MovegenParams* __re
     }
   }
   if (keep_from == 0) return 1ull << 63;
-  emitted = flush21(Pp, pos, player, blot, rk, buf_off, keep_from, n_res, emitted);
+  emitted = flush21<C>(Pp, pos, player, blot, rk, buf_off, keep_from, n_res, emitted, single);
   n_res -= keep_from;
-  rehash21(buf_off, 0, n_res);
+  rehash21<C>(buf_off, 0, n_res);
   return (unsigned long long)emitted | ((unsigned long long)n_res << 32);
 }
 
@@ -439,12 +452,13 @@ __device__ __noinline__ unsigned long long make_room21(const MovegenParams* __re
 // to dst[n ..).  mode 0: non-doubles (pinfo = src1 | dst1 << 5 | die0 of the second sub-move << 10 | single << 13 | last << 14 |
 // id << 25); mode 1: doubles (pinfo = the parent's sorted sources (20 bits) | last << 20 | id << 25; the child records its slot).
 // Sub-batches of <= DCAP candidates; returns n | (resume + 1) << 16 when the next sub-batch would not fit below `cap` or would
-// push the hash set past TLIVE keys (dst[key_base .. n) are the keys it holds); the caller makes room and calls again with
+// push the hash set past C::TLIVE keys (dst[key_base .. n) are the keys it holds); the caller makes room and calls again with
 // start = resume.  High half 0: the batch is done.
 // ---------------------------------------------------------------------------------------------------------------------------
+template <class C>
 __device__ __noinline__ uint32_t expand21(int mode, uint32_t pinfo, uint32_t m, int start, int dst_off, int n, int cap, int key_base, int player,
                                           uint32_t blot) {
-  uint32_t* const W = wsm();
+  uint32_t* const W = wsm<C>();
   uint16_t* const desc = reinterpret_cast<uint16_t*>(W + O_DESC);
   uint32_t* const tab = W + O_TAB;
   uint32_t* const dst = W + dst_off;
@@ -468,7 +482,7 @@ __device__ __noinline__ uint32_t expand21(int mode, uint32_t pinfo, uint32_t m, 
     const uint32_t nofit = __ballot_sync(BG_FULL, inc > limit);
     const int next_start = nofit ? __shfl_sync(BG_FULL, exc, __ffs(nofit) - 1) : total;
     const int ncand = next_start - start;
-    if (n + ncand > cap || n - key_base + ncand > TLIVE) return (uint32_t)n | ((uint32_t)(start + 1) << 16);
+    if (n + ncand > cap || n - key_base + ncand > C::TLIVE) return (uint32_t)n | ((uint32_t)(start + 1) << 16);
     if (exc >= start && inc <= limit) {
       uint32_t mm = mm0;
       int o = exc - start;
@@ -520,7 +534,7 @@ __device__ __noinline__ uint32_t expand21(int mode, uint32_t pinfo, uint32_t m, 
       const uint32_t grp = __match_any_sync(BG_FULL, cv ? key : (0x80000000u | (uint32_t)lane));
       bool isnew = false;
       if (cv && (__ffs(grp) - 1) == lane) {
-        uint32_t idx = hash_key(key);
+        uint32_t idx = hash_key<C>(key);
         while (true) {
           const uint32_t old = atomicCAS(&tab[idx], 0u, key);
           if (old == 0u) {
@@ -528,7 +542,7 @@ __device__ __noinline__ uint32_t expand21(int mode, uint32_t pinfo, uint32_t m, 
             break;
           }
           if (old == key) break;
-          idx = (idx + 1) & (TCAP - 1);
+          idx = (idx + 1) & (C::TCAP - 1);
         }
       }
       const uint32_t bal = __ballot_sync(BG_FULL, isnew);
@@ -581,9 +595,9 @@ __device__ __forceinline__ uint32_t node_mask(uint32_t w, const Root& r, uint32_
   return m;
 }
 
-template <bool ALL>
-__global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid_constant__ MovegenParams P) {
-  uint32_t* const W = wsm();
+template <bool ALL, class C>
+__global__ void __launch_bounds__(C::WARPS * 32, C::CTAS) k_movegen21(const __grid_constant__ MovegenParams P) {
+  uint32_t* const W = wsm<C>();
   const int lane = threadIdx.x & 31;
   const uint32_t* const boards32 = reinterpret_cast<const uint32_t*>(P.boards);
   const long long n_work = (!ALL && P.in_list) ? (long long)(*P.in_count) : P.B;
@@ -595,17 +609,19 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
     if constexpr (!ALL) {
       if (P.in_list) pos = P.in_list[pos];  // single-roll mode as a tail tier: the items another tier handed over
     }
+    // single-roll mode: `pos` is the ITEM; in a position-major batch its board is shared by 21 items
+    const long long src = (!ALL && P.all_rolls) ? pos / 21 : pos;
     __syncwarp();
-    if (P.active && !P.active[pos]) {
+    if (P.active && !P.active[src]) {
       if (lane < (ALL ? 21 : 1)) {
         P.out_count[ALL ? pos * 21 + lane : pos] = 0;
         P.out_offsets[ALL ? pos * 21 + lane : pos] = 0;
       }
       continue;
     }
-    if (lane < 13) W[O_ROOT + lane] = boards32[pos * 13 + lane];
+    if (lane < 13) W[O_ROOT + lane] = boards32[src * 13 + lane];
     __syncwarp();
-    const int player = P.players[pos] & 1;
+    const int player = P.players[src] & 1;
     // ---- root (as movegen.cu generate()) ------------------------------------------------------------------------------
     const int ob = player * 6, pb = (1 - player) * 6;
     uint32_t bad = 0;
@@ -615,7 +631,19 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
     int my_rid = -1, need = 0x3f;
     bool dbl_item = true;
     if constexpr (!ALL) {
-      const int d0 = P.rolls[2 * pos], d1 = P.rolls[2 * pos + 1];
+      int d0, d1;
+      if (P.all_rolls) {  // roll index -> (d0 <= d1), lexicographic
+        int ri = (int)(pos - src * 21);
+        d0 = 1;
+        while (ri >= 7 - d0) {
+          ri -= 7 - d0;
+          ++d0;
+        }
+        d1 = d0 + ri;
+      } else {
+        d0 = P.rolls[2 * pos];
+        d1 = P.rolls[2 * pos + 1];
+      }
       if (d0 < 1 || d0 > 6 || d1 < 1 || d1 > 6) bad = 1u;
       const int lo0 = (d0 < d1 ? d0 : d1) - 1, hi0 = (d0 < d1 ? d1 : d0) - 1;
       my_rid = lo0 * 6 - lo0 * (lo0 - 1) / 2 + (hi0 - lo0);  // index in the (1,1), (1,2), ... (6,6) order
@@ -745,7 +773,7 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
       if (lane >= 15) pinc = 0x7fffffff;
       const int pexc = pinc - pe;
       const uint32_t rinfo = (uint32_t)cnt0 | (sg0 << 6) | (sg1 << 7);
-      if (PE > 0) clear_tab(W + O_TAB, lane);
+      if (PE > 0) clear_tab<C>(W + O_TAB, lane);
       bool nd_abort = false;
       for (int e0 = 0; e0 < PE && !nd_abort; e0 += 32) {
         const int e = e0 + lane;
@@ -776,11 +804,11 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
         }
         int st = 0;
         while (true) {
-          const uint32_t rc = expand21(0, pinfo, m, st, O_BUF, n_res, BCAP, 0, player, r.blot);
+          const uint32_t rc = expand21<C>(0, pinfo, m, st, C::O_BUF, n_res, C::BCAP, 0, player, r.blot);
           n_res = (int)(rc & 0xffffu);
           if ((rc >> 16) == 0u) break;
           st = (int)(rc >> 16) - 1;
-          const unsigned long long mr = make_room21(&P, pos, player, r.blot, rk, O_BUF, n_res, pending_id(pinfo, m, st, lane), emitted);
+          const unsigned long long mr = make_room21<C>(&P, pos, player, r.blot, rk, C::O_BUF, n_res, pending_id(pinfo, m, st, lane), emitted, !ALL);
           if (mr >> 63) {  // one roll alone exceeds the buffer (not observed: a non-double has <= ~120 results)
             nd_abort = true;
             break;
@@ -799,7 +827,7 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
         emitted |= ~DBL_IDS & 0x1fffffu;
       }
     }
-    emitted = flush21(&P, pos, player, r.blot, rk, O_BUF, n_res, n_res, emitted);
+    emitted = flush21<C>(&P, pos, player, r.blot, rk, C::O_BUF, n_res, n_res, emitted, !ALL);
     n_res = 0;
 
     // ---- doubles (handle_move_types.py:84-193): breadth-first by ply, the six trees together ------------------------------------
@@ -807,7 +835,7 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
       // ply 1 -> 2 for every die: parents are the children table (their move sets are in it), nodes go to the bottom of the arena
       int n2 = 0;
       bool fail = false;
-      clear_tab(W + O_TAB, lane);
+      clear_tab<C>(W + O_TAB, lane);
       for (int c0 = 0; c0 < N1 && !fail; c0 += 32) {
         const int c = c0 + lane;
         uint32_t pinfo = 0, m = 0;
@@ -823,7 +851,7 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
           }
           pinfo = ((info >> 5) & 31u) | (NONE5 << 5) | (NONE5 << 10) | (NONE5 << 15) | ((m >> 27) << 20) | (id_of_die0((int)d0) << 25);
         }
-        const uint32_t rc = expand21(1, pinfo, m, 0, O_BUF, n2, F2CAP, 0, player, r.blot);
+        const uint32_t rc = expand21<C>(1, pinfo, m, 0, C::O_BUF, n2, C::F2CAP, 0, player, r.blot);
         n2 = (int)(rc & 0xffffu);
         fail = (rc >> 16) != 0u;
       }
@@ -832,10 +860,10 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
         emitted |= DBL_IDS;
       } else {
         // per-die ranges of the ply-2 frontier (lane = die - 1; lane 6 = end)
-        const int st2 = lower_bound_id(W + O_BUF, n2, lane < 6 ? id_of_die0(lane) : 31u);
+        const int st2 = lower_bound_id(W + C::O_BUF, n2, lane < 6 ? id_of_die0(lane) : 31u);
         const int cnt2 = __shfl_down_sync(BG_FULL, st2, 1) - st2;
-        const int fb_off = O_BUF + n2;
-        const int avail = BCAP - n2;
+        const int fb_off = C::O_BUF + n2;
+        const int avail = C::BCAP - n2;
         int d = 0;
         bool singles = false;
         while (d < 6) {
@@ -859,18 +887,18 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
           // ply 2 -> 3
           int n3 = 0;
           if (a1 > a0) {
-            clear_tab(W + O_TAB, lane);
-            const int cap3 = avail - RES_RESERVE;
+            clear_tab<C>(W + O_TAB, lane);
+            const int cap3 = avail - C::RES_RESERVE;
             for (int p0 = a0; p0 < a1 && ok; p0 += 32) {
               uint32_t pinfo = 0, m = 0;
               if (p0 + lane < a1) {
-                const uint32_t w = W[O_BUF + p0 + lane];
+                const uint32_t w = W[C::O_BUF + p0 + lane];
                 if ((todo >> (die_of_id(w >> 25) - 1)) & 1u) {
                   m = node_mask(w, r, rk0, rk1, rk2, rk3);
                   pinfo = (w & 0xfffffu) | ((m >> 27) << 20) | (w & (31u << 25));
                 }
               }
-              const uint32_t rc = expand21(1, pinfo, m, 0, fb_off, n3, cap3, 0, player, r.blot);
+              const uint32_t rc = expand21<C>(1, pinfo, m, 0, fb_off, n3, cap3, 0, player, r.blot);
               n3 = (int)(rc & 0xffffu);
               ok = (rc >> 16) == 0u;
             }
@@ -890,7 +918,7 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
               const int n_add = c2 == 0 ? __shfl_sync(BG_FULL, n1, e) : c2;
               const int src = c2 == 0 ? __shfl_sync(BG_FULL, exc1, e) : __shfl_sync(BG_FULL, st2, e);
               if (n_res + n_add > res_cap) {
-                emitted = flush21(&P, pos, player, r.blot, rk, res_off, n_res, n_res, emitted);
+                emitted = flush21<C>(&P, pos, player, r.blot, rk, res_off, n_res, n_res, emitted, !ALL);
                 n_res = 0;
               }
               if (n_add > res_cap) {
@@ -900,14 +928,14 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
               const uint32_t id = id_of_die0(e);
               for (int i = lane; i < n_add; i += 32)
                 W[res_off + n_res + i] = c2 == 0 ? (((W[O_C1INFO + src + i] >> 5) & 31u) | (NONE5 << 5) | (NONE5 << 10) | (NONE5 << 15) | (id << 25))
-                                                 : W[O_BUF + src + i];
+                                                 : W[C::O_BUF + src + i];
               n_res += n_add;
               __syncwarp();
             }
           }
           // ply 3 -> 4: straight into the result buffer
           if (ok && n3 > 0) {
-            clear_tab(W + O_TAB, lane);
+            clear_tab<C>(W + O_TAB, lane);
             int key_base = n_res;
             for (int p0 = 0; p0 < n3 && ok; p0 += 32) {
               uint32_t pinfo = 0, m = 0;
@@ -918,11 +946,11 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
               }
               int st = 0;
               while (true) {
-                const uint32_t rc = expand21(1, pinfo, m, st, res_off, n_res, res_cap, key_base, player, r.blot);
+                const uint32_t rc = expand21<C>(1, pinfo, m, st, res_off, n_res, res_cap, key_base, player, r.blot);
                 n_res = (int)(rc & 0xffffu);
                 if ((rc >> 16) == 0u) break;
                 st = (int)(rc >> 16) - 1;
-                const unsigned long long mr = make_room21(&P, pos, player, r.blot, rk, res_off, n_res, pending_id(pinfo, m, st, lane), emitted);
+                const unsigned long long mr = make_room21<C>(&P, pos, player, r.blot, rk, res_off, n_res, pending_id(pinfo, m, st, lane), emitted, !ALL);
                 if (mr >> 63) {  // this die's fourth ply alone does not fit
                   ok = false;
                   break;
@@ -946,7 +974,7 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
               if (c3 == 0 || ((present >> (id_of_die0(e) - 1)) & 1u)) continue;
               const int src = __shfl_sync(BG_FULL, st3, e);
               if (n_res + c3 > res_cap) {
-                emitted = flush21(&P, pos, player, r.blot, rk, res_off, n_res, n_res, emitted);
+                emitted = flush21<C>(&P, pos, player, r.blot, rk, res_off, n_res, n_res, emitted, !ALL);
                 n_res = 0;
               }
               if (c3 > res_cap) {
@@ -959,7 +987,7 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
             }
           }
           if (ok) {
-            emitted = flush21(&P, pos, player, r.blot, rk, res_off, n_res, n_res, emitted);
+            emitted = flush21<C>(&P, pos, player, r.blot, rk, res_off, n_res, n_res, emitted, !ALL);
             n_res = 0;
             d = g;
           } else {
@@ -989,34 +1017,29 @@ __global__ void __launch_bounds__(WARPS21 * 32, CTAS21) k_movegen21(const __grid
   }
 }
 
-}  // namespace
-
-size_t movegen21_smem_bytes() { return (size_t)WARPS21 * WARP_WORDS * 4; }
-
-int32_t movegen21_launch_kernel(const MovegenParams& P, cudaStream_t stream) {
+template <bool ALL, class C>
+int32_t launch21(const MovegenParams& P, cudaStream_t stream) {
   static DeviceOnce once;
-  int32_t rc0 = once.run([]() -> int32_t {
-    cudaError_t e1 = cudaFuncSetAttribute(k_movegen21<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)movegen21_smem_bytes());
-    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_movegen21<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)movegen21_smem_bytes());
-    return check_cuda(e1, "cudaFuncSetAttribute(k_movegen21)");
-  });
+  int32_t rc0 = once.run([]() -> int32_t { return check_cuda(opt_in_shared(k_movegen21<ALL, C>, C::SMEM_BYTES), "cudaFuncSetAttribute(k_movegen21)"); });
   if (rc0 != BG_OK) return rc0;
-  cudaError_t e;
-  int64_t want = P.in_list ? (int64_t)148 * CTAS21 : (P.B + WARPS21 - 1) / WARPS21;
-  int ctas_per_sm = CTAS21;
+  int64_t want = P.in_list ? (int64_t)148 * C::CTAS : (P.B + C::WARPS - 1) / C::WARPS;
+  int ctas_per_sm = C::CTAS;
   if (const char* lim = getenv("BG_MG21_CTAS")) {  // development: fewer resident CTAs per SM (co-residency experiments)
     const int v = atoi(lim);
-    if (v >= 1 && v < CTAS21) ctas_per_sm = v;
+    if (v >= 1 && v < C::CTAS) ctas_per_sm = v;
   }
   const int64_t full = (int64_t)148 * ctas_per_sm;
   const int grid = (int)(want < full ? want : full);
-  if (P.all_rolls)
-    k_movegen21<true><<<grid, WARPS21 * 32, movegen21_smem_bytes(), stream>>>(P);
-  else
-    k_movegen21<false><<<grid, WARPS21 * 32, movegen21_smem_bytes(), stream>>>(P);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return check_cuda(e, "k_movegen21 launch");
-  return BG_OK;
+  k_movegen21<ALL, C><<<grid, C::WARPS * 32, C::SMEM_BYTES, stream>>>(P);
+  return check_cuda(cudaGetLastError(), "k_movegen21 launch");
+}
+
+}  // namespace
+
+// big == 0: the bulk tier (Std21); big != 0: the tail tier for items too wide for it (Big21; always consumes P.in_list)
+int32_t movegen21_launch_kernel(const MovegenParams& P, cudaStream_t stream, int big) {
+  if (big) return launch21<false, Big21>(P, stream);  // one warp per ITEM (of a per-item or of a position-major batch)
+  return P.all_rolls ? launch21<true, Std21>(P, stream) : launch21<false, Std21>(P, stream);
 }
 
 }  // namespace bg
