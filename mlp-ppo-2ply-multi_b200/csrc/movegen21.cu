@@ -76,7 +76,13 @@ struct Cfg21 {
 #ifndef BG21_CTAS
 #define BG21_CTAS 5
 #endif
-using Std21 = Cfg21<10, 1024, 512, 352, BG21_WARPS, BG21_CTAS>;
+#ifndef BG21_TLOG2
+#define BG21_TLOG2 10
+#define BG21_BCAP 1024
+#define BG21_F2 512
+#define BG21_RES 352
+#endif
+using Std21 = Cfg21<BG21_TLOG2, BG21_BCAP, BG21_F2, BG21_RES, BG21_WARPS, BG21_CTAS>;
 using Big21 = Cfg21<13, 8192, 2048, 2560, 1, 3>;
 
 // the 15 non-double rolls in roll-index order: 0-based (lo, hi) dice, 3 bits each
@@ -556,7 +562,7 @@ __device__ __noinline__ uint32_t expand21(int mode, uint32_t pinfo, uint32_t m, 
 }
 
 // roll id of the parent that candidate `st` of a batch belongs to (parents are in item order)
-__device__ __forceinline__ uint32_t pending_id(uint32_t pinfo, uint32_t m, int st, int lane) {
+__device__ __noinline__ uint32_t pending_id(uint32_t pinfo, uint32_t m, int st, int lane) {
   int inl = __popc(m & 0x7ffffffu);
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -574,7 +580,7 @@ __device__ __forceinline__ void push_overflow(const MovegenParams& P, long long 
 
 // move set of a doubles node (its sorted sources in w) for its die, pruned: a slot below the slot `t` that created the node is dropped
 // when its move was already legal one ply earlier, i.e. unless it moves the checker that has just landed alone on t's destination
-__device__ __forceinline__ uint32_t node_mask(uint32_t w, const Root& r, uint32_t rk0, uint32_t rk1, uint32_t rk2, uint32_t rk3) {
+__device__ __noinline__ uint32_t node_mask(uint32_t w, const Root r, uint32_t rk0, uint32_t rk1, uint32_t rk2, uint32_t rk3) {
   const int die = die_of_id(w >> 25);
   uint32_t k0 = rk0, k1 = rk1, k2 = rk2, k3 = rk3;
 #pragma unroll 1
@@ -716,7 +722,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, C::CTAS) k_movegen21(const __gr
         uint32_t k0 = rk0, k1 = rk1, k2 = rk2, k3 = rk3;
         key_move(k0, k1, k2, k3, r, s, e);
         const View v = make_view(k0, k1, k2, k3, r);
-#pragma unroll
+#pragma unroll 1
         for (int b = 0; b < 6; ++b) {
           const uint32_t m = view_mask(v, r, b + 1);
           W[O_C1MASK + b * C1CAP + c] = m;
@@ -884,40 +890,79 @@ __global__ void __launch_bounds__(C::WARPS * 32, C::CTAS) k_movegen21(const __gr
             continue;
           }
           bool ok = true;
-          // ply 2 -> 3
-          int n3 = 0;
-          if (a1 > a0) {
-            clear_tab<C>(W + O_TAB, lane);
-            const int cap3 = avail - C::RES_RESERVE;
-            for (int p0 = a0; p0 < a1 && ok; p0 += 32) {
-              uint32_t pinfo = 0, m = 0;
-              if (p0 + lane < a1) {
-                const uint32_t w = W[C::O_BUF + p0 + lane];
-                if ((todo >> (die_of_id(w >> 25) - 1)) & 1u) {
-                  m = node_mask(w, r, rk0, rk1, rk2, rk3);
-                  pinfo = (w & 0xfffffu) | ((m >> 27) << 20) | (w & (31u << 25));
+          int n3 = 0, cnt3 = 0, st3 = 0;
+          int res_off = fb_off, res_cap = avail;
+          n_res = 0;
+          // ply 2 -> 3 (into the frontier behind the ply-2 nodes), then ply 3 -> 4 (straight into the result buffer behind that)
+          for (int ply = 2; ply <= 3 && ok; ++ply) {
+            const bool last = ply == 3;
+            const int src_off = last ? fb_off : C::O_BUF + a0, n_src = last ? n3 : a1 - a0;
+            const int dst_off = last ? res_off : fb_off, cap = last ? res_cap : avail - C::RES_RESERVE;
+            int n_dst = last ? n_res : 0;
+            if (n_src > 0) {
+              clear_tab<C>(W + O_TAB, lane);
+              int key_base = n_dst;
+              for (int p0 = 0; p0 < n_src && ok; p0 += 32) {
+                uint32_t pinfo = 0, m = 0;
+                if (p0 + lane < n_src) {
+                  const uint32_t w = W[src_off + p0 + lane];
+                  if ((todo >> (die_of_id(w >> 25) - 1)) & 1u) {
+                    m = node_mask(w, r, rk0, rk1, rk2, rk3);
+                    pinfo = (w & 0xfffffu) | ((m >> 27) << 20) | (w & (31u << 25));
+                  }
+                }
+                int st = 0;
+                while (true) {
+                  const uint32_t rc = expand21<C>(1, pinfo, m, st, dst_off, n_dst, cap, key_base, player, r.blot);
+                  n_dst = (int)(rc & 0xffffu);
+                  if ((rc >> 16) == 0u) break;
+                  st = (int)(rc >> 16) - 1;
+                  // a frontier that does not fit fails the group; results make room by emitting the dice that are complete
+                  const unsigned long long mr = last ? make_room21<C>(&P, pos, player, r.blot, rk, res_off, n_dst, pending_id(pinfo, m, st, lane), emitted, !ALL)
+                                                     : 1ull << 63;
+                  if (mr >> 63) {
+                    ok = false;
+                    break;
+                  }
+                  emitted = (uint32_t)mr;
+                  n_dst = (int)(mr >> 32);
+                  key_base = 0;
                 }
               }
-              const uint32_t rc = expand21<C>(1, pinfo, m, 0, fb_off, n3, cap3, 0, player, r.blot);
-              n3 = (int)(rc & 0xffffu);
-              ok = (rc >> 16) == 0u;
             }
-          }
-          int cnt3 = 0;
-          const int res_off = fb_off + n3;
-          const int res_cap = avail - n3;
-          n_res = 0;
-          if (ok) {
-            const int st3 = lower_bound_id(W + fb_off, n3, lane < 6 ? id_of_die0(lane) : 31u);
-            cnt3 = __shfl_down_sync(BG_FULL, st3, 1) - st3;
-            // dice whose tree ends at ply 1 or 2: that ply's nodes are the results
+            if (!ok) break;
+            // dice whose tree ended one ply earlier: that ply's nodes are their results (after ply 2 -> 3: the ones that stop at ply 1 or 2;
+            // after ply 3 -> 4: the ones that stop at ply 3, i.e. have ply-3 nodes but neither results in the buffer nor written ones)
+            uint32_t present = emitted;
+            if (!last) {
+              n3 = n_dst;
+              res_off = fb_off + n3;
+              res_cap = avail - n3;
+              st3 = lower_bound_id(W + fb_off, n3, lane < 6 ? id_of_die0(lane) : 31u);
+              cnt3 = __shfl_down_sync(BG_FULL, st3, 1) - st3;
+            } else {
+              n_res = n_dst;
+              for (int i0 = 0; i0 < n_res; i0 += 32) {
+                const int i = i0 + lane;
+                present |= __reduce_or_sync(BG_FULL, i < n_res ? 1u << ((W[res_off + i] >> 25) - 1u) : 0u);
+              }
+            }
             for (int e = d; e < g && ok; ++e) {
               if (!((todo >> e) & 1u)) continue;
               const int c2 = __shfl_sync(BG_FULL, cnt2, e), c3 = __shfl_sync(BG_FULL, cnt3, e);
-              if (c2 > 0 && c3 > 0) continue;
-              const int n_add = c2 == 0 ? __shfl_sync(BG_FULL, n1, e) : c2;
-              const int src = c2 == 0 ? __shfl_sync(BG_FULL, exc1, e) : __shfl_sync(BG_FULL, st2, e);
-              if (n_res + n_add > res_cap) {
+              int n_add, src;
+              uint32_t child_id = 0;
+              if (!last) {
+                if (c2 > 0 && c3 > 0) continue;
+                n_add = c2 == 0 ? __shfl_sync(BG_FULL, n1, e) : c2;
+                src = c2 == 0 ? O_C1INFO + __shfl_sync(BG_FULL, exc1, e) : C::O_BUF + __shfl_sync(BG_FULL, st2, e);
+                child_id = c2 == 0 ? id_of_die0(e) : 0u;
+              } else {
+                if (c3 == 0 || ((present >> (id_of_die0(e) - 1)) & 1u)) continue;
+                n_add = c3;
+                src = fb_off + __shfl_sync(BG_FULL, st3, e);
+              }
+              if (n_res + n_add > res_cap) {  // everything buffered is complete: emit it
                 emitted = flush21<C>(&P, pos, player, r.blot, rk, res_off, n_res, n_res, emitted, !ALL);
                 n_res = 0;
               }
@@ -925,64 +970,11 @@ __global__ void __launch_bounds__(C::WARPS * 32, C::CTAS) k_movegen21(const __gr
                 ok = false;
                 break;
               }
-              const uint32_t id = id_of_die0(e);
-              for (int i = lane; i < n_add; i += 32)
-                W[res_off + n_res + i] = c2 == 0 ? (((W[O_C1INFO + src + i] >> 5) & 31u) | (NONE5 << 5) | (NONE5 << 10) | (NONE5 << 15) | (id << 25))
-                                                 : W[C::O_BUF + src + i];
+              for (int i = lane; i < n_add; i += 32) {
+                const uint32_t w = W[src + i];
+                W[res_off + n_res + i] = child_id ? (((w >> 5) & 31u) | (NONE5 << 5) | (NONE5 << 10) | (NONE5 << 15) | (child_id << 25)) : w;
+              }
               n_res += n_add;
-              __syncwarp();
-            }
-          }
-          // ply 3 -> 4: straight into the result buffer
-          if (ok && n3 > 0) {
-            clear_tab<C>(W + O_TAB, lane);
-            int key_base = n_res;
-            for (int p0 = 0; p0 < n3 && ok; p0 += 32) {
-              uint32_t pinfo = 0, m = 0;
-              if (p0 + lane < n3) {
-                const uint32_t w = W[fb_off + p0 + lane];
-                m = node_mask(w, r, rk0, rk1, rk2, rk3);
-                pinfo = (w & 0xfffffu) | ((m >> 27) << 20) | (w & (31u << 25));
-              }
-              int st = 0;
-              while (true) {
-                const uint32_t rc = expand21<C>(1, pinfo, m, st, res_off, n_res, res_cap, key_base, player, r.blot);
-                n_res = (int)(rc & 0xffffu);
-                if ((rc >> 16) == 0u) break;
-                st = (int)(rc >> 16) - 1;
-                const unsigned long long mr = make_room21<C>(&P, pos, player, r.blot, rk, res_off, n_res, pending_id(pinfo, m, st, lane), emitted, !ALL);
-                if (mr >> 63) {  // this die's fourth ply alone does not fit
-                  ok = false;
-                  break;
-                }
-                emitted = (uint32_t)mr;
-                n_res = (int)(mr >> 32);
-                key_base = 0;
-              }
-            }
-          }
-          if (ok && n3 > 0) {
-            // dice whose tree ends at ply 3
-            uint32_t present = emitted;
-            for (int i0 = 0; i0 < n_res; i0 += 32) {
-              const int i = i0 + lane;
-              present |= __reduce_or_sync(BG_FULL, i < n_res ? 1u << ((W[res_off + i] >> 25) - 1u) : 0u);
-            }
-            const int st3 = lower_bound_id(W + fb_off, n3, lane < 6 ? id_of_die0(lane) : 31u);
-            for (int e = d; e < g && ok; ++e) {
-              const int c3 = __shfl_sync(BG_FULL, cnt3, e);
-              if (c3 == 0 || ((present >> (id_of_die0(e) - 1)) & 1u)) continue;
-              const int src = __shfl_sync(BG_FULL, st3, e);
-              if (n_res + c3 > res_cap) {
-                emitted = flush21<C>(&P, pos, player, r.blot, rk, res_off, n_res, n_res, emitted, !ALL);
-                n_res = 0;
-              }
-              if (c3 > res_cap) {
-                ok = false;
-                break;
-              }
-              for (int i = lane; i < c3; i += 32) W[res_off + n_res + i] = W[fb_off + src + i];
-              n_res += c3;
               __syncwarp();
             }
           }
