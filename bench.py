@@ -400,7 +400,7 @@ def main():
     e2e_value = n_after_all / (float(te[0]) / args.steps * 1e-3)
     h2d = h_b.numel() + h_p.numel()
     d2h = h_act.numel() * 4 + h_cnt.numel() * 4
-    n_step_kernels = 6  # k_movegen21 + the 512 / 2048 / 4096 per-item tail tiers + k_eval_tc twice (bulk-tier rows on the side stream, tail rows after)
+    n_step_kernels = 5  # k_movegen21<Std> (bulk) + k_movegen21<Big> + k_movegen<4096> (tail tiers) + k_eval_tc twice (bulk-tier rows on the side stream, tail rows after)
     n_e2e_kernels = (n_step_kernels + 2) * n_chunks  # + status fold + k_select, per chunk
     e2e_check = int((h_cnt.to(torch.int64).clamp(max=500)).sum().item())  # must reproduce the afterstate count of the resident path
     pipe.close()
@@ -410,7 +410,7 @@ def main():
     peak, peak_src = load_peaks()
     eval_bytes = n_after * (52 + 1 + 4)  # board in + flag in + value out
     movegen_bytes = P * (52 + 1) + B * (8 + 4) + n_after * (52 + 1)  # position in, item offset / count out, board + flag out
-    k_mg, k_ev = "bg::k_movegen21 (+ 512 / 2048 / 4096 tail tiers)", "bg::k_eval_tc (tcgen05, H=128)"
+    k_mg, k_ev = "bg::k_movegen21<Std> (+ tail tiers k_movegen21<Big>, k_movegen<4096>)", "bg::k_eval_tc (tcgen05, H=128)"
     kern = {k_ev: (t_eval, eval_bytes), k_mg: (t_movegen, movegen_bytes)}
     dom = max(kern, key=lambda k: kern[k][0])
     ach = kern[dom][1] / (kern[dom][0] * 1e-3) / 1e9
@@ -679,7 +679,7 @@ def main():
                     "what": f"bg_hostpipe_run (C ABI; bg.HostPipeline): pinned host positions + players -> {n_chunks} chunks on {args.e2e_streams} library streams (H2D, bg_movegen_eval_all_rolls, bg_select(greedy), D2H) -> 21 host (action, count) pairs per position",
                     "afterstates_check": e2e_check},
             "gpu_launches": n_step_kernels * args.steps,
-            "gpu_launches_note": f"timed region, per step (bg_movegen_eval_all_rolls): k_movegen21 + per-item tail tiers k_movegen<512|2048|4096> + k_eval_tc twice (bulk-tier rows on the side stream, tail-tier rows after); unfused ms_per_step {unfused_ms_per_step:.2f}; the e2e region launches {n_e2e_kernels} per step (the same six + status fold + k_select, per chunk)",
+            "gpu_launches_note": f"timed region, per step (bg_movegen_eval_all_rolls): k_movegen21<Std> (bulk tier) + tail tiers k_movegen21<Big>, k_movegen<4096> + k_eval_tc twice (bulk-tier rows on the side stream, tail-tier rows after); unfused ms_per_step {unfused_ms_per_step:.2f}; the e2e region launches {n_e2e_kernels} per step (the same five + status fold + k_select, per chunk)",
             "roofline": roofline, "roofline_movegen": roofline_movegen, "roofline_eval": roofline_eval, "roofline_encode": roofline_encode, "cpu_baseline": cpu, "clocks": clocks, "selfplay_1ply": selfplay, "selfplay_2ply": selfplay2,
             "selfplay_2ply_all_candidates": selfplay2b, "learner": learner, "td0_loop": td0}
     print(json.dumps(line), flush=True)

@@ -31,6 +31,7 @@
 #include "movegen.cuh"
 #include "movegen_dev.cuh"
 
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace bg {
@@ -40,6 +41,24 @@ namespace {
 constexpr int C1CAP = 64;      // first-move children over the six dice (observed max 70 in 20,000 positions, p99 44)
 constexpr int DCAP = 128;      // candidate descriptors per sub-batch
 constexpr uint32_t NONE5 = 31u;
+// -DBG_CHECKED=1: index / capacity assertions on every shared-memory write of this file (compute-sanitizer is closed on the GPU pool this was
+// developed on, so the checked build is the memcheck stand-in: the GPU suite is run once with it, profiles/r02_checked_build_gpu_tests.txt)
+#ifndef BG_CHECKED
+#define BG_CHECKED 0
+#endif
+#if BG_CHECKED
+#define BG_CHECK(cond, what)                                                                                         \
+  do {                                                                                                               \
+    if (!(cond)) {                                                                                                   \
+      printf("BG_CHECK failed: %s (%s:%d) block %d thread %d\n", what, __FILE__, __LINE__, blockIdx.x, threadIdx.x); \
+      asm volatile("trap;");                                                                                          \
+    }                                                                                                                \
+  } while (0)
+#else
+#define BG_CHECK(cond, what) \
+  do {                       \
+  } while (0)
+#endif
 #ifndef BG_EMIT_NIBBLE
 #define BG_EMIT_NIBBLE 0
 #endif
@@ -261,6 +280,7 @@ __device__ __noinline__ uint32_t flush21(const MovegenParams* __restrict__ Pp, l
       const uint32_t id = res[i] >> 25;
       const uint32_t pid = i > 0 ? res[i - 1] >> 25 : 0u;
       const uint32_t nid = i + 1 < n_emit ? res[i + 1] >> 25 : 0u;
+      BG_CHECK(id >= 1 && id <= 21, "roll id of a result");
       if (id != pid) W[C::O_ISTART + id] = (uint32_t)i;
       if (id != nid) W[C::O_ISTART + 24 + id] = (uint32_t)(i + 1);
     }
@@ -365,6 +385,7 @@ __device__ __noinline__ uint32_t flush21(const MovegenParams* __restrict__ Pp, l
 #else
         // the root's 13 words, then one byte decrement / increment per checker moved or hit
         uint32_t* const row = stage + ph + lane * 13;
+        BG_CHECK(ph + lane * 13 + 13 <= C::TCAP, "staging row");
 #pragma unroll
         for (int q = 0; q < 13; ++q) row[q] = rw[q];
         uint8_t* const rb = reinterpret_cast<uint8_t*>(row);
@@ -495,6 +516,7 @@ __device__ __noinline__ uint32_t expand21(int mode, uint32_t pinfo, uint32_t m, 
       while (mm) {
         const int slot = __ffs(mm) - 1;
         mm &= mm - 1u;
+        BG_CHECK(o >= 0 && o < DCAP, "descriptor index");
         desc[o++] = (uint16_t)(lane | (slot << 5));
       }
     }
@@ -541,6 +563,8 @@ __device__ __noinline__ uint32_t expand21(int mode, uint32_t pinfo, uint32_t m, 
       bool isnew = false;
       if (cv && (__ffs(grp) - 1) == lane) {
         uint32_t idx = hash_key<C>(key);
+        int probes = 0;
+        (void)probes;
         while (true) {
           const uint32_t old = atomicCAS(&tab[idx], 0u, key);
           if (old == 0u) {
@@ -549,9 +573,11 @@ __device__ __noinline__ uint32_t expand21(int mode, uint32_t pinfo, uint32_t m, 
           }
           if (old == key) break;
           idx = (idx + 1) & (C::TCAP - 1);
+          BG_CHECK(++probes <= C::TCAP, "hash set full");
         }
       }
       const uint32_t bal = __ballot_sync(BG_FULL, isnew);
+      BG_CHECK(n + __popc(bal) <= cap && dst_off + n + __popc(bal) <= C::O_BUF + C::BCAP, "append beyond the arena");
       if (isnew) dst[n + __popc(bal & lt)] = word;
       n += __popc(bal);
     }
@@ -729,6 +755,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, C::CTAS) k_movegen21(const __gr
           nz |= ((m & 0x7ffffffu) != 0u ? 1u : 0u) << b;
         }
         const uint32_t lone = (e < 24u && key_count(k0, k1, k2, e) == 1u) ? 1u : 0u;
+        BG_CHECK(c < C1CAP && s <= 24u && e <= 25u, "children table");
         W[O_C1INFO + c] = slot | (s << 5) | (e << 10) | ((uint32_t)d << 15) | (lone << 18);
       }
       has2a |= __reduce_or_sync(BG_FULL, (valid && d < 5) ? nz << (6 * d) : 0u);
@@ -970,6 +997,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, C::CTAS) k_movegen21(const __gr
                 ok = false;
                 break;
               }
+              BG_CHECK(res_off + n_res + n_add <= C::O_BUF + C::BCAP, "results beyond the arena");
               for (int i = lane; i < n_add; i += 32) {
                 const uint32_t w = W[src + i];
                 W[res_off + n_res + i] = child_id ? (((w >> 5) & 31u) | (NONE5 << 5) | (NONE5 << 10) | (NONE5 << 15) | (child_id << 25)) : w;
