@@ -145,6 +145,31 @@ int32_t bg_movegen_eval_all_rolls(const int8_t* boards /*[P,52]*/, const uint8_t
                                   int32_t* out_status /*[1]*/, void* workspace, int64_t workspace_bytes, const float* prepared, int32_t H,
                                   float* out_v /*[pool_cap]*/, void* stream);
 
+/*
+ * COMPACT forms of the position-major operators: the pool holds one uint64 per legal afterstate -- low word = the move's CODE (sorted sources /
+ * destinations of the sub-moves, see csrc/codes.cuh), high word = the index of the position it applies to -- instead of a 52-byte board.
+ * This is what callers that only need values / actions want (worker.py:101-143 looks at the afterstates' VALUES and then steps the env
+ * with the chosen index; two_ply.py:93-150 looks at reply values only): move generation does not materialise 25 GB of boards per 10^6
+ * positions and the evaluator rebuilds each afterstate on chip while it builds its feature row (bg_eval_codes / the fused call).
+ * Order, counts, offsets and values are exactly those of the board forms.  bg_afterstates_from_codes materialises the boards of selected
+ * pool rows (rows[j] < 0 -> zeros; rows == NULL -> rows 0..n-1), e.g. the afterstate of each item's chosen action: rows[i] = out_offsets[i] + action[i].
+ * Items whose tree exceeds the code-based tiers (more than ~6,000 afterstates; none is known for a legal position) get BG_ERR_CAPACITY.
+ */
+int32_t bg_movegen_all_rolls_compact(const int8_t* boards /*[P,52]*/, const uint8_t* players /*[P]*/, int64_t P, int32_t item_cap,
+                                     int64_t pool_cap, uint64_t* out_codes /*[pool_cap]*/, int64_t* out_offsets /*[21*P]*/,
+                                     int32_t* out_count /*[21*P]*/, int64_t* out_total /*[1]*/, int32_t* out_status /*[1]*/, void* workspace,
+                                     int64_t workspace_bytes, void* stream);
+/* values of the rows of a compact pool; N rows, or *N_dev (<= max_N) when N_dev != NULL */
+int32_t bg_eval_codes(const int8_t* boards /*[P,52]*/, const uint8_t* players /*[P]*/, const uint64_t* codes /*[N]*/, int64_t N,
+                      const int64_t* N_dev /*or NULL*/, int64_t max_N, const float* prepared, int32_t H, float* out_v /*[N]*/, void* stream);
+int32_t bg_movegen_eval_all_rolls_compact(const int8_t* boards /*[P,52]*/, const uint8_t* players /*[P]*/, int64_t P, int32_t item_cap,
+                                          int64_t pool_cap, uint64_t* out_codes /*[pool_cap]*/, int64_t* out_offsets /*[21*P]*/,
+                                          int32_t* out_count /*[21*P]*/, int64_t* out_total /*[2]*/, int32_t* out_status /*[1]*/,
+                                          void* workspace, int64_t workspace_bytes, const float* prepared, int32_t H,
+                                          float* out_v /*[pool_cap]*/, void* stream);
+int32_t bg_afterstates_from_codes(const int8_t* boards /*[P,52]*/, const uint8_t* players /*[P]*/, const uint64_t* codes /*pool*/,
+                                  const int64_t* rows /*[n] or NULL*/, int64_t n, int8_t* out_boards /*[n,52]*/, void* stream);
+
 /* Diagnostic for the tcgen05 evaluator (batches >= 32768 rows with per-row flags, any H: 128 hidden units per pass, smaller nets
  * zero-padded, wider nets in two passes; set BG_EVAL_PATH=ffma to force the CUDA-core kernels): synchronises and returns 0, or non-zero if one of its bounded mbarrier waits ever timed out. */
 int32_t bg_eval_tc_status(void);

@@ -221,6 +221,62 @@ int32_t bg_movegen_eval_all_rolls(const int8_t* boards, const uint8_t* players, 
   return movegen_eval_overlapped(a, out_total, prepared, H, out_v, c, (cudaStream_t)stream);
 }
 
+/* ---- compact (code) pools ---- */
+
+int32_t bg_movegen_all_rolls_compact(const int8_t* boards, const uint8_t* players, int64_t P, int32_t item_cap, int64_t pool_cap, uint64_t* out_codes,
+                                     int64_t* out_offsets, int32_t* out_count, int64_t* out_total, int32_t* out_status, void* workspace,
+                                     int64_t workspace_bytes, void* stream) {
+  BG_REQUIRE(P >= 0, "bg_movegen_all_rolls_compact: P < 0");
+  BG_REQUIRE(P == 0 || (boards && players && out_offsets && out_count), "bg_movegen_all_rolls_compact: null input/output pointer");
+  BG_REQUIRE(out_codes && workspace, "bg_movegen_all_rolls_compact: null pointer");
+  int32_t rc = require_device();
+  if (rc != BG_OK) return rc;
+  MovegenArgs a{boards,  players, nullptr,     P,         item_cap,  pool_cap,   nullptr,   nullptr,
+                nullptr, nullptr, out_offsets, out_count, out_total, out_status, workspace, workspace_bytes, nullptr};
+  a.all_rolls = 1;
+  a.out_codes = reinterpret_cast<uint2*>(out_codes);
+  return movegen_launch(a, (cudaStream_t)stream);
+}
+
+int32_t bg_eval_codes(const int8_t* boards, const uint8_t* players, const uint64_t* codes, int64_t N, const int64_t* N_dev, int64_t max_N,
+                      const float* prepared, int32_t H, float* out_v, void* stream) {
+  BG_REQUIRE(boards && players && codes && prepared && out_v, "bg_eval_codes: null pointer");
+  BG_REQUIRE(N_dev ? max_N >= 0 : N >= 0, "bg_eval_codes: bad N");
+  int32_t rc = require_device();
+  if (rc != BG_OK) return rc;
+  EvalArgs a{boards, players, nullptr, nullptr, N_dev ? 0 : N, N_dev, N_dev ? max_N : N, prepared, H, out_v};
+  a.codes = reinterpret_cast<const uint2*>(codes);
+  return eval_launch(a, (cudaStream_t)stream);
+}
+
+int32_t bg_movegen_eval_all_rolls_compact(const int8_t* boards, const uint8_t* players, int64_t P, int32_t item_cap, int64_t pool_cap,
+                                          uint64_t* out_codes, int64_t* out_offsets, int32_t* out_count, int64_t* out_total /*[2]*/,
+                                          int32_t* out_status, void* workspace, int64_t workspace_bytes, const float* prepared, int32_t H,
+                                          float* out_v, void* stream) {
+  BG_REQUIRE(P >= 0, "bg_movegen_eval_all_rolls_compact: P < 0");
+  BG_REQUIRE(P == 0 || (boards && players && out_offsets && out_count), "bg_movegen_eval_all_rolls_compact: null input/output pointer");
+  BG_REQUIRE(out_codes && out_total && out_v && prepared && workspace, "bg_movegen_eval_all_rolls_compact: null pointer");
+  int32_t rc = require_device();
+  if (rc != BG_OK) return rc;
+  std::lock_guard<std::mutex> lk(g_fused_mu);
+  SideCtx* c = nullptr;
+  if ((rc = fused_ctx(&c)) != BG_OK) return rc;
+  MovegenArgs a{boards,  players, nullptr,     P,         item_cap,  pool_cap,   nullptr,   nullptr,
+                nullptr, nullptr, out_offsets, out_count, out_total, out_status, workspace, workspace_bytes, nullptr};
+  a.all_rolls = 1;
+  a.out_codes = reinterpret_cast<uint2*>(out_codes);
+  return movegen_eval_overlapped(a, out_total, prepared, H, out_v, c, (cudaStream_t)stream);
+}
+
+int32_t bg_afterstates_from_codes(const int8_t* boards, const uint8_t* players, const uint64_t* codes, const int64_t* rows, int64_t n,
+                                  int8_t* out_boards, void* stream) {
+  BG_REQUIRE(n >= 0, "bg_afterstates_from_codes: n < 0");
+  BG_REQUIRE(n == 0 || (boards && players && codes && out_boards), "bg_afterstates_from_codes: null pointer");
+  int32_t rc = require_device();
+  if (rc != BG_OK) return rc;
+  return materialize_launch(boards, players, reinterpret_cast<const uint2*>(codes), rows, n, out_boards, (cudaStream_t)stream);
+}
+
 /* ---- host-resident batches ---- */
 
 int32_t bg_hostpipe_create(bg_hostpipe** out, int32_t device, int32_t H, int64_t chunk_units, int32_t all_rolls, int32_t item_cap,

@@ -10,6 +10,7 @@
 // i.e. one 512-byte (H=128) conflict-free row read per occupied point instead of a dense 198xH contraction; features
 // never exist in memory.  One warp per board, lane owns H/32 hidden units; fp32 FFMA (meets the 1e-5 contract; a bf16
 // tensor-core path would not).  Persistent CTAs keep the 100 KB table resident in shared memory.
+#include "codes.cuh"
 #include "eval.cuh"
 
 #include <stdlib.h>
@@ -388,7 +389,11 @@ int32_t eval_launch(const EvalArgs& a, cudaStream_t stream) {
   {
     // large batches go to the tensor-core kernel, 128 hidden units per pass: smaller nets zero-padded, wider nets in two passes
     const int64_t bound = a.N_dev ? a.max_N : a.N;
-    if (tc_mode() == 1 && a.flags && bound >= 32768) {
+    if (a.codes && !a.flags) {
+      set_error("bg_eval: the compact form needs the positions' players");
+      return BG_ERR_ARG;
+    }
+    if (a.codes || (tc_mode() == 1 && a.flags && bound >= 32768)) {
       if (!g_tc_err) {
         cudaError_t e = cudaMalloc(&g_tc_err, 4);
         if (e == cudaSuccess) e = cudaMemset(g_tc_err, 0, 4);
@@ -439,6 +444,34 @@ int32_t encode_launch(const int8_t* boards, const uint8_t* flags, int64_t N, flo
   return BG_OK;
 }
 
+// rows of a compact pool -> boards: out[j] = position board of codes[rows[j]] with the code applied (rows == nullptr: rows 0 .. n-1)
+__global__ void __launch_bounds__(256) k_materialize(const int8_t* __restrict__ boards, const uint8_t* __restrict__ players, const uint2* __restrict__ codes,
+                                                     const long long* __restrict__ rows, int64_t n, int8_t* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (j >= n) return;
+  const long long rrow = rows ? rows[j] : j;
+  uint32_t w[13];
+  if (rrow < 0) {  // an item without a legal move (action -1): zeros
+#pragma unroll
+    for (int q = 0; q < 13; ++q) reinterpret_cast<uint32_t*>(out)[j * 13 + q] = 0u;
+    return;
+  }
+  const uint2 e = codes[rrow];
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(boards) + (int64_t)e.y * 13;
+#pragma unroll
+  for (int q = 0; q < 13; ++q) w[q] = src[q];
+  apply_code_bytes(reinterpret_cast<uint8_t*>(w), e.x, players[e.y] & 1);
+#pragma unroll
+  for (int q = 0; q < 13; ++q) reinterpret_cast<uint32_t*>(out)[j * 13 + q] = w[q];
+}
+
+int32_t materialize_launch(const int8_t* boards, const uint8_t* players, const uint2* codes, const int64_t* rows, int64_t n, int8_t* out,
+                           cudaStream_t stream) {
+  if (n <= 0) return BG_OK;
+  k_materialize<<<(int)((n + 255) / 256), 256, 0, stream>>>(boards, players, codes, reinterpret_cast<const long long*>(rows), n, out);
+  return check_cuda(cudaGetLastError(), "k_materialize launch");
+}
+
 int32_t side_ctx_create(SideCtx* c, bool high_priority) {
   if (c->stream) return BG_OK;
   int lo = 0, hi = 0;
@@ -466,6 +499,11 @@ int32_t movegen_eval_overlapped(MovegenArgs m, int64_t* total2, const float* pre
   if (!side || !side->stream) {
     if ((rc = movegen_launch(m, stream)) != BG_OK) return rc;
     EvalArgs ev{m.out_boards, m.out_flags, nullptr, nullptr, 0, total2, m.pool_cap, prepared, H, out_v};
+    if (m.out_codes) {
+      ev.boards = m.boards;
+      ev.flags = m.players;
+      ev.codes = m.out_codes;
+    }
     return eval_launch(ev, stream);
   }
   m.tier1_total = total2 + 1;
@@ -474,10 +512,17 @@ int32_t movegen_eval_overlapped(MovegenArgs m, int64_t* total2, const float* pre
   cudaError_t e = cudaStreamWaitEvent(side->stream, side->ev_t1, 0);
   if (e != cudaSuccess) return check_cuda(e, "wait bulk tier");
   EvalArgs e1{m.out_boards, m.out_flags, nullptr, nullptr, 0, total2 + 1, m.pool_cap, prepared, H, out_v};
+  if (m.out_codes) {  // compact pool: the evaluator rebuilds each afterstate from its position + code
+    e1.boards = m.boards;
+    e1.flags = m.players;
+    e1.codes = m.out_codes;
+  }
   if ((rc = eval_launch(e1, side->stream)) != BG_OK) return rc;
   e = cudaEventRecord(side->ev_side, side->stream);
   if (e != cudaSuccess) return check_cuda(e, "record side");
-  EvalArgs e2{m.out_boards, m.out_flags, nullptr, nullptr, 0, total2, m.pool_cap, prepared, H, out_v, total2 + 1};
+  EvalArgs e2 = e1;
+  e2.N_dev = total2;
+  e2.start_dev = total2 + 1;
   if ((rc = eval_launch(e2, stream)) != BG_OK) return rc;
   return check_cuda(cudaStreamWaitEvent(stream, side->ev_side, 0), "join side stream");
 }

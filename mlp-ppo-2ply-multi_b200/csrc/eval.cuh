@@ -17,6 +17,9 @@ struct EvalArgs {
   int32_t H;
   float* out_v;
   const int64_t* start_dev = nullptr;  // optional device counter: evaluate rows [*start_dev, N) only (rows before it are left untouched)
+  // compact pool (codes.cuh): rows are (code, position index) pairs; `boards` / `flags` are then the POSITIONS' boards and players.  Always
+  // evaluated by the tensor-core kernel.
+  const uint2* codes = nullptr;
 };
 
 int64_t prepared_weights_bytes(int32_t H);
@@ -45,6 +48,8 @@ int32_t side_ctx_create(SideCtx* c, bool high_priority);
 void side_ctx_destroy(SideCtx* c);
 int32_t movegen_eval_overlapped(MovegenArgs m, int64_t* total2, const float* prepared, int32_t H, float* out_v, SideCtx* side,
                                 cudaStream_t stream);
+int32_t materialize_launch(const int8_t* boards, const uint8_t* players, const uint2* codes, const int64_t* rows, int64_t n, int8_t* out,
+                           cudaStream_t stream);
 int32_t encode_launch(const int8_t* boards, const uint8_t* flags, int64_t N, float* out, cudaStream_t stream);
 
 }  // namespace bg

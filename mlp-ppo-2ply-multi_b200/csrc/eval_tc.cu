@@ -18,6 +18,7 @@
 //   MMA thread; tcgen05.commit -> done[g] -> workers.  All waits are bounded (an error flag instead of a hang).
 #include <cuda_fp16.h>
 
+#include "codes.cuh"
 #include "eval.cuh"
 
 namespace bg {
@@ -127,10 +128,15 @@ __device__ __forceinline__ void point_words(uint32_t c, uint32_t& w0, uint32_t& 
   w1 = (c >= 3 ? ONE : 0u) | (ex << 16);
 }
 
+// CODES: the rows are (code, position index) pairs of the compact pool (codes.cuh); `boards` / `flags` are then the POSITIONS' boards and
+// players, and each worker thread rebuilds its afterstate in a 52-byte shared-memory scratch row (13 word stores, a few byte updates, 13 word
+// loads: ~6 % more instructions in a kernel that is tensor-bound) -- the afterstate boards never exist in HBM.
+constexpr int SCRATCH_BYTES = 2 * 128 * 13 * 4;
+template <bool CODES>
 __global__ void __launch_bounds__(THREADS, 1)
     k_eval_tc(const int8_t* __restrict__ boards, const uint8_t* __restrict__ flags, int64_t N_host, const int64_t* __restrict__ N_dev,
               int64_t max_N, const uint8_t* __restrict__ img, float* __restrict__ out_v, int32_t* __restrict__ err,
-              const int64_t* __restrict__ start_dev, int accumulate) {
+              const int64_t* __restrict__ start_dev, int accumulate, const uint2* __restrict__ codes) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sB = smem;                                             // B operand image
   float* sW2 = reinterpret_cast<float*>(smem + B_BYTES);          // w2[128], b2
@@ -172,8 +178,12 @@ __global__ void __launch_bounds__(THREADS, 1)
     int64_t start = start_dev ? *start_dev : 0;
     if (start > N) start = N;
     if (start < 0) start = 0;
-    boards += start * BG_BOARD_BYTES;
-    if (flags) flags += start;
+    if constexpr (CODES) {
+      codes += start;
+    } else {
+      boards += start * BG_BOARD_BYTES;
+      if (flags) flags += start;
+    }
     out_v += start;
     N -= start;
   }
@@ -189,13 +199,20 @@ __global__ void __launch_bounds__(THREADS, 1)
     uint32_t it = 0;
     // board words of the CURRENT tile live in registers; the next tile's are fetched before waiting on the tensor core
     uint32_t bw[13];
-    uint32_t flag = 0;
+    uint32_t flag = 0, code = 0;
+    uint32_t* const scr = reinterpret_cast<uint32_t*>(smem + B_BYTES + 1024 + 128) + (g * 128 + row) * 13;  // CODES: this thread's scratch row
     auto fetch = [&](int64_t tile) {
       const int64_t i = tile * 128 + row;
       if (tile < n_tiles && i < N) {
+        int64_t src = i;
+        if constexpr (CODES) {
+          const uint2 e = __ldg(codes + i);
+          code = e.x;
+          src = (int64_t)e.y;  // consecutive rows share their position: these loads hit L1
+        }
 #pragma unroll
-        for (int w = 0; w < 13; ++w) bw[w] = __ldg(b32 + i * 13 + w);
-        flag = flags[i] & 1u;
+        for (int w = 0; w < 13; ++w) bw[w] = __ldg(b32 + src * 13 + w);
+        flag = flags[src] & 1u;
       } else {
 #pragma unroll
         for (int w = 0; w < 13; ++w) bw[w] = 0u;
@@ -207,6 +224,15 @@ __global__ void __launch_bounds__(THREADS, 1)
     for (int64_t t = (int64_t)blockIdx.x * 2 + g; t < n_tiles; t += tstride, ++it) {
       const int64_t i = t * 128 + row;
       const bool valid = i < N;
+      if constexpr (CODES) {
+        if (valid) {  // position board -> afterstate board, in this thread's scratch row (13-word stride: conflict free)
+#pragma unroll
+          for (int w = 0; w < 13; ++w) scr[w] = bw[w];
+          apply_code_bytes(reinterpret_cast<uint8_t*>(scr), code, (int)flag);
+#pragma unroll
+          for (int w = 0; w < 13; ++w) bw[w] = scr[w];
+        }
+      }
       // ---- build this board's fp16 feature row, 8 TMEM columns (= one K16 step = four points) at a time ----
 #pragma unroll
       for (int wd = 0; wd < 12; ++wd) {  // board word wd: 4 points -> 16 features -> 8 columns
@@ -354,14 +380,20 @@ int32_t eval_tc_launch(const EvalArgs& a, const uint8_t* img, int32_t* err_flag,
     }
     cudaError_t e = cudaMemcpyToSymbol(c_off15_split, h, sizeof(h));
     if (e != cudaSuccess) return check_cuda(e, "cudaMemcpyToSymbol(c_off15_split)");
-    return check_cuda(opt_in_shared(k_eval_tc, smem), "cudaFuncSetAttribute(k_eval_tc)");
+    e = opt_in_shared(k_eval_tc<false>, smem);
+    if (e == cudaSuccess) e = opt_in_shared(k_eval_tc<true>, smem + SCRATCH_BYTES);
+    return check_cuda(e, "cudaFuncSetAttribute(k_eval_tc)");
   });
   if (rc0 != BG_OK) return rc0;
   const int64_t bound = a.N_dev ? a.max_N : a.N;
   int64_t want = (bound + 255) / 256;
   if (want < 1) want = 1;
   const int grid = (int)(want < NUM_SMS ? want : NUM_SMS);
-  k_eval_tc<<<grid, THREADS, smem, stream>>>(a.boards, a.flags, a.N, a.N_dev, a.max_N, img, a.out_v, err_flag, a.start_dev, accumulate);
+  if (a.codes)
+    k_eval_tc<true><<<grid, THREADS, smem + SCRATCH_BYTES, stream>>>(a.boards, a.flags, a.N, a.N_dev, a.max_N, img, a.out_v, err_flag, a.start_dev, accumulate,
+                                                                     a.codes);
+  else
+    k_eval_tc<false><<<grid, THREADS, smem, stream>>>(a.boards, a.flags, a.N, a.N_dev, a.max_N, img, a.out_v, err_flag, a.start_dev, accumulate, nullptr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return check_cuda(e, "k_eval_tc launch");
   return BG_OK;

@@ -24,7 +24,8 @@ struct Slot {
   int8_t* boards = nullptr;
   uint8_t* players = nullptr;
   uint8_t* rolls = nullptr;
-  int8_t* pool = nullptr;
+  int8_t* pool = nullptr;   // boards (per-item batches)
+  uint2* codes = nullptr;   // compact pool (position-major batches): 8 bytes per afterstate
   uint8_t* flags = nullptr;
   float* v = nullptr;
   int64_t* offsets = nullptr;
@@ -67,6 +68,7 @@ int32_t hostpipe_destroy(HostPipe* p) {
     cudaFree(s.players);
     cudaFree(s.rolls);
     cudaFree(s.pool);
+    cudaFree(s.codes);
     cudaFree(s.flags);
     cudaFree(s.v);
     cudaFree(s.offsets);
@@ -117,8 +119,10 @@ int32_t hostpipe_create(HostPipe** out, int32_t device, int32_t H, int64_t chunk
     if (e == cudaSuccess) e = cudaMalloc(&s.boards, (size_t)chunk_units * 52);
     if (e == cudaSuccess) e = cudaMalloc(&s.players, (size_t)chunk_units);
     if (e == cudaSuccess && !all_rolls) e = cudaMalloc(&s.rolls, (size_t)chunk_units * 2);
-    if (e == cudaSuccess) e = cudaMalloc(&s.pool, (size_t)p->pool_cap * 52);
-    if (e == cudaSuccess) e = cudaMalloc(&s.flags, (size_t)p->pool_cap);
+    // position-major batches only need actions and counts back: compact pool, the evaluator rebuilds the afterstates on chip
+    if (e == cudaSuccess && all_rolls) e = cudaMalloc(&s.codes, (size_t)p->pool_cap * 8);
+    if (e == cudaSuccess && !all_rolls) e = cudaMalloc(&s.pool, (size_t)p->pool_cap * 52);
+    if (e == cudaSuccess && !all_rolls) e = cudaMalloc(&s.flags, (size_t)p->pool_cap);
     if (e == cudaSuccess) e = cudaMalloc(&s.v, (size_t)p->pool_cap * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s.offsets, (size_t)p->chunk_items * 8);
     if (e == cudaSuccess) e = cudaMalloc(&s.counts, (size_t)p->chunk_items * 4);
@@ -163,6 +167,7 @@ int32_t hostpipe_run(HostPipe* p, const int8_t* h_boards, const uint8_t* h_playe
     m.pool_cap = p->pool_cap;
     m.out_boards = s.pool;
     m.out_flags = s.flags;
+    m.out_codes = s.codes;
     m.out_offsets = s.offsets;
     m.out_count = s.counts;
     m.out_status = s.status;

@@ -396,9 +396,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_movegen(MovegenParams P) {
       }
       ItemOut io;
       const int rc = generate<CAP, GLOBAL, MOVES>(F, rootw, player, d0, d1, lane, io);
-      if (rc == ITEM_OVERFLOW) {
+      if (rc == ITEM_OVERFLOW || (rc == ITEM_OK && P.out_codes)) {  // compact mode: this kernel writes boards, not codes -> the item fails
         if (lane == 0) {
-          if (P.ovf_list) {
+          if (P.ovf_list && !P.out_codes) {
             const int q = atomicAdd(P.ovf_count, 1);
             P.ovf_list[q] = item;
           } else {
@@ -617,6 +617,10 @@ int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream) {
     set_error("bg_movegen: bad sizes (B=%lld item_cap=%d pool_cap=%lld)", (long long)a.B, a.item_cap, (long long)a.pool_cap);
     return BG_ERR_ARG;
   }
+  if (a.out_codes && (!a.all_rolls || a.out_submoves || getenv("BG_MOVEGEN_LEGACY"))) {
+    set_error("bg_movegen: compact (code) output needs a position-major batch without sub-moves");
+    return BG_ERR_ARG;
+  }
   const int64_t n_items = a.all_rolls ? a.B * 21 : a.B;
   if (n_items >= (1ll << 31)) {
     set_error("bg_movegen: too many items (%lld)", (long long)n_items);
@@ -649,6 +653,7 @@ int32_t movegen_launch(const MovegenArgs& a, cudaStream_t stream) {
   P.gfront = (uint32_t*)(ws + HDR_BYTES + lists);
   P.active = a.active;
   P.all_rolls = a.all_rolls;
+  P.out_codes = a.out_codes;
   int32_t* ctr = (int32_t*)(ws + 12);
   int32_t* const l0 = (int32_t*)(ws + HDR_BYTES);
   int32_t* const ovf[N_OVF] = {l0, l0 + n_items, l0 + 2 * n_items, l0 + 3 * n_items};

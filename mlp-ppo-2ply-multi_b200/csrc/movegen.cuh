@@ -32,6 +32,9 @@ struct MovegenArgs {
   // position-major mode (movegen21.cu): boards / players / active are per POSITION (B of them), `rolls` is ignored, and the items are
   // position * 21 + roll index in the roll order of src/multi/two_ply.py:10-32; out_offsets / out_count have 21 * B entries
   int32_t all_rolls = 0;
+  // compact mode (position-major batches only): the pool holds (code, position index) pairs (codes.cuh) instead of boards; out_boards is
+  // ignored.  8 bytes per afterstate instead of 53, and no board is materialised unless a consumer asks for it.
+  uint2* out_codes = nullptr;
 };
 
 // kernel parameter block
@@ -59,6 +62,7 @@ struct MovegenParams {
   int32_t grab;
   const uint8_t* active;
   int32_t all_rolls;  // items are position * 21 + roll index; boards / players / active are indexed by position
+  uint2* out_codes;   // compact mode: (code, position index) per pool row instead of a board
 };
 
 int64_t movegen_workspace_bytes(int64_t B);  // B = number of ITEMS (21 per position in position-major mode)

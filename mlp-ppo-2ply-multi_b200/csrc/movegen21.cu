@@ -328,7 +328,13 @@ __device__ __noinline__ uint32_t flush21(const MovegenParams* __restrict__ Pp, l
     P.out_offsets[item] = base < 0 ? -1ll : base + (long long)rs;
   }
   emitted |= __ballot_sync(BG_FULL, true_count > 0) >> 1;
-  if (base >= 0 && !(P.grab & 8)) {
+  if (base >= 0 && P.out_codes) {
+    // compact mode: the code and the position it applies to; nothing is materialised
+    const uint32_t src_pos = (uint32_t)((single && P.all_rolls) ? pos / 21 : pos);
+    for (int i = lane; i < n_rows; i += 32) P.out_codes[base + i] = make_uint2(res[i], src_pos);
+    if (P.out_flags)
+      for (int i = lane; i < n_rows; i += 32) P.out_flags[base + i] = (uint8_t)player;
+  } else if (base >= 0 && !(P.grab & 8)) {
     uint32_t* const stage = W + O_TAB;
     Root r;
     r.player = player;

@@ -119,7 +119,7 @@ Layout make_layout(int64_t C) {
   L.o_tot = o;
   o += 256;
   L.o_pool = o;
-  o += align256(L.rows * 52);
+  o += align256(L.rows * 8);  // compact pool: (code, candidate index) per reply -- the reply boards are never materialised
   L.o_owner = o;
   o += align256(L.rows);
   L.o_val = o;
@@ -172,10 +172,11 @@ int32_t two_ply_launch(const TwoPlyArgs& a, cudaStream_t s) {
     m.B = nc;
     m.item_cap = BG_MAX_ITEM_MOVES;
     m.pool_cap = L.rows;
-    m.out_boards = (int8_t*)(w + L.o_pool);
+    m.out_boards = nullptr;
+    m.out_codes = (uint2*)(w + L.o_pool);
     m.out_submoves = nullptr;
     m.out_owner = nullptr;
-    m.out_flags = (uint8_t*)(w + L.o_owner);
+    m.out_flags = nullptr;
     m.out_offsets = (int64_t*)(w + L.o_off);
     m.out_count = (int32_t*)(w + L.o_cnt);
     m.out_status = (int32_t*)(w + L.o_tot + 16);

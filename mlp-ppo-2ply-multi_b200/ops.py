@@ -264,6 +264,86 @@ def movegen_evaluate_all_rolls(boards: torch.Tensor, players: torch.Tensor, weig
     return res, out_values
 
 
+@dataclass
+class CompactResult:
+    """bg_movegen[_eval]_all_rolls_compact: one uint64 (code | position << 32) per legal afterstate instead of a board."""
+
+    codes: torch.Tensor  # int64 [pool_cap] (bit pattern of the uint64 entries)
+    offsets: torch.Tensor  # int64 [21 * P]
+    counts: torch.Tensor  # int32 [21 * P] TRUE number of legal moves
+    total_dev: torch.Tensor  # int64 [1]
+    status_dev: torch.Tensor  # int32 [1]
+    item_cap: int
+    boards: torch.Tensor  # the POSITIONS' boards [P, 52] and players [P] the codes refer to
+    players: torch.Tensor
+
+    @property
+    def total(self) -> int:
+        return int(self.total_dev.item())
+
+    def raise_for_status(self):
+        st = int(self.status_dev.item())
+        if st != 0:
+            raise _lib.BgError(st, "bg_movegen_all_rolls_compact reported a capacity/invariant problem")
+
+    def afterstates(self, rows: Optional[torch.Tensor] = None, n: Optional[int] = None) -> torch.Tensor:
+        """boards [n,52] of the given pool rows (int64; negative -> zeros), or of rows 0..n-1"""
+        if rows is not None:
+            rows = _req(rows, torch.int64, "rows")
+            n = rows.numel()
+        out = torch.empty((n, BOARD_BYTES), dtype=torch.int8, device=self.codes.device)
+        check(lib().bg_afterstates_from_codes(self.boards.data_ptr(), self.players.data_ptr(), self.codes.data_ptr(), _ptr(rows), n, out.data_ptr(), _stream()))
+        return out
+
+    def chosen_afterstates(self, actions: torch.Tensor) -> torch.Tensor:
+        """the afterstate of each item's action (what env.step(action) moves to); zeros where action < 0"""
+        a = actions.to(torch.int64)
+        return self.afterstates(torch.where(a >= 0, self.offsets + a, torch.full_like(a, -1)))
+
+
+def movegen_all_rolls_compact(boards: torch.Tensor, players: torch.Tensor, weights: Optional[PreparedWeights] = None, item_cap: int = 500,
+                              pool_cap: Optional[int] = None, out_codes: Optional[torch.Tensor] = None, out_values: Optional[torch.Tensor] = None,
+                              workspace: Optional[torch.Tensor] = None, check_status: bool = False):
+    """Position-major move generation into a COMPACT pool (8 bytes per afterstate, no boards); with `weights` also the value of every
+    afterstate (bg_movegen_eval_all_rolls_compact: the evaluator rebuilds each afterstate on chip).  -> CompactResult[, values]"""
+    boards = _req(boards, torch.int8, "boards").reshape(-1, BOARD_BYTES)
+    P = boards.shape[0]
+    B = 21 * P
+    players = _req(players, torch.uint8, "players").reshape(P)
+    dev = boards.device
+    if pool_cap is None:
+        pool_cap = out_codes.numel() if out_codes is not None else max(1024, B * 64)
+    if out_codes is None:
+        out_codes = torch.empty(pool_cap, dtype=torch.int64, device=dev)
+    offsets = torch.empty(B, dtype=torch.int64, device=dev)
+    counts = torch.empty(B, dtype=torch.int32, device=dev)
+    total = torch.zeros(2, dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = workspace if workspace is not None else _workspace(B, dev)
+    if weights is None:
+        check(lib().bg_movegen_all_rolls_compact(boards.data_ptr(), players.data_ptr(), P, item_cap, pool_cap, out_codes.data_ptr(), offsets.data_ptr(),
+                                                 counts.data_ptr(), total.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    else:
+        if out_values is None:
+            out_values = torch.empty(pool_cap, dtype=torch.float32, device=dev)
+        check(lib().bg_movegen_eval_all_rolls_compact(boards.data_ptr(), players.data_ptr(), P, item_cap, pool_cap, out_codes.data_ptr(),
+                                                      offsets.data_ptr(), counts.data_ptr(), total.data_ptr(), status.data_ptr(), ws.data_ptr(),
+                                                      ws.numel(), weights.table.data_ptr(), weights.H, out_values.data_ptr(), _stream()))
+    res = CompactResult(out_codes, offsets, counts, total[:1], status, item_cap, boards, players)
+    if check_status:
+        res.raise_for_status()
+    return res if weights is None else (res, out_values)
+
+
+def evaluate_codes(res: CompactResult, weights: PreparedWeights, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """values of every row of a compact pool (bg_eval_codes, row count read on the device)"""
+    if out is None:
+        out = torch.empty(res.codes.numel(), dtype=torch.float32, device=res.codes.device)
+    check(lib().bg_eval_codes(res.boards.data_ptr(), res.players.data_ptr(), res.codes.data_ptr(), 0, res.total_dev.data_ptr(), res.codes.numel(),
+                              weights.table.data_ptr(), weights.H, out.data_ptr(), _stream()))
+    return out
+
+
 def select(values: torch.Tensor, offsets: torch.Tensor, counts: torch.Tensor, temperature: float, seed: int = 0, ctr: int = 0,
            item_cap: int = 500, item_id_base: int = 0) -> torch.Tensor:
     """softmax(V/T) sampling (reference worker.py:136-143) or, temperature <= 0, first-index argmax (play_versus_ai.py:188-195)."""

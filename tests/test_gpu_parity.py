@@ -244,6 +244,58 @@ def test_movegen_eval_all_rolls_equals_item_form(bg, oracle, golden):
     assert np.abs(vals[rows].cpu().numpy() - want).max() < 1e-5
 
 
+def test_compact_pool_equals_board_pool(bg, oracle, golden):
+    """bg_movegen[_eval]_all_rolls_compact (8-byte (code, position) rows, afterstates rebuilt inside the evaluator) == the board forms:
+    counts, order, values; bg_afterstates_from_codes rebuilds every board bit-exactly (vs the oracle), also under item_cap truncation"""
+    v = golden("values")
+    H = int(v["H"])
+    w = bg.prepare_weights(dev(v["packed"]), H)
+    boards, players = oracle.random_positions(4000, seed=123)
+    rng = np.random.default_rng(5)
+    wide = []
+    for k in range(24):  # wide doubles trees: the big code tier
+        b = np.zeros(52, np.int8)
+        pts = rng.choice(np.arange(0, 20), size=[8, 10, 12, 13, 15, 15][k % 6], replace=False)
+        for p in pts:
+            b[p] += 1
+        b[int(pts[0])] += 15 - b[:24].sum()
+        b[24 + 23] = 15
+        wide.append(b)
+    boards = np.concatenate([boards, np.array(wide, np.int8)])
+    players = np.concatenate([players, np.zeros(24, np.uint8)])
+    for cap in (4096, 500, 40):
+        cnt, off, ob = all_rolls_reference(oracle, boards, players, cap)
+        T = int(off[-1])
+        res, vals = bg.movegen_all_rolls_compact(dev(boards), dev(players), w, item_cap=cap, pool_cap=T + 4096, check_status=True)
+        assert np.array_equal(res.counts.cpu().numpy(), cnt) and res.total == T
+        kept = torch.clamp(res.counts.to(torch.int64), max=cap)
+        o2 = torch.zeros(kept.numel() + 1, dtype=torch.int64, device="cuda")
+        o2[1:] = torch.cumsum(kept, 0)
+        item = torch.repeat_interleave(torch.arange(kept.numel(), device="cuda"), kept)
+        rows = res.offsets[item] + (torch.arange(T, device="cuda") - o2[item])
+        assert np.array_equal(res.afterstates(rows).cpu().numpy(), ob)  # every afterstate, in action order, vs the oracle
+        want = oracle.value(v["packed"], H, ob, np.repeat(np.repeat(players, 21), np.minimum(cnt, cap)))
+        assert np.abs(vals[rows].cpu().numpy() - want).max() < 1e-5
+        v2 = bg.evaluate_codes(res, w)
+        assert torch.equal(v2[rows], vals[rows])
+        if cap == 500:  # same tiles, same operands: the board path gives the same bits
+            pool = torch.empty((T + 4096, 52), dtype=torch.int8, device="cuda")
+            flags = torch.empty(T + 4096, dtype=torch.uint8, device="cuda")
+            vb = torch.empty(T + 4096, dtype=torch.float32, device="cuda")
+            rb, vb = bg.movegen_evaluate_all_rolls(dev(boards), dev(players), w, pool, flags, vb, item_cap=cap)
+            kb = torch.clamp(rb.counts.to(torch.int64), max=cap)
+            rows_b = rb.offsets[item] + (torch.arange(T, device="cuda") - o2[item])
+            assert torch.equal(kb, kept) and (vb[rows_b] - vals[rows]).abs().max().item() < 1e-6
+            act = bg.select(vals, res.offsets, res.counts, temperature=0.0, item_cap=cap)
+            chosen = res.chosen_afterstates(act).cpu().numpy()
+            a = act.cpu().numpy()
+            for i in np.random.default_rng(1).choice(len(a), 300, replace=False):
+                if a[i] >= 0:
+                    assert np.array_equal(chosen[i], ob[off[i] + a[i]])
+                else:
+                    assert cnt[i] == 0 and not chosen[i].any()
+
+
 def test_encode_bit_exact(bg, oracle, golden):
     g = golden("features")
     f = bg.encode(dev(g["boards"]), dev(g["flags"])).cpu().numpy()
