@@ -213,6 +213,13 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
         for (int w = 0; w < 13; ++w) bw[w] = __ldg(b32 + src * 13 + w);
         flag = flags[src] & 1u;
+        if constexpr (CODES) {  // position board -> afterstate board, in this thread's scratch row (13-word stride: conflict free)
+#pragma unroll
+          for (int w = 0; w < 13; ++w) scr[w] = bw[w];
+          apply_code_bytes(reinterpret_cast<uint8_t*>(scr), code, (int)flag);
+#pragma unroll
+          for (int w = 0; w < 13; ++w) bw[w] = scr[w];
+        }
       } else {
 #pragma unroll
         for (int w = 0; w < 13; ++w) bw[w] = 0u;
@@ -224,15 +231,6 @@ __global__ void __launch_bounds__(THREADS, 1)
     for (int64_t t = (int64_t)blockIdx.x * 2 + g; t < n_tiles; t += tstride, ++it) {
       const int64_t i = t * 128 + row;
       const bool valid = i < N;
-      if constexpr (CODES) {
-        if (valid) {  // position board -> afterstate board, in this thread's scratch row (13-word stride: conflict free)
-#pragma unroll
-          for (int w = 0; w < 13; ++w) scr[w] = bw[w];
-          apply_code_bytes(reinterpret_cast<uint8_t*>(scr), code, (int)flag);
-#pragma unroll
-          for (int w = 0; w < 13; ++w) bw[w] = scr[w];
-        }
-      }
       // ---- build this board's fp16 feature row, 8 TMEM columns (= one K16 step = four points) at a time ----
 #pragma unroll
       for (int wd = 0; wd < 12; ++wd) {  // board word wd: 4 points -> 16 features -> 8 columns
