@@ -293,15 +293,16 @@ def main():
     P = boards.shape[0]
     B = 21 * P  # items: (position, roll), roll order of src/multi/two_ply.py:10-32
     pool_cap = int(B * 26) + (1 << 20)
-    pool = torch.empty((pool_cap, 52), dtype=torch.int8, device=dev)
+    codes = torch.empty(pool_cap, dtype=torch.int64, device=dev)  # compact pool: (code, position) per afterstate
     values = torch.empty(pool_cap, dtype=torch.float32, device=dev)
-    pflags = torch.empty(pool_cap, dtype=torch.uint8, device=dev)
     ws = torch.empty(bg._lib.lib().bg_movegen_workspace_bytes(B), dtype=torch.uint8, device=dev)
 
     def step():
-        # one pass of the hot path over the batch: bg_movegen_eval_all_rolls = position-major move generation + bg_eval over the pool, the
-        # evaluation of the bulk tier's afterstates overlapping the generation of the tail tiers (the few doubles trees too wide for it)
-        res, _ = bg.movegen_evaluate_all_rolls(boards, players, weights, pool, pflags, values, workspace=ws, item_cap=500)
+        # one pass of the hot path over the batch, one C-ABI call (bg_movegen_eval_all_rolls_compact): position-major move generation into a
+        # compact pool + fused encode / value of every afterstate (the evaluator rebuilds each afterstate on chip from its position + move code);
+        # the evaluation of the bulk tier's rows overlaps the tail tiers.  Afterstate boards are materialised on demand
+        # (bg_afterstates_from_codes), e.g. the one the chosen action leads to; `board_pool` below times the form that writes all of them.
+        res, _ = bg.movegen_all_rolls_compact(boards, players, weights, item_cap=500, out_codes=codes, out_values=values, workspace=ws)
         return res
 
     sampler = ClockSampler(local_rank) if rank == 0 else None  # nvidia-smi needs ~0.5 s to start: begin before the warm-up; idle samples are filtered by power
@@ -330,9 +331,9 @@ def main():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     ev[0].record()
     for k in range(args.steps):
-        r = bg.movegen_all_rolls(boards, players, item_cap=500, out_boards=pool, check_status=False, workspace=ws, out_flags=pflags)
+        r = bg.movegen_all_rolls_compact(boards, players, None, item_cap=500, out_codes=codes, workspace=ws)
         ev[3 * k + 1].record()
-        bg.evaluate(pool, r.flags, weights, n_dev=r.total_dev, out=values)
+        bg.evaluate_codes(r, weights, out=values)
         ev[3 * k + 2].record()
         ev[3 * k + 3].record()
     barrier()
@@ -360,6 +361,20 @@ def main():
     h_act = torch.empty(B, dtype=torch.int32).pin_memory()
     h_cnt = torch.empty(B, dtype=torch.int32).pin_memory()
     res = r = None
+    # ---- the same step with every afterstate board materialised in HBM (bg_movegen_eval_all_rolls: the 52-byte board pool of round 1) ----
+    pool = torch.empty((pool_cap, 52), dtype=torch.int8, device=dev)
+    pflags = torch.empty(pool_cap, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        bg.movegen_evaluate_all_rolls(boards, players, weights, pool, pflags, values, workspace=ws, item_cap=500)
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record()
+    for _ in range(args.steps):
+        bg.movegen_evaluate_all_rolls(boards, players, weights, pool, pflags, values, workspace=ws, item_cap=500)
+    b1.record()
+    torch.cuda.synchronize()
+    board_ms = b0.elapsed_time(b1) / args.steps
+    board_pool = {"what": "bg_movegen_eval_all_rolls: the same step writing every afterstate as a 52-byte board (+ flag) to HBM and reading it back in the evaluator",
+                  "ms_per_step": board_ms, "afterstates_per_sec_this_gpu": n_after / (board_ms * 1e-3)}
     # ---- the materialising encoder alone (bg_encode: 52 + 1 bytes in, 198 fp32 out per row): the one purely bandwidth-bound kernel ----
     n_enc = int(min(n_after, 1 << 22))
     feat = torch.empty((n_enc, 198), dtype=torch.float32, device=dev)
@@ -376,7 +391,7 @@ def main():
     torch.cuda.synchronize()
     t_enc = q0.elapsed_time(q1) / 10
     del feat
-    del pool, values, pflags, ws
+    del pool, values, pflags, ws, codes
     torch.cuda.empty_cache()
     n_chunks = args.e2e_chunks if args.e2e_chunks > 0 else (12 if P >= (1 << 19) else 3)
     pipe = bg.HostPipeline(weights, items_per_chunk=(P + n_chunks - 1) // n_chunks, device=dev, item_cap=500, n_streams=args.e2e_streams, all_rolls=True)
@@ -408,8 +423,8 @@ def main():
 
     # ---- roofline of the dominant kernel (algorithmic bytes / measured kernel time) -----------------------------------------
     peak, peak_src = load_peaks()
-    eval_bytes = n_after * (52 + 1 + 4)  # board in + flag in + value out
-    movegen_bytes = P * (52 + 1) + B * (8 + 4) + n_after * (52 + 1)  # position in, item offset / count out, board + flag out
+    eval_bytes = n_after * (8 + 4) + P * (52 + 1)  # (code, position) in + value out per afterstate; position boards / players in
+    movegen_bytes = P * (52 + 1) + B * (8 + 4) + n_after * 8  # position in, item offset / count out, (code, position) out per afterstate
     k_mg, k_ev = "bg::k_movegen21<Std> (+ tail tiers k_movegen21<Big>, k_movegen<4096>)", "bg::k_eval_tc (tcgen05, H=128)"
     kern = {k_ev: (t_eval, eval_bytes), k_mg: (t_movegen, movegen_bytes)}
     dom = max(kern, key=lambda k: kern[k][0])
@@ -423,12 +438,8 @@ def main():
         if int(td.get("positions", -1)) == P:
             traffic = {k_mg: td.get("movegen_bytes"), k_ev: td.get("eval_bytes")}
             traffic_src = "profiles/r02_traffic.json <- " + str(td.get("source"))
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic.get(dom),
-                "traffic_source": traffic_src, "algorithmic_bytes": kern[dom][1],
-                "peak_source": peak_src, "ms_per_launch": kern[dom][0],
-                "note": "both kernels are issue / tensor bound, not bandwidth bound: algorithmic bytes are tiny (SURVEY.md 8(d)); see roofline_movegen and roofline_eval",
-                "kernels_ms": {k: v[0] for k, v in kern.items()}, "movegen_ms_per_step": t_movegen_all,
-                "eval_fp32_tflops_dense_equiv": n_after * FLOP_PER_AFTERSTATE / (t_eval * 1e-3) / 1e12}
+    roofline_dom_hbm = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic.get(dom),
+                        "traffic_source": traffic_src, "algorithmic_bytes": kern[dom][1], "peak_source": peak_src, "ms_per_launch": kern[dom][0]}
     roofline_movegen = {"bound": "hbm", "kernel": k_mg, "achieved": movegen_bytes / (t_movegen * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": movegen_bytes / (t_movegen * 1e-3) / 1e9 / peak, "traffic": traffic.get(k_mg), "algorithmic_bytes": movegen_bytes,
                         "ms_per_launch": t_movegen, "items_per_sec": B / (t_movegen * 1e-3)}
@@ -447,8 +458,15 @@ def main():
     tach = tc_flops / (t_eval * 1e-3) / 1e12
     roofline_eval = {"bound": "tensor", "kernel": "bg::k_eval_tc (tcgen05, H=128)", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s",
                      "frac": tach / tpeak, "traffic": traffic.get("bg::k_eval_tc (tcgen05, H=128)"), "peak_source": tsrc, "ms_per_launch": t_eval,
-                     "note": "16-bit tensor FLOPs issued: 2 fp16 weight pieces x 2*208*128 per afterstate (fp32-exact layer 1); dense fp32-equivalent is 1/2.09 of this. ncu (profiles/r01_ncu_eval_tc_final_fp16x2.txt): tensor pipe 60 %, MUFU (ex2/rcp of the 128 sigmoids per board) 47 %, issue slots 53 % -- latency/co-limited with two worker warps per scheduler"}
+                     "note": "16-bit tensor FLOPs issued: 2 fp16 weight pieces x 2*208*128 per afterstate (fp32-exact layer 1: one fp16 piece misses the 1e-5 contract); dense fp32-equivalent is 1/2.09 of this. At 26 M128 N128 K16 MMAs per 128-row tile the kernel runs at ~0.9 of the measured sustained bf16 cuBLAS rate: it is tensor-bound (profiles/r02_*)"}
 
+    roofline_eval["traffic_source"] = traffic_src
+    roofline_eval["kernels_ms"] = {k: v[0] for k, v in kern.items()}
+    roofline_eval["movegen_ms_per_step"] = t_movegen_all
+    roofline_eval["eval_fp32_tflops_dense_equiv"] = n_after * FLOP_PER_AFTERSTATE / (t_eval * 1e-3) / 1e12
+    roofline_eval["hbm_view"] = roofline_dom_hbm if dom == k_ev else None
+    # the dominant kernel of the step is the tcgen05 evaluator (tensor-bound); the move generator's roofline is reported next to it
+    roofline = roofline_eval if dom == k_ev else dict(roofline_dom_hbm, kernels_ms={k: v[0] for k, v in kern.items()})
     torch.cuda.empty_cache()
 
     # ---- secondary: BASELINE configs[2] / configs[3], self-play with 65,536 concurrent games per GPU (all ranks, sharded by game id) ----
@@ -676,11 +694,11 @@ def main():
                        "positions_from_fixture": int(n_fixture),
                        "l2": "inputs+outputs per step (>25 GB) far exceed the 126 MB L2", "parallelism": f"{world} x independent shards"},
             "e2e": {"value": e2e_value, "unit": "afterstates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "what": f"bg_hostpipe_run (C ABI; bg.HostPipeline): pinned host positions + players -> {n_chunks} chunks on {args.e2e_streams} library streams (H2D, bg_movegen_eval_all_rolls, bg_select(greedy), D2H) -> 21 host (action, count) pairs per position",
+                    "what": f"bg_hostpipe_run (C ABI; bg.HostPipeline): pinned host positions + players -> {n_chunks} chunks on {args.e2e_streams} library streams (H2D, bg_movegen_eval_all_rolls_compact, bg_select(greedy), D2H) -> 21 host (action, count) pairs per position",
                     "afterstates_check": e2e_check},
             "gpu_launches": n_step_kernels * args.steps,
-            "gpu_launches_note": f"timed region, per step (bg_movegen_eval_all_rolls): k_movegen21<Std> (bulk tier) + tail tiers k_movegen21<Big>, k_movegen<4096> + k_eval_tc twice (bulk-tier rows on the side stream, tail-tier rows after); unfused ms_per_step {unfused_ms_per_step:.2f}; the e2e region launches {n_e2e_kernels} per step (the same five + status fold + k_select, per chunk)",
-            "roofline": roofline, "roofline_movegen": roofline_movegen, "roofline_eval": roofline_eval, "roofline_encode": roofline_encode, "cpu_baseline": cpu, "clocks": clocks, "selfplay_1ply": selfplay, "selfplay_2ply": selfplay2,
+            "gpu_launches_note": f"timed region, per step (bg_movegen_eval_all_rolls_compact): k_movegen21<Std> (bulk tier) + tail tiers k_movegen21<Big>, k_movegen<4096> + k_eval_tc twice (bulk-tier rows on the side stream, tail-tier rows after); unfused ms_per_step {unfused_ms_per_step:.2f}; the e2e region launches {n_e2e_kernels} per step (the same five + status fold + k_select, per chunk)",
+            "board_pool": board_pool, "roofline": roofline, "roofline_movegen": roofline_movegen, "roofline_eval": roofline_eval, "roofline_encode": roofline_encode, "cpu_baseline": cpu, "clocks": clocks, "selfplay_1ply": selfplay, "selfplay_2ply": selfplay2,
             "selfplay_2ply_all_candidates": selfplay2b, "learner": learner, "td0_loop": td0}
     print(json.dumps(line), flush=True)
     if dist is not None:
