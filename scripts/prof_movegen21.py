@@ -1,5 +1,5 @@
 """Profiling driver: position-major move generation (+ evaluation) at a given number of positions.
-    python scripts/prof_movegen21.py [positions] [reps] [mode: gen|fused]
+    python scripts/prof_movegen21.py [positions] [reps] [mode: gen|fused|compact]
 """
 import os
 import sys
@@ -22,6 +22,7 @@ def main():
     pool_cap = P * 21 * 26 + (1 << 20)
     pool = torch.empty((pool_cap, 52), dtype=torch.int8, device=dev)
     flags = torch.empty(pool_cap, dtype=torch.uint8, device=dev)
+    codes = torch.empty(pool_cap, dtype=torch.int64, device=dev)
     values = torch.empty(pool_cap, dtype=torch.float32, device=dev)
     ws = torch.empty(bg._lib.lib().bg_movegen_workspace_bytes(21 * P), dtype=torch.uint8, device=dev)
     w = bg.prepare_weights(packed_random_weights(0).to(dev), H)
@@ -30,6 +31,8 @@ def main():
     for _ in range(reps):
         if mode == "gen":
             r = bg.movegen_all_rolls(boards, players, item_cap=500, out_boards=pool, workspace=ws, out_flags=flags, check_status=False)
+        elif mode == "compact":  # the bench step: compact pool, afterstates rebuilt inside the evaluator
+            r, _ = bg.movegen_all_rolls_compact(boards, players, w, item_cap=500, out_codes=codes, out_values=values, workspace=ws)
         else:
             r, _ = bg.movegen_evaluate_all_rolls(boards, players, w, pool, flags, values, workspace=ws, item_cap=500)
     torch.cuda.synchronize()
