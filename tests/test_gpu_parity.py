@@ -212,6 +212,15 @@ def test_movegen_all_rolls_vs_oracle(bg, oracle, golden):
         own = res.owner[:T].to(torch.int64)
         assert bool((res.flags[:T] == dev(players)[own // 21]).all())
     assert cnt.max() > 1024
+    # a pool that is too small: BG_ERR_CAPACITY, the items that did not fit are marked, nothing is written out of bounds
+    small = int(off[-1]) // 3
+    guard = torch.full((small + 4096, 52), 77, dtype=torch.int8, device="cuda")
+    res = bg.movegen_all_rolls(dev(boards), dev(players), item_cap=40, pool_cap=small, out_boards=guard[:small], check_status=False)
+    assert int(res.status_dev.item()) == -3 and bool((guard[small:] == 77).all())
+    o = res.offsets.cpu().numpy()
+    assert (o == -1).any() and np.array_equal(res.counts.cpu().numpy(), cnt)
+    ok_items = np.nonzero(o >= 0)[0]
+    assert ((o[ok_items] + np.minimum(cnt[ok_items], 40)) <= small).all()
     # an invalid board poisons only its own position
     bad = boards[:64].copy()
     bad[5, 3] = 17
