@@ -109,7 +109,8 @@ _workspaces: dict = {}
 
 def _workspace(B: int, device) -> torch.Tensor:
     need = lib().bg_movegen_workspace_bytes(B)
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    # one scratch buffer per (device, stream): two streams generating moves at the same time must not share overflow lists / counters
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, dtype=torch.uint8, device=device)
