@@ -29,13 +29,36 @@ constexpr int H = 128, KP = 208, KSTEPS = KP / 16, NSPLIT = 2;
 constexpr int KCHUNK_BYTES = 16 * 128;                      // one 8-wide K chunk of all 128 rows: 16 N-groups x 128 B
 constexpr int SPLIT_BYTES = (KP / 8) * KCHUNK_BYTES;        // 26 chunks = 53,248 B
 constexpr int B_BYTES = NSPLIT * SPLIT_BYTES;               // 106,496 B
-constexpr int THREADS = 288;                                // warps 0-3 group 0, 4-7 group 1, warp 8 MMA issuer
+#ifndef BG_TC_BUILDER_SETS
+#define BG_TC_BUILDER_SETS 2
+#endif
+constexpr int NB = BG_TC_BUILDER_SETS;                      // builder warp sets (4 warps each); set b builds local tiles b, b + NB, ...
+constexpr int EPI_WARP0 = 4 * NB, MMA_WARP = 4 * NB + 8;    // warps [0, 4 NB) builders, 8 epilogue warps, one MMA issuer (see k_eval_tc)
+constexpr int THREADS = 32 * (MMA_WARP + 1);
 constexpr int TMEM_COLS = 512, A_COLS = 128, D_COLS = 128;  // per group: A at +0 (104 used), D at +128
 constexpr int NUM_SMS = 148;
 // instruction descriptor, kind::f16: D = F32 (bit 4), A = B = F16 (format fields 0), N = 128, M = 128
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 __constant__ uint32_t c_off15_split[16][2];  // n/15 = hi + mid + lo in fp16: [n][0] = hi | mid << 16, [n][1] = lo
+
+// -DBG_TC_STAMPS=1 (development builds only; see scripts/dev_tc_stamps.py): clock64 stamps of CTA 0's phases for the 64 local tiles
+// starting at BG_TC_STAMP_FIRST -- [0] builder warp 0, [1] the epilogue warp of lane quarter 0 that owns the tile, [2] the MMA issuer
+#ifdef BG_TC_STAMPS
+#ifndef BG_TC_STAMP_FIRST
+#define BG_TC_STAMP_FIRST 0
+#endif
+__device__ long long g_tc_stamps[3][64][8];
+#define TC_STAMP(cond, who, it, slot)                                                                               \
+  do {                                                                                                             \
+    if ((cond) && blockIdx.x == 0 && (it) >= BG_TC_STAMP_FIRST && (it) < BG_TC_STAMP_FIRST + 64u)                  \
+      g_tc_stamps[who][(it) - BG_TC_STAMP_FIRST][slot] = clock64();                                                \
+  } while (0)
+#else
+#define TC_STAMP(cond, who, it, slot) \
+  do {                                \
+  } while (0)
+#endif
 
 // feature index -> source row of the packed weights for the K-padded operand (198..201: off/15 mid/lo terms, 202: bias)
 __device__ __forceinline__ int krow_source(int k) {
@@ -76,17 +99,18 @@ __device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t addr) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
 }
-// bounded wait: returns false on timeout (so a descriptor / protocol bug raises an error instead of hanging the GPU)
+// bounded wait: returns false on timeout (so a descriptor / protocol bug raises an error instead of hanging the GPU).  try_wait suspends the
+// thread in hardware for up to ~1 us per call and wakes it when the phase completes (no polling back-off on the tile hand-offs)
 __device__ __forceinline__ bool mbar_wait(uint32_t addr, uint32_t parity) {
-  for (uint32_t it = 0; it < (1u << 22); ++it) {
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 20); ++it) {
     uint32_t ok;
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(1000u)
         : "memory");
     if (ok) return true;
-    if (it > 64) __nanosleep(64);
   }
   return false;
 }
@@ -106,6 +130,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+
+// tcgen05.wait::ld that also names the 32 destination registers of the load it covers, so the compiler cannot schedule their
+// consumers above the wait while another load is already in flight behind it
+__device__ __forceinline__ void tmem_wait_ld32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+                 "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]),
+                 "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]),
+                 "+r"(r[31])
+               :
+               : "memory");
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -128,23 +164,124 @@ __device__ __forceinline__ void point_words(uint32_t c, uint32_t& w0, uint32_t& 
   w1 = (c >= 3 ? ONE : 0u) | (ex << 16);
 }
 
+// ---- packed fp32 pairs (FFMA2 / FMUL2 / FADD2: one issue slot for two lanes of the epilogue's arithmetic) ----
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// Position board + result code -> afterstate board (codes.cuh; same result as apply_code_bytes for every code the move generator emits),
+// shaped for a builder thread: words 0..11 (the 48 points) go through this thread's shared-memory scratch row because the points a code touches
+// are data dependent; word 12 (bars / borne-off counts) stays in a register.  The only state a sub-move reads -- "does the landing point hold
+// exactly one opposing checker" -- is taken from the ORIGINAL board (a point is hit by the first checker that lands on it, later landings on
+// the same point find it empty), so all reads are issued together and every change is an independent fire-and-forget shared-memory add of
+// +-1 into the right byte: no load -> modify -> store chains (the byte-wise form spent 1,200-2,500 cycles per tile on them).
+__device__ __forceinline__ void rebuild_afterstate(uint32_t* scr, const uint32_t (&raw)[13], uint32_t (&cur)[13], uint32_t code, uint32_t player) {
+#pragma unroll
+  for (int w = 0; w < 12; ++w) scr[w] = raw[w];
+  const uint32_t own = player * 24u, opp = 24u - own;
+  const bool dbl = code_is_double(code);
+  const int die = code_die(code);
+  const int step = player == 0 ? die : -die;
+  const uint32_t enter = player == 0 ? (uint32_t)(die - 1) : (uint32_t)(24 - die);
+  uint32_t src[4], dst[4], oc[4];
+  bool ok[4];
+  bool alive = true;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    src[q] = (code >> (5 * q)) & 31u;
+    alive = alive && src[q] != CODE_NONE && (dbl || q < 2);
+    ok[q] = alive;
+    const int ee = (int)src[q] + step;
+    const uint32_t ed = src[q] == 24u ? enter : ((ee < 0 || ee > 23) ? 25u : (uint32_t)ee);
+    dst[q] = dbl ? ed : ((code >> (10 + 5 * (q & 1))) & 31u);
+  }
+  const uint8_t* rb = reinterpret_cast<const uint8_t*>(scr);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) oc[q] = (ok[q] && dst[q] < 24u) ? rb[opp + dst[q]] : 0u;
+  auto bump = [&](uint32_t byte, uint32_t delta) { atomicAdd(&scr[byte >> 2], delta << ((byte & 3u) * 8u)); };
+  uint32_t d12 = 0, hits = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (ok[q]) {
+      if (src[q] == 24u)
+        d12 -= 1u << (8u * player);  // from the bar
+      else
+        bump(own + src[q], 0xffffffffu);
+      if (dst[q] < 24u) {
+        bump(own + dst[q], 1u);
+        bool first = true;
+#pragma unroll
+        for (int j = 0; j < q; ++j) first = first && !(ok[j] && dst[j] == dst[q]);
+        if (oc[q] == 1u && first) {  // blot hit
+          bump(opp + dst[q], 0xffffffffu);
+          ++hits;
+        }
+      } else {
+        d12 += 1u << (8u * (2u + player));  // borne off
+      }
+    }
+  }
+  if (!dbl) {
+    const uint32_t in = (code >> 20) & 31u;
+    if (in != CODE_NONE) {  // the blot on the point a checker only passed through
+      bump(opp + in, 0xffffffffu);
+      ++hits;
+    }
+  }
+  d12 += hits << (8u * (1u - player));  // hit checkers go to the opponent's bar
+#pragma unroll
+  for (int w = 0; w < 12; ++w) cur[w] = scr[w];
+  cur[12] = raw[12] + d12;
+}
+
+// Roles of the 13 warps of the persistent CTA (one CTA per SM; TMEM lane quarter of a warp = warp % 4 = its scheduler):
+//   warps 0-3   BUILDERS: thread (q, lane) owns row q * 32 + lane of EVERY tile: fetches the row two tiles ahead, (CODES) rebuilds the
+//               afterstate one tile ahead, writes the fp16 feature row into TMEM operand A[slot] as soon as the MMAs that read it are done;
+//   warps 4-11  EPILOGUE: warps 4-7 read accumulator D[0] (even local tiles), warps 8-11 D[1] (odd ones): sigmoid, w2 dot product, store;
+//   warp 12     lane 0 issues the 26 tcgen05.mma of a tile when A[slot] is full and D[slot] has been drained.
+// Local tile n of a CTA uses slot n & 1; TMEM = [A0 | D0 | A1 | D1].  mbarriers: a_full[s] (128 builder arrivals), mma_done[s] (tcgen05.commit;
+// frees A[s] for the builders and hands D[s] to its epilogue warps), d_free[s] (128 epilogue arrivals, made as soon as the accumulator sits in
+// registers).  With the roles apart the tensor pipe only waits when a builder or an epilogue falls behind a whole tile; in the round-1 form
+// (the same threads built, waited and ran the epilogue) the next tile's global loads sat on the critical path: clock64 stamps showed
+// 2,300-4,000 of the 6,100 cycles of a two-tile period inside that fetch.
+constexpr int SCRATCH_BYTES = NB * 128 * 13 * 4;
+constexpr int BAR_OFF = B_BYTES + 1024, SCRATCH_OFF = BAR_OFF + 128;
+constexpr size_t SMEM_BYTES = (size_t)SCRATCH_OFF + SCRATCH_BYTES;
+
 // CODES: the rows are (code, position index) pairs of the compact pool (codes.cuh); `boards` / `flags` are then the POSITIONS' boards and
-// players, and each worker thread rebuilds its afterstate in a 52-byte shared-memory scratch row (13 word stores, a few byte updates, 13 word
-// loads: ~6 % more instructions in a kernel that is tensor-bound) -- the afterstate boards never exist in HBM.
-constexpr int SCRATCH_BYTES = 2 * 128 * 13 * 4;
+// players, and each builder thread rebuilds its afterstate in a 52-byte shared-memory scratch row (13 word stores, a few byte updates, 13
+// word loads) -- the afterstate boards never exist in HBM.
 template <bool CODES>
 __global__ void __launch_bounds__(THREADS, 1)
     k_eval_tc(const int8_t* __restrict__ boards, const uint8_t* __restrict__ flags, int64_t N_host, const int64_t* __restrict__ N_dev,
               int64_t max_N, const uint8_t* __restrict__ img, float* __restrict__ out_v, int32_t* __restrict__ err,
               const int64_t* __restrict__ start_dev, int accumulate, const uint2* __restrict__ codes) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sB = smem;                                             // B operand image
-  float* sW2 = reinterpret_cast<float*>(smem + B_BYTES);          // w2[128], b2
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_BYTES + 1024);  // full[2], done[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B_BYTES + 1024 + 64);
+  uint8_t* sB = smem;                                                   // B operand image
+  float* sW2 = reinterpret_cast<float*>(smem + B_BYTES);                // w2 as (w0, w2, w1, w3) per four units, then b2
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);         // a_full[2], mma_done[2], d_free[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 64);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // the four fp16 thermometer features of a point by checker count: one 8-byte table read instead of ~10 ALU instructions per point
-  // (16 entries x 8 B cover the 32 banks exactly once: conflict free for any mix of counts)
   __shared__ uint2 s_xtab[16];
   if (tid < 16) {
     uint32_t w0, w1;
@@ -153,15 +290,20 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
 
   for (int i = tid; i < B_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(img)[i];
-  for (int i = tid; i <= H; i += THREADS) sW2[i] = reinterpret_cast<const float*>(img + B_BYTES)[i];
+  for (int i = tid; i <= H; i += THREADS) {
+    const int j = i == H ? H : (i & ~3) | ((i & 1) << 1) | ((i & 2) >> 1);  // units (0, 1, 2, 3) of a group sit at (0, 2, 1, 3)
+    sW2[j] = reinterpret_cast<const float*>(img + B_BYTES)[i];
+  }
   if (tid == 0) {
     mbar_init(smem_u32(&bars[0]), 128);
     mbar_init(smem_u32(&bars[1]), 128);
     mbar_init(smem_u32(&bars[2]), 1);
     mbar_init(smem_u32(&bars[3]), 1);
+    mbar_init(smem_u32(&bars[4]), 128);
+    mbar_init(smem_u32(&bars[5]), 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -188,54 +330,89 @@ __global__ void __launch_bounds__(THREADS, 1)
     N -= start;
   }
   const int64_t n_tiles = (N + 127) / 128;
-  // tile t of the grid is owned by CTA (t / 2) % gridDim.x, group t & 1
-  if (warp < 8) {
-    // ================= workers: one thread per TMEM lane / board =================
-    const int g = warp >> 2, q = warp & 3, row = q * 32 + lane;
-    const uint32_t tA = tmem_base + (uint32_t)(g * (A_COLS + D_COLS)) + ((uint32_t)(q * 32) << 16);
-    const uint32_t tD = tA + A_COLS;
-    const uint32_t full = smem_u32(&bars[g]), done = smem_u32(&bars[2 + g]);
+  // local tile n of this CTA is grid tile (n >> 1) * 2 * gridDim.x + 2 * blockIdx.x + (n & 1): pairs of neighbouring tiles stay on one SM
+  // (compact pools: neighbouring rows share their position's board, so its 13 words come out of L1)
+  const int64_t tstride = (int64_t)gridDim.x * 2, tfirst = (int64_t)blockIdx.x * 2;
+  auto tile_of = [&](uint32_t n) -> int64_t { return (int64_t)(n >> 1) * tstride + tfirst + (n & 1u); };
+
+  if (warp < EPI_WARP0) {
+    // ================= builders: one thread per TMEM lane / row =================
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t bset = (uint32_t)warp >> 2;
+    const uint32_t tA_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t* b32 = reinterpret_cast<const uint32_t*>(boards);
-    uint32_t it = 0;
-    // board words of the CURRENT tile live in registers; the next tile's are fetched before waiting on the tensor core
-    uint32_t bw[13];
-    uint32_t flag = 0, code = 0;
-    uint32_t* const scr = reinterpret_cast<uint32_t*>(smem + B_BYTES + 1024 + 128) + (g * 128 + row) * 13;  // CODES: this thread's scratch row
-    auto fetch = [&](int64_t tile) {
-      const int64_t i = tile * 128 + row;
-      if (tile < n_tiles && i < N) {
-        int64_t src = i;
+    uint32_t* const scr = reinterpret_cast<uint32_t*>(smem + SCRATCH_OFF) + ((int)bset * 128 + row) * 13;  // CODES: this thread's scratch row (13-word stride)
+    // software pipeline over local tiles: `cur` = afterstate words of tile n, `raw` = board words of tile n + 1 (loads in flight since the
+    // previous iteration), `pos2` = the row -> position index of tile n + 2 (CODES: loaded one iteration before its board words)
+    uint32_t cur[13], raw[13];
+    uint32_t cur_flag = 0, raw_flag = 0, raw_code = 0, code2 = 0;
+    int64_t pos2 = -1;  // -1: no such row
+    bool cur_valid = false, raw_valid = false;
+    auto load_index = [&](uint32_t n) {  // stage 1: which board does row `row` of local tile n read?
+      const int64_t t = tile_of(n), i = t * 128 + row;
+      pos2 = -1;
+      code2 = 0;
+      if (t < n_tiles && i < N) {
         if constexpr (CODES) {
           const uint2 e = __ldg(codes + i);
-          code = e.x;
-          src = (int64_t)e.y;  // consecutive rows share their position: these loads hit L1
+          code2 = e.x;
+          pos2 = (int64_t)e.y;
+        } else {
+          pos2 = i;
         }
+      }
+    };
+    auto load_raw = [&]() {  // stage 2: issue the loads of the 13 board words + player flag of (pos2, code2)
+      raw_valid = pos2 >= 0;
+      raw_code = code2;
+      if (raw_valid) {
 #pragma unroll
-        for (int w = 0; w < 13; ++w) bw[w] = __ldg(b32 + src * 13 + w);
-        flag = flags[src] & 1u;
-        if constexpr (CODES) {  // position board -> afterstate board, in this thread's scratch row (13-word stride: conflict free)
+        for (int w = 0; w < 13; ++w) raw[w] = __ldg(b32 + pos2 * 13 + w);
+        raw_flag = flags[pos2] & 1u;
+      } else {
 #pragma unroll
-          for (int w = 0; w < 13; ++w) scr[w] = bw[w];
-          apply_code_bytes(reinterpret_cast<uint8_t*>(scr), code, (int)flag);
+        for (int w = 0; w < 13; ++w) raw[w] = 0u;
+        raw_flag = 0u;
+      }
+    };
+    auto finish_raw = [&]() {  // stage 3: raw -> cur (CODES: position board -> afterstate board in the scratch row)
+      cur_valid = raw_valid;
+      cur_flag = raw_flag;
+      if constexpr (CODES) {
+        if (raw_valid) {
+          rebuild_afterstate(scr, raw, cur, raw_code, raw_flag);
+        } else {
 #pragma unroll
-          for (int w = 0; w < 13; ++w) bw[w] = scr[w];
+          for (int w = 0; w < 13; ++w) cur[w] = 0u;
         }
       } else {
 #pragma unroll
-        for (int w = 0; w < 13; ++w) bw[w] = 0u;
-        flag = 0u;
+        for (int w = 0; w < 13; ++w) cur[w] = raw[w];
       }
     };
-    const int64_t tstride = (int64_t)gridDim.x * 2;
-    fetch((int64_t)blockIdx.x * 2 + g);
-    for (int64_t t = (int64_t)blockIdx.x * 2 + g; t < n_tiles; t += tstride, ++it) {
-      const int64_t i = t * 128 + row;
-      const bool valid = i < N;
-      // ---- build this board's fp16 feature row, 8 TMEM columns (= one K16 step = four points) at a time ----
+    load_index(bset);
+    load_raw();
+    load_index(bset + NB);
+    finish_raw();  // this set's first tile is ready
+    load_raw();    // its second one in flight
+    load_index(bset + 2 * NB);
+    for (uint32_t n = bset; tile_of(n) < n_tiles; n += NB) {
+      const uint32_t s = n & 1u, k = n >> 1;
+      const uint32_t tA = tA_lane + s * (uint32_t)(A_COLS + D_COLS);
+      TC_STAMP(lane == 0 && q == 0, 0, n, 0);
+      if (k >= 1) {  // A[s] is free once the MMAs of local tile n - 2 are done
+        if (!mbar_wait(smem_u32(&bars[2 + s]), (k - 1) & 1u)) {
+          if (lane == 0) atomicExch(err, 1);
+          break;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      TC_STAMP(lane == 0 && q == 0, 0, n, 1);
+      // ---- this row's fp16 features, 8 TMEM columns (= one K16 step = four points) at a time ----
 #pragma unroll
       for (int wd = 0; wd < 12; ++wd) {  // board word wd: 4 points -> 16 features -> 8 columns
         uint32_t r[8];
-        const uint2 p0 = s_xtab[bw[wd] & 15u], p1 = s_xtab[(bw[wd] >> 8) & 15u], p2 = s_xtab[(bw[wd] >> 16) & 15u], p3 = s_xtab[(bw[wd] >> 24) & 15u];
+        const uint2 p0 = s_xtab[cur[wd] & 15u], p1 = s_xtab[(cur[wd] >> 8) & 15u], p2 = s_xtab[(cur[wd] >> 16) & 15u], p3 = s_xtab[(cur[wd] >> 24) & 15u];
         r[0] = p0.x;
         r[1] = p0.y;
         r[2] = p1.x;
@@ -248,7 +425,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
       {
         const uint32_t ONE = 0x3c00u;
-        const uint32_t w12 = bw[12];
+        const uint32_t w12 = cur[12];
         const uint32_t bar0 = w12 & 0xffu, bar1 = (w12 >> 8) & 0xffu, off0 = (w12 >> 16) & 15u, off1 = (w12 >> 24) & 15u;
         const uint32_t hb0 = __half_as_ushort(__float2half_rn((float)bar0 * 0.5f));
         const uint32_t hb1 = __half_as_ushort(__float2half_rn((float)bar1 * 0.5f));
@@ -257,97 +434,147 @@ __global__ void __launch_bounds__(THREADS, 1)
         uint32_t r[8];
         r[0] = hb0 | ((s0a & 0xffffu) << 16);                       // 192 bar0/2, 193 off0 hi
         r[1] = hb1 | ((s1a & 0xffffu) << 16);                       // 194 bar1/2, 195 off1 hi
-        r[2] = valid ? (flag ? ONE << 16 : ONE) : 0u;               // 196, 197 flag one-hot
+        r[2] = cur_valid ? (cur_flag ? ONE << 16 : ONE) : 0u;       // 196, 197 flag one-hot
         r[3] = (s0a >> 16) | (s0b << 16);                           // 198 off0 mid, 199 off0 lo
         r[4] = (s1a >> 16) | (s1b << 16);                           // 200 off1 mid, 201 off1 lo
-        r[5] = valid ? ONE : 0u;                                    // 202 constant 1 (bias column), 203 = 0
+        r[5] = cur_valid ? ONE : 0u;                                // 202 constant 1 (bias column), 203 = 0
         r[6] = 0u;
         r[7] = 0u;
         tmem_st8(tA + 96, r);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(full);
-      fetch(t + tstride);  // overlaps the MMAs
-      // ---- wait for the 26 MMAs of this tile, then the epilogue straight out of TMEM ----
-      if (!mbar_wait(done, it & 1u)) {
-        if (lane == 0) atomicExch(err, 1);
+      mbar_arrive(smem_u32(&bars[s]));
+      TC_STAMP(lane == 0 && q == 0, 0, n, 2);
+      finish_raw();  // this set's next tile: its loads were issued one iteration ago
+      TC_STAMP(lane == 0 && q == 0, 0, n, 3);
+      load_raw();    // the one after: its index was loaded one iteration ago
+      TC_STAMP(lane == 0 && q == 0, 0, n, 4);
+      load_index(n + 3 * NB);
+      TC_STAMP(lane == 0 && q == 0, 0, n, 5);
+    }
+  } else if (warp < MMA_WARP) {
+    // ================= epilogue: the first four warps drain D[0] (even local tiles), the other four D[1] =================
+    const uint32_t s = (uint32_t)(warp - EPI_WARP0) >> 2;
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t tD = tmem_base + ((uint32_t)(q * 32) << 16) + s * (uint32_t)(A_COLS + D_COLS) + A_COLS;
+    const uint32_t done = smem_u32(&bars[2 + s]), dfree = smem_u32(&bars[4 + s]);
+    const float b2 = sW2[H];
+    const u64 one2 = pack2(1.0f, 1.0f);
+    for (uint32_t k = 0; tile_of(2 * k + s) < n_tiles; ++k) {
+      const int64_t i = tile_of(2 * k + s) * 128 + row;
+      TC_STAMP(lane == 0 && q == 0, 1, 2 * k + s, 0);
+      if (!mbar_wait(done, k & 1u)) {
+        if (lane == 0) atomicExch(err, 3);
         break;
       }
+      TC_STAMP(lane == 0 && q == 0, 1, 2 * k + s, 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float v = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < H; c0 += 32) {
-        uint32_t z[32];
-        tmem_ld32(tD + c0, z);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      u64 va = pack2(0.f, 0.f), vb = va;
+      // 32 hidden units of this row at a time.  The accumulator holds y = -z log2(e) (scaled weights), a sigmoid is 1 / (1 + 2^y).  MUFU (ex2
+      // and rcp share one 4-lane-per-scheduler pipe) and issue slots bound this loop, so FOUR sigmoids share one reciprocal -- with
+      // (a, b, c, d) = 1 + 2^y, p = ab, q = cd, r = 1 / (pq):  1/a = b q r, 1/b = a q r, 1/c = d p r, 1/d = c p r -- and the adds /
+      // multiplies / FMAs run as packed pairs.  y is clamped at 28.85 (z >= -20: sigmoid < 2.1e-9, far below the 1e-5 contract) so that
+      // the product of four terms stays below 5.5e34.
+      auto consume = [&](const uint32_t (&z)[32], int c0) {
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
-          // the epilogue is SFU-bound (ex2 and rcp share the 16-lane MUFU pipe), so FOUR sigmoids share one reciprocal:
-          // with p = (1+a)(1+b), q = (1+c)(1+d), r = 1/(pq):  1/(1+a) = (1+b) q r, ...  The accumulator is y = -z log2(e) (scaled
-          // weights); y is clamped at 28.85 (z >= -20: sigmoid < 2.1e-9, far below the 1e-5 contract) so that the product of four terms
-          // stays below 5.5e34
-          const float a1 = 1.0f + ex2_approx(fminf(__uint_as_float(z[c]), 28.853901f));
-          const float b1 = 1.0f + ex2_approx(fminf(__uint_as_float(z[c + 1]), 28.853901f));
-          const float c1 = 1.0f + ex2_approx(fminf(__uint_as_float(z[c + 2]), 28.853901f));
-          const float d1 = 1.0f + ex2_approx(fminf(__uint_as_float(z[c + 3]), 28.853901f));
-          const float p = a1 * b1, q = c1 * d1;
-          const float r = rcp_approx(p * q);
-          const float rp = r * q, rq = r * p;  // 1/p, 1/q
-          const float4 w4 = *reinterpret_cast<const float4*>(&sW2[c0 + c]);  // one broadcast 16-byte read per four units
-          v = fmaf(w4.x, b1 * rp, v);
-          v = fmaf(w4.y, a1 * rp, v);
-          v = fmaf(w4.z, d1 * rq, v);
-          v = fmaf(w4.w, c1 * rq, v);
+          const float e0 = ex2_approx(fminf(__uint_as_float(z[c]), 28.853901f));
+          const float e1 = ex2_approx(fminf(__uint_as_float(z[c + 1]), 28.853901f));
+          const float e2 = ex2_approx(fminf(__uint_as_float(z[c + 2]), 28.853901f));
+          const float e3 = ex2_approx(fminf(__uint_as_float(z[c + 3]), 28.853901f));
+          const u64 ac = add2(pack2(e0, e2), one2), bd = add2(pack2(e1, e3), one2);
+          const u64 pq = mul2(ac, bd);
+          float p, qq;
+          unpack2(pq, p, qq);
+          const float r = rcp_approx(p * qq);
+          const u64 inv = pack2(r * qq, r * p);  // (1/p, 1/q)
+          const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(&sW2[c0 + c]);  // (w0, w2), (w1, w3): one broadcast 16-byte read
+          va = fma2(mul2(bd, inv), w4.x, va);  // (1/a, 1/c): units c, c + 2
+          vb = fma2(mul2(ac, inv), w4.y, vb);  // (1/b, 1/d): units c + 1, c + 3
         }
-      }
-      if (valid) out_v[i] = (accumulate ? out_v[i] : 0.f) + (v + sW2[H]);  // accumulate: second half of the units of a wider net
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // D / A of this group are free again after our loads
+      };
+      // the TMEM read of the next 32 columns is in flight while the current 32 are consumed
+      uint32_t za[32], zb[32];
+      tmem_ld32(tD, za);
+      tmem_wait_ld32(za);
+      tmem_ld32(tD + 32, zb);
+      consume(za, 0);
+      tmem_wait_ld32(zb);
+      tmem_ld32(tD + 64, za);
+      consume(zb, 32);
+      tmem_wait_ld32(za);
+      tmem_ld32(tD + 96, zb);
+      consume(za, 64);
+      tmem_wait_ld32(zb);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(dfree);  // the accumulator sits in registers: D[s] may be overwritten
+      TC_STAMP(lane == 0 && q == 0, 1, 2 * k + s, 2);
+      consume(zb, 96);
+      float v0, v1, v2, v3;
+      unpack2(va, v0, v1);
+      unpack2(vb, v2, v3);
+      const float v = (v0 + v1) + (v2 + v3);
+      if (i < N) out_v[i] = (accumulate ? out_v[i] : 0.f) + (v + b2);  // accumulate: second half of the units of a wider net
+      TC_STAMP(lane == 0 && q == 0, 1, 2 * k + s, 3);
     }
   } else if (lane == 0) {
     // ================= MMA issuer (one thread) =================
     const uint32_t sB_addr = smem_u32(sB);
-    uint32_t it = 0;
-    bool ok = true;
-    for (int64_t t0 = (int64_t)blockIdx.x * 2; t0 < n_tiles && ok; t0 += (int64_t)gridDim.x * 2, ++it) {
-      for (int g = 0; g < 2 && ok; ++g) {
-        if (t0 + g >= n_tiles) break;
-        if (!mbar_wait(smem_u32(&bars[g]), it & 1u)) {
-          atomicExch(err, 2);
-          ok = false;
-          break;
-        }
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tA = tmem_base + (uint32_t)(g * (A_COLS + D_COLS)), tD = tA + A_COLS;
-#pragma unroll 1
-        for (int s = 0; s < KSTEPS; ++s) {
-#pragma unroll
-          for (int j = 0; j < NSPLIT; ++j) {
-            const uint32_t baddr = sB_addr + j * SPLIT_BYTES + s * 2 * KCHUNK_BYTES;
-            // K-major, no swizzle: LBO = distance between the two 8-wide K chunks, SBO = distance between 8-row groups
-            const uint64_t bdesc = (uint64_t)((baddr >> 4) & 0x3fffu) | ((uint64_t)(KCHUNK_BYTES >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
-                                   (1ull << 46);
-            const uint32_t acc = (s | j) ? 1u : 0u;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-                ::"r"(tD), "r"(tA + s * 8), "l"(bdesc), "r"(IDESC), "r"(acc), "r"(0u)
-                : "memory");
-          }
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[2 + g])) : "memory");
+    // K-major, no swizzle: LBO = distance between the two 8-wide K chunks, SBO = distance between 8-row groups
+    const uint64_t bdesc0 = (uint64_t)((sB_addr >> 4) & 0x3fffu) | ((uint64_t)(KCHUNK_BYTES >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+    for (uint32_t n = 0; tile_of(n) < n_tiles; ++n) {
+      const uint32_t s = n & 1u, k = n >> 1;
+      if (!mbar_wait(smem_u32(&bars[s]), k & 1u)) {  // A[s] written
+        atomicExch(err, 2);
+        break;
       }
+      TC_STAMP(true, 2, n, 0);
+      if (k >= 1 && !mbar_wait(smem_u32(&bars[4 + s]), (k - 1) & 1u)) {  // D[s] drained
+        atomicExch(err, 4);
+        break;
+      }
+      TC_STAMP(true, 2, n, 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tA = tmem_base + s * (uint32_t)(A_COLS + D_COLS), tD = tA + A_COLS;
+      // 26 dispatches, fully unrolled: every descriptor is bdesc0 plus a compile-time offset in its low word (no carry out of the 14-bit
+      // address field: shared memory ends below 0x3900 << 4)
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+#pragma unroll
+        for (int j = 0; j < NSPLIT; ++j) {
+          const uint64_t bdesc = bdesc0 + (uint64_t)((j * SPLIT_BYTES + ks * 2 * KCHUNK_BYTES) >> 4);
+          if (ks == 0 && j == 0)  // the first dispatch overwrites the accumulator
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%4, %4, %4, %4}, p;\n\t}"
+                ::"r"(tD), "r"(tA + ks * 8), "l"(bdesc), "r"(IDESC), "r"(0u)
+                : "memory");
+          else
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%4, %4, %4, %4}, p;\n\t}"
+                ::"r"(tD), "r"(tA + ks * 8), "l"(bdesc), "r"(IDESC), "r"(0u)
+                : "memory");
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[2 + s])) : "memory");
+      TC_STAMP(true, 2, n, 2);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
 }  // namespace
+
+#ifdef BG_TC_STAMPS
+extern "C" int32_t bg_dev_tc_stamps(long long* host_out) { return (int32_t)cudaMemcpyFromSymbol(host_out, g_tc_stamps, sizeof(g_tc_stamps)); }
+#endif
 
 int64_t eval_tc_image_bytes() { return ((int64_t)B_BYTES + (H + 1) * 4 + 255) / 256 * 256; }
 
@@ -360,7 +587,7 @@ int32_t eval_tc_prepare(const float* packed, int32_t H_src, int32_t unit0, uint8
 
 int32_t eval_tc_launch(const EvalArgs& a, const uint8_t* img, int32_t* err_flag, cudaStream_t stream, int accumulate) {
   static DeviceOnce once;
-  constexpr size_t smem = (size_t)B_BYTES + 1024 + 128;
+  constexpr size_t smem = SMEM_BYTES;
   int32_t rc0 = once.run([&]() -> int32_t {
     uint32_t h[16][2];
     for (int n = 0; n < 16; ++n) {
@@ -379,7 +606,7 @@ int32_t eval_tc_launch(const EvalArgs& a, const uint8_t* img, int32_t* err_flag,
     cudaError_t e = cudaMemcpyToSymbol(c_off15_split, h, sizeof(h));
     if (e != cudaSuccess) return check_cuda(e, "cudaMemcpyToSymbol(c_off15_split)");
     e = opt_in_shared(k_eval_tc<false>, smem);
-    if (e == cudaSuccess) e = opt_in_shared(k_eval_tc<true>, smem + SCRATCH_BYTES);
+    if (e == cudaSuccess) e = opt_in_shared(k_eval_tc<true>, smem);
     return check_cuda(e, "cudaFuncSetAttribute(k_eval_tc)");
   });
   if (rc0 != BG_OK) return rc0;
@@ -388,7 +615,7 @@ int32_t eval_tc_launch(const EvalArgs& a, const uint8_t* img, int32_t* err_flag,
   if (want < 1) want = 1;
   const int grid = (int)(want < NUM_SMS ? want : NUM_SMS);
   if (a.codes)
-    k_eval_tc<true><<<grid, THREADS, smem + SCRATCH_BYTES, stream>>>(a.boards, a.flags, a.N, a.N_dev, a.max_N, img, a.out_v, err_flag, a.start_dev, accumulate,
+    k_eval_tc<true><<<grid, THREADS, smem, stream>>>(a.boards, a.flags, a.N, a.N_dev, a.max_N, img, a.out_v, err_flag, a.start_dev, accumulate,
                                                                      a.codes);
   else
     k_eval_tc<false><<<grid, THREADS, smem, stream>>>(a.boards, a.flags, a.N, a.N_dev, a.max_N, img, a.out_v, err_flag, a.start_dev, accumulate, nullptr);
