@@ -198,19 +198,22 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
 // exactly one opposing checker" -- is taken from the ORIGINAL board (a point is hit by the first checker that lands on it, later landings on
 // the same point find it empty), so all reads are issued together and every change is an independent fire-and-forget shared-memory add of
 // +-1 into the right byte: no load -> modify -> store chains (the byte-wise form spent 1,200-2,500 cycles per tile on them).
+// DOUBLES = false: the caller knows that no row of the warp carries a double's code (two sub-moves, explicit destinations).
+template <bool DOUBLES>
 __device__ __forceinline__ void rebuild_afterstate(uint32_t* scr, const uint32_t (&raw)[13], uint32_t (&cur)[13], uint32_t code, uint32_t player) {
 #pragma unroll
   for (int w = 0; w < 12; ++w) scr[w] = raw[w];
   const uint32_t own = player * 24u, opp = 24u - own;
-  const bool dbl = code_is_double(code);
-  const int die = code_die(code);
+  constexpr int NQ = DOUBLES ? 4 : 2;
+  const bool dbl = DOUBLES && code_is_double(code);
+  const int die = DOUBLES ? code_die(code) : 0;
   const int step = player == 0 ? die : -die;
   const uint32_t enter = player == 0 ? (uint32_t)(die - 1) : (uint32_t)(24 - die);
-  uint32_t src[4], dst[4], oc[4];
-  bool ok[4];
+  uint32_t src[NQ], dst[NQ], oc[NQ];
+  bool ok[NQ];
   bool alive = true;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < NQ; ++q) {
     src[q] = (code >> (5 * q)) & 31u;
     alive = alive && src[q] != CODE_NONE && (dbl || q < 2);
     ok[q] = alive;
@@ -220,11 +223,11 @@ __device__ __forceinline__ void rebuild_afterstate(uint32_t* scr, const uint32_t
   }
   const uint8_t* rb = reinterpret_cast<const uint8_t*>(scr);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) oc[q] = (ok[q] && dst[q] < 24u) ? rb[opp + dst[q]] : 0u;
+  for (int q = 0; q < NQ; ++q) oc[q] = (ok[q] && dst[q] < 24u) ? rb[opp + dst[q]] : 0u;
   auto bump = [&](uint32_t byte, uint32_t delta) { atomicAdd(&scr[byte >> 2], delta << ((byte & 3u) * 8u)); };
   uint32_t d12 = 0, hits = 0;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < NQ; ++q) {
     if (ok[q]) {
       if (src[q] == 24u)
         d12 -= 1u << (8u * player);  // from the bar
@@ -285,12 +288,14 @@ __global__ void __launch_bounds__(THREADS, 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);         // a_full[2], mma_done[2], d_free[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 64);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // the four fp16 thermometer features of a point by checker count: one 8-byte table read instead of ~10 ALU instructions per point
-  __shared__ uint2 s_xtab[16];
-  if (tid < 16) {
-    uint32_t w0, w1;
-    point_words((uint32_t)tid, w0, w1);
-    s_xtab[tid] = make_uint2(w0, w1);
+  // the 2 x 4 fp16 thermometer features of TWO neighbouring points by their checker counts (c0 + 16 c1): one 16-byte table read per pair of
+  // points instead of ~10 ALU instructions per point
+  __shared__ uint4 s_xtab[256];
+  if (tid < 256) {
+    uint32_t a0, a1, b0, b1;
+    point_words((uint32_t)tid & 15u, a0, a1);
+    point_words((uint32_t)tid >> 4, b0, b1);
+    s_xtab[tid] = make_uint4(a0, a1, b0, b1);
   }
 
   for (int i = tid; i < B_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(img)[i];
@@ -383,8 +388,13 @@ __global__ void __launch_bounds__(THREADS, 1)
       cur_valid = raw_valid;
       cur_flag = raw_flag;
       if constexpr (CODES) {
+        // neighbouring rows mostly share their (position, roll): the four-sub-move form only runs for warps that hold a double's row
+        const bool warp_has_double = __any_sync(BG_FULL, raw_valid && code_is_double(raw_code));
         if (raw_valid) {
-          rebuild_afterstate(scr, raw, cur, raw_code, raw_flag);
+          if (warp_has_double)
+            rebuild_afterstate<true>(scr, raw, cur, raw_code, raw_flag);
+          else
+            rebuild_afterstate<false>(scr, raw, cur, raw_code, raw_flag);
         } else {
 #pragma unroll
           for (int w = 0; w < 13; ++w) cur[w] = 0u;
@@ -416,15 +426,17 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
       for (int wd = 0; wd < 12; ++wd) {  // board word wd: 4 points -> 16 features -> 8 columns
         uint32_t r[8];
-        const uint2 p0 = s_xtab[cur[wd] & 15u], p1 = s_xtab[(cur[wd] >> 8) & 15u], p2 = s_xtab[(cur[wd] >> 16) & 15u], p3 = s_xtab[(cur[wd] >> 24) & 15u];
-        r[0] = p0.x;
-        r[1] = p0.y;
-        r[2] = p1.x;
-        r[3] = p1.y;
-        r[4] = p2.x;
-        r[5] = p2.y;
-        r[6] = p3.x;
-        r[7] = p3.y;
+        const uint32_t w = cur[wd] & 0x0f0f0f0fu, t = w | (w >> 4);  // bytes 0 and 2 of t: c0 + 16 c1, c2 + 16 c3
+        const uint4 p01 = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(s_xtab) + ((t << 4) & 0xff0u));
+        const uint4 p23 = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(s_xtab) + ((t >> 12) & 0xff0u));
+        r[0] = p01.x;
+        r[1] = p01.y;
+        r[2] = p01.z;
+        r[3] = p01.w;
+        r[4] = p23.x;
+        r[5] = p23.y;
+        r[6] = p23.z;
+        r[7] = p23.w;
         tmem_st8(tA + wd * 8, r);
       }
       {
