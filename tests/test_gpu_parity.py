@@ -490,6 +490,23 @@ def test_eval_tensor_core_and_ffma_kernels_agree_with_oracle(bg, oracle, golden,
     assert np.abs(v_ff - v_tc).max() < 2e-6
 
 
+def test_eval_tensor_core_tile_schedules(bg, oracle, golden):
+    """The tcgen05 evaluator hands local tile n of a CTA to TMEM slot n & 1, builder set n & 1 and the epilogue warps of that slot: row counts
+    around the schedule's edges -- one tile per CTA, an odd number of tiles (a CTA whose second slot is never used), exactly one / two tiles
+    for each of the 148 CTAs, a ragged last tile -- must give the FFMA kernel's values and leave the status word clear."""
+    g = golden("values")
+    w = bg.prepare_weights(dev(g["packed"]), 128)
+    boards, players = oracle.random_positions(3 * 37888 + 300, seed=4242)
+    d_b, d_p = dev(boards), dev(players)
+    v_ff = torch.cat([bg.evaluate(d_b[i:i + 30000], d_p[i:i + 30000], w) for i in range(0, len(boards), 30000)])
+    ref = oracle.value(g["packed"], 128, boards[:4096], players[:4096])
+    assert np.abs(v_ff[:4096].cpu().numpy() - ref).max() < 1e-5
+    for n in (32768, 32769, 32768 + 3 * 128 + 5, 148 * 128 * 2 - 1, 148 * 128 * 2, 148 * 128 * 2 + 1, 148 * 128 * 3, 148 * 128 * 3 + 129, 3 * 37888 + 300):
+        v_tc = bg.evaluate(d_b[:n], d_p[:n], w)
+        assert bg._lib.lib().bg_eval_tc_status() == 0
+        assert (v_tc - v_ff[:n]).abs().max().item() < 2e-6, n
+
+
 @pytest.mark.parametrize("H", [32, 64, 96, 160, 224, 256])
 def test_eval_other_nets_on_the_tensor_core_path(bg, oracle, H):
     """every hidden size runs on the tcgen05 kernel for batches >= 32768 rows: fewer than 128 units zero-padded to 128, more than 128 in
