@@ -574,52 +574,110 @@ def main():
         lstream = torch.cuda.Stream(device=dev)  # the learner kernel (one 8-CTA cluster) overlaps the next self-play ply
         n_iter = [0]
 
+        staged = [None]  # (batch, event) gathered in the previous iteration
+        unpublished = [False]  # an update launched by rank 0 that has not been published yet (tracked identically on every rank)
+        host = {}  # host time per section of an iteration (perf_counter; the drains include their wait for the GPU)
+
+        trace = [] if os.environ.get("BG_LOOP_TRACE") else None  # development: GPU timeline of the loop (events on both streams)
+
+        def mark(row, name, stream=None):
+            if trace is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream if stream is not None else torch.cuda.current_stream(dev))
+                row.append((name, e))
+
+        def lap(name, t0):
+            t1 = time.perf_counter()
+            host[name] = host.get(name, 0.0) + (t1 - t0)
+            return t1
+
         def iteration(timed):
-            # ply u of every game (weights of update u-2) || learner update u-1 on its own stream; then publish update u-1,
-            # hand 200 fresh episodes to the learner, drop the surplus (the sequential learner is the bottleneck)
+            # Host order matters: the loop is paced by what the HOST has to do between two learner launches.  (1) publish update u-1 and
+            # launch update u on the batch staged in the previous iteration -- nothing the host did not already have; (2) the next ply of
+            # every game (|| update u on its own stream), drain 200 // world finished episodes, gather them for update u+1, drop the
+            # surplus (the sequential learner is the bottleneck).  The drains read counts back: they block the host behind everything
+            # enqueued on the arena's stream -- including the wait for update u-1 -- which is why they come AFTER the learner launch.
+            t = time.perf_counter()
+            m = None
+            row = []
+            if trace is not None:
+                trace.append(row)
+            if rank == 0:
+                mark(row, "main:top")
+                m = tr.finish(metrics=False)  # stream-ordered wait, set_packed -> (broadcast) -> arena.set_weights; no host read-back
+                mark(row, "main:published")
+                t = lap("publish", t)
+                if staged[0] is not None:
+                    # the update needs its batch, not the publication enqueued above (the learner owns its weights; what is published
+                    # is a snapshot taken on the learner's stream)
+                    lstream.wait_event(staged[0][1])
+                    with torch.cuda.stream(lstream):
+                        if timed is not None:
+                            timed[0].record()
+                        mark(row, "learner:start")
+                        tr.update_async(staged[0][0])
+                        mark(row, "learner:end")
+                        if timed is not None:
+                            timed[1].record()
+                t = lap("launch_update", t)
+            elif unpublished[0]:  # rank 0 publishes the update it launched in the previous iteration
+                pm.sync_from_source()
+                t = lap("publish", t)
+            unpublished[0] = staged[0] is not None  # (the same on every rank) rank 0 launches an update in this iteration
             ar.step(1)
+            mark(row, "main:ply done")
+            t = lap("step", t)
             quota = 200 // world  # every rank's arena feeds the trainer, as every worker process feeds the reference's queue
             batch = ar.drain(max_episodes=quota)
             while batch.n_episodes < quota:  # not reached with tens of thousands of games in flight
                 ar.step(1)
                 batch = ar.drain(max_episodes=quota)
+            t = lap("drain_quota(blocks)", t)
             if world > 1:
-                # each field the trainer reads gathered straight into its final padded array: no host sync, no unpacking copies
+                # each field the trainer reads gathered straight into its final padded array (two buffer sets in turn: update u may still
+                # be reading the previous one): no host sync, no unpacking copies, one coalesced NCCL launch
                 batch = bgd.all_gather_episodes(batch, quota, quota * 300, compact=False, fields=bgd.LEARNER_FIELDS)
-            # only now wait for update u-1 (it ran next to the ply, the drain and the gather) and publish it
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(dev))
+            staged[0] = (batch, ready)
+            n_iter[0] += 1
+            t = lap("gather", t)
+            ar.drain(max_episodes=G, max_experiences=G * 48)
+            mark(row, "main:drained")
+            lap("drain_surplus(blocks)", t)
+            return m
+
+        def flush():  # publish what is in flight and read its metrics (every rank takes part in the broadcast)
             m = None
             if rank == 0:
-                m = tr.finish(metrics=False)  # stream-ordered wait, set_packed -> (broadcast) -> arena.set_weights; no host read-back
-            elif n_iter[0] > 0:  # rank 0 publishes update u-1 in iteration u: nothing to receive in the very first one
+                m = tr.finish()
+            elif unpublished[0]:
                 pm.sync_from_source()
-            if rank == 0:
-                lstream.wait_stream(torch.cuda.current_stream(dev))
-                with torch.cuda.stream(lstream):
-                    if timed is not None:
-                        timed[0].record()
-                    tr.update_async(batch)
-                    if timed is not None:
-                        timed[1].record()
-            n_iter[0] += 1
-            ar.drain(max_episodes=G, max_experiences=G * 48)
+            unpublished[0] = False
             return m
 
         for _ in range(3):
             iteration(None)
+        flush()  # warm-up includes one metrics read-back: its ~25 small device ops load their modules outside the timed region
         barrier()
         s0 = ar.stats()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_updates)]
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         last = None
+        host.clear()
+        h0 = time.perf_counter()
         for u in range(n_updates):
             last = iteration(evs[u]) or last
-        if rank == 0:
-            last = tr.finish() or last
-        elif n_updates:
-            pm.sync_from_source()
+        host_ms = (time.perf_counter() - h0) * 1e3 / max(n_updates, 1)  # enqueue time per iteration (no synchronisation inside the loop)
+        last = flush() or last
         a1.record()
         barrier()
+        if trace and rank == 0:
+            torch.cuda.synchronize()
+            base = trace[-12][0][1]
+            for row in trace[-12:-4]:
+                print("trace", [(n, round(base.elapsed_time(e), 3)) for n, e in row], file=sys.stderr)
         s1 = ar.stats()
         ms = a0.elapsed_time(a1)
         d = torch.tensor([float(s1["games"] - s0["games"]), float(s1["wait_steps"] - s0["wait_steps"]), ms], dtype=torch.float64, device=dev)
@@ -636,7 +694,7 @@ def main():
             out = {"workload": f"config5: {G} self-play games per GPU -> Trainer.update on 200-episode batches (sequential TD(0)/Adam, rank 0) -> packed weights "
                                f"published to every arena ({'episodes all-gathered from every rank, one NCCL broadcast of the weights' if world > 1 else 'single GPU'}); surplus episodes dropped",
                    "updates_per_sec": n_updates / (ms * 1e-3), "episodes_trained_per_sec": 200 * n_updates / (ms * 1e-3),
-                   "games_played_per_sec": float(d[0]) / (ms * 1e-3), "ms_per_update_kernel": upd_ms, "ms_per_iteration": ms / n_updates,
+                   "games_played_per_sec": float(d[0]) / (ms * 1e-3), "ms_per_update_kernel": upd_ms, "ms_per_iteration": ms / n_updates, "host_enqueue_ms_per_iteration": host_ms, "host_ms_per_section": {k: round(v * 1e3 / max(n_updates, 1), 4) for k, v in host.items()},
                    "actor_wait_steps": int(d[1]), "weights_version": pm.get_version(), "temperature": pm.get_temperature(),
                    "last_update": {k: v for k, v in last.items() if isinstance(v, float)}}
         ar.close()

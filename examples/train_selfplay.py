@@ -46,33 +46,39 @@ def main():
     quota = 200 // world
     arena.reset()
     t0, metrics = time.time(), {}
-    for u in range(args.updates):
-        arena.step(1)                                           # next ply of every game || the previous update on learn_stream
+    staged = None                                               # (batch, event) gathered in the previous iteration
+    for u in range(args.updates + 1):                           # iteration u launches update u-1 (the batch is staged one iteration ahead)
+        # host order: publish + launch first (nothing the host has to wait for), then the ply / drain / gather for the NEXT update --
+        # the drains read counts back and would otherwise hold the host behind the wait for the running update
+        if rank == 0:
+            metrics = trainer.finish() or metrics               # publish update u-2 (one broadcast when world > 1)
+            if staged is not None:
+                learn_stream.wait_event(staged[1])              # the learner waits for its batch, NOT for the publication enqueued above
+                with torch.cuda.stream(learn_stream):
+                    trainer.update_async(staged[0])             # 200 sequential TD(0)/Adam steps, one kernel launch, no host sync
+        elif u > 1:
+            pm.sync_from_source()
+        arena.step(1)                                           # next ply of every game || the running update on learn_stream
         batch = arena.drain(max_episodes=quota)
         while batch.n_episodes < quota:
             arena.step(1)
             batch = arena.drain(max_episodes=quota)
         if world > 1:
-            batch = bgd.all_gather_episodes(batch, quota, quota * arena.max_plies, compact=False)
-        if rank == 0:
-            metrics = trainer.finish() or metrics               # publish update u-1 (one broadcast when world > 1)
-        elif u > 0:
-            pm.sync_from_source()
-        if rank == 0:
-            learn_stream.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(learn_stream):
-                trainer.update_async(batch)                     # 200 sequential TD(0)/Adam steps, one kernel launch, no host sync
+            batch = bgd.all_gather_episodes(batch, quota, quota * arena.max_plies, compact=False)  # two buffer sets in turn
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        staged = (batch, ready)
         arena.drain(max_episodes=args.games, max_experiences=args.games * 48)  # the sequential learner is the bottleneck: drop the surplus
-        if rank == 0 and args.eval_every and (u + 1) % args.eval_every == 0:
-            # evaluate the weights that ARE published (update u-1).  Publication is a collective: calling trainer.finish() here would
+        if rank == 0 and u and args.eval_every and u % args.eval_every == 0:
+            # evaluate the weights that ARE published.  Publication is a collective: calling trainer.finish() here would
             # issue a broadcast the other ranks do not take part in
             if world == 1:
                 trainer.finish()
             now = bg.pack_weights(pm.get_parameters()).to(dev)
             m = bg.play_match(now, initial, n_games=4096, hidden_size=args.hidden, device=dev, seed=u)
-            print(f"update {u + 1:6d}  version {pm.get_version()}  T {pm.get_temperature():.3f}  loss {metrics.get('Loss/Training Loss', 0):.5f}  "
+            print(f"update {u:6d}  version {pm.get_version()}  T {pm.get_temperature():.3f}  loss {metrics.get('Loss/Training Loss', 0):.5f}  "
                   f"len {metrics.get('Episode/Average Episode Length', 0):.1f}  vs initial: win {m['a_win_rate']:.3f}  ppg {m['a_points_per_game']:+.3f}  "
-                  f"[{(u + 1) * 200 / (time.time() - t0):,.0f} episodes/s]", flush=True)
+                  f"[{u * 200 / (time.time() - t0):,.0f} episodes/s]", flush=True)
     if rank == 0:
         trainer.finish()
         if args.save:

@@ -173,6 +173,10 @@ int32_t bg_afterstates_from_codes(const int8_t* boards /*[P,52]*/, const uint8_t
 /* Diagnostic for the tcgen05 evaluator (batches >= 32768 rows with per-row flags, any H: 128 hidden units per pass, smaller nets
  * zero-padded, wider nets in two passes; set BG_EVAL_PATH=ffma to force the CUDA-core kernels): synchronises and returns 0, or non-zero if one of its bounded mbarrier waits ever timed out. */
 int32_t bg_eval_tc_status(void);
+/* Tile schedule of the tcgen05 evaluator: -1 (default) = by size -- launches of up to 2^23 rows (a self-play ply, a 2-ply candidate set: they
+ * run next to other kernels) claim their 128-row tiles from a grid-wide counter, larger (bulk) passes split them statically --, 0 = always
+ * static, 1 = always dynamic.  Process-wide; returns the previous setting.  Results do not depend on it. */
+int32_t bg_eval_tc_tile_schedule(int32_t mode);
 
 /*
  * Action selection over ragged value segments.  Replaces softmax(V/T) + Categorical.sample

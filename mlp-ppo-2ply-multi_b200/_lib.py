@@ -44,6 +44,7 @@ SIGNATURES = {
     "bg_movegen_eval_all_rolls_compact": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp]),
     "bg_afterstates_from_codes": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "bg_eval_tc_status": (_i32, []),
+    "bg_eval_tc_tile_schedule": (_i32, [_i32]),
     "bg_select": (_i32, [_vp, _vp, _vp, _i32, _i64, _f32, _u64, _u64, _i64, _vp, _vp]),
     "bg_two_ply_workspace_bytes": (_i64, [_i64]),
     "bg_two_ply": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _i64, _vp]),

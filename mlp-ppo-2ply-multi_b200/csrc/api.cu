@@ -151,6 +151,7 @@ int32_t bg_select(const float* v, const int64_t* offsets, const int32_t* counts,
 }
 
 int32_t bg_eval_tc_status(void) { return eval_tc_status(); }
+int32_t bg_eval_tc_tile_schedule(int32_t mode) { return eval_tc_tile_schedule(mode); }
 
 int64_t bg_two_ply_workspace_bytes(int64_t N) { return two_ply_workspace_bytes(N); }
 

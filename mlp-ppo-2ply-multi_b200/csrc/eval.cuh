@@ -20,7 +20,10 @@ struct EvalArgs {
   // compact pool (codes.cuh): rows are (code, position index) pairs; `boards` / `flags` are then the POSITIONS' boards and players.  Always
   // evaluated by the tensor-core kernel.
   const uint2* codes = nullptr;
+  // tensor-core kernel: -1 = choose by size (dynamic tile schedule up to EVAL_TC_DYNAMIC_MAX_ROWS rows, see eval_tc.cu), 0 = static, 1 = dynamic
+  int32_t dynamic_tiles = -1;
 };
+constexpr int64_t EVAL_TC_DYNAMIC_MAX_ROWS = 1ll << 23;
 
 int64_t prepared_weights_bytes(int32_t H);
 int32_t prepare_weights_launch(const float* packed, int32_t H, float* prepared, cudaStream_t stream);
@@ -35,6 +38,7 @@ int32_t eval128_launch(const EvalArgs& a, const float* t128, cudaStream_t stream
 int64_t eval_tc_image_bytes();
 int32_t eval_tc_prepare(const float* packed, int32_t H_src, int32_t unit0, uint8_t* img, cudaStream_t stream);
 int32_t eval_tc_launch(const EvalArgs& a, const uint8_t* img, int32_t* err_flag, cudaStream_t stream, int accumulate = 0);
+int32_t eval_tc_tile_schedule(int32_t mode);  // -1 by size, 0 static, 1 dynamic (process-wide default of EvalArgs::dynamic_tiles < 0); returns the previous one
 int32_t eval_tc_status();  // synchronising: 0 ok, != 0 a bounded mbarrier wait timed out in k_eval_tc
 // Move generation + evaluation of the whole afterstate pool with the tail tiers overlapped: the rows written by the move generator's
 // bulk tier are evaluated on `side->stream` as soon as that tier is done, while `stream` runs the tail tiers (a few very wide doubles

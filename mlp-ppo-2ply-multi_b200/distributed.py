@@ -44,38 +44,51 @@ _EP_FIELDS = (("after_boards", torch.int8, 52), ("meta", torch.uint8, 1), ("rewa
 
 
 class _GatherWorkspace:
-    """per-(device, quota, world) send / receive buffers of all_gather_episodes(compact=False), allocated once"""
+    """per-(device, quota, world) send / receive buffers of all_gather_episodes(compact=False), allocated once.  SLOTS buffer sets are handed
+    out in turn, so a returned batch stays valid until the SECOND next call with the same quota: the consumer of batch u (the learner kernel, on
+    its own stream) may still be reading it while batch u + 1 is being gathered."""
 
+    SLOTS = 2
     cache: dict = {}
 
     @classmethod
     def get(cls, dev, world, max_episodes, max_experiences, cols_info):
         key = (str(dev), world, max_episodes, max_experiences, cols_info)
-        w = cls.cache.get(key)
-        if w is None:
-            w = {"send": {}, "recv": {}}
-            for name, dt, cols in _EP_FIELDS:
-                shape = (max_experiences, cols) if cols > 1 else (max_experiences,)
-                w["send"][name] = torch.zeros(shape, dtype=dt, device=dev)
-                w["recv"][name] = torch.zeros((world * max_experiences,) + shape[1:], dtype=dt, device=dev)
-            w["send"]["hdr"] = torch.zeros(max_episodes + 3, dtype=torch.int64, device=dev)  # E, N, offsets[max_episodes + 1]
-            w["recv"]["hdr"] = torch.zeros((world, max_episodes + 3), dtype=torch.int64, device=dev)
-            w["send"]["info"] = torch.zeros((max_episodes, cols_info), dtype=torch.int32, device=dev)
-            w["recv"]["info"] = torch.zeros((world * max_episodes, cols_info), dtype=torch.int32, device=dev)
-            cls.cache[key] = w
-        return w
+        ring = cls.cache.get(key)
+        if ring is None:
+            ring = {"next": 0, "sets": []}
+            for _ in range(cls.SLOTS):
+                w = {"send": {}, "recv": {}}
+                for name, dt, cols in _EP_FIELDS:
+                    shape = (max_experiences, cols) if cols > 1 else (max_experiences,)
+                    w["send"][name] = torch.zeros(shape, dtype=dt, device=dev)
+                    w["recv"][name] = torch.zeros((world * max_experiences,) + shape[1:], dtype=dt, device=dev)
+                w["send"]["hdr"] = torch.zeros(max_episodes + 3, dtype=torch.int64, device=dev)  # E, N, offsets[max_episodes + 1]
+                w["recv"]["hdr"] = torch.zeros((world, max_episodes + 3), dtype=torch.int64, device=dev)
+                w["send"]["info"] = torch.zeros((max_episodes, cols_info), dtype=torch.int32, device=dev)
+                w["recv"]["info"] = torch.zeros((world * max_episodes, cols_info), dtype=torch.int32, device=dev)
+                ring["sets"].append(w)
+            # constants of the offset arithmetic below
+            ring["j"] = torch.arange(max_episodes, device=dev).reshape(1, -1)
+            ring["rank_base"] = torch.arange(world, device=dev).reshape(-1, 1) * max_experiences
+            ring["end"] = torch.full((1,), world * max_experiences, dtype=torch.int64, device=dev)
+            cls.cache[key] = ring
+        w = ring["sets"][ring["next"]]
+        ring["next"] = (ring["next"] + 1) % cls.SLOTS
+        return w, ring
 
 
 def _all_gather_padded(batch, max_episodes, max_experiences, group, fields):
     """compact=False path: every field is gathered straight into its final [world * quota, ...] array (the layout bg_learner_update reads with
-    explicit episode lengths): no host synchronisation, no unpacking copies, buffers reused across calls."""
+    explicit episode lengths): no host synchronisation, no unpacking copies, buffers reused across calls (two sets, alternating); on NCCL the
+    per-field all-gathers are issued as ONE coalesced group (one launch, one host dispatch)."""
     from .episode import EpisodeBatch
 
     E, N = int(batch.n_episodes), int(batch.n_experiences)
     dev = batch.after_boards.device
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     cols_info = batch.ep_info.shape[1]
-    w = _GatherWorkspace.get(dev, world, max_episodes, max_experiences, cols_info)
+    w, ring = _GatherWorkspace.get(dev, world, max_episodes, max_experiences, cols_info)
     names = [n for n, _, _ in _EP_FIELDS if fields is None or n in fields]
     for name in names:
         if N:
@@ -87,21 +100,31 @@ def _all_gather_padded(batch, max_episodes, max_experiences, group, fields):
         w["send"]["info"][:E].copy_(batch.ep_info[:E])
     pairs = [(w["recv"][n], w["send"][n]) for n in names] + [(w["recv"]["hdr"], hdr), (w["recv"]["info"], w["send"]["info"])]
     if world > 1:
-        for out, inp in pairs:  # as bytes: int16 is not a collective dtype
-            ob, ib = out.reshape(-1).view(torch.uint8), inp.reshape(-1).view(torch.uint8)
-            if dev.type == "cuda":
-                dist.all_gather_into_tensor(ob, ib, group=group)
-            else:  # gloo (CPU tests): list form
+        byte_pairs = [(out.reshape(-1).view(torch.uint8), inp.reshape(-1).view(torch.uint8)) for out, inp in pairs]  # int16 is not a collective dtype
+        if dev.type == "cuda":
+            done = False
+            cm = getattr(dist, "_coalescing_manager", None)
+            if cm is not None and not _GatherWorkspace.cache.get("no_coalescing"):
+                try:
+                    with cm(group=group, device=dev, async_ops=False):
+                        for ob, ib in byte_pairs:
+                            dist.all_gather_into_tensor(ob, ib, group=group)
+                    done = True
+                except (RuntimeError, TypeError, NotImplementedError):  # a backend / version without coalesced all-gather: one call per field
+                    _GatherWorkspace.cache["no_coalescing"] = True
+            if not done:
+                for ob, ib in byte_pairs:
+                    dist.all_gather_into_tensor(ob, ib, group=group)
+        else:  # gloo (CPU tests): list form
+            for ob, ib in byte_pairs:
                 dist.all_gather(list(ob.reshape(world, -1).unbind(0)), ib, group=group)
     else:
         for out, inp in pairs:
             out.reshape(inp.shape).copy_(inp)
     H = w["recv"]["hdr"]
     offs = H[:, 2:]
-    j = torch.arange(max_episodes, device=dev).reshape(1, -1)
-    ep_len = torch.where(j < H[:, 0:1], offs[:, 1:] - offs[:, :-1], torch.zeros_like(offs[:, 1:])).clamp_(min=0)
-    begin = offs[:, :-1] + torch.arange(world, device=dev).reshape(-1, 1) * max_experiences
-    ep_offsets = torch.cat([begin.reshape(-1), torch.full((1,), world * max_experiences, dtype=torch.int64, device=dev)])
+    ep_len = torch.where(ring["j"] < H[:, 0:1], offs[:, 1:] - offs[:, :-1], 0).clamp_(min=0)
+    ep_offsets = torch.cat([(offs[:, :-1] + ring["rank_base"]).reshape(-1), ring["end"]])
     g = lambda n: w["recv"][n] if n in names else None  # noqa: E731
     return EpisodeBatch(world * max_episodes, world * max_experiences, g("after_boards"), g("meta"), g("reward"), g("state_value"),
                         g("next_state_value"), g("n_moves"), g("action"), g("roll"), ep_offsets.contiguous(), w["recv"]["info"],
@@ -120,7 +143,7 @@ def all_gather_episodes(batch, max_episodes: int, max_experiences: int, group=No
     compact=True : ONE all_gather of a fixed-size byte buffer per rank; the result is a dense CSR batch (one small host read-back for the
                    per-rank sizes).
     compact=False: no host synchronisation and no unpacking copies -- each field is gathered straight into its final padded array (buffers
-                   are cached: the returned batch is valid until the next call with the same quota) and the batch carries explicit episode
+                   are cached, two sets in turn: the returned batch is valid until the SECOND next call with the same quota) and the batch carries explicit episode
                    lengths (EpisodeBatch.ep_len; bg_learner_update's ep_len argument); n_episodes = world * max_episodes, ranks that supplied
                    fewer episodes contribute zero-length ones, which the learner skips.  fields=LEARNER_FIELDS gathers only what the trainer
                    reads (the other record fields are None)."""

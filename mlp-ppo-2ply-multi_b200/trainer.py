@@ -192,16 +192,23 @@ class Trainer:
         dev = self.device
         if isinstance(episodes, EpisodeBatch):
             met = self.learner.update_batch(episodes, check_status=False)
-            info = episodes.ep_info[:n].to(torch.float32)
-            lens = episodes.episode_lengths().to(torch.float32)
-            # padded batches (all_gather_episodes(compact=False)) carry zero-length filler episodes: averages are over the real ones
-            n_real = (lens > 0).sum().clamp(min=1).to(torch.float32)
-            wins = torch.stack([(info[:, 0] == k).sum() for k in (1, 2, 3)]).to(torch.float32)
-            seen = torch.stack([((episodes.ep_info[:n, 8] >> p) & 1).sum() for p in (0, 1)]).to(torch.float32)
-            # the reference adds the episode's count dict once per EXPERIENCE (trainer.py:88-100)
-            close = torch.stack([(info[:, 4 + p] * lens).sum() for p in (0, 1)])
-            prime = torch.stack([(info[:, 6 + p] * lens).sum() for p in (0, 1)])
-            summary = torch.cat([met.sum(dim=0) / n_real, wins, seen, close, prime, self.learner.last_status.to(torch.float32)])  # read back once, in finish()
+            status = self.learner.last_status
+
+            def summary():
+                # built only when finish() is asked for the metrics (~25 small device ops: a training loop that publishes every update
+                # but reads metrics now and then should not pay their launch cost per update); `episodes` is kept alive and must stay
+                # unchanged until then
+                info = episodes.ep_info[:n].to(torch.float32)
+                lens = episodes.episode_lengths().to(torch.float32)
+                # padded batches (all_gather_episodes(compact=False)) carry zero-length filler episodes: averages are over the real ones
+                n_real = (lens > 0).sum().clamp(min=1).to(torch.float32)
+                wins = torch.stack([(info[:, 0] == k).sum() for k in (1, 2, 3)]).to(torch.float32)
+                seen = torch.stack([((episodes.ep_info[:n, 8] >> p) & 1).sum() for p in (0, 1)]).to(torch.float32)
+                # the reference adds the episode's count dict once per EXPERIENCE (trainer.py:88-100)
+                close = torch.stack([(info[:, 4 + p] * lens).sum() for p in (0, 1)])
+                prime = torch.stack([(info[:, 6 + p] * lens).sum() for p in (0, 1)])
+                return torch.cat([met.sum(dim=0) / n_real, wins, seen, close, prime, status.to(torch.float32)])  # read back once, in finish()
+
             host = None
         else:
             obs = torch.stack([x.observation for ep in episodes for x in ep.experiences]).to(dev)
@@ -209,7 +216,8 @@ class Trainer:
             off = torch.tensor([0] + [len(ep.experiences) for ep in episodes], dtype=torch.int64).cumsum(0).to(dev)
             boards, flags = features_to_boards(obs)
             met = self.learner.update(boards, flags, rew.contiguous(), off, check_status=False)
-            summary = torch.cat([met.mean(dim=0), self.learner.last_status.to(torch.float32)])
+            row = torch.cat([met.mean(dim=0), self.learner.last_status.to(torch.float32)])
+            summary = lambda: row  # noqa: E731
             wins = {"regular": 0, "gammon": 0, "backgammon": 0}
             close, prime = {}, {}
             for ep in episodes:
@@ -236,7 +244,7 @@ class Trainer:
         torch.cuda.current_stream(self.device).wait_event(done)
         vals = None
         if metrics:
-            vals = summary.tolist()
+            vals = summary().tolist()
             if vals[-1] != 0:  # checked BEFORE the weights are published: a partial update never reaches the arenas
                 raise RuntimeError(f"bg_learner_update: an episode exceeded {MAX_T} experiences and was skipped")
         if hasattr(self.parameter_manager, "set_packed"):

@@ -11,6 +11,8 @@ from bench import H, make_positions, packed_random_weights
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1048576
 dev = torch.device("cuda:0")
+if os.environ.get("BG_TILES"):  # development: force the evaluator's tile schedule (0 static, 1 dynamic)
+    bg._lib.lib().bg_eval_tc_tile_schedule(int(os.environ["BG_TILES"]))
 boards, players = make_positions(bg, n, dev, 2026)
 P = boards.shape[0]
 pool_cap = P * 21 * 26 + (1 << 20)

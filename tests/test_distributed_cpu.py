@@ -47,16 +47,17 @@ def _worker(rank, world, port, out_dir):
         pm.sync_from_source()
     packed = bg.pack_weights(pm.get_parameters())
     assert len(fa.got) == 3 and fa.got[-1][1] == 3 and torch.equal(fa.got[-1][0], packed) and pm.check_version_sync()
-    # the training loop of examples/train_selfplay.py with evaluation enabled: rank 0 publishes update u-1 in iteration u, the other ranks
-    # receive it at the same point, and the evaluation branch issues NO collective (it reads the already published weights)
-    for u in range(5):
-        torch.distributed.all_reduce(torch.zeros(1))  # stands for the episode gather
+    # the training loop of examples/train_selfplay.py with evaluation enabled: iteration u launches update u-1 on the batch staged one
+    # iteration earlier, so rank 0 publishes from iteration 2 on, the other ranks receive at the same point (before the episode gather), and
+    # the evaluation branch issues NO collective (it reads the already published weights)
+    for u in range(6):
         if rank == 0:
-            if u > 0:
+            if u > 1:
                 pm.set_packed(packed + u)
-        elif u > 0:
+        elif u > 1:
             pm.sync_from_source()
-        if rank == 0 and (u + 1) % 2 == 0:
+        torch.distributed.all_reduce(torch.zeros(1))  # stands for the episode gather
+        if rank == 0 and u and u % 2 == 0:
             _ = bg.pack_weights(pm.get_parameters())  # evaluation: no publish, no finish
     if rank == 0:
         pm.set_packed(packed + 5)

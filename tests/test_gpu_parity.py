@@ -490,10 +490,12 @@ def test_eval_tensor_core_and_ffma_kernels_agree_with_oracle(bg, oracle, golden,
     assert np.abs(v_ff - v_tc).max() < 2e-6
 
 
-def test_eval_tensor_core_tile_schedules(bg, oracle, golden):
+@pytest.mark.parametrize("schedule", [0, 1])
+def test_eval_tensor_core_tile_schedules(bg, oracle, golden, schedule):
     """The tcgen05 evaluator hands local tile n of a CTA to TMEM slot n & 1, builder set n & 1 and the epilogue warps of that slot: row counts
     around the schedule's edges -- one tile per CTA, an odd number of tiles (a CTA whose second slot is never used), exactly one / two tiles
-    for each of the 148 CTAs, a ragged last tile -- must give the FFMA kernel's values and leave the status word clear."""
+    for each of the 148 CTAs, a ragged last tile -- must give the FFMA kernel's values and leave the status word clear, under the static
+    split (0) and under the dynamic one (1: tile pairs claimed from a grid-wide counter), for board pools and for compact (code) pools."""
     g = golden("values")
     w = bg.prepare_weights(dev(g["packed"]), 128)
     boards, players = oracle.random_positions(3 * 37888 + 300, seed=4242)
@@ -501,10 +503,24 @@ def test_eval_tensor_core_tile_schedules(bg, oracle, golden):
     v_ff = torch.cat([bg.evaluate(d_b[i:i + 30000], d_p[i:i + 30000], w) for i in range(0, len(boards), 30000)])
     ref = oracle.value(g["packed"], 128, boards[:4096], players[:4096])
     assert np.abs(v_ff[:4096].cpu().numpy() - ref).max() < 1e-5
-    for n in (32768, 32769, 32768 + 3 * 128 + 5, 148 * 128 * 2 - 1, 148 * 128 * 2, 148 * 128 * 2 + 1, 148 * 128 * 3, 148 * 128 * 3 + 129, 3 * 37888 + 300):
-        v_tc = bg.evaluate(d_b[:n], d_p[:n], w)
+    prev = bg._lib.lib().bg_eval_tc_tile_schedule(schedule)
+    try:
+        for n in (32768, 32769, 32768 + 3 * 128 + 5, 148 * 128 * 2 - 1, 148 * 128 * 2, 148 * 128 * 2 + 1, 148 * 128 * 3, 148 * 128 * 3 + 129, 3 * 37888 + 300):
+            v_tc = bg.evaluate(d_b[:n], d_p[:n], w)
+            assert bg._lib.lib().bg_eval_tc_status() == 0
+            assert (v_tc - v_ff[:n]).abs().max().item() < 2e-6, n
+        # compact pools always run on the tensor-core kernel: all 21 rolls of 1,500 positions, values against the FFMA kernel on the
+        # afterstates materialised from the codes
+        pb, pp = oracle.random_positions(1500, seed=99)
+        res, vals = bg.movegen_all_rolls_compact(dev(pb), dev(pp), w, item_cap=500, check_status=True)
         assert bg._lib.lib().bg_eval_tc_status() == 0
-        assert (v_tc - v_ff[:n]).abs().max().item() < 2e-6, n
+        T = int(res.total)
+        ab = res.afterstates(torch.arange(T, device="cuda"))
+        fl = dev(pp)[(res.codes[:T] >> 32).to(torch.int64)]
+        v_f = torch.cat([bg.evaluate(ab[i:i + 30000], fl[i:i + 30000], w) for i in range(0, T, 30000)])
+        assert (vals[:T] - v_f).abs().max().item() < 2e-6
+    finally:
+        bg._lib.lib().bg_eval_tc_tile_schedule(prev)
 
 
 @pytest.mark.parametrize("H", [32, 64, 96, 160, 224, 256])
