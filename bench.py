@@ -544,13 +544,21 @@ def main():
                 "games_finished": int(v["games"]), "mean_steps_per_game": v["steps"] / max(v["games"], 1.0),
                 "pass_rate": v["passes"] / max(v["steps"], 1.0), "wait_steps": int(v["wait_steps"]), "errors": int(v["errors"])}
 
-    selfplay = selfplay2 = selfplay2b = None
+    selfplay = selfplay2 = selfplay2b = selfplay2s = None
     if not args.no_selfplay:
         G = args.selfplay_games
         selfplay = run_selfplay(G, args.selfplay_plies, 1, None,
                                 f"config3: {G} concurrent 1-ply self-play games per GPU, T=1.5, Philox dice, episodes drained on device")
         selfplay2 = run_selfplay(G, args.selfplay2_plies, 2, (4, 5, 1.0, 0.9),
                                  f"config4 (reference setting, two_ply.py): {G} games per GPU, top-4 candidates x 21 rolls, mean of top-5 replies, score = S - 0.9 W")
+        # the lookahead exactly as shipped: the reference evaluates only random.sample(replies, 50) of the rolls 1-1 / 2-2 / 3-3
+        # (two_ply.py:119-121); here a reproducible Philox-keyed sample taken before evaluation (bg_two_ply_reply_sampling)
+        bg.set_reply_sampling(50, 2026)
+        try:
+            selfplay2s = run_selfplay(G, args.selfplay2_plies, 2, (4, 5, 1.0, 0.9),
+                                      f"config4 as shipped (two_ply.py incl. random.sample(replies, 50) on 1-1 / 2-2 / 3-3): {G} games per GPU, top-4 candidates x 21 rolls, mean of top-5 replies")
+        finally:
+            bg.set_reply_sampling(0, 0)
         G2 = max(G // 8, 1)
         selfplay2b = run_selfplay(G2, args.selfplay2_plies, 2, (0, 1, 1.0, 1.0),
                                   f"config4 (north-star expectimax): {G2} games per GPU, ALL candidates x 21 rolls, best reply, score = S - W")
@@ -798,7 +806,7 @@ def main():
                     "afterstates_check": e2e_check},
             "gpu_launches": n_step_kernels * args.steps,
             "gpu_launches_note": f"timed region, per step (bg_movegen_eval_all_rolls_compact): k_movegen21<Std> (bulk tier) + tail tiers k_movegen21<Big>, k_movegen<4096> + k_eval_tc twice (bulk-tier rows on the side stream, tail-tier rows after); unfused ms_per_step {unfused_ms_per_step:.2f}; the e2e region launches {n_e2e_kernels} per step (the same five + status fold + k_select, per chunk)",
-            "board_pool": board_pool, "roofline": roofline, "roofline_movegen": roofline_movegen, "roofline_eval": roofline_eval, "roofline_encode": roofline_encode, "cpu_baseline": cpu, "clocks": clocks, "selfplay_1ply": selfplay, "selfplay_2ply": selfplay2,
+            "board_pool": board_pool, "roofline": roofline, "roofline_movegen": roofline_movegen, "roofline_eval": roofline_eval, "roofline_encode": roofline_encode, "cpu_baseline": cpu, "clocks": clocks, "selfplay_1ply": selfplay, "selfplay_2ply": selfplay2, "selfplay_2ply_sampled_replies": selfplay2s,
             "selfplay_2ply_all_candidates": selfplay2b, "learner": learner, "td0_loop": td0}
     print(json.dumps(line), flush=True)
     if dist is not None:

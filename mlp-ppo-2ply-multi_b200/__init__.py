@@ -15,9 +15,9 @@ from .types import BoardState, FullMove, Player, Position, SubMove
 from ._lib import BgError, SO_PATH
 from .ops import (DICE_ROLLS, HostPipeline, MovegenResult, PreparedWeights, encode, evaluate, CompactResult, evaluate_codes, movegen, movegen_all_rolls, movegen_all_rolls_compact, movegen_evaluate,
                   movegen_evaluate_all_rolls,
-                  pack_weights, prepare_weights, select, two_ply, unpack_weights)
+                  pack_weights, prepare_weights, select, set_reply_sampling, two_ply, unpack_weights)
 
 __all__ = ["HostPipeline", "agent_play_step", "select_highest_value_action", "play_match", "Trainer", "TD0Learner", "features_to_boards", "ImmutableBoard", "BackgammonEnv", "ParameterManager", "BackgammonPolicyNetwork", "execute_full_move_on_board_copy",
            "generate_all_board_features", "get_all_possible_moves", "Arena", "temperature_for_version", "Episode", "EpisodeBatch", "Experience", "BoardState", "FullMove", "Player",
            "Position", "SubMove", "ops", "BgError", "SO_PATH", "DICE_ROLLS", "MovegenResult", "PreparedWeights", "encode", "evaluate", "CompactResult", "evaluate_codes", "movegen_all_rolls_compact", "movegen", "movegen_all_rolls", "movegen_evaluate", "movegen_evaluate_all_rolls",
-           "pack_weights", "prepare_weights", "select", "two_ply", "unpack_weights"]
+           "pack_weights", "prepare_weights", "select", "set_reply_sampling", "two_ply", "unpack_weights"]

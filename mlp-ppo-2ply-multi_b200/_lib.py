@@ -47,6 +47,7 @@ SIGNATURES = {
     "bg_eval_tc_tile_schedule": (_i32, [_i32]),
     "bg_select": (_i32, [_vp, _vp, _vp, _i32, _i64, _f32, _u64, _u64, _i64, _vp, _vp]),
     "bg_two_ply_workspace_bytes": (_i64, [_i64]),
+    "bg_two_ply_reply_sampling": (_i32, [_i32, _u64]),
     "bg_two_ply": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "bg_hostpipe_create": (_i32, [_vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32]),
     "bg_hostpipe_destroy": (_i32, [_vp]),

@@ -154,6 +154,7 @@ int32_t bg_eval_tc_status(void) { return eval_tc_status(); }
 int32_t bg_eval_tc_tile_schedule(int32_t mode) { return eval_tc_tile_schedule(mode); }
 
 int64_t bg_two_ply_workspace_bytes(int64_t N) { return two_ply_workspace_bytes(N); }
+int32_t bg_two_ply_reply_sampling(int32_t cap, uint64_t seed) { return two_ply_reply_sampling(cap, seed); }
 
 int32_t bg_two_ply(const int8_t* cand_boards, const uint8_t* mover, const float* S, int64_t N, const float* prepared, int32_t H,
                    int32_t top_k, float alpha, float beta, float* out_score, int64_t* out_replies, int32_t* out_status, void* workspace,

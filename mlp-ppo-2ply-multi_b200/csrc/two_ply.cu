@@ -6,11 +6,16 @@
 //   (eval.cu), take the mean of the top_k reply values (all of them if fewer; a roll with no reply adds 0), and
 //   W = sum_r p_r * mean_r;  score = alpha * S - beta * W.
 // top_k = 5, alpha = 1, beta = 0.9 is the reference's setting; top_k = 1 is north_star's "best reply" expectimax.
-// The reference's random.sample(replies, 50) on 1-1/2-2/3-3 (two_ply.py:119-121) is NOT reproduced: it is
-// nondeterministic there; every reply is evaluated here.
+// The reference's random.sample(replies, 50) on 1-1/2-2/3-3 (two_ply.py:119-121) is OFF by default (every reply is evaluated; it is
+// nondeterministic there) and available as an option (two_ply_reply_sampling): the replies of those three rolls are
+// cut to a uniform sample WITHOUT replacement of `cap` of them BEFORE they are evaluated -- the "as shipped" cost of the lookahead --, keyed
+// by (seed, candidate, roll) so that a run is reproducible: row j of the sample is reply perm(j), perm = a 4-round Feistel permutation of
+// [0, 2^b) (b = the even number of bits that covers the reply count), cycle-walked into [0, n), round keys = Philox4x32-10(seed ^ KEY, item).
 // Composition: position-major movegen (one warp per candidate, all 21 rolls; overflow -> per-item tiers) -> k_eval -> k_reduce (warp per candidate, top-k
 // selection and the 21-term expectation entirely in registers).  Candidates are processed in workspace-sized chunks.
 #include "two_ply.cuh"
+
+#include <atomic>
 
 #include "eval.cuh"
 #include "movegen.cuh"
@@ -94,15 +99,75 @@ __global__ void __launch_bounds__(256) k_reduce(const float* __restrict__ v, con
   }
 }
 
+constexpr uint64_t KEY_SAMPLE = 0x3c6ef372fe94f82bull;
+
+// Optional reply sampling (see the header comment): warp per (candidate, roll) item; copies the item's rows into a second pool -- all of them,
+// or, for 1-1 / 2-2 / 3-3 with more than `cap` replies, the rows perm(0) .. perm(cap - 1) -- and writes the item's new offset / count.
+__global__ void __launch_bounds__(256) k_sample_replies(const uint2* __restrict__ pool, const long long* __restrict__ off, const int32_t* __restrict__ cnt,
+                                                        int64_t n_items, int cap, uint64_t seed, int64_t item_id_base, uint2* __restrict__ pool2,
+                                                        long long* __restrict__ off2, int32_t* __restrict__ cnt2, unsigned long long* __restrict__ cursor2) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t it = warp; it < n_items; it += nwarps) {
+    const int n = cnt[it];
+    const long long o = off[it];
+    if (n <= 0 || o < 0) {  // no reply, or an item the generator could not hold: k_reduce sees the same (count, offset)
+      if (lane == 0) {
+        cnt2[it] = n;
+        off2[it] = o;
+      }
+      continue;
+    }
+    const int r = (int)(it % 21);
+    const bool sampled = (r == 0 || r == 6 || r == 11) && n > cap;  // two_ply.py:119-121: dice_roll in ([1, 1], [2, 2], [3, 3])
+    const int m = sampled ? cap : n;
+    unsigned long long dst = 0;
+    if (lane == 0) dst = atomicAdd(cursor2, (unsigned long long)m);
+    dst = __shfl_sync(BG_FULL, dst, 0);
+    if (!sampled) {
+      for (int i = lane; i < n; i += 32) pool2[dst + i] = pool[o + i];
+    } else {
+      uint32_t k[4];
+      Philox::gen(seed ^ KEY_SAMPLE, (uint64_t)(item_id_base + it), 0ull, k);
+      int bits = 2;
+      while ((1 << bits) < n) bits += 2;
+      const int half = bits >> 1;
+      const uint32_t mask = (1u << half) - 1u;
+      for (int j = lane; j < cap; j += 32) {
+        uint32_t x = (uint32_t)j;
+        do {
+          uint32_t L = x >> half, R = x & mask;
+#pragma unroll
+          for (int rd = 0; rd < 4; ++rd) {
+            const uint32_t t = L ^ (mix32(R, k[rd], (uint32_t)rd, 0x9E3779B9u) & mask);
+            L = R;
+            R = t;
+          }
+          x = (L << half) | R;
+        } while (x >= (uint32_t)n);
+        pool2[dst + j] = pool[o + x];
+      }
+    }
+    if (lane == 0) {
+      cnt2[it] = m;
+      off2[it] = (long long)dst;
+    }
+  }
+}
+
+std::atomic<int32_t> g_sample_cap{0};
+std::atomic<uint64_t> g_sample_seed{0};
+
 struct Layout {
   int64_t C;  // candidates per chunk
   int64_t items, rows;
   int64_t o_ip, o_act, o_off, o_cnt, o_tot, o_pool, o_owner, o_val, o_ws, ws_bytes, total;
+  int64_t o_pool2, o_off2, o_cnt2;  // reply sampling only
 };
 
 int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
 
-Layout make_layout(int64_t C) {
+Layout make_layout(int64_t C, bool sampled = false) {
   Layout L;
   L.C = C;
   L.items = C * 21;
@@ -127,6 +192,15 @@ Layout make_layout(int64_t C) {
   L.o_ws = o;
   L.ws_bytes = movegen_workspace_bytes(L.items);
   o += align256(L.ws_bytes);
+  L.o_pool2 = L.o_off2 = L.o_cnt2 = 0;
+  if (sampled) {  // the second (sampled) pool and its item table
+    L.o_pool2 = o;
+    o += align256(L.rows * 8);
+    L.o_off2 = o;
+    o += align256(L.items * 8);
+    L.o_cnt2 = o;
+    o += align256(L.items * 4);
+  }
   L.total = o;
   return L;
 }
@@ -140,16 +214,24 @@ int64_t two_ply_workspace_bytes(int64_t N) {
   return make_layout(N < DEFAULT_CHUNK ? N : DEFAULT_CHUNK).total;
 }
 
+int32_t two_ply_reply_sampling(int32_t cap, uint64_t seed) {
+  g_sample_seed.store(seed);
+  return g_sample_cap.exchange(cap > 0 ? cap : 0);
+}
+
 int32_t two_ply_launch(const TwoPlyArgs& a, cudaStream_t s) {
   if (a.N <= 0) return BG_OK;
+  const int32_t sample_cap = g_sample_cap.load();
+  const uint64_t sample_seed = g_sample_seed.load();
+  const bool sampled = sample_cap > 0;
   if (a.top_k < 1 || a.top_k > MAX_TOPK) {
     set_error("bg_two_ply: top_k must be in [1,%d]", MAX_TOPK);
     return BG_ERR_ARG;
   }
   // largest chunk that fits the caller's workspace
   int64_t C = a.N < DEFAULT_CHUNK ? a.N : DEFAULT_CHUNK;
-  while (C > 1 && make_layout(C).total > a.workspace_bytes) C = (C + 1) / 2;
-  Layout L = make_layout(C);
+  while (C > 1 && make_layout(C, sampled).total > a.workspace_bytes) C = (C + 1) / 2;  // (sampling needs a second pool: smaller chunks)
+  Layout L = make_layout(C, sampled);
   if (L.total > a.workspace_bytes) {
     set_error("bg_two_ply: workspace too small (%lld bytes; need >= %lld)", (long long)a.workspace_bytes, (long long)L.total);
     return BG_ERR_ARG;
@@ -183,9 +265,32 @@ int32_t two_ply_launch(const TwoPlyArgs& a, cudaStream_t s) {
     m.workspace = w + L.o_ws;
     m.workspace_bytes = L.ws_bytes;
     m.active = (const uint8_t*)(w + L.o_act);
-    int32_t rc = movegen_eval_overlapped(m, (int64_t*)(w + L.o_tot), a.prepared, a.H, (float*)(w + L.o_val), a.side, s);
-    if (rc != BG_OK) return rc;
-    k_reduce<<<grid, 256, 0, s>>>((const float*)(w + L.o_val), (const long long*)(w + L.o_off), (const int32_t*)(w + L.o_cnt), a.S, c0, nc,
+    const long long* red_off = (const long long*)(w + L.o_off);
+    const int32_t* red_cnt = (const int32_t*)(w + L.o_cnt);
+    if (!sampled) {
+      int32_t rc = movegen_eval_overlapped(m, (int64_t*)(w + L.o_tot), a.prepared, a.H, (float*)(w + L.o_val), a.side, s);
+      if (rc != BG_OK) return rc;
+    } else {
+      // generate every reply, cut 1-1 / 2-2 / 3-3 to the sample, evaluate only what is left
+      m.out_total = (int64_t*)(w + L.o_tot);
+      int32_t rc = movegen_launch(m, s);
+      if (rc != BG_OK) return rc;
+      unsigned long long* cursor2 = (unsigned long long*)(w + L.o_tot + 32);
+      cudaError_t ce = cudaMemsetAsync(cursor2, 0, 8, s);
+      if (ce != cudaSuccess) return check_cuda(ce, "memset sample cursor");
+      const int64_t n_items = nc * 21;
+      const int64_t sb = (n_items + 7) / 8;
+      k_sample_replies<<<(int)(sb < 148 * 16 ? sb : 148 * 16), 256, 0, s>>>((const uint2*)(w + L.o_pool), red_off, red_cnt, n_items, sample_cap, sample_seed,
+                                                                            c0 * 21, (uint2*)(w + L.o_pool2), (long long*)(w + L.o_off2),
+                                                                            (int32_t*)(w + L.o_cnt2), cursor2);
+      EvalArgs ev{m.boards, m.players, nullptr, nullptr, 0, (const int64_t*)cursor2, L.rows, a.prepared, a.H, (float*)(w + L.o_val)};
+      ev.codes = (const uint2*)(w + L.o_pool2);
+      rc = eval_launch(ev, s);
+      if (rc != BG_OK) return rc;
+      red_off = (const long long*)(w + L.o_off2);
+      red_cnt = (const int32_t*)(w + L.o_cnt2);
+    }
+    k_reduce<<<grid, 256, 0, s>>>((const float*)(w + L.o_val), red_off, red_cnt, a.S, c0, nc,
                                   a.top_k, a.alpha, a.beta, a.out_score, (long long*)a.out_replies, (const int32_t*)(w + L.o_tot + 16),
                                   a.out_status, a.reply_counter);
     cudaError_t e = cudaGetLastError();

@@ -25,6 +25,9 @@ struct TwoPlyArgs {
 };
 
 int64_t two_ply_workspace_bytes(int64_t N);
+// process-wide option of every 2-ply scorer call (bg_two_ply, bg_arena_step(lookahead = 2)): cap > 0 cuts the replies of 1-1 / 2-2 / 3-3 to a
+// uniform sample of `cap` before they are evaluated (reference two_ply.py:119-121 with cap = 50); returns the previous cap
+int32_t two_ply_reply_sampling(int32_t cap, uint64_t seed);
 int32_t two_ply_launch(const TwoPlyArgs& a, cudaStream_t s);
 
 }  // namespace bg

@@ -381,6 +381,13 @@ def two_ply(cand_boards: torch.Tensor, mover: torch.Tensor, S: torch.Tensor, wei
     return out, nrep
 
 
+def set_reply_sampling(cap: int = 0, seed: int = 0) -> int:
+    """Process-wide option of the 2-ply scorer (two_ply, Arena.step(lookahead=2)): cap > 0 reproduces the reference's
+    `random.sample(opponent_moves, 50)` on the rolls 1-1 / 2-2 / 3-3 (two_ply.py:119-121) as a reproducible uniform sample of `cap`
+    replies taken BEFORE evaluation; 0 (default) evaluates every reply.  -> the previous cap"""
+    return int(lib().bg_two_ply_reply_sampling(int(cap), int(seed) & ((1 << 64) - 1)))
+
+
 class HostPipeline:
     """The per-decision hot path for HOST-resident batches (bg_hostpipe_*): pinned (boards, players[, rolls]) in, (action, count) per
     item out.  Chunking, the copy / kernel overlap over n_streams streams and every device buffer live inside libbgarena.so; this class

@@ -460,6 +460,115 @@ def test_two_ply_reference_setting_and_best_reply(bg, oracle, golden):
         assert np.array_equal(got2.cpu().numpy(), got.cpu().numpy())
 
 
+def _philox4x32(key, ctr):
+    """Philox4x32-10 (csrc/bg_common.cuh Philox::gen with ctr_hi = 0)"""
+    M0, M1, m32 = 0xD2511F53, 0xCD9E8D57, 0xFFFFFFFF
+    k0, k1 = key & m32, (key >> 32) & m32
+    c = [ctr & m32, (ctr >> 32) & m32, 0, 0]
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & m32, p1 & m32, ((p0 >> 32) ^ c[3] ^ k1) & m32, p0 & m32]
+        k0, k1 = (k0 + 0x9E3779B9) & m32, (k1 + 0xBB67AE85) & m32
+    return c
+
+
+def _mix32(a, b, c, d):
+    m32 = 0xFFFFFFFF
+    h = (a * 0x9E3779B1) & m32
+    h = ((h ^ (h >> 15)) + b * 0x85EBCA77) & m32
+    h = ((h ^ (h >> 13)) + c * 0xC2B2AE3D) & m32
+    h = ((h ^ (h >> 16)) + d * 0x27D4EB2F) & m32
+    h ^= h >> 15
+    h = (h * 0x2C1B3C6D) & m32
+    return h ^ (h >> 12)
+
+
+def _sample_rows(seed, item, n, cap):
+    """rows perm(0) .. perm(cap - 1) of an item with n replies, as documented at bg_two_ply_reply_sampling (include/bgarena.h)"""
+    k = _philox4x32(seed ^ 0x3C6EF372FE94F82B, item)
+    bits = 2
+    while (1 << bits) < n:
+        bits += 2
+    half, out = bits >> 1, []
+    mask = (1 << half) - 1
+    for j in range(cap):
+        x = j
+        while True:
+            L, R = x >> half, x & mask
+            for rd in range(4):
+                L, R = R, L ^ (_mix32(R, k[rd], rd, 0x9E3779B9) & mask)
+            x = (L << half) | R
+            if x < n:
+                break
+        out.append(x)
+    return out
+
+
+def test_two_ply_reply_sampling_option(bg, oracle, golden):
+    """bg_two_ply_reply_sampling: the reference's random.sample(opponent_moves, 50) on 1-1 / 2-2 / 3-3 (two_ply.py:119-121) as a reproducible
+    option.  The sampled rows are recomputed here from the documented permutation (Philox keys, 4-round Feistel, cycle walking), the expected
+    scores from the oracle's replies and values: exact reply counts, scores within 1e-5; the sample is a subset, so no score drops below the
+    unsampled one (beta > 0); same seed -> same bits, other seed -> other sample; a cap above every count changes nothing; chunking (a
+    small workspace) does not change the sample."""
+    v = golden("values")
+    H = int(v["H"])
+    w = bg.prepare_weights(dev(v["packed"]), H)
+    boards, players = oracle.random_positions(400, seed=61)
+    ib, ip, ir = oracle.all_rolls_items(boards[:30], players[:30])
+    o_off, o_b, _ = oracle.movegen_batch(ib, ip, ir, want_moves=False)
+    mover = np.repeat(ip, np.diff(o_off))
+    sel = np.random.default_rng(3).choice(len(o_b), size=160, replace=False)
+    cb, mv = o_b[sel], mover[sel]
+    S = oracle.value(v["packed"], H, cb, mv)
+    cap, seed, top_k, alpha, beta = 50, 1234567, 5, 1.0, 0.9
+    # the oracle's replies of every (candidate, roll) item, in action order, and their values
+    rb, rp, rr = oracle.all_rolls_items(cb, 1 - mv)
+    r_off, r_b, _ = oracle.movegen_batch(rb, rp, rr, want_moves=False)
+    r_val = oracle.value(v["packed"], H, r_b, np.repeat(rp, np.diff(r_off)))
+    want = np.zeros(len(cb))
+    want_rep = np.zeros(len(cb), np.int64)
+    n_sampled_items = 0
+    for c in range(len(cb)):
+        W = 0.0
+        for r in range(21):
+            it = c * 21 + r
+            vals = r_val[r_off[it]:r_off[it + 1]]
+            n = len(vals)
+            if n == 0:
+                continue
+            if r in (0, 6, 11) and n > cap:
+                vals = vals[_sample_rows(seed, it, n, cap)]
+                n_sampled_items += 1
+            want_rep[c] += len(vals)
+            top = np.sort(vals)[::-1][:top_k]
+            W += float(top.astype(np.float32).mean()) * ((1.0 if r in (0, 6, 11, 15, 18, 20) else 2.0) / 36.0)
+        want[c] = alpha * S[c] - beta * W
+    assert n_sampled_items > 50  # the option has something to do on this sample
+    full, full_rep = bg.two_ply(dev(cb), dev(mv), dev(S), w, top_k=top_k, alpha=alpha, beta=beta)
+    prev = bg.set_reply_sampling(cap, seed)
+    try:
+        assert prev == 0
+        got, rep = bg.two_ply(dev(cb), dev(mv), dev(S), w, top_k=top_k, alpha=alpha, beta=beta)
+        assert np.array_equal(rep.cpu().numpy(), want_rep)
+        assert np.abs(got.cpu().numpy() - want).max() < 1e-5
+        assert (got - full).min().item() > -1e-6 and (rep <= full_rep).all() and (rep < full_rep).any()
+        again, _ = bg.two_ply(dev(cb), dev(mv), dev(S), w, top_k=top_k, alpha=alpha, beta=beta)
+        assert torch.equal(again, got)
+        ws_small = torch.empty(bg._lib.lib().bg_two_ply_workspace_bytes(24), dtype=torch.uint8, device=DEV)
+        chunked, _ = bg.two_ply(dev(cb), dev(mv), dev(S), w, top_k=top_k, alpha=alpha, beta=beta, workspace=ws_small)
+        assert torch.equal(chunked, got)
+        bg.set_reply_sampling(cap, seed + 1)
+        other, rep2 = bg.two_ply(dev(cb), dev(mv), dev(S), w, top_k=top_k, alpha=alpha, beta=beta)
+        assert torch.equal(rep2, rep) and not torch.equal(other, got)
+        bg.set_reply_sampling(100000, seed)
+        same, rep3 = bg.two_ply(dev(cb), dev(mv), dev(S), w, top_k=top_k, alpha=alpha, beta=beta)
+        assert torch.equal(same, full) and torch.equal(rep3, full_rep)
+    finally:
+        bg.set_reply_sampling(0, 0)
+    off, _ = bg.two_ply(dev(cb), dev(mv), dev(S), w, top_k=top_k, alpha=alpha, beta=beta)
+    assert torch.equal(off, full)
+
+
 @pytest.mark.parametrize("which", ["packed", "packed_init0"])
 def test_eval_tensor_core_and_ffma_kernels_agree_with_oracle(bg, oracle, golden, which):
     """H = 128 has two evaluators: tcgen05/TMEM (two fp16 weight pieces, batches >= 32768 rows) and FFMA gather (smaller
