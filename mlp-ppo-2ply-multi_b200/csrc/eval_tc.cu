@@ -9,13 +9,14 @@
 //   rounding error fp32 itself has (valid for |W| < 65504; fp16 subnormals keep the low piece of tiny weights to 3e-8 abs).
 //   The 2 x 13 tcgen05.mma (kind::f16, M128 N128 K16, fp32 accumulate in TMEM) form every product exactly and only the
 //   accumulation rounds.  (Round 1 first used three bf16 pieces: same accuracy, 1.5x the tensor work.)
-// * A never touches shared memory: each of 128 worker threads owns one TMEM lane (= one board), builds its 208-entry
-//   fp16 feature row in registers and tcgen05.st's it into TMEM (A-from-TMEM "TS" MMA); B (2 x 128 x 208 fp16 = 104 KB,
-//   no-swizzle K-major core-matrix layout) stays resident in shared memory; D is read back with tcgen05.ld and the
-//   sigmoid / w2 dot product / +b2 epilogue runs one thread per board.
-// * two worker groups (2 x 4 warps) alternate tiles against one MMA-issuer warp, TMEM = [A0 | D0 | A1 | D1] (512 columns),
-//   so one group's epilogue + next feature build overlaps the other group's MMAs.  mbarriers: full[g] (128 arrivals) ->
-//   MMA thread; tcgen05.commit -> done[g] -> workers.  All waits are bounded (an error flag instead of a hang).
+// * A never touches shared memory: a builder thread owns one TMEM lane (= one board), builds its 208-entry fp16 feature row in
+//   registers and tcgen05.st's it into TMEM (A-from-TMEM "TS" MMA); B (2 x 128 x 208 fp16 = 104 KB, no-swizzle K-major core-matrix
+//   layout) stays resident in shared memory; D is read back with tcgen05.ld and the sigmoid / w2 dot product / +b2 epilogue runs one
+//   thread per board.
+// * persistent CTA (one per SM), warp roles apart: 8 builder warps, 8 epilogue warps, one MMA-issuer thread, one tile-scheduler thread, two
+//   TMEM slots [A0 | D0 | A1 | D1] (512 columns) handed round by mbarriers -- see the comment at k_eval_tc.  All waits are bounded (a
+//   status word instead of a hang).  Development switches: BG_TC_STAMPS (clock64 phase stamps), BG_TC_EXP (energy-split experiments,
+//   DESIGN.md 4.4), BG_TC_BUILDER_SETS.
 #include <cuda_fp16.h>
 
 #include <atomic>
@@ -44,7 +45,7 @@ constexpr int SCHED_WARP = MMA_WARP + 1;                      // lane 0: tile sc
 constexpr int THREADS = 32 * (SCHED_WARP + 1);
 constexpr int RING = 32, RUNAHEAD = 24, END_PAD = 8;          // tile ring entries, scheduler run-ahead over the slowest epilogue, END entries
 constexpr uint32_t TILE_END = 0xffffffffu;
-constexpr int TMEM_COLS = 512, A_COLS = 128, D_COLS = 128;  // per group: A at +0 (104 used), D at +128
+constexpr int TMEM_COLS = 512, A_COLS = 128, D_COLS = 128;  // per slot: A at +0 (104 columns used), D at +128
 constexpr int NUM_SMS = 148;
 // instruction descriptor, kind::f16: D = F32 (bit 4), A = B = F16 (format fields 0), N = 128, M = 128
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -265,16 +266,19 @@ __device__ __forceinline__ void rebuild_afterstate(uint32_t* scr, const uint32_t
   cur[12] = raw[12] + d12;
 }
 
-// Roles of the 13 warps of the persistent CTA (one CTA per SM; TMEM lane quarter of a warp = warp % 4 = its scheduler):
-//   warps 0-3   BUILDERS: thread (q, lane) owns row q * 32 + lane of EVERY tile: fetches the row two tiles ahead, (CODES) rebuilds the
-//               afterstate one tile ahead, writes the fp16 feature row into TMEM operand A[slot] as soon as the MMAs that read it are done;
-//   warps 4-11  EPILOGUE: warps 4-7 read accumulator D[0] (even local tiles), warps 8-11 D[1] (odd ones): sigmoid, w2 dot product, store;
-//   warp 12     lane 0 issues the 26 tcgen05.mma of a tile when A[slot] is full and D[slot] has been drained.
+// Roles of the 4 NB + 10 = 18 warps of the persistent CTA (one CTA per SM; TMEM lane quarter of a warp = warp % 4 = its scheduler):
+//   warps 0-7   BUILDERS, two sets of four (set b = local tiles b, b + 2, ...): thread (q, lane) owns row q * 32 + lane: a three-stage register
+//               pipeline loads the row's (code, position) two of its tiles ahead, the position's board words one tile ahead, (CODES) rebuilds
+//               the afterstate, and writes the fp16 feature row into TMEM operand A[slot] as soon as the MMAs that read it are done;
+//   warps 8-15  EPILOGUE: warps 8-11 read accumulator D[0] (even local tiles), warps 12-15 D[1] (odd ones): sigmoid, w2 dot product, store;
+//   warp 16     lane 0 issues the 26 tcgen05.mma of a tile when A[slot] is full and D[slot] has been drained;
+//   warp 17     lane 0 is the tile scheduler of the dynamic schedule (idle under the static one; see tile_of below).
 // Local tile n of a CTA uses slot n & 1; TMEM = [A0 | D0 | A1 | D1].  mbarriers: a_full[s] (128 builder arrivals), mma_done[s] (tcgen05.commit;
 // frees A[s] for the builders and hands D[s] to its epilogue warps), d_free[s] (128 epilogue arrivals, made as soon as the accumulator sits in
-// registers).  With the roles apart the tensor pipe only waits when a builder or an epilogue falls behind a whole tile; in the round-1 form
-// (the same threads built, waited and ran the epilogue) the next tile's global loads sat on the critical path: clock64 stamps showed
-// 2,300-4,000 of the 6,100 cycles of a two-tile period inside that fetch.
+// registers).  A role lags its slot's barrier by at most one phase (parity waits): hence exactly two builder sets.  With the roles apart the
+// tensor pipe only waits when a builder or an epilogue falls behind a whole tile; in the round-1 form (the same threads built, waited and ran
+// the epilogue) the next tile's fetch + rebuild sat on the critical path: clock64 stamps showed 2,300-4,000 of the 6,100 cycles of a
+// two-tile period there (profiles/r02_eval_tc_phase_stamps.txt).
 constexpr int SCRATCH_BYTES = NB * 128 * 13 * 4;
 constexpr int BAR_OFF = B_BYTES + 1024, RING_OFF = BAR_OFF + 128, SCRATCH_OFF = RING_OFF + RING * 8 + 64;
 constexpr size_t SMEM_BYTES = (size_t)SCRATCH_OFF + SCRATCH_BYTES;
