@@ -284,8 +284,8 @@ constexpr int BAR_OFF = B_BYTES + 1024, RING_OFF = BAR_OFF + 128, SCRATCH_OFF = 
 constexpr size_t SMEM_BYTES = (size_t)SCRATCH_OFF + SCRATCH_BYTES;
 
 // CODES: the rows are (code, position index) pairs of the compact pool (codes.cuh); `boards` / `flags` are then the POSITIONS' boards and
-// players, and each builder thread rebuilds its afterstate in a 52-byte shared-memory scratch row (13 word stores, a few byte updates, 13
-// word loads) -- the afterstate boards never exist in HBM.
+// players, and each builder thread rebuilds its afterstate in its shared-memory scratch row (rebuild_afterstate: 12 word stores, a few
+// independent +-1 adds, 12 word loads) -- the afterstate boards never exist in HBM.
 template <bool CODES>
 __global__ void __launch_bounds__(THREADS, 1)
     k_eval_tc(const int8_t* __restrict__ boards, const uint8_t* __restrict__ flags, int64_t N_host, const int64_t* __restrict__ N_dev,
