@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sB = smem;                                                   // B operand image
   float* sW2 = reinterpret_cast<float*>(smem + B_BYTES);                // w2 as (w0, w2, w1, w3) per four units, then b2
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);         // a_full[2], mma_done[2], d_free[2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);         // a_full[2], mma_done[2], d_free[2], b_loaded
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 64);
   volatile uint64_t* ring = reinterpret_cast<volatile uint64_t*>(smem + RING_OFF);               // [RING] (local tile index << 32) | grid tile
   volatile uint32_t* progress = reinterpret_cast<volatile uint32_t*>(smem + RING_OFF + RING * 8);  // [2] local tiles finished per slot (+1)
@@ -311,7 +311,6 @@ __global__ void __launch_bounds__(THREADS, 1)
     s_xtab[tid] = make_uint4(a0, a1, b0, b1);
   }
 
-  for (int i = tid; i < B_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(img)[i];
   for (int i = tid; i <= H; i += THREADS) {
     const int j = i == H ? H : (i & ~3) | ((i & 1) << 1) | ((i & 2) >> 1);  // units (0, 1, 2, 3) of a group sit at (0, 2, 1, 3)
     sW2[j] = reinterpret_cast<const float*>(img + B_BYTES)[i];
@@ -323,7 +322,16 @@ __global__ void __launch_bounds__(THREADS, 1)
     mbar_init(smem_u32(&bars[3]), 1);
     mbar_init(smem_u32(&bars[4]), 128);
     mbar_init(smem_u32(&bars[5]), 128);
+    mbar_init(smem_u32(&bars[6]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the 104 KB B operand image: two bulk copies by the TMA engine (one per weight piece), completion counted in bytes on bars[6]; they
+    // run while the other threads build the tables and the MMA warp allocates TMEM
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(&bars[6])), "r"((uint32_t)B_BYTES) : "memory");
+#pragma unroll
+    for (int j = 0; j < NSPLIT; ++j)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sB + j * SPLIT_BYTES)),
+                   "l"(img + j * SPLIT_BYTES), "r"((uint32_t)SPLIT_BYTES), "r"(smem_u32(&bars[6]))
+                   : "memory");
   }
   if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
@@ -335,9 +343,14 @@ __global__ void __launch_bounds__(THREADS, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // the B image has landed (async-proxy writes: visible to the tensor core without a proxy fence); on a timeout the status word is set and
+  // the CTA runs through with zero rows (so that TMEM is still released below)
+  const bool b_ok = mbar_wait(smem_u32(&bars[6]), 0u);
+  if (!b_ok && tid == 0) atomicExch(err, 7);
 
   int64_t N = N_dev ? *N_dev : N_host;
   if (N > max_N) N = max_N;
+  if (!b_ok) N = 0;
   {  // optional device-side start row: shift the row-indexed arrays once, everything below is unchanged
     int64_t start = start_dev ? *start_dev : 0;
     if (start > N) start = N;
