@@ -207,9 +207,9 @@ int64_t bg_two_ply_workspace_bytes(int64_t N);
  * the process: a uniform sample WITHOUT replacement of `cap` replies, reproducible: keyed by (seed, candidate index, roll).  Row j of an
  * item's sample is its reply perm(j): perm = 4-round Feistel permutation over the even number of bits that covers the reply count n,
  * cycle-walked into [0, n), round function mix32(R, key[round], round, 0x9E3779B9) of csrc/bg_common.cuh, keys =
- * Philox4x32-10(seed ^ 0x3c6ef372fe94f82b, counter = candidate * 21 + roll index).  With sampling on, a workspace of
- * bg_two_ply_workspace_bytes(N) bytes is processed in smaller chunks (a second reply pool lives in it).  cap <= 0 (default): every reply
- * is evaluated.  Returns the previous cap. */
+ * Philox4x32-10(seed ^ 0x3c6ef372fe94f82b, counter = candidate * 21 + roll index).  A second reply pool lives in the workspace while the
+ * option is on: bg_two_ply_workspace_bytes includes it when called with the option on; a workspace sized before is still legal (smaller
+ * chunks).  cap <= 0 (default): every reply is evaluated.  Returns the previous cap. */
 int32_t bg_two_ply_reply_sampling(int32_t cap, uint64_t seed);
 int32_t bg_two_ply(const int8_t* cand_boards /*[N,52]*/, const uint8_t* mover /*[N]*/, const float* S /*[N]*/, int64_t N,
                    const float* prepared, int32_t H, int32_t top_k, float alpha, float beta, float* out_score /*[N]*/,

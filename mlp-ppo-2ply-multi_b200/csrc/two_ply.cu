@@ -211,7 +211,7 @@ constexpr int64_t DEFAULT_CHUNK = 65536;
 
 int64_t two_ply_workspace_bytes(int64_t N) {
   if (N < 1) N = 1;
-  return make_layout(N < DEFAULT_CHUNK ? N : DEFAULT_CHUNK).total;
+  return make_layout(N < DEFAULT_CHUNK ? N : DEFAULT_CHUNK, g_sample_cap.load() > 0).total;  // (the second pool of the sampling option, if it is on)
 }
 
 int32_t two_ply_reply_sampling(int32_t cap, uint64_t seed) {
