@@ -494,7 +494,7 @@ def main():
     roofline_eval = {"bound": "tensor", "kernel": "bg::k_eval_tc (tcgen05, H=128)", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s",
                      "frac": tach / tpeak, "traffic": traffic.get("bg::k_eval_tc (tcgen05, H=128)"), "peak_source": tsrc, "ms_per_launch": t_eval,
                      "peak_burst": t_burst, "peak_sustained": t_sust, "sustained": eval_sustained,
-                     "note": "16-bit tensor FLOPs issued: 2 fp16 weight pieces x 2*208*128 per afterstate (fp32-exact layer 1: one fp16 piece misses the 1e-5 contract); dense fp32-equivalent is 1/2.09 of this. 26 M128 N128 K16 tcgen05.mma per 128-row tile; ncu: tensor pipe 75 % active at 1.9 GHz (profiles/r02_ncu_eval_tc_roles.txt); back to back the kernel is POWER limited (~1 kW, SM clock ~1.68 GHz) at the measured sustained cuBLAS bf16 rate"}
+                     "note": "16-bit tensor FLOPs issued: 2 fp16 weight pieces x 2*208*128 per afterstate (fp32-exact layer 1: one fp16 piece misses the 1e-5 contract); dense fp32-equivalent is 1/2.09 of this. 26 M128 N128 K16 tcgen05.mma per 128-row tile; ncu: tensor pipe 73-75 % active at 1.9 GHz (profiles/r02_ncu_eval_tc_roles.txt); back to back the kernel is POWER limited (~1 kW, SM clock ~1.68 GHz) at the measured sustained cuBLAS bf16 rate"}
 
     roofline_eval["traffic_source"] = traffic_src
     roofline_eval["kernels_ms"] = {k: v[0] for k, v in kern.items()}
