@@ -50,6 +50,7 @@ class _GatherWorkspace:
 
     SLOTS = 2
     cache: dict = {}
+    coalescing = True  # cleared the first time the backend refuses a coalesced all-gather
 
     @classmethod
     def get(cls, dev, world, max_episodes, max_experiences, cols_info):
@@ -104,14 +105,14 @@ def _all_gather_padded(batch, max_episodes, max_experiences, group, fields):
         if dev.type == "cuda":
             done = False
             cm = getattr(dist, "_coalescing_manager", None)
-            if cm is not None and not _GatherWorkspace.cache.get("no_coalescing"):
+            if cm is not None and _GatherWorkspace.coalescing:
                 try:
                     with cm(group=group, device=dev, async_ops=False):
                         for ob, ib in byte_pairs:
                             dist.all_gather_into_tensor(ob, ib, group=group)
                     done = True
                 except (RuntimeError, TypeError, NotImplementedError):  # a backend / version without coalesced all-gather: one call per field
-                    _GatherWorkspace.cache["no_coalescing"] = True
+                    _GatherWorkspace.coalescing = False
             if not done:
                 for ob, ib in byte_pairs:
                     dist.all_gather_into_tensor(ob, ib, group=group)
