@@ -15,6 +15,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _forced_tile_schedule():
+    """BG_TEST_TILE_SCHEDULE=0|1 runs the whole GPU suite with the tcgen05 evaluator's static / dynamic tile schedule forced for every
+    launch (the default picks by size), so that both code paths see every test."""
+    mode = os.environ.get("BG_TEST_TILE_SCHEDULE")
+    if mode in ("0", "1"):
+        import mlp_ppo_2ply_multi_b200 as bg
+
+        bg._lib.lib().bg_eval_tc_tile_schedule(int(mode))
+    yield
+
+
 @pytest.fixture(scope="session")
 def oracle():
     """The CPU oracle (oracle/bg_oracle.c) -- the checker, never the thing under test on the GPU path."""
