@@ -532,6 +532,31 @@ int32_t launch_tail_tier(MovegenParams P, int in, int out, int ctas, int32_t* ct
   return BG_OK;
 }
 
+// Longest-first order for SMALL per-item batches (one self-play ply): a double's tree costs several times a non-double's, and the warps take
+// items dynamically, so the last items decide when the bulk tier ends.  The items with d0 == d1 go to the front of the list, the others
+// fill it from the back.  cursors[0] / cursors[1] (zeroed with the workspace header) count the two classes; *count = B.
+__global__ void __launch_bounds__(256) k_order_items(const uint8_t* __restrict__ rolls, int64_t B, int32_t* __restrict__ list, int32_t* __restrict__ count,
+                                                     int32_t* __restrict__ cursors) {
+  const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *count = (int32_t)B;
+  for (int64_t base = ((int64_t)blockIdx.x * 256 + threadIdx.x) & ~31ll; base < B; base += (int64_t)gridDim.x * 256) {
+    const int64_t i = base + lane;
+    const bool in = i < B;
+    const bool dbl = in && rolls[2 * i] == rolls[2 * i + 1];
+    const uint32_t md = __ballot_sync(BG_FULL, dbl), mn = __ballot_sync(BG_FULL, in && !dbl);
+    int bd = 0, bn = 0;
+    if (lane == 0) {
+      if (md) bd = atomicAdd(&cursors[0], __popc(md));
+      if (mn) bn = atomicAdd(&cursors[1], __popc(mn));
+    }
+    bd = __shfl_sync(BG_FULL, bd, 0);
+    bn = __shfl_sync(BG_FULL, bn, 0);
+    const uint32_t below = (1u << lane) - 1u;
+    if (dbl) list[bd + __popc(md & below)] = (int32_t)i;
+    else if (in) list[B - 1 - (bn + __popc(mn & below))] = (int32_t)i;
+  }
+}
+
 template <bool MOVES>
 int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* const (&ovf)[N_OVF], int32_t* const (&ovf_n)[N_OVF],
                      int64_t* tier1_total, cudaEvent_t tier1_event, int32_t tier2_ctas, cudaStream_t stream) {
@@ -559,6 +584,12 @@ int32_t launch_tiers(MovegenParams P, int64_t B, int32_t* ctr, int32_t* const (&
   } else {
     if ((rc = prepare_tier<T1_CAP, false, MOVES, T1_WARPS, T1_CTAS_PER_SM>()) != BG_OK) return rc;
     P.grab = B > (1 << 20) ? 8 : 1;
+    if (B < (1 << 20) && B >= 4096 && P.rolls && !getenv("BG_MOVEGEN_NO_ORDER")) {
+      // overflow list 1 is only used by the 256-node tier of batches >= 2^20 items: free here for the ordered item list
+      k_order_items<<<(int)((B + 255) / 256 < 592 ? (B + 255) / 256 : 592), 256, 0, stream>>>(P.rolls, B, ovf[1], ovf_n[1], ctr + 12);
+      P.in_list = ovf[1];
+      P.in_count = ovf_n[1];
+    }
     int64_t want = (B + T1_WARPS - 1) / T1_WARPS;
     int grid = (int)(want < (int64_t)NUM_SMS * T1_CTAS_PER_SM ? want : (int64_t)NUM_SMS * T1_CTAS_PER_SM);
     k_movegen<T1_CAP, false, MOVES, T1_WARPS, T1_CTAS_PER_SM><<<grid, T1_WARPS * 32, smem_bytes(T1_CAP, false, MOVES, T1_WARPS), stream>>>(P);
