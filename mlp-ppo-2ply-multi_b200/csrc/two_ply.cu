@@ -205,7 +205,7 @@ Layout make_layout(int64_t C, bool sampled = false) {
   return L;
 }
 
-constexpr int64_t DEFAULT_CHUNK = 65536;
+constexpr int64_t DEFAULT_CHUNK = 262144;
 
 }  // namespace
 
