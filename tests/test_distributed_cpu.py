@@ -93,6 +93,16 @@ def _worker(rank, world, port, out_dir):
     np.savez(os.path.join(out_dir, f"ep{rank}.npz"), n=np.array([merged.n_episodes, merged.n_experiences]), off=merged.ep_offsets.numpy(),
              after=merged.after_boards.numpy(), reward=merged.reward.numpy(), info=merged.ep_info.numpy(), roll=merged.roll.numpy(),
              action=merged.action.numpy(), my_after=eb.after_boards[:N].numpy(), my_reward=eb.reward[:N].numpy())
+    # the padded form hands out TWO buffer sets in turn: a batch stays valid until the second next gather with the same quota (the learner
+    # kernel may still be reading batch u while batch u + 1 is gathered)
+    slim = bgd.all_gather_episodes(eb, max_episodes=4, max_experiences=12, compact=False, fields=bgd.LEARNER_FIELDS)
+    keep = slim.after_boards.clone()
+    eb2 = EpisodeBatch(E, N, torch.zeros_like(eb.after_boards), eb.meta, eb.reward, eb.state_value, eb.next_state_value, eb.n_moves, eb.action, eb.roll,
+                       eb.ep_offsets, eb.ep_info)
+    nxt = bgd.all_gather_episodes(eb2, max_episodes=4, max_experiences=12, compact=False, fields=bgd.LEARNER_FIELDS)
+    assert nxt.after_boards.data_ptr() != slim.after_boards.data_ptr() and torch.equal(slim.after_boards, keep) and int(nxt.after_boards.abs().sum()) == 0
+    third = bgd.all_gather_episodes(eb, max_episodes=4, max_experiences=12, compact=False, fields=bgd.LEARNER_FIELDS)
+    assert third.after_boards.data_ptr() == slim.after_boards.data_ptr() and torch.equal(third.after_boards, keep)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), packed=packed.numpy(), version=pm.get_version(), temperature=pm.get_temperature(),
              n_local=n_local, base=base, games=stats["games"], steps=stats["steps"], after=stats["afterstates"], w=w.numpy(), ver=ver, temp=temp)
     dist.destroy_process_group()
